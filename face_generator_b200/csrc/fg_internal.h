@@ -1,0 +1,232 @@
+// Internal declarations shared by the translation units of libfg_b200.so.
+// Everything on the device is NHWC fp32; the NCHW reference layouts exist only at the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "fg_b200.h"
+
+void fg_set_error(const char* fmt, ...);
+
+#define FG_CUDA(call)                                                                               \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess) {                                                                       \
+      fg_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));          \
+      return FG_ERR_CUDA;                                                                           \
+    }                                                                                               \
+  } while (0)
+#define FG_TRY(call)                  \
+  do {                                \
+    int r__ = (call);                 \
+    if (r__ != FG_OK) return r__;     \
+  } while (0)
+#define FG_REQUIRE(cond, ...)         \
+  do {                                \
+    if (!(cond)) {                    \
+      fg_set_error(__VA_ARGS__);      \
+      return FG_ERR_INVALID;          \
+    }                                 \
+  } while (0)
+
+constexpr int kMaskPerSample = 1984;  // 64+128+256+512 SpatialDropout + 512+512 Dropout keep flags
+constexpr int kNoiseDim = 100;
+constexpr int kGradTail = 8;          // extra floats behind each flat gradient (DP-reduced scalars)
+
+// Geometry of one stride-1 "same" convolution seen as a sum over taps of shifted GEMMs.
+// Output pixels p = (b,y,x) in [0,B)x[0,H)x[0,W); the stored input is [B][H/ups][W/ups][Cin]
+// (ups = 2 folds nn.SpatialUpSamplingNearest(2) into the addressing).  Linear layers are k=1,H=W=1.
+struct ConvGeom {
+  int B, H, W, Cin, Cout, k, ups;
+};
+
+// Flat parameter layouts (getParameters() order), float offsets.
+struct GLayout {
+  int64_t L1W, L1b, a1, C1W, C1b, g1, be1, a2, C2W, C2b, g2, be2, a3, C3W, C3b, total;
+};
+struct DLayout {
+  int64_t cW[4], cb[4], ca[4], L1W, L1b, a5, L2W, L2b, a6, L3W, L3b, total;
+};
+GLayout make_g_layout(int C);
+DLayout make_d_layout(int C);
+
+struct DeviceStats {  // lives in device memory; mirrored to fg_step_stats
+  float loss_D, loss_G;
+  int conf[4];
+  int trained_D;
+  int t_D, t_G;
+  float acc_D;
+  // gate state
+  int acc_count, acc_head;
+  float step_D, step_G;  // Adam step sizes prepared by adam_prep
+  int do_train_D, do_train_G;
+};
+constexpr int kAccHistMax = 1024;
+
+struct TimerRec {
+  double ms = 0;
+  int64_t launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct fg_ctx {
+  int device = 0, maxB = 0, C = 3;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int64_t launches = 0;
+  int conv_impl = FG_CONV_SIMT;
+  int sm_count = 148;
+  GLayout gl;
+  DLayout dl;
+  // flat buffers (owned)
+  float *PG = nullptr, *PD = nullptr, *gG = nullptr, *gD = nullptr;
+  float *mG = nullptr, *vG = nullptr, *mD = nullptr, *vD = nullptr;
+  float* bnG = nullptr;  // [768] running stats
+  DeviceStats* dstats = nullptr;
+  float* acc_hist = nullptr;  // [kAccHistMax]
+  DeviceStats* hstats = nullptr;  // pinned mirror
+  // packed weights (forward packs [tap][n][c], dgrad packs [tap'][c][n])
+  float *G_L1p = nullptr, *G_L1pd = nullptr, *G_C1p = nullptr, *G_C1pd = nullptr, *G_C2p = nullptr, *G_C2pd = nullptr,
+        *G_C3p = nullptr, *G_C3pd = nullptr;
+  float *D_cp[4] = {nullptr, nullptr, nullptr, nullptr}, *D_cpd[4] = {nullptr, nullptr, nullptr, nullptr};
+  float *D_L1p = nullptr, *D_L1pd = nullptr, *D_L2pd = nullptr, *D_L3pd = nullptr;
+  bool G_packed = false, D_packed = false;
+  float* wgrad_ws = nullptr;  // packed weight-gradient workspace (largest layer)
+  size_t wgrad_ws_elems = 0;
+  // G activations (NHWC)
+  int G_B = 0;
+  bool G_train = true, G_fwd_valid = false;
+  float *G_noise = nullptr, *G_z0 = nullptr, *G_h0 = nullptr, *G_z1 = nullptr, *G_h1 = nullptr, *G_z2 = nullptr,
+        *G_h2 = nullptr, *G_z3 = nullptr, *G_y = nullptr;
+  double* bn_acc = nullptr;  // [4][256] double accumulators (sum, sumsq / sum g, sum g xhat)
+  float *bn_mean1 = nullptr, *bn_istd1 = nullptr, *bn_mean2 = nullptr, *bn_istd2 = nullptr, *bn_mg = nullptr;
+  float *G_dz3 = nullptr, *G_dfull = nullptr, *G_dz2 = nullptr, *G_dz1 = nullptr, *G_dz0 = nullptr;
+  // D activations (NHWC)
+  int D_B = 0;
+  bool D_train = true, D_fwd_valid = false;
+  float *D_x = nullptr, *D_z[4] = {nullptr, nullptr, nullptr, nullptr}, *D_p[4] = {nullptr, nullptr, nullptr, nullptr};
+  float *D_zl1 = nullptr, *D_hl1 = nullptr, *D_zl2 = nullptr, *D_hl2 = nullptr, *D_logit = nullptr, *D_out = nullptr;
+  float* D_masks = nullptr;
+  float D_drop_scale = 2.0f, D_spatial_eval = 0.8f;  // 1/(1-p_drop), 1-p_spatial of the last forward
+  float *D_dlogit = nullptr, *D_dh = nullptr, *D_dzl = nullptr, *D_dz = nullptr, *D_dp = nullptr, *D_dx = nullptr;
+  float* D_targets = nullptr;
+  // staging
+  float* stage_pinned = nullptr;
+  size_t stage_pinned_bytes = 0;
+  float* io_dev = nullptr;  // device staging for NCHW images / misc
+  size_t io_dev_elems = 0;
+  float* io_dev2 = nullptr;
+  float *in_real = nullptr, *in_noiseD = nullptr, *in_noiseG = nullptr, *in_masksD = nullptr, *in_masksG = nullptr;
+  float* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_elems[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // data parallel
+  void* nccl_comm = nullptr;
+  int world = 1, rank = 0;
+  // timing
+  cudaEvent_t events[16] = {};
+  bool timing = false;
+  std::map<std::string, TimerRec> timers;
+  // tcgen05 path state (k_conv_tc.cu)
+  void* tc = nullptr;
+};
+
+struct ScopedTimer {
+  fg_ctx* c;
+  TimerRec* rec = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ScopedTimer(fg_ctx* c_, const char* name) : c(c_) {
+    if (c->timing) {
+      rec = &c->timers[name];
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, c->stream);
+    }
+  }
+  ~ScopedTimer() {
+    if (rec) {
+      cudaEventRecord(e1, c->stream);
+      rec->pending.emplace_back(e0, e1);
+    }
+  }
+};
+
+// ---- k_elem.cu -------------------------------------------------------------------------------------
+int k_fill(fg_ctx* c, float* p, float v, int64_t n);
+int k_nchw_to_nhwc(fg_ctx* c, const float* src, float* dst, int B, int C, int HW);
+int k_nhwc_to_nchw(fg_ctx* c, const float* src, float* dst, int B, int C, int HW);
+// weight packing: flat W[N][Cc][KK] -> fwd pack [t][n'][c'] and (optional) dgrad pack [KK-1-t][c'][n'].
+// (nA,nS)/(cA,cS): index permutation j=a*S+s -> j'=s*A+a on rows / columns (0,0 = identity).
+int k_pack_weights(fg_ctx* c, const float* W, float* Wp, float* Wpd, int N, int Cc, int KK, int nA, int nS, int cA,
+                   int cS);
+// grads: dW[n][c][t] += scale * dWp[t][n'][c']
+int k_unpack_wgrad(fg_ctx* c, const float* dWp, float* dW, int N, int Cc, int KK, int nA, int nS, int cA, int cS);
+int k_colsum_add(fg_ctx* c, const float* X, float* out, int64_t P, int N, int nA, int nS);  // out[perm^-1(n)] += sum_p X[p][n]
+int k_prelu_fwd(fg_ctx* c, const float* z, const float* slope, float* h, int64_t n);
+// dz = pool?(dh) * (z>0?1:a); *dslope += sum_{z<=0} dh*z.  pool: dh is [B][2H][2W][C] summed 2x2.
+int k_prelu_bwd(fg_ctx* c, const float* dh, const float* z, const float* slope, float* dz, float* dslope, int B, int H,
+                int W, int C, int pool);
+int k_bn_stats(fg_ctx* c, const float* z, double* acc2C, int64_t P, int C);
+int k_bn_finalize(fg_ctx* c, double* acc2C, float* mean, float* istd, float* run_mean, float* run_var, int64_t P,
+                  int C);
+int k_bn_eval_prep(fg_ctx* c, const float* run_mean, const float* run_var, float* mean, float* istd, int C);
+int k_bn_prelu_apply(fg_ctx* c, const float* z, const float* mean, const float* istd, const float* gamma,
+                     const float* beta, const float* slope, float* h, int64_t P, int C);
+int k_bn_prelu_bwd_reduce(fg_ctx* c, const float* dh, const float* z, const float* mean, const float* istd,
+                          const float* gamma, const float* beta, const float* slope, double* acc2C, float* dslope,
+                          int B, int H, int W, int C, int pool);
+int k_bn_bwd_finalize(fg_ctx* c, double* acc2C, float* mg2C, float* dgamma, float* dbeta, int64_t P, int C);
+int k_bn_prelu_bwd_apply(fg_ctx* c, const float* dh, const float* z, const float* mean, const float* istd,
+                         const float* gamma, const float* beta, const float* slope, const float* mg2C, float* dz,
+                         int B, int H, int W, int C, int pool);
+int k_sigmoid_fwd(fg_ctx* c, const float* z, float* y, int64_t n);
+int k_sigmoid_bwd(fg_ctx* c, const float* dy, const float* y, float* dz, int64_t n);
+int k_masks_generate(fg_ctx* c, float* masks, int B, uint64_t seed, float p_spatial, float p_drop);
+int k_d_act_pool_fwd(fg_ctx* c, const float* z, const float* slope, const float* masks, int moff, float eval_scale,
+                     float* p, int B, int H, int W, int C);
+int k_d_act_pool_bwd(fg_ctx* c, const float* dp, const float* z, const float* slope, const float* masks, int moff,
+                     float eval_scale, float* dz, float* dslope, int B, int H, int W, int C);
+int k_lin_act_drop_fwd(fg_ctx* c, const float* z, const float* slope, const float* masks, int moff, float scale,
+                       float* h, int B, int N);
+int k_lin_act_drop_bwd(fg_ctx* c, const float* dh, const float* z, const float* slope, const float* masks, int moff,
+                       float scale, float* dz, float* dslope, int B, int N);
+// out=sigmoid(logit); loss (mean BCE) -> *loss_out; dlogit = bce_grad*y(1-y); targets: first n_ones are 1.
+// conf (may be null) gets [pred1&t1, pred0&t1, pred1&t0, pred0&t0] as floats in tail4 (for the DP allreduce)
+int k_sigmoid_bce(fg_ctx* c, const float* logit, float* out, float* dlogit, float* loss_out, float* tail4, int B,
+                  int n_ones);
+int k_bce_fwd(fg_ctx* c, const float* x, const float* t, int n, float* loss_out);
+int k_bce_bwd(fg_ctx* c, const float* x, const float* t, int n, float* dx);
+int k_sigmoid_grad_mul(fg_ctx* c, const float* dout, const float* out, float* dlogit, int n);
+// optimizer
+int k_penalty_loss(fg_ctx* c, const float* p, int64_t n, float l1, float l2, float* loss_inout);
+int k_gate_and_prep(fg_ctx* c, int net, const fg_hyper* h, const float* tail4, int B, float world);
+int k_adam(fg_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+           float l1_grad, float l2, float clampv, float grad_scale, const float* step_dev, const int* flag_dev,
+           float step_host, float* g_out);
+
+// ---- k_conv_simt.cu --------------------------------------------------------------------------------
+// out[p][n] = bias[n] + sum_{t,c} in[pix(p,t)][c] * Wp[t][n][c]
+int k_conv_simt(fg_ctx* c, const float* in, const float* Wp, const float* bias, float* out, ConvGeom g);
+// dWp[t][n][c] = sum_p dY[p][n] * in[pix(p,t)][c]   (dWp is overwritten)
+int k_wgrad_simt(fg_ctx* c, const float* in, const float* dY, float* dWp, ConvGeom g);
+
+// ---- k_conv_tc.cu ----------------------------------------------------------------------------------
+int tc_init(fg_ctx* c);
+void tc_destroy(fg_ctx* c);
+
+// ---- nets.cu ---------------------------------------------------------------------------------------
+int net_alloc(fg_ctx* c);
+void net_free(fg_ctx* c);
+int net_pack_G(fg_ctx* c);
+int net_pack_D(fg_ctx* c);
+int net_G_forward(fg_ctx* c, const float* noise_dev, int B, bool training);                 // -> c->G_y (NHWC)
+int net_G_backward(fg_ctx* c, const float* dy_nhwc, float* dnoise_dev);                      // accumulates c->gG
+int net_D_forward(fg_ctx* c, const float* x_nhwc, int B, bool training, const fg_hyper* h);  // masks in c->D_masks
+int net_D_backward(fg_ctx* c, const float* dlogit_dev, bool want_wgrad, bool want_dx);       // -> c->D_dx (NHWC)
+int net_optim(fg_ctx* c, int net, const fg_hyper* h, float grad_scale, bool gate);
+int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real_nchw_dev, const float* noiseD_dev,
+                   const float* noiseG_dev, const float* masksD_dev, const float* masksG_dev, uint64_t seed);
+int net_allreduce(fg_ctx* c, float* buf, int64_t n);

@@ -1,0 +1,283 @@
+// L-op level of the C ABI: single layers at the nn.Module boundary (NCHW fp32, host or device
+// pointers).  These are what the Lua `b200.*` nn.Module shims call from updateOutput /
+// updateGradInput / accGradParameters; they reuse the same kernels as the fused nets and convert
+// NCHW <-> NHWC around them (the fused L-net / L-step paths never pay that conversion).
+#include <cstring>
+
+#include "fg_internal.h"
+
+namespace {
+bool is_dev(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+int scratch(fg_ctx* c, int slot, size_t n, float** out) {
+  if (c->scratch_elems[slot] < n) {
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->scratch[slot]) FG_CUDA(cudaFree(c->scratch[slot]));
+    c->scratch[slot] = nullptr;
+    c->scratch_elems[slot] = 0;
+    FG_CUDA(cudaMalloc((void**)&c->scratch[slot], n * sizeof(float)));
+    c->scratch_elems[slot] = n;
+  }
+  *out = c->scratch[slot];
+  return FG_OK;
+}
+// device copy of a user tensor (slot used only for host pointers)
+int in_dev(fg_ctx* c, const float* p, size_t n, int slot, const float** out) {
+  if (is_dev(p)) {
+    *out = p;
+    return FG_OK;
+  }
+  float* s;
+  FG_TRY(scratch(c, slot, n, &s));
+  FG_CUDA(cudaMemcpyAsync(s, p, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  *out = s;
+  return FG_OK;
+}
+// device buffer to produce a user output in; finish with out_done()
+int out_dev(fg_ctx* c, float* user, size_t n, int slot, float** dev, bool load) {
+  if (is_dev(user)) {
+    *dev = user;
+    return FG_OK;
+  }
+  FG_TRY(scratch(c, slot, n, dev));
+  if (load) FG_CUDA(cudaMemcpyAsync(*dev, user, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  return FG_OK;
+}
+int out_done(fg_ctx* c, float* user, const float* dev, size_t n) {
+  if (user == dev) return FG_OK;
+  FG_CUDA(cudaMemcpyAsync(user, dev, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  FG_CUDA(cudaStreamSynchronize(c->stream));
+  return FG_OK;
+}
+}  // namespace
+
+#define ENTER(c)                                      \
+  do {                                                \
+    if (!(c)) {                                       \
+      fg_set_error("null fg_ctx");                    \
+      return FG_ERR_INVALID;                          \
+    }                                                 \
+    FG_CUDA(cudaSetDevice((c)->device));              \
+  } while (0)
+
+extern "C" {
+
+int fg_conv2d_forward(fg_ctx* c, const float* x, const float* w, const float* b, float* y, int N, int Cin, int H, int W,
+                      int Cout, int k) {
+  ENTER(c);
+  FG_REQUIRE(x && w && y && N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0 && k >= 1 && (k & 1),
+             "fg_conv2d_forward: bad arguments (odd kernel sizes only: same padding (k-1)/2)");
+  const size_t nx = (size_t)N * Cin * H * W, ny = (size_t)N * Cout * H * W, nw = (size_t)Cout * Cin * k * k;
+  const float *xd, *wd, *bd = nullptr;
+  FG_TRY(in_dev(c, x, nx, 0, &xd));
+  FG_TRY(in_dev(c, w, nw, 1, &wd));
+  if (b) FG_TRY(in_dev(c, b, Cout, 2, &bd));
+  float *xn, *wp, *yn, *yd;
+  FG_TRY(scratch(c, 3, nx, &xn));
+  FG_TRY(scratch(c, 4, nw, &wp));
+  FG_TRY(scratch(c, 5, ny, &yn));
+  FG_TRY(k_nchw_to_nhwc(c, xd, xn, N, Cin, H * W));
+  FG_TRY(k_pack_weights(c, wd, wp, nullptr, Cout, Cin, k * k, 0, 0, 0, 0));
+  FG_TRY(k_conv_simt(c, xn, wp, bd, yn, ConvGeom{N, H, W, Cin, Cout, k, 1}));
+  FG_TRY(out_dev(c, y, ny, 6, &yd, false));
+  FG_TRY(k_nhwc_to_nchw(c, yn, yd, N, Cout, H * W));
+  return out_done(c, y, yd, ny);
+}
+
+int fg_conv2d_backward_data(fg_ctx* c, const float* dy, const float* w, float* dx, int N, int Cin, int H, int W, int Cout,
+                            int k) {
+  ENTER(c);
+  FG_REQUIRE(dy && w && dx && N > 0 && (k & 1), "fg_conv2d_backward_data: bad arguments");
+  const size_t nx = (size_t)N * Cin * H * W, ny = (size_t)N * Cout * H * W, nw = (size_t)Cout * Cin * k * k;
+  const float *dyd, *wd;
+  FG_TRY(in_dev(c, dy, ny, 0, &dyd));
+  FG_TRY(in_dev(c, w, nw, 1, &wd));
+  float *dyn, *wpd, *dxn, *dxd;
+  FG_TRY(scratch(c, 3, ny, &dyn));
+  FG_TRY(scratch(c, 4, nw, &wpd));
+  FG_TRY(scratch(c, 5, nx, &dxn));
+  FG_TRY(k_nchw_to_nhwc(c, dyd, dyn, N, Cout, H * W));
+  FG_TRY(k_pack_weights(c, wd, nullptr, wpd, Cout, Cin, k * k, 0, 0, 0, 0));
+  FG_TRY(k_conv_simt(c, dyn, wpd, nullptr, dxn, ConvGeom{N, H, W, Cout, Cin, k, 1}));
+  FG_TRY(out_dev(c, dx, nx, 6, &dxd, false));
+  FG_TRY(k_nhwc_to_nchw(c, dxn, dxd, N, Cin, H * W));
+  return out_done(c, dx, dxd, nx);
+}
+
+int fg_conv2d_backward_filter(fg_ctx* c, const float* x, const float* dy, float* dw, float* db, int N, int Cin, int H,
+                              int W, int Cout, int k) {
+  ENTER(c);
+  FG_REQUIRE(x && dy && dw && N > 0 && (k & 1), "fg_conv2d_backward_filter: bad arguments");
+  const size_t nx = (size_t)N * Cin * H * W, ny = (size_t)N * Cout * H * W, nw = (size_t)Cout * Cin * k * k;
+  const float *xd, *dyd;
+  FG_TRY(in_dev(c, x, nx, 0, &xd));
+  FG_TRY(in_dev(c, dy, ny, 1, &dyd));
+  float *xn, *dyn, *ws, *dwd, *dbd = nullptr;
+  FG_TRY(scratch(c, 3, nx, &xn));
+  FG_TRY(scratch(c, 4, ny, &dyn));
+  FG_TRY(scratch(c, 5, nw, &ws));
+  FG_TRY(k_nchw_to_nhwc(c, xd, xn, N, Cin, H * W));
+  FG_TRY(k_nchw_to_nhwc(c, dyd, dyn, N, Cout, H * W));
+  FG_TRY(k_wgrad_simt(c, xn, dyn, ws, ConvGeom{N, H, W, Cin, Cout, k, 1}));
+  FG_TRY(out_dev(c, dw, nw, 6, &dwd, true));
+  FG_TRY(k_unpack_wgrad(c, ws, dwd, Cout, Cin, k * k, 0, 0, 0, 0));
+  if (db) {
+    FG_TRY(out_dev(c, db, Cout, 7, &dbd, true));
+    FG_TRY(k_colsum_add(c, dyn, dbd, (int64_t)N * H * W, Cout, 0, 0));
+  }
+  FG_TRY(out_done(c, dw, dwd, nw));
+  if (db) FG_TRY(out_done(c, db, dbd, Cout));
+  return FG_OK;
+}
+
+int fg_linear_forward(fg_ctx* c, const float* x, const float* w, const float* b, float* y, int N, int in, int out) {
+  ENTER(c);
+  FG_REQUIRE(x && w && y && N > 0 && in > 0 && out > 0, "fg_linear_forward: bad arguments");
+  const float *xd, *wd, *bd = nullptr;
+  FG_TRY(in_dev(c, x, (size_t)N * in, 0, &xd));
+  FG_TRY(in_dev(c, w, (size_t)out * in, 1, &wd));
+  if (b) FG_TRY(in_dev(c, b, out, 2, &bd));
+  float* yd;
+  FG_TRY(out_dev(c, y, (size_t)N * out, 6, &yd, false));
+  FG_TRY(k_conv_simt(c, xd, wd, bd, yd, ConvGeom{N, 1, 1, in, out, 1, 1}));  // W[out][in] is already [n][c]
+  return out_done(c, y, yd, (size_t)N * out);
+}
+
+int fg_linear_backward(fg_ctx* c, const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int N,
+                       int in, int out) {
+  ENTER(c);
+  FG_REQUIRE(x && w && dy && N > 0, "fg_linear_backward: bad arguments");
+  const float *xd, *wd, *dyd;
+  FG_TRY(in_dev(c, x, (size_t)N * in, 0, &xd));
+  FG_TRY(in_dev(c, w, (size_t)out * in, 1, &wd));
+  FG_TRY(in_dev(c, dy, (size_t)N * out, 2, &dyd));
+  if (dx) {
+    float *wpd, *dxd;
+    FG_TRY(scratch(c, 3, (size_t)out * in, &wpd));
+    FG_TRY(k_pack_weights(c, wd, nullptr, wpd, out, in, 1, 0, 0, 0, 0));
+    FG_TRY(out_dev(c, dx, (size_t)N * in, 6, &dxd, false));
+    FG_TRY(k_conv_simt(c, dyd, wpd, nullptr, dxd, ConvGeom{N, 1, 1, out, in, 1, 1}));
+    FG_TRY(out_done(c, dx, dxd, (size_t)N * in));
+  }
+  if (dw) {
+    float *ws, *dwd;
+    FG_TRY(scratch(c, 4, (size_t)out * in, &ws));
+    FG_TRY(k_wgrad_simt(c, xd, dyd, ws, ConvGeom{N, 1, 1, in, out, 1, 1}));
+    FG_TRY(out_dev(c, dw, (size_t)out * in, 6, &dwd, true));
+    FG_TRY(k_unpack_wgrad(c, ws, dwd, out, in, 1, 0, 0, 0, 0));
+    FG_TRY(out_done(c, dw, dwd, (size_t)out * in));
+  }
+  if (db) {
+    float* dbd;
+    FG_TRY(out_dev(c, db, out, 7, &dbd, true));
+    FG_TRY(k_colsum_add(c, dyd, dbd, N, out, 0, 0));
+    FG_TRY(out_done(c, db, dbd, out));
+  }
+  return FG_OK;
+}
+
+int fg_bn_forward_train(fg_ctx* c, const float* x, const float* gamma, const float* beta, float* y, float* save_mean,
+                        float* save_istd, float* run_mean, float* run_var, int N, int C, int HW) {
+  ENTER(c);
+  FG_REQUIRE(x && gamma && beta && y && save_mean && save_istd && N > 0 && C > 0 && C <= 1024,
+             "fg_bn_forward_train: bad arguments (C <= 1024)");
+  const size_t n = (size_t)N * C * HW;
+  const float *xd, *gd, *bd;
+  FG_TRY(in_dev(c, x, n, 0, &xd));
+  FG_TRY(in_dev(c, gamma, C, 1, &gd));
+  FG_TRY(in_dev(c, beta, C, 2, &bd));
+  float *xn, *yn, *small, *yd;
+  FG_TRY(scratch(c, 3, n, &xn));
+  FG_TRY(scratch(c, 4, n, &yn));
+  FG_TRY(scratch(c, 5, (size_t)8 * C + 16, &small));  // [acc 2C doubles = 4C floats][mean C][istd C][rm C][rv C]
+  double* acc = (double*)small;
+  float *mean = small + 4 * C, *istd = mean + C, *rm = istd + C, *rv = rm + C;
+  if (run_mean) FG_CUDA(cudaMemcpyAsync(rm, run_mean, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  if (run_var) FG_CUDA(cudaMemcpyAsync(rv, run_var, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  FG_TRY(k_nchw_to_nhwc(c, xd, xn, N, C, HW));
+  FG_TRY(k_bn_stats(c, xn, acc, (int64_t)N * HW, C));
+  FG_TRY(k_bn_finalize(c, acc, mean, istd, run_mean ? rm : nullptr, run_var ? rv : nullptr, (int64_t)N * HW, C));
+  FG_TRY(k_bn_prelu_apply(c, xn, mean, istd, gd, bd, nullptr, yn, (int64_t)N * HW, C));
+  FG_TRY(out_dev(c, y, n, 6, &yd, false));
+  FG_TRY(k_nhwc_to_nchw(c, yn, yd, N, C, HW));
+  FG_TRY(out_done(c, y, yd, n));
+  FG_CUDA(cudaMemcpyAsync(save_mean, mean, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  FG_CUDA(cudaMemcpyAsync(save_istd, istd, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  if (run_mean) FG_CUDA(cudaMemcpyAsync(run_mean, rm, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  if (run_var) FG_CUDA(cudaMemcpyAsync(run_var, rv, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  FG_CUDA(cudaStreamSynchronize(c->stream));
+  return FG_OK;
+}
+
+int fg_bn_backward(fg_ctx* c, const float* x, const float* gamma, const float* save_mean, const float* save_istd,
+                   const float* dy, float* dx, float* dgamma, float* dbeta, int N, int C, int HW) {
+  ENTER(c);
+  FG_REQUIRE(x && gamma && save_mean && save_istd && dy && dx && N > 0 && C > 0 && C <= 1024,
+             "fg_bn_backward: bad arguments (C <= 1024)");
+  const size_t n = (size_t)N * C * HW;
+  const float *xd, *dyd;
+  FG_TRY(in_dev(c, x, n, 0, &xd));
+  FG_TRY(in_dev(c, dy, n, 1, &dyd));
+  float *xn, *dyn, *dxn, *small, *dxd;
+  FG_TRY(scratch(c, 2, n, &xn));
+  FG_TRY(scratch(c, 3, n, &dyn));
+  FG_TRY(scratch(c, 4, n, &dxn));
+  FG_TRY(scratch(c, 5, (size_t)12 * C + 16, &small));
+  double* acc = (double*)small;
+  float *gd = small + 4 * C, *mean = gd + C, *istd = mean + C, *mg = istd + C, *dg = mg + 2 * C, *db = dg + C,
+        *zero = db + C;
+  FG_CUDA(cudaMemcpyAsync(gd, gamma, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  FG_CUDA(cudaMemcpyAsync(mean, save_mean, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  FG_CUDA(cudaMemcpyAsync(istd, save_istd, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  FG_CUDA(cudaMemsetAsync(zero, 0, C * sizeof(float), c->stream));
+  if (dgamma) FG_CUDA(cudaMemcpyAsync(dg, dgamma, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  if (dbeta) FG_CUDA(cudaMemcpyAsync(db, dbeta, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  FG_TRY(k_nchw_to_nhwc(c, xd, xn, N, C, HW));
+  FG_TRY(k_nchw_to_nhwc(c, dyd, dyn, N, C, HW));
+  // H=HW, W=1 flattening is fine: no pooling here
+  FG_TRY(k_bn_prelu_bwd_reduce(c, dyn, xn, mean, istd, gd, zero, nullptr, acc, nullptr, N, HW, 1, C, 0));
+  FG_TRY(k_bn_bwd_finalize(c, acc, mg, dgamma ? dg : nullptr, dbeta ? db : nullptr, (int64_t)N * HW, C));
+  FG_TRY(k_bn_prelu_bwd_apply(c, dyn, xn, mean, istd, gd, zero, nullptr, mg, dxn, N, HW, 1, C, 0));
+  FG_TRY(out_dev(c, dx, n, 6, &dxd, false));
+  FG_TRY(k_nhwc_to_nchw(c, dxn, dxd, N, C, HW));
+  FG_TRY(out_done(c, dx, dxd, n));
+  if (dgamma) FG_CUDA(cudaMemcpyAsync(dgamma, dg, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  if (dbeta) FG_CUDA(cudaMemcpyAsync(dbeta, db, C * sizeof(float), cudaMemcpyDefault, c->stream));
+  FG_CUDA(cudaStreamSynchronize(c->stream));
+  return FG_OK;
+}
+
+int fg_prelu_forward(fg_ctx* c, const float* x, const float* slope, float* y, int64_t n) {
+  ENTER(c);
+  FG_REQUIRE(x && slope && y && n > 0, "fg_prelu_forward: bad arguments");
+  const float *xd, *sd;
+  FG_TRY(in_dev(c, x, n, 0, &xd));
+  FG_TRY(in_dev(c, slope, 1, 1, &sd));
+  float* yd;
+  FG_TRY(out_dev(c, y, n, 6, &yd, false));
+  FG_TRY(k_prelu_fwd(c, xd, sd, yd, n));
+  return out_done(c, y, yd, n);
+}
+int fg_prelu_backward(fg_ctx* c, const float* x, const float* slope, const float* dy, float* dx, float* dslope, int64_t n) {
+  ENTER(c);
+  FG_REQUIRE(x && slope && dy && dx && n > 0 && n < (int64_t)1 << 31, "fg_prelu_backward: bad arguments");
+  const float *xd, *sd, *dyd;
+  FG_TRY(in_dev(c, x, n, 0, &xd));
+  FG_TRY(in_dev(c, slope, 1, 1, &sd));
+  FG_TRY(in_dev(c, dy, n, 2, &dyd));
+  float *dxd, *dsd = nullptr;
+  FG_TRY(out_dev(c, dx, n, 6, &dxd, false));
+  if (dslope) FG_TRY(out_dev(c, dslope, 1, 7, &dsd, true));
+  FG_TRY(k_prelu_bwd(c, dyd, xd, sd, dxd, dsd, 1, (int)n, 1, 1, 0));
+  FG_TRY(out_done(c, dx, dxd, n));
+  if (dslope) FG_TRY(out_done(c, dslope, dsd, 1));
+  return FG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,447 @@
+// Orchestration of G (models.lua:57-81), D (models.lua:382-416) and the adversarial.lua loop body
+// (adversarial.lua:54-300) on one stream.  Kernels live in k_elem.cu / k_conv_simt.cu / k_conv_tc.cu.
+#include <algorithm>
+
+#include "fg_internal.h"
+
+GLayout make_g_layout(int C) {
+  GLayout L;
+  int64_t o = 0;
+  L.L1W = o; o += 8192 * 100;
+  L.L1b = o; o += 8192;
+  L.a1 = o; o += 1;
+  L.C1W = o; o += 256 * 128 * 25;
+  L.C1b = o; o += 256;
+  L.g1 = o; o += 256;
+  L.be1 = o; o += 256;
+  L.a2 = o; o += 1;
+  L.C2W = o; o += 128 * 256 * 25;
+  L.C2b = o; o += 128;
+  L.g2 = o; o += 128;
+  L.be2 = o; o += 128;
+  L.a3 = o; o += 1;
+  L.C3W = o; o += (int64_t)C * 128 * 9;
+  L.C3b = o; o += C;
+  L.total = o;
+  return L;
+}
+DLayout make_d_layout(int C) {
+  DLayout L;
+  const int cin[4] = {C, 64, 128, 256}, cout[4] = {64, 128, 256, 512};
+  int64_t o = 0;
+  for (int i = 0; i < 4; ++i) {
+    L.cW[i] = o; o += (int64_t)cout[i] * cin[i] * 9;
+    L.cb[i] = o; o += cout[i];
+    L.ca[i] = o; o += 1;
+  }
+  L.L1W = o; o += 512 * 2048;
+  L.L1b = o; o += 512;
+  L.a5 = o; o += 1;
+  L.L2W = o; o += 512 * 512;
+  L.L2b = o; o += 512;
+  L.a6 = o; o += 1;
+  L.L3W = o; o += 512;
+  L.L3b = o; o += 1;
+  L.total = o;
+  return L;
+}
+
+namespace {
+const int kDcin[4] = {0 /*C*/, 64, 128, 256}, kDcout[4] = {64, 128, 256, 512}, kDhw[4] = {32, 16, 8, 4};
+const int kDmoff[4] = {0, 64, 192, 448};
+inline int dcin(const fg_ctx* c, int i) { return i == 0 ? c->C : kDcin[i]; }
+
+std::vector<void*>& allocs(fg_ctx* c);
+struct AllocList {
+  std::vector<void*> v;
+};
+std::map<fg_ctx*, AllocList> g_allocs;
+std::vector<void*>& allocs(fg_ctx* c) { return g_allocs[c].v; }
+
+int dalloc(fg_ctx* c, float** p, size_t n) {
+  void* q = nullptr;
+  FG_CUDA(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(float)));
+  FG_CUDA(cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(float), c->stream));
+  allocs(c).push_back(q);
+  *p = (float*)q;
+  return FG_OK;
+}
+}  // namespace
+
+int net_alloc(fg_ctx* c) {
+  const size_t B = c->maxB, C = c->C;
+  c->gl = make_g_layout(c->C);
+  c->dl = make_d_layout(c->C);
+  const size_t nG = c->gl.total, nD = c->dl.total;
+  FG_TRY(dalloc(c, &c->PG, nG));
+  FG_TRY(dalloc(c, &c->PD, nD));
+  FG_TRY(dalloc(c, &c->gG, nG + kGradTail));
+  FG_TRY(dalloc(c, &c->gD, nD + kGradTail));
+  FG_TRY(dalloc(c, &c->mG, nG));
+  FG_TRY(dalloc(c, &c->vG, nG));
+  FG_TRY(dalloc(c, &c->mD, nD));
+  FG_TRY(dalloc(c, &c->vD, nD));
+  FG_TRY(dalloc(c, &c->bnG, 768));
+  {  // running_mean = 0, running_var = 1 (nn.SpatialBatchNormalization init)
+    std::vector<float> init(768, 0.f);
+    for (int i = 256; i < 512; ++i) init[i] = 1.f;
+    for (int i = 640; i < 768; ++i) init[i] = 1.f;
+    FG_CUDA(cudaMemcpyAsync(c->bnG, init.data(), 768 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  float* tmp = nullptr;
+  FG_TRY(dalloc(c, &tmp, (sizeof(DeviceStats) + 3) / 4));
+  c->dstats = (DeviceStats*)tmp;
+  FG_TRY(dalloc(c, &c->acc_hist, kAccHistMax));
+  FG_CUDA(cudaMallocHost((void**)&c->hstats, sizeof(DeviceStats)));
+  memset(c->hstats, 0, sizeof(DeviceStats));
+  // packs
+  FG_TRY(dalloc(c, &c->G_L1p, 8192 * 100 + 8192));  // + permuted bias behind the weights
+  FG_TRY(dalloc(c, &c->G_L1pd, 8192 * 100));
+  FG_TRY(dalloc(c, &c->G_C1p, 25 * 256 * 128));
+  FG_TRY(dalloc(c, &c->G_C1pd, 25 * 256 * 128));
+  FG_TRY(dalloc(c, &c->G_C2p, 25 * 256 * 128));
+  FG_TRY(dalloc(c, &c->G_C2pd, 25 * 256 * 128));
+  FG_TRY(dalloc(c, &c->G_C3p, 9 * C * 128));
+  FG_TRY(dalloc(c, &c->G_C3pd, 9 * C * 128));
+  for (int i = 0; i < 4; ++i) {
+    const size_t n = (size_t)9 * kDcout[i] * dcin(c, i);
+    FG_TRY(dalloc(c, &c->D_cp[i], n));
+    FG_TRY(dalloc(c, &c->D_cpd[i], n));
+  }
+  FG_TRY(dalloc(c, &c->D_L1p, 512 * 2048));
+  FG_TRY(dalloc(c, &c->D_L1pd, 512 * 2048));
+  FG_TRY(dalloc(c, &c->D_L2pd, 512 * 512));
+  c->wgrad_ws_elems = 9 * 512 * 256;
+  FG_TRY(dalloc(c, &c->wgrad_ws, c->wgrad_ws_elems));
+  // G activations
+  FG_TRY(dalloc(c, &c->G_noise, B * kNoiseDim));
+  FG_TRY(dalloc(c, &c->G_z0, B * 8192));
+  FG_TRY(dalloc(c, &c->G_h0, B * 8192));
+  FG_TRY(dalloc(c, &c->G_z1, B * 65536));
+  FG_TRY(dalloc(c, &c->G_h1, B * 65536));
+  FG_TRY(dalloc(c, &c->G_z2, B * 131072));
+  FG_TRY(dalloc(c, &c->G_h2, B * 131072));
+  FG_TRY(dalloc(c, &c->G_z3, B * 1024 * C));
+  FG_TRY(dalloc(c, &c->G_y, B * 1024 * C));
+  FG_TRY(dalloc(c, &tmp, 4 * 256 * 2));  // doubles
+  c->bn_acc = (double*)tmp;
+  FG_TRY(dalloc(c, &c->bn_mean1, 256));
+  FG_TRY(dalloc(c, &c->bn_istd1, 256));
+  FG_TRY(dalloc(c, &c->bn_mean2, 128));
+  FG_TRY(dalloc(c, &c->bn_istd2, 128));
+  FG_TRY(dalloc(c, &c->bn_mg, 512));
+  FG_TRY(dalloc(c, &c->G_dz3, B * 1024 * C));
+  FG_TRY(dalloc(c, &c->G_dfull, B * 262144));
+  FG_TRY(dalloc(c, &c->G_dz2, B * 131072));
+  FG_TRY(dalloc(c, &c->G_dz1, B * 65536));
+  FG_TRY(dalloc(c, &c->G_dz0, B * 8192));
+  // D activations
+  FG_TRY(dalloc(c, &c->D_x, B * 1024 * C));
+  for (int i = 0; i < 4; ++i) {
+    const size_t n = B * (size_t)kDhw[i] * kDhw[i] * kDcout[i];
+    FG_TRY(dalloc(c, &c->D_z[i], n));
+    FG_TRY(dalloc(c, &c->D_p[i], n / 4));
+  }
+  FG_TRY(dalloc(c, &c->D_zl1, B * 512));
+  FG_TRY(dalloc(c, &c->D_hl1, B * 512));
+  FG_TRY(dalloc(c, &c->D_zl2, B * 512));
+  FG_TRY(dalloc(c, &c->D_hl2, B * 512));
+  FG_TRY(dalloc(c, &c->D_logit, B));
+  FG_TRY(dalloc(c, &c->D_out, B));
+  FG_TRY(dalloc(c, &c->D_masks, B * kMaskPerSample));
+  FG_TRY(dalloc(c, &c->D_dlogit, B));
+  FG_TRY(dalloc(c, &c->D_dh, B * 512));
+  FG_TRY(dalloc(c, &c->D_dzl, B * 512));
+  FG_TRY(dalloc(c, &c->D_dz, B * 65536));
+  FG_TRY(dalloc(c, &c->D_dp, B * 16384));
+  FG_TRY(dalloc(c, &c->D_dx, B * 1024 * C));
+  FG_TRY(dalloc(c, &c->D_targets, B));
+  c->io_dev_elems = std::max<size_t>(B * 1024 * C, B * kMaskPerSample);
+  FG_TRY(dalloc(c, &c->io_dev, c->io_dev_elems));
+  FG_TRY(dalloc(c, &c->io_dev2, c->io_dev_elems));
+  FG_TRY(dalloc(c, &c->in_real, B * 1024 * C));
+  FG_TRY(dalloc(c, &c->in_noiseD, B * kNoiseDim));
+  FG_TRY(dalloc(c, &c->in_noiseG, B * kNoiseDim));
+  FG_TRY(dalloc(c, &c->in_masksD, B * kMaskPerSample));
+  FG_TRY(dalloc(c, &c->in_masksG, B * kMaskPerSample));
+  FG_CUDA(cudaStreamSynchronize(c->stream));
+  return FG_OK;
+}
+
+void net_free(fg_ctx* c) {
+  for (void* p : allocs(c)) cudaFree(p);
+  g_allocs.erase(c);
+  if (c->hstats) cudaFreeHost(c->hstats);
+  if (c->stage_pinned) cudaFreeHost(c->stage_pinned);
+  for (int i = 0; i < 8; ++i)
+    if (c->scratch[i]) cudaFree(c->scratch[i]);
+}
+
+int net_pack_G(fg_ctx* c) {
+  if (c->G_packed) return FG_OK;
+  const GLayout& L = c->gl;
+  FG_TRY(k_pack_weights(c, c->PG + L.L1W, c->G_L1p, c->G_L1pd, 8192, 100, 1, 128, 64, 0, 0));
+  FG_TRY(k_pack_weights(c, c->PG + L.L1b, c->G_L1p + 8192 * 100, nullptr, 8192, 1, 1, 128, 64, 0, 0));
+  FG_TRY(k_pack_weights(c, c->PG + L.C1W, c->G_C1p, c->G_C1pd, 256, 128, 25, 0, 0, 0, 0));
+  FG_TRY(k_pack_weights(c, c->PG + L.C2W, c->G_C2p, c->G_C2pd, 128, 256, 25, 0, 0, 0, 0));
+  FG_TRY(k_pack_weights(c, c->PG + L.C3W, c->G_C3p, c->G_C3pd, c->C, 128, 9, 0, 0, 0, 0));
+  c->G_packed = true;
+  return FG_OK;
+}
+int net_pack_D(fg_ctx* c) {
+  if (c->D_packed) return FG_OK;
+  const DLayout& L = c->dl;
+  for (int i = 0; i < 4; ++i)
+    FG_TRY(k_pack_weights(c, c->PD + L.cW[i], c->D_cp[i], c->D_cpd[i], kDcout[i], dcin(c, i), 9, 0, 0, 0, 0));
+  // View(2048) flattens [512][2][2] in (c,h,w) order; ours is NHWC (h,w,c): permute the columns
+  FG_TRY(k_pack_weights(c, c->PD + L.L1W, c->D_L1p, c->D_L1pd, 512, 2048, 1, 0, 0, 512, 4));
+  FG_TRY(k_pack_weights(c, c->PD + L.L2W, nullptr, c->D_L2pd, 512, 512, 1, 0, 0, 0, 0));
+  c->D_packed = true;
+  return FG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv dispatch (SIMT now; tcgen05 variants are selected in k_conv_tc.cu)
+// ---------------------------------------------------------------------------------------------------
+static int conv_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp, const float* bias, float* out,
+                    ConvGeom g) {
+  ScopedTimer t(c, tag);
+  return k_conv_simt(c, in, Wp, bias, out, g);
+}
+static int conv_wgrad(fg_ctx* c, const char* tag, const float* in, const float* dY, ConvGeom g, float* dW, int nA, int nS,
+                      int cA, int cS) {
+  {
+    ScopedTimer t(c, tag);
+    FG_TRY(k_wgrad_simt(c, in, dY, c->wgrad_ws, g));
+  }
+  return k_unpack_wgrad(c, c->wgrad_ws, dW, g.Cout, g.Cin, g.k * g.k, nA, nS, cA, cS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// G
+// ---------------------------------------------------------------------------------------------------
+int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
+  FG_REQUIRE(B >= 1 && B <= c->maxB, "G forward: batch %d out of range [1,%d]", B, c->maxB);
+  FG_TRY(net_pack_G(c));
+  const GLayout& L = c->gl;
+  float* P = c->PG;
+  if (noise != c->G_noise)
+    FG_CUDA(cudaMemcpyAsync(c->G_noise, noise, sizeof(float) * B * kNoiseDim, cudaMemcpyDeviceToDevice, c->stream));
+  c->G_B = B;
+  c->G_train = training;
+  FG_TRY(conv_fwd(c, "G.L1.fwd", c->G_noise, c->G_L1p, c->G_L1p + 8192 * 100, c->G_z0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}));
+  FG_TRY(k_prelu_fwd(c, c->G_z0, P + L.a1, c->G_h0, (int64_t)B * 8192));
+  FG_TRY(conv_fwd(c, "G.C1.fwd", c->G_h0, c->G_C1p, P + L.C1b, c->G_z1, ConvGeom{B, 16, 16, 128, 256, 5, 2}));
+  if (training) {
+    FG_TRY(k_bn_stats(c, c->G_z1, c->bn_acc, (int64_t)B * 256, 256));
+    FG_TRY(k_bn_finalize(c, c->bn_acc, c->bn_mean1, c->bn_istd1, c->bnG, c->bnG + 256, (int64_t)B * 256, 256));
+  } else {
+    FG_TRY(k_bn_eval_prep(c, c->bnG, c->bnG + 256, c->bn_mean1, c->bn_istd1, 256));
+  }
+  FG_TRY(k_bn_prelu_apply(c, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->G_h1, (int64_t)B * 256,
+                          256));
+  FG_TRY(conv_fwd(c, "G.C2.fwd", c->G_h1, c->G_C2p, P + L.C2b, c->G_z2, ConvGeom{B, 32, 32, 256, 128, 5, 2}));
+  if (training) {
+    FG_TRY(k_bn_stats(c, c->G_z2, c->bn_acc, (int64_t)B * 1024, 128));
+    FG_TRY(k_bn_finalize(c, c->bn_acc, c->bn_mean2, c->bn_istd2, c->bnG + 512, c->bnG + 640, (int64_t)B * 1024, 128));
+  } else {
+    FG_TRY(k_bn_eval_prep(c, c->bnG + 512, c->bnG + 640, c->bn_mean2, c->bn_istd2, 128));
+  }
+  FG_TRY(k_bn_prelu_apply(c, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->G_h2, (int64_t)B * 1024,
+                          128));
+  FG_TRY(conv_fwd(c, "G.C3.fwd", c->G_h2, c->G_C3p, P + L.C3b, c->G_z3, ConvGeom{B, 32, 32, 128, c->C, 3, 1}));
+  FG_TRY(k_sigmoid_fwd(c, c->G_z3, c->G_y, (int64_t)B * 1024 * c->C));
+  c->G_fwd_valid = true;
+  return FG_OK;
+}
+
+int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
+  if (!c->G_fwd_valid || !c->G_train) {
+    fg_set_error("G backward needs a preceding training-mode G forward");
+    return FG_ERR_STATE;
+  }
+  const GLayout& L = c->gl;
+  float *P = c->PG, *G = c->gG;
+  const int B = c->G_B, C = c->C;
+  FG_TRY(k_sigmoid_bwd(c, dy, c->G_y, c->G_dz3, (int64_t)B * 1024 * C));
+  // C3
+  FG_TRY(conv_wgrad(c, "G.C3.wgrad", c->G_h2, c->G_dz3, ConvGeom{B, 32, 32, 128, C, 3, 1}, G + L.C3W, 0, 0, 0, 0));
+  FG_TRY(k_colsum_add(c, c->G_dz3, G + L.C3b, (int64_t)B * 1024, C, 0, 0));
+  FG_TRY(conv_fwd(c, "G.C3.dgrad", c->G_dz3, c->G_C3pd, nullptr, c->G_dfull, ConvGeom{B, 32, 32, C, 128, 3, 1}));
+  // BN2 + PReLU
+  FG_TRY(k_bn_prelu_bwd_reduce(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_acc,
+                               G + L.a3, B, 32, 32, 128, 0));
+  FG_TRY(k_bn_bwd_finalize(c, c->bn_acc, c->bn_mg, G + L.g2, G + L.be2, (int64_t)B * 1024, 128));
+  FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_mg,
+                              c->G_dz2, B, 32, 32, 128, 0));
+  // C2
+  FG_TRY(conv_wgrad(c, "G.C2.wgrad", c->G_h1, c->G_dz2, ConvGeom{B, 32, 32, 256, 128, 5, 2}, G + L.C2W, 0, 0, 0, 0));
+  FG_TRY(k_colsum_add(c, c->G_dz2, G + L.C2b, (int64_t)B * 1024, 128, 0, 0));
+  FG_TRY(conv_fwd(c, "G.C2.dgrad", c->G_dz2, c->G_C2pd, nullptr, c->G_dfull, ConvGeom{B, 32, 32, 128, 256, 5, 1}));
+  // BN1 + PReLU (the 2x2 sum = backward of the nearest upsample is folded into the loads)
+  FG_TRY(k_bn_prelu_bwd_reduce(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_acc,
+                               G + L.a2, B, 16, 16, 256, 1));
+  FG_TRY(k_bn_bwd_finalize(c, c->bn_acc, c->bn_mg, G + L.g1, G + L.be1, (int64_t)B * 256, 256));
+  FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_mg,
+                              c->G_dz1, B, 16, 16, 256, 1));
+  // C1
+  FG_TRY(conv_wgrad(c, "G.C1.wgrad", c->G_h0, c->G_dz1, ConvGeom{B, 16, 16, 128, 256, 5, 2}, G + L.C1W, 0, 0, 0, 0));
+  FG_TRY(k_colsum_add(c, c->G_dz1, G + L.C1b, (int64_t)B * 256, 256, 0, 0));
+  FG_TRY(conv_fwd(c, "G.C1.dgrad", c->G_dz1, c->G_C1pd, nullptr, c->G_dfull, ConvGeom{B, 16, 16, 256, 128, 5, 1}));
+  FG_TRY(k_prelu_bwd(c, c->G_dfull, c->G_z0, P + L.a1, c->G_dz0, G + L.a1, B, 8, 8, 128, 1));
+  // L1
+  FG_TRY(conv_wgrad(c, "G.L1.wgrad", c->G_noise, c->G_dz0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}, G + L.L1W, 128, 64, 0, 0));
+  FG_TRY(k_colsum_add(c, c->G_dz0, G + L.L1b, B, 8192, 128, 64));
+  if (dnoise)
+    FG_TRY(conv_fwd(c, "G.L1.dgrad", c->G_dz0, c->G_L1pd, nullptr, dnoise, ConvGeom{B, 1, 1, 8192, 100, 1, 1}));
+  return FG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// D
+// ---------------------------------------------------------------------------------------------------
+int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hyper* h) {
+  FG_REQUIRE(B >= 1 && B <= c->maxB, "D forward: batch %d out of range [1,%d]", B, c->maxB);
+  FG_TRY(net_pack_D(c));
+  const DLayout& L = c->dl;
+  float* P = c->PD;
+  if (x != c->D_x)
+    FG_CUDA(cudaMemcpyAsync(c->D_x, x, sizeof(float) * (size_t)B * 1024 * c->C, cudaMemcpyDeviceToDevice, c->stream));
+  c->D_B = B;
+  c->D_train = training;
+  const float* masks = training ? c->D_masks : nullptr;
+  const float* cur = c->D_x;
+  static const char* tags[4] = {"D.C1.fwd", "D.C2.fwd", "D.C3.fwd", "D.C4.fwd"};
+  for (int i = 0; i < 4; ++i) {
+    const int H = kDhw[i];
+    FG_TRY(conv_fwd(c, tags[i], cur, c->D_cp[i], P + L.cb[i], c->D_z[i], ConvGeom{B, H, H, dcin(c, i), kDcout[i], 3, 1}));
+    FG_TRY(k_d_act_pool_fwd(c, c->D_z[i], P + L.ca[i], masks, kDmoff[i], 1.0f - h->p_spatial, c->D_p[i], B, H, H,
+                            kDcout[i]));
+    cur = c->D_p[i];
+  }
+  const float scale = 1.0f / (1.0f - h->p_drop);
+  c->D_drop_scale = scale;
+  c->D_spatial_eval = 1.0f - h->p_spatial;
+  FG_TRY(conv_fwd(c, "D.L1.fwd", c->D_p[3], c->D_L1p, P + L.L1b, c->D_zl1, ConvGeom{B, 1, 1, 2048, 512, 1, 1}));
+  FG_TRY(k_lin_act_drop_fwd(c, c->D_zl1, P + L.a5, masks, 960, scale, c->D_hl1, B, 512));
+  FG_TRY(conv_fwd(c, "D.L2.fwd", c->D_hl1, P + L.L2W, P + L.L2b, c->D_zl2, ConvGeom{B, 1, 1, 512, 512, 1, 1}));
+  FG_TRY(k_lin_act_drop_fwd(c, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_hl2, B, 512));
+  FG_TRY(conv_fwd(c, "D.L3.fwd", c->D_hl2, P + L.L3W, P + L.L3b, c->D_logit, ConvGeom{B, 1, 1, 512, 1, 1, 1}));
+  c->D_fwd_valid = true;
+  return FG_OK;
+}
+
+int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx) {
+  if (!c->D_fwd_valid) {
+    fg_set_error("D backward needs a preceding D forward");
+    return FG_ERR_STATE;
+  }
+  const DLayout& L = c->dl;
+  float *P = c->PD, *G = c->gD;
+  const int B = c->D_B;
+  const float* masks = c->D_train ? c->D_masks : nullptr;
+  const float scale = c->D_drop_scale, eval_scale = c->D_spatial_eval;
+  // L3
+  if (want_wgrad) {
+    FG_TRY(conv_wgrad(c, "D.L3.wgrad", c->D_hl2, dlogit, ConvGeom{B, 1, 1, 512, 1, 1, 1}, G + L.L3W, 0, 0, 0, 0));
+    FG_TRY(k_colsum_add(c, dlogit, G + L.L3b, B, 1, 0, 0));
+  }
+  FG_TRY(conv_fwd(c, "D.L3.dgrad", dlogit, P + L.L3W, nullptr, c->D_dh, ConvGeom{B, 1, 1, 1, 512, 1, 1}));
+  FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_dzl, want_wgrad ? G + L.a6 : nullptr, B,
+                            512));
+  // L2
+  if (want_wgrad) {
+    FG_TRY(conv_wgrad(c, "D.L2.wgrad", c->D_hl1, c->D_dzl, ConvGeom{B, 1, 1, 512, 512, 1, 1}, G + L.L2W, 0, 0, 0, 0));
+    FG_TRY(k_colsum_add(c, c->D_dzl, G + L.L2b, B, 512, 0, 0));
+  }
+  FG_TRY(conv_fwd(c, "D.L2.dgrad", c->D_dzl, c->D_L2pd, nullptr, c->D_dh, ConvGeom{B, 1, 1, 512, 512, 1, 1}));
+  FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl1, P + L.a5, masks, 960, scale, c->D_dzl, want_wgrad ? G + L.a5 : nullptr, B,
+                            512));
+  // L1
+  if (want_wgrad) {
+    FG_TRY(conv_wgrad(c, "D.L1.wgrad", c->D_p[3], c->D_dzl, ConvGeom{B, 1, 1, 2048, 512, 1, 1}, G + L.L1W, 0, 0, 512, 4));
+    FG_TRY(k_colsum_add(c, c->D_dzl, G + L.L1b, B, 512, 0, 0));
+  }
+  FG_TRY(conv_fwd(c, "D.L1.dgrad", c->D_dzl, c->D_L1pd, nullptr, c->D_dp, ConvGeom{B, 1, 1, 512, 2048, 1, 1}));
+  static const char* wt[4] = {"D.C1.wgrad", "D.C2.wgrad", "D.C3.wgrad", "D.C4.wgrad"};
+  static const char* dt[4] = {"D.C1.dgrad", "D.C2.dgrad", "D.C3.dgrad", "D.C4.dgrad"};
+  for (int i = 3; i >= 0; --i) {
+    const int H = kDhw[i], cin = dcin(c, i), cout = kDcout[i];
+    FG_TRY(k_d_act_pool_bwd(c, c->D_dp, c->D_z[i], P + L.ca[i], masks, kDmoff[i], eval_scale, c->D_dz,
+                            want_wgrad ? G + L.ca[i] : nullptr, B, H, H, cout));
+    const float* in = i == 0 ? c->D_x : c->D_p[i - 1];
+    if (want_wgrad) {
+      FG_TRY(conv_wgrad(c, wt[i], in, c->D_dz, ConvGeom{B, H, H, cin, cout, 3, 1}, G + L.cW[i], 0, 0, 0, 0));
+      FG_TRY(k_colsum_add(c, c->D_dz, G + L.cb[i], (int64_t)B * H * H, cout, 0, 0));
+    }
+    if (i > 0 || want_dx)
+      FG_TRY(conv_fwd(c, dt[i], c->D_dz, c->D_cpd[i], nullptr, i == 0 ? c->D_dx : c->D_dp,
+                      ConvGeom{B, H, H, cout, cin, 3, 1}));
+  }
+  return FG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// optimizer: penalty -> clamp -> interruptableAdam, all on device
+// ---------------------------------------------------------------------------------------------------
+int net_optim(fg_ctx* c, int net, const fg_hyper* h, float grad_scale, bool gate) {
+  (void)gate;
+  const bool isD = net == FG_NET_D;
+  float *p = isD ? c->PD : c->PG, *g = isD ? c->gD : c->gG, *m = isD ? c->mD : c->mG, *v = isD ? c->vD : c->vG;
+  const int64_t n = isD ? c->dl.total : c->gl.total;
+  const float l1 = isD ? h->D_L1 : h->G_L1, l2 = isD ? h->D_L2 : h->G_L2;
+  const bool pen = l1 != 0.f || l2 != 0.f;
+  // G quirk: the L1 gradient term is multiplied by G_L2 (adversarial.lua:223)
+  const float l1_grad = !pen ? 0.f : (isD ? l1 : l2);
+  if (pen) FG_TRY(k_penalty_loss(c, p, n, l1, l2, isD ? &c->dstats->loss_D : &c->dstats->loss_G));
+  FG_TRY(k_adam(c, p, g, m, v, n, h->beta1, h->beta2, h->eps, l1_grad, pen ? l2 : 0.f, isD ? h->D_clamp : h->G_clamp,
+                grad_scale, isD ? &c->dstats->step_D : &c->dstats->step_G,
+                isD ? &c->dstats->do_train_D : &c->dstats->do_train_G, 0.f, nullptr));
+  if (isD) c->D_packed = false; else c->G_packed = false;
+  return FG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// one iteration of the adversarial.lua loop body (D_iterations = G_iterations = 1)
+// ---------------------------------------------------------------------------------------------------
+int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const float* noiseD, const float* noiseG,
+                   const float* masksD, const float* masksG, uint64_t seed) {
+  FG_REQUIRE(B >= 4 && B % 2 == 0 && B <= c->maxB, "train step: batch %d must be even, >=4 and <= %d", B, c->maxB);
+  const int Bh = B / 2, C = c->C;
+  const size_t img = (size_t)C * 1024;
+  const float world = (float)c->world;
+  // ---- D step (adversarial.lua:240-268) ----
+  FG_TRY(net_G_forward(c, noiseD, Bh, true));  // createImages: G in training mode (nn_utils.lua:52)
+  FG_TRY(k_nchw_to_nhwc(c, real, c->D_x, Bh, C, 1024));
+  FG_CUDA(cudaMemcpyAsync(c->D_x + Bh * img, c->G_y, sizeof(float) * Bh * img, cudaMemcpyDeviceToDevice, c->stream));
+  if (masksD)
+    FG_CUDA(cudaMemcpyAsync(c->D_masks, masksD, sizeof(float) * (size_t)B * kMaskPerSample, cudaMemcpyDeviceToDevice,
+                            c->stream));
+  else
+    FG_TRY(k_masks_generate(c, c->D_masks, B, seed * 2 + 1, h->p_spatial, h->p_drop));
+  FG_CUDA(cudaMemsetAsync(c->gD, 0, sizeof(float) * (c->dl.total + kGradTail), c->stream));
+  FG_TRY(net_D_forward(c, c->D_x, B, true, h));
+  FG_TRY(k_sigmoid_bce(c, c->D_logit, c->D_out, c->D_dlogit, &c->dstats->loss_D, c->gD + c->dl.total, B, Bh));
+  FG_TRY(net_D_backward(c, c->D_dlogit, true, false));
+  if (c->world > 1) FG_TRY(net_allreduce(c, c->gD, c->dl.total + kGradTail));
+  FG_TRY(k_gate_and_prep(c, FG_NET_D, h, c->gD + c->dl.total, B, world));
+  FG_TRY(net_optim(c, FG_NET_D, h, 1.0f / world, true));
+  // ---- G step (adversarial.lua:275-288) ----
+  FG_CUDA(cudaMemsetAsync(c->gG, 0, sizeof(float) * (c->gl.total + kGradTail), c->stream));
+  FG_TRY(net_G_forward(c, noiseG, B, true));
+  if (masksG)
+    FG_CUDA(cudaMemcpyAsync(c->D_masks, masksG, sizeof(float) * (size_t)B * kMaskPerSample, cudaMemcpyDeviceToDevice,
+                            c->stream));
+  else
+    FG_TRY(k_masks_generate(c, c->D_masks, B, seed * 2 + 2, h->p_spatial, h->p_drop));
+  FG_TRY(net_D_forward(c, c->G_y, B, true, h));
+  FG_TRY(k_sigmoid_bce(c, c->D_logit, c->D_out, c->D_dlogit, &c->dstats->loss_G, c->gG + c->gl.total, B, B));
+  FG_TRY(net_D_backward(c, c->D_dlogit, false, true));  // D's weight grads are discarded by the reference (:209 vs :92)
+  FG_TRY(net_G_backward(c, c->D_dx, nullptr));
+  if (c->world > 1) FG_TRY(net_allreduce(c, c->gG, c->gl.total + kGradTail));
+  FG_TRY(k_gate_and_prep(c, FG_NET_G, h, c->gG + c->gl.total, B, world));
+  FG_TRY(net_optim(c, FG_NET_G, h, 1.0f / world, false));
+  FG_CUDA(cudaMemcpyAsync(c->hstats, c->dstats, sizeof(DeviceStats), cudaMemcpyDeviceToHost, c->stream));
+  return FG_OK;
+}

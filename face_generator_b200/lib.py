@@ -1,0 +1,345 @@
+"""ctypes binding of libfg_b200.so -- a 1:1 mirror of face_generator_b200/lua/fg_ffi.lua.
+
+Fails loudly when the shared library is missing or a call returns an error; never falls back to
+a CPU implementation (the CPU oracle under oracle/ is test infrastructure and is not imported here).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfg_b200.so")
+MASK_PER_SAMPLE = 1984
+NOISE_DIM = 100
+NET_G, NET_D = 0, 1
+CONV_SIMT, CONV_TC_DENSE, CONV_TC_COLLAPSED = 0, 1, 2
+
+
+class FGError(RuntimeError):
+    pass
+
+
+class Hyper(C.Structure):
+    _fields_ = [("lr_D", C.c_float), ("lr_G", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("D_L1", C.c_float), ("D_L2", C.c_float), ("G_L1", C.c_float),
+                ("G_L2", C.c_float), ("D_clamp", C.c_float), ("G_clamp", C.c_float), ("D_maxAcc", C.c_float),
+                ("accs_interval", C.c_int32), ("p_spatial", C.c_float), ("p_drop", C.c_float)]
+
+
+class StepStats(C.Structure):
+    _fields_ = [("loss_D", C.c_float), ("loss_G", C.c_float), ("conf", C.c_int32 * 4), ("trained_D", C.c_int32),
+                ("t_D", C.c_int32), ("t_G", C.c_int32), ("acc_D", C.c_float)]
+
+
+# every symbol include/fg_b200.h declares: name -> (restype, argtypes)
+_P, _F, _I, _L, _U64, _SZ = C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_uint64, C.c_size_t
+SYMBOLS = {
+    "fg_version": (C.c_char_p, []),
+    "fg_last_error": (C.c_char_p, []),
+    "fg_hyper_default": (None, [C.POINTER(Hyper)]),
+    "fg_create": (_I, [C.POINTER(_P), _I, _I, _I]),
+    "fg_destroy": (_I, [_P]),
+    "fg_set_stream": (_I, [_P, _P]),
+    "fg_sync": (_I, [_P]),
+    "fg_set_option": (_I, [_P, C.c_char_p, _L]),
+    "fg_get_option": (_L, [_P, C.c_char_p]),
+    "fg_param_count": (_L, [_I, _I]),
+    "fg_set_params": (_I, [_P, _I, _P]),
+    "fg_get_params": (_I, [_P, _I, _P]),
+    "fg_get_grads": (_I, [_P, _I, _P]),
+    "fg_zero_grads": (_I, [_P, _I]),
+    "fg_params_ptr": (_P, [_P, _I]),
+    "fg_grads_ptr": (_P, [_P, _I]),
+    "fg_set_adam_state": (_I, [_P, _I, _P, _P, _I]),
+    "fg_get_adam_state": (_I, [_P, _I, _P, _P, C.POINTER(_I)]),
+    "fg_set_bn_state": (_I, [_P, _P]),
+    "fg_get_bn_state": (_I, [_P, _P]),
+    "fg_G_forward": (_I, [_P, _P, _I, _I, _P]),
+    "fg_G_backward": (_I, [_P, _P, _P]),
+    "fg_D_forward": (_I, [_P, _P, _I, _I, _P, _U64, _P]),
+    "fg_D_backward": (_I, [_P, _P, _I, _P]),
+    "fg_bce_forward": (_I, [_P, _P, _P, _I, _P]),
+    "fg_bce_backward": (_I, [_P, _P, _P, _I, _P]),
+    "fg_optim_step": (_I, [_P, _I, C.POINTER(Hyper), _F]),
+    "fg_adam_step": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _F, _F, _F]),
+    "fg_conv2d_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I]),
+    "fg_conv2d_backward_data": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I]),
+    "fg_conv2d_backward_filter": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I]),
+    "fg_linear_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I]),
+    "fg_linear_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
+    "fg_bn_forward_train": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
+    "fg_bn_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
+    "fg_prelu_forward": (_I, [_P, _P, _P, _P, _L]),
+    "fg_prelu_backward": (_I, [_P, _P, _P, _P, _P, _P, _L]),
+    "fg_train_step": (_I, [_P, C.POINTER(Hyper), _I, _P, _P, _P, _P, _P, _U64, C.POINTER(StepStats)]),
+    "fg_sample": (_I, [_P, _P, _I, _I, _P]),
+    "fg_dp_unique_id": (_I, [_P]),
+    "fg_dp_init": (_I, [_P, _P, _I, _I]),
+    "fg_dp_broadcast_params": (_I, [_P]),
+    "fg_dp_world": (_I, [_P]),
+    "fg_dev_alloc": (_P, [_SZ]),
+    "fg_dev_free": (_I, [_P]),
+    "fg_host_alloc_pinned": (_P, [_SZ]),
+    "fg_host_free_pinned": (_I, [_P]),
+    "fg_memcpy": (_I, [_P, _P, _P, _SZ]),
+    "fg_kernel_launches": (_L, [_P]),
+    "fg_debug_tensor": (_L, [_P, C.c_char_p, _P, _L]),
+    "fg_event_record": (_I, [_P, _I]),
+    "fg_event_elapsed_ms": (_I, [_P, _I, _I, C.POINTER(C.c_double)]),
+    "fg_timing_enable": (_I, [_P, _I]),
+    "fg_timing_get": (_I, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(_L)]),
+}
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libfg_b200.so and bind every declared symbol.  Raises FGError if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _SO
+    if not os.path.exists(path):
+        raise FGError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError => the .so does not match include/fg_b200.h
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise FGError("%s failed (%d): %s" % (what, rc, load_library().fg_last_error().decode()))
+
+
+def hyper_default(**kw):
+    h = Hyper()
+    load_library().fg_hyper_default(C.byref(h))
+    for k, v in kw.items():
+        if not hasattr(h, k):
+            raise KeyError(k)
+        setattr(h, k, v)
+    return h
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float32 and a.flags.c_contiguous, "float32 C-contiguous arrays only"
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))  # raw (device or pinned host) address
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class PinnedArray:
+    """float32 numpy view over cudaMallocHost memory (so H2D copies in the e2e path are truly async)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+        n = int(np.prod(self.shape))
+        self.addr = load_library().fg_host_alloc_pinned(max(n, 1) * 4)
+        if not self.addr:
+            raise FGError("fg_host_alloc_pinned failed: " + load_library().fg_last_error().decode())
+        buf = (C.c_float * n).from_address(self.addr)
+        self.array = np.frombuffer(buf, dtype=np.float32).reshape(self.shape)
+
+    def free(self):
+        if self.addr:
+            load_library().fg_host_free_pinned(self.addr)
+            self.addr = None
+
+
+class Context:
+    """One fg_ctx (one GPU).  Mirrors face_generator_b200/lua/b200.lua's `b200.Context`."""
+
+    def __init__(self, device=0, max_batch=256, channels=3):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib.fg_create(C.byref(h), device, max_batch, channels), "fg_create")
+        self.h, self.C, self.max_batch, self.device = h, channels, max_batch, device
+        self.nG = int(self.lib.fg_param_count(NET_G, channels))
+        self.nD = int(self.lib.fg_param_count(NET_D, channels))
+
+    def close(self):
+        if self.h:
+            self.lib.fg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters ----
+    def count(self, net):
+        return self.nD if net == NET_D else self.nG
+
+    def set_params(self, net, p):
+        p = f32(p)
+        assert p.size == self.count(net)
+        _check(self.lib.fg_set_params(self.h, net, _ptr(p)), "fg_set_params")
+
+    def get_params(self, net):
+        out = np.empty(self.count(net), np.float32)
+        _check(self.lib.fg_get_params(self.h, net, _ptr(out)), "fg_get_params")
+        return out
+
+    def get_grads(self, net):
+        out = np.empty(self.count(net), np.float32)
+        _check(self.lib.fg_get_grads(self.h, net, _ptr(out)), "fg_get_grads")
+        return out
+
+    def zero_grads(self, net):
+        _check(self.lib.fg_zero_grads(self.h, net), "fg_zero_grads")
+
+    def set_adam_state(self, net, m, v, t):
+        _check(self.lib.fg_set_adam_state(self.h, net, _ptr(f32(m)), _ptr(f32(v)), int(t)), "fg_set_adam_state")
+
+    def get_adam_state(self, net):
+        m, v, t = np.empty(self.count(net), np.float32), np.empty(self.count(net), np.float32), C.c_int(0)
+        _check(self.lib.fg_get_adam_state(self.h, net, _ptr(m), _ptr(v), C.byref(t)), "fg_get_adam_state")
+        return m, v, t.value
+
+    def set_bn_state(self, s):
+        _check(self.lib.fg_set_bn_state(self.h, _ptr(f32(s))), "fg_set_bn_state")
+
+    def get_bn_state(self):
+        out = np.empty(768, np.float32)
+        _check(self.lib.fg_get_bn_state(self.h, _ptr(out)), "fg_get_bn_state")
+        return out
+
+    def set_option(self, key, value):
+        _check(self.lib.fg_set_option(self.h, key.encode(), int(value)), "fg_set_option(%s)" % key)
+
+    def get_option(self, key):
+        return int(self.lib.fg_get_option(self.h, key.encode()))
+
+    def sync(self):
+        _check(self.lib.fg_sync(self.h), "fg_sync")
+
+    # ---- L-net ----
+    def G_forward(self, noise, training=True, want_images=True):
+        noise = f32(noise)
+        B = noise.shape[0]
+        out = np.empty((B, self.C, 32, 32), np.float32) if want_images else None
+        _check(self.lib.fg_G_forward(self.h, _ptr(noise), B, int(training), _ptr(out)), "fg_G_forward")
+        return out
+
+    def G_backward(self, d_images, want_dnoise=False):
+        d_images = f32(d_images)
+        dn = np.empty((d_images.shape[0], NOISE_DIM), np.float32) if want_dnoise else None
+        _check(self.lib.fg_G_backward(self.h, _ptr(d_images), _ptr(dn)), "fg_G_backward")
+        return dn
+
+    def D_forward(self, images, masks=None, training=True, seed=0):
+        images = f32(images)
+        B = images.shape[0]
+        masks = f32(masks) if masks is not None else None
+        out = np.empty(B, np.float32)
+        _check(self.lib.fg_D_forward(self.h, _ptr(images), B, int(training), _ptr(masks), seed, _ptr(out)), "fg_D_forward")
+        return out
+
+    def D_backward(self, d_out, want_wgrad=True, want_dimages=True):
+        d_out = f32(d_out)
+        B = d_out.shape[0]
+        di = np.empty((B, self.C, 32, 32), np.float32) if want_dimages else None
+        _check(self.lib.fg_D_backward(self.h, _ptr(d_out), int(want_wgrad), _ptr(di)), "fg_D_backward")
+        return di
+
+    def bce_forward(self, x, t):
+        x, t = f32(x).ravel(), f32(t).ravel()
+        out = np.empty(1, np.float32)
+        _check(self.lib.fg_bce_forward(self.h, _ptr(x), _ptr(t), x.size, _ptr(out)), "fg_bce_forward")
+        return float(out[0])
+
+    def bce_backward(self, x, t):
+        x, t = f32(x).ravel(), f32(t).ravel()
+        dx = np.empty(x.size, np.float32)
+        _check(self.lib.fg_bce_backward(self.h, _ptr(x), _ptr(t), x.size, _ptr(dx)), "fg_bce_backward")
+        return dx
+
+    def optim_step(self, net, hyper, grad_scale=1.0):
+        _check(self.lib.fg_optim_step(self.h, net, C.byref(hyper), grad_scale), "fg_optim_step")
+
+    # ---- L-step ----
+    def train_step(self, hyper, B, real, noise_D, noise_G, masks_D=None, masks_G=None, seed=0, want_stats=True):
+        """Pointers may be numpy float32 arrays (host) or raw addresses (device / pinned)."""
+        st = StepStats() if want_stats else None
+        _check(self.lib.fg_train_step(self.h, C.byref(hyper), B, _ptr(real), _ptr(noise_D), _ptr(noise_G),
+                                      _ptr(masks_D), _ptr(masks_G), seed, C.byref(st) if st is not None else None),
+               "fg_train_step")
+        if st is None:
+            return None
+        return dict(loss_D=st.loss_D, loss_G=st.loss_G, conf=list(st.conf), trained_D=st.trained_D, t_D=st.t_D,
+                    t_G=st.t_G, acc_D=st.acc_D)
+
+    def sample(self, noise, chunk):
+        noise = f32(noise)
+        N = noise.shape[0]
+        out = np.empty((N, self.C, 32, 32), np.float32)
+        _check(self.lib.fg_sample(self.h, _ptr(noise), N, chunk, _ptr(out)), "fg_sample")
+        return out
+
+    # ---- device memory helpers ----
+    def dev_array(self, host):
+        host = f32(host)
+        p = self.lib.fg_dev_alloc(max(host.nbytes, 4))
+        if not p:
+            raise FGError("fg_dev_alloc failed")
+        _check(self.lib.fg_memcpy(self.h, p, _ptr(host), host.nbytes), "fg_memcpy")
+        return p
+
+    def dev_free(self, p):
+        self.lib.fg_dev_free(p)
+
+    def debug_tensor(self, name):
+        n = self.lib.fg_debug_tensor(self.h, name.encode(), None, 0)
+        if n < 0:
+            raise FGError("fg_debug_tensor(%s): %d" % (name, n))
+        out = np.empty(n, np.float32)
+        r = self.lib.fg_debug_tensor(self.h, name.encode(), _ptr(out), n)
+        if r < 0:
+            raise FGError("fg_debug_tensor(%s): %d" % (name, r))
+        return out
+
+    def launches(self):
+        return int(self.lib.fg_kernel_launches(self.h))
+
+    def event_record(self, slot):
+        _check(self.lib.fg_event_record(self.h, slot), "fg_event_record")
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double(0)
+        _check(self.lib.fg_event_elapsed_ms(self.h, a, b, C.byref(ms)), "fg_event_elapsed_ms")
+        return ms.value
+
+    def timing_enable(self, on=True):
+        _check(self.lib.fg_timing_enable(self.h, int(on)), "fg_timing_enable")
+
+    def timing_get(self, prefix):
+        ms, n = C.c_double(0), C.c_int64(0)
+        _check(self.lib.fg_timing_get(self.h, prefix.encode(), C.byref(ms), C.byref(n)), "fg_timing_get")
+        return ms.value, n.value
+
+    # ---- data parallel ----
+    def dp_unique_id(self):
+        buf = (C.c_ubyte * 128)()
+        _check(self.lib.fg_dp_unique_id(buf), "fg_dp_unique_id")
+        return bytes(buf)
+
+    def dp_init(self, id_bytes, nranks, rank):
+        buf = (C.c_ubyte * 128).from_buffer_copy(id_bytes)
+        _check(self.lib.fg_dp_init(self.h, buf, nranks, rank), "fg_dp_init")
+
+    def dp_broadcast_params(self):
+        _check(self.lib.fg_dp_broadcast_params(self.h), "fg_dp_broadcast_params")

@@ -1,0 +1,183 @@
+/* fg_b200.h -- C ABI of the B200-native GAN train-step hot path of aleju/face-generator.
+ *
+ * The reference (Lua/Torch7) has NO native FFI for this path: its "plugin surface" is Torch7's
+ * Lua-level nn.Module protocol plus train.lua's globals.  This header is
+ * therefore the ABI a LuaJIT `ffi.cdef` binds (see INTEGRATION.md and
+ * face_generator_b200/lua/fg_ffi.lua); each entry cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain C types only.  Every call returns 0 (FG_OK) or a negative FG_ERR_*;
+ *     nothing throws or exits.  fg_last_error() returns a description of the last failure.
+ *   - Tensors at the boundary are dense fp32 in the REFERENCE layouts: images NCHW
+ *     [B][C][32][32], noise [B][100], flat parameter vectors in getParameters() order with conv
+ *     weights [Cout][Cin][kH][kW] and Linear weights [out][in].  (Internally everything is NHWC.)
+ *   - Data pointers may be HOST or DEVICE pointers (classified with cudaPointerGetAttributes);
+ *     host buffers are staged through pinned memory on the context's stream -- this is the
+ *     replacement of the reference's nn.Copy host<->device hops (utils/nn_utils.lua:355-362).
+ *   - One fg_ctx per GPU, no concurrent calls on one ctx (Lua is single-threaded).
+ *   - There is NO CPU fallback: every entry needs a CUDA device of compute capability 10.x.
+ */
+#ifndef FG_B200_H
+#define FG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fg_ctx fg_ctx;
+
+enum {
+  FG_OK = 0,
+  FG_ERR_INVALID = -1,      /* bad argument (odd batch, batch > max_batch, NULL, ...) */
+  FG_ERR_CUDA = -2,         /* CUDA runtime / driver error (sticky on the ctx)        */
+  FG_ERR_NCCL = -3,         /* NCCL error                                             */
+  FG_ERR_UNSUPPORTED = -4,  /* valid request the library does not implement           */
+  FG_ERR_STATE = -5         /* call order violated (backward without forward, ...)    */
+};
+enum { FG_NET_G = 0, FG_NET_D = 1 };
+
+/* Which implementation the big convolutions use (fg_set_option "conv_impl"). */
+enum {
+  FG_CONV_SIMT = 0,         /* fp32 FFMA implicit GEMM (first correct path, any shape)          */
+  FG_CONV_TC_DENSE = 1,     /* tcgen05 3xTF32 implicit GEMM, dense 5x5 taps on the low-res input */
+  FG_CONV_TC_COLLAPSED = 2  /* tcgen05 3xTF32, upsample folded into four 3x3 phase convolutions  */
+};
+
+/* Hyper-parameters of one adversarial.lua loop body; defaults = train.lua:16-50 +
+ * interruptable_optimizers.lua:53-57. */
+typedef struct fg_hyper {
+  float lr_D, lr_G;         /* Adam learning rates (--D_adam_lr/--G_adam_lr; -1 there => 1e-3)   */
+  float beta1, beta2, eps;  /* 0.9, 0.999, 1e-8                                                   */
+  float D_L1, D_L2;         /* 0, 1e-4   (adversarial.lua:103-109)                                */
+  float G_L1, G_L2;         /* 0, 0      (adversarial.lua:218-224; L1 grad term uses G_L2, :223)  */
+  float D_clamp, G_clamp;   /* 1, 5      (adversarial.lua:121-123, :226-228); 0 = off             */
+  float D_maxAcc;           /* 1.01: D is only stepped while mean accuracy < this (:156-178)      */
+  int32_t accs_interval;    /* length of the accuracy history (train.lua:207)                     */
+  float p_spatial, p_drop;  /* 0.2, 0.5  SpatialDropout / Dropout probabilities (models.lua)      */
+} fg_hyper;
+
+typedef struct fg_step_stats {
+  float loss_D, loss_G;     /* f returned by fevalD / fevalG_on_D (incl. penalty terms)           */
+  int32_t conf[4];          /* D-step confusion: [pred1&real, pred0&real, pred1&fake, pred0&fake] */
+  int32_t trained_D;        /* 0 when the accuracy gate skipped D's Adam step                     */
+  int32_t t_D, t_G;         /* Adam step counters after this iteration                            */
+  float acc_D;              /* D's accuracy on this batch (confusionBatchD.totalValid)            */
+} fg_step_stats;
+
+const char* fg_version(void);
+const char* fg_last_error(void);
+void fg_hyper_default(fg_hyper* h);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* channels = IMG_DIMENSIONS[1] (1 or 3, train.lua:92-93); max_batch = largest OPT.batchSize.    */
+int fg_create(fg_ctx** out, int device, int max_batch, int channels);
+int fg_destroy(fg_ctx* ctx);
+int fg_set_stream(fg_ctx* ctx, void* cuda_stream);      /* cutorch's current stream; NULL = own  */
+int fg_sync(fg_ctx* ctx);
+int fg_set_option(fg_ctx* ctx, const char* key, int64_t value);  /* "conv_impl", "graphs", ...    */
+int64_t fg_get_option(fg_ctx* ctx, const char* key);
+
+/* ---- parameters: replaces MODEL:getParameters() (train.lua:151-152) -------------------------- */
+int64_t fg_param_count(int net, int channels);
+int fg_set_params(fg_ctx* ctx, int net, const float* src);
+int fg_get_params(fg_ctx* ctx, int net, float* dst);
+int fg_get_grads(fg_ctx* ctx, int net, float* dst);
+int fg_zero_grads(fg_ctx* ctx, int net);                 /* GRAD_PARAMETERS_x:zero()              */
+float* fg_params_ptr(fg_ctx* ctx, int net);              /* device pointers for Torch aliasing    */
+float* fg_grads_ptr(fg_ctx* ctx, int net);
+/* OPTSTATE.adam.{D,G}.{m,v,t} (interruptable_optimizers.lua:69-75); any pointer may be NULL     */
+int fg_set_adam_state(fg_ctx* ctx, int net, const float* m, const float* v, int t);
+int fg_get_adam_state(fg_ctx* ctx, int net, float* m, float* v, int* t);
+/* G's BatchNorm running statistics [rm1(256) rv1(256) rm2(128) rv2(128)]                          */
+int fg_set_bn_state(fg_ctx* ctx, const float* src768);
+int fg_get_bn_state(fg_ctx* ctx, float* dst768);
+
+/* ---- L-net: MODEL_G / MODEL_D :forward / :backward ------------------------------------------- */
+/* models.lua:57-81.  noise [B][100] -> images [B][C][32][32] (may be NULL to keep on device).   */
+int fg_G_forward(fg_ctx* ctx, const float* noise, int B, int training, float* images_out);
+/* d_images [B][C][32][32]; accumulates into G's grad buffer; d_noise may be NULL.               */
+int fg_G_backward(fg_ctx* ctx, const float* d_images, float* d_noise);
+/* models.lua:382-416.  masks: [B][1984] keep flags (0/1) per sample =
+ * [64|128|256|512] SpatialDropout + [512|512] Dropout; NULL => drawn in-kernel from `seed`.
+ * training=0 => evaluate() semantics.  out [B] sigmoid outputs (may be NULL).                   */
+int fg_D_forward(fg_ctx* ctx, const float* images, int B, int training, const float* masks, uint64_t seed,
+                 float* out);
+/* d_out [B]; want_wgrad=0 skips D's weight gradients (the G step discards them,
+ * adversarial.lua:209 vs :92); d_images [B][C][32][32] may be NULL.                             */
+int fg_D_backward(fg_ctx* ctx, const float* d_out, int want_wgrad, float* d_images);
+/* nn.BCECriterion forward/backward (train.lua:148); x,t length n.                               */
+int fg_bce_forward(fg_ctx* ctx, const float* x, const float* t, int n, float* loss_out);
+int fg_bce_backward(fg_ctx* ctx, const float* x, const float* t, int n, float* dx);
+/* penalty + clamp + interruptableAdam on the ctx's own buffers (adversarial.lua:103-123,
+ * interruptable_optimizers.lua:49-94).  grad_scale multiplies the gradient first (1/N for DP).  */
+int fg_optim_step(fg_ctx* ctx, int net, const fg_hyper* h, float grad_scale);
+
+/* ---- L-op: raw-pointer optimizer for b200.Adam (DEVICE pointers) ----------------------------- */
+int fg_adam_step(fg_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                 float beta2, float eps, int t, float l1_grad, float l2, float clampv, float grad_scale);
+
+/* ---- L-op: single layers at the nn.Module boundary (NCHW, DEVICE or HOST pointers) ----------- */
+/* cudnn.SpatialConvolution / nn.SpatialConvolution, stride 1, pad (k-1)/2 (models.lua:64,69,73,385-400)
+ * and layers/cudnnSpatialConvolutionUpsample.lua with factor=1 (identical math).                 */
+int fg_conv2d_forward(fg_ctx* ctx, const float* x, const float* w, const float* b, float* y, int N, int Cin, int H,
+                      int W, int Cout, int k);
+int fg_conv2d_backward_data(fg_ctx* ctx, const float* dy, const float* w, float* dx, int N, int Cin, int H, int W,
+                            int Cout, int k);
+/* accumulates (dw += , db +=) like accGradParameters; db may be NULL                             */
+int fg_conv2d_backward_filter(fg_ctx* ctx, const float* x, const float* dy, float* dw, float* db, int N, int Cin,
+                              int H, int W, int Cout, int k);
+/* nn.Linear (models.lua:59,406-412)                                                              */
+int fg_linear_forward(fg_ctx* ctx, const float* x, const float* w, const float* b, float* y, int N, int in, int out);
+int fg_linear_backward(fg_ctx* ctx, const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
+                       int N, int in, int out);
+/* nn.SpatialBatchNormalization training mode (models.lua:65,70); save_mean/save_istd [C]         */
+int fg_bn_forward_train(fg_ctx* ctx, const float* x, const float* gamma, const float* beta, float* y,
+                        float* save_mean, float* save_istd, float* run_mean, float* run_var, int N, int C, int HW);
+int fg_bn_backward(fg_ctx* ctx, const float* x, const float* gamma, const float* save_mean, const float* save_istd,
+                   const float* dy, float* dx, float* dgamma, float* dbeta, int N, int C, int HW);
+/* nn.PReLU with one shared slope (models.lua:61,...)                                             */
+int fg_prelu_forward(fg_ctx* ctx, const float* x, const float* slope, float* y, int64_t n);
+int fg_prelu_backward(fg_ctx* ctx, const float* x, const float* slope, const float* dy, float* dx, float* dslope,
+                      int64_t n);
+
+/* ---- L-step: the adversarial.lua:54-300 loop body -------------------------------------------- */
+/* real [B/2][C][32][32] in [0,1]; noise_D [B/2][100], noise_G [B][100] ~ U(-1,1)
+ * (utils/nn_utils.lua:35-39); masks_D / masks_G [B][1984] or NULL (then drawn from seed).
+ * Runs 1 D iteration + 1 G iteration incl. both Adam updates.  stats may be NULL (fully
+ * asynchronous); otherwise the call synchronises the stream and fills it.                        */
+int fg_train_step(fg_ctx* ctx, const fg_hyper* h, int B, const float* real, const float* noise_D,
+                  const float* noise_G, const float* masks_D, const float* masks_G, uint64_t seed,
+                  fg_step_stats* stats);
+/* sample.lua:80 / nn_utils.lua:45-69: G forward over N noise vectors in chunks (train-mode BN). */
+int fg_sample(fg_ctx* ctx, const float* noise, int N, int chunk, float* images_out);
+
+/* ---- data parallel: one process per GPU, NCCL over NVLink (new functionality) ----- */
+int fg_dp_unique_id(void* out128);                        /* ncclGetUniqueId, 128 bytes           */
+int fg_dp_init(fg_ctx* ctx, const void* id128, int nranks, int rank);
+int fg_dp_broadcast_params(fg_ctx* ctx);                  /* rank 0's G/D params+state to all     */
+int fg_dp_world(fg_ctx* ctx);                             /* nranks (1 when DP is off)            */
+
+/* ---- plain device-memory helpers for FFI hosts without a CUDA binding ------------------------ */
+void* fg_dev_alloc(size_t bytes);
+int fg_dev_free(void* p);
+void* fg_host_alloc_pinned(size_t bytes);
+int fg_host_free_pinned(void* p);
+int fg_memcpy(fg_ctx* ctx, void* dst, const void* src, size_t bytes);   /* any direction, on ctx stream */
+
+/* ---- introspection used by tests / bench ------------------------------------------------------ */
+int64_t fg_kernel_launches(fg_ctx* ctx);                  /* kernels launched by this ctx so far   */
+/* copy an internal activation (NHWC) to dst: names "G.z0","G.h0","G.z1","G.h1","G.z2","G.h2","G.z3" */
+int64_t fg_debug_tensor(fg_ctx* ctx, const char* name, float* dst, int64_t max_elems);
+/* timing of the dominant kernel family inside the last fg_train_step (CUDA events on the ctx
+ * stream): returns ms in out[0..n) for the names in fg_timing_names(); 0 when not enabled.       */
+/* whole-step timing on the ctx stream: record CUDA event `slot` (0..15), elapsed ms between two. */
+int fg_event_record(fg_ctx* ctx, int slot);
+int fg_event_elapsed_ms(fg_ctx* ctx, int slot_a, int slot_b, double* ms);
+int fg_timing_enable(fg_ctx* ctx, int on);
+int fg_timing_get(fg_ctx* ctx, const char* name, double* ms_total, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FG_B200_H */

@@ -1,0 +1,46 @@
+"""Shared helpers for the parity tests: seeded cases, oracle runs, error norms."""
+import numpy as np
+
+from oracle import oracle as O
+import torch_ref as R
+
+HYPER = dict(lr_D=1e-3, lr_G=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, D_L1=0.0, D_L2=1e-4, G_L1=0.0, G_L2=0.0,
+             D_clamp=1.0, G_clamp=5.0)
+
+
+def relerr(a, b):
+    """normwise relative error max|a-b| / max|b| (the parity bar is 1e-4, BASELINE.json north_star)."""
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
+
+
+def make_case(B, C, seed, init="trained"):
+    rng = np.random.default_rng(seed)
+    if init == "trained":
+        PG, PD = R.trained_like_G(C, rng), R.trained_like_D(C, rng)
+    else:  # the reference's own init: N(0, 0.005^2) weights (incl. BN gamma, PReLU slope), N(0, 0.001^2) biases
+        PG = rng.standard_normal(O.G_param_count(C)) * 0.005
+        PD = rng.standard_normal(O.D_param_count(C)) * 0.005
+        for lay, P in ((O.G_layout(C), PG), (O.D_layout(C), PD)):
+            for k, (o, s) in lay.items():
+                if k.endswith("b") or k.startswith("be"):
+                    n = int(np.prod(s))
+                    P[o:o + n] = rng.standard_normal(n) * 0.001
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    return dict(PG=f(PG), PD=f(PD), real=f(rng.random((B // 2, C, 32, 32))),
+                noise_D=f(rng.uniform(-1, 1, (B // 2, 100))), noise_G=f(rng.uniform(-1, 1, (B, 100))),
+                masks_D=f(R.make_masks(B, rng)), masks_G=f(R.make_masks(B, rng)))
+
+
+def fresh_state(case, dtype=np.float64):
+    PD, PG = case["PD"].astype(dtype), case["PG"].astype(dtype)
+    return dict(PD=PD, PG=PG, mD=np.zeros_like(PD), vD=np.zeros_like(PD), mG=np.zeros_like(PG), vG=np.zeros_like(PG),
+                tD=0, tG=0, bnG=np.concatenate([np.zeros(256), np.ones(256), np.zeros(128), np.ones(128)]).astype(dtype))
+
+
+def oracle_iteration(case, B, C, hyper=None, state=None):
+    st = state or fresh_state(case)
+    res = O.f64.train_iteration(B, C, hyper or HYPER, case["real"], case["noise_D"], case["noise_G"], case["masks_D"],
+                                case["masks_G"], st)
+    res["state"] = st
+    return res

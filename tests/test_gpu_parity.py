@@ -1,0 +1,259 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on seeded inputs.
+Bar (BASELINE.json north_star): normwise relative error <= 1e-4 per tensor, fp32."""
+import numpy as np
+import pytest
+
+import parity_utils as PU
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def fg():
+    import face_generator_b200 as fg
+    return fg
+
+
+def nhwc_to_nchw(flat, B, H, W, C):
+    return flat.reshape(B, H, W, C).transpose(0, 3, 1, 2)
+
+
+def check_grads(layout, got, ref, skip=(), tol=TOL):
+    scale = np.abs(ref).max()
+    worst = 0.0
+    for k, (o, s) in layout.items():
+        n = int(np.prod(s))
+        a, b = got[o:o + n].astype(np.float64), ref[o:o + n]
+        if k in skip:  # analytically-zero gradients (conv bias feeding BatchNorm): only rounding noise
+            assert np.abs(a).max() <= 1e-3 * scale + 1e-6, k
+            continue
+        e = np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+        worst = max(worst, e)
+        assert e < tol, "%s: relerr %.3e" % (k, e)
+    return worst
+
+
+@pytest.mark.parametrize("C,B,impl", [(3, 4, 0), (1, 6, 0)])
+def test_G_forward_backward(fg, C, B, impl):
+    from face_generator_b200.lib import NET_G
+    case = PU.make_case(2 * B, C, seed=31 + C)
+    rng = np.random.default_rng(7)
+    noise = case["noise_G"][:B]
+    dout = rng.standard_normal((B, C, 32, 32)).astype(np.float32)
+    g = O.f64.G()
+    ref_out = g.forward(case["PG"], noise, C)
+    ref_dP, ref_dn = g.backward(dout, want_dnoise=True)
+    ctx = fg.Context(0, max_batch=8, channels=C)
+    ctx.set_option("conv_impl", impl)
+    ctx.set_params(NET_G, case["PG"])
+    out = ctx.G_forward(noise)
+    assert PU.relerr(out, ref_out) < TOL
+    for name, (H, W, Cc) in {"z0": (8, 8, 128), "h0": (8, 8, 128), "z1": (16, 16, 256), "h1": (16, 16, 256),
+                             "z2": (32, 32, 128), "h2": (32, 32, 128), "z3": (32, 32, C)}.items():
+        got = nhwc_to_nchw(ctx.debug_tensor("G." + name), B, H, W, Cc)
+        assert PU.relerr(got, g.tap(name)) < TOL, name
+    ctx.zero_grads(NET_G)
+    dn = ctx.G_backward(dout, want_dnoise=True)
+    check_grads(O.G_layout(C), ctx.get_grads(NET_G), ref_dP, skip=("C1b", "C2b"))
+    assert PU.relerr(dn, ref_dn) < TOL
+    # BN running statistics after one training forward
+    bn = ctx.get_bn_state()
+    st = PU.fresh_state(case)["bnG"]
+    O.f64.G().forward(case["PG"], noise, C, True, st)
+    assert PU.relerr(bn, st) < TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("C,B", [(3, 6), (1, 4)])
+def test_D_forward_backward(fg, C, B):
+    from face_generator_b200.lib import NET_D
+    case = PU.make_case(B, C, seed=41 + C)
+    rng = np.random.default_rng(8)
+    img = rng.random((B, C, 32, 32)).astype(np.float32)
+    dout = rng.standard_normal(B).astype(np.float32)
+    d = O.f64.D()
+    ref_out = d.forward(case["PD"], img, case["masks_D"])
+    ref_dP, ref_dimg = d.backward(dout)
+    ctx = fg.Context(0, max_batch=8, channels=C)
+    ctx.set_params(NET_D, case["PD"])
+    out = ctx.D_forward(img, masks=case["masks_D"])
+    assert PU.relerr(out, ref_out) < TOL
+    ctx.zero_grads(NET_D)
+    dimg = ctx.D_backward(dout)
+    check_grads(O.D_layout(C), ctx.get_grads(NET_D), ref_dP)
+    assert PU.relerr(dimg, ref_dimg) < TOL
+    # evaluate(): dropout off (SpatialDropout scales by 1-p, Dropout is the identity)
+    ref_eval = d.forward(case["PD"], img, None, training=False)
+    assert PU.relerr(ctx.D_forward(img, training=False), ref_eval) < TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("C,B,init", [(1, 16, "trained"), (3, 8, "trained"), (3, 8, "reference")])
+def test_train_step_matches_oracle(fg, C, B, init):
+    """BASELINE config 1 (gray, B=16: 8 real + 8 fake for D, 16 for G) and a colour case, two iterations."""
+    from face_generator_b200.lib import NET_D, NET_G
+    case = PU.make_case(B, C, seed=51 + C, init=init)
+    ctx = fg.Context(0, max_batch=16, channels=C)
+    ctx.set_params(NET_G, case["PG"])
+    ctx.set_params(NET_D, case["PD"])
+    hyper = fg.hyper_default()
+    st = ctx.train_step(hyper, B, case["real"], case["noise_D"], case["noise_G"], case["masks_D"], case["masks_G"])
+    ref = PU.oracle_iteration(case, B, C)
+    assert abs(st["loss_D"] - ref["lossD"]) < TOL * max(1.0, abs(ref["lossD"]))
+    assert abs(st["loss_G"] - ref["lossG"]) < TOL * max(1.0, abs(ref["lossG"]))
+    assert st["conf"] == [int(v) for v in ref["conf"]]
+    assert st["t_D"] == 1 and st["t_G"] == 1 and st["trained_D"] == 1
+    gD, gG = ctx.get_grads(NET_D), ctx.get_grads(NET_G)
+    # post-penalty, post-clamp gradients (what Adam consumed)
+    assert PU.relerr(gD, ref["gradD"]) < TOL
+    if init == "trained":
+        check_grads(O.G_layout(C), gG, ref["gradG"], skip=("C1b", "C2b"))
+    else:
+        assert PU.relerr(gG, ref["gradG"]) < TOL
+    # Adam moments are linear in the gradient => well conditioned
+    mD, vD, tD = ctx.get_adam_state(NET_D)
+    assert PU.relerr(mD, ref["state"]["mD"]) < TOL and tD == 1
+    # parameters: |update| = lr at t=1 whatever |g| is, so compare only where the gradient is not noise
+    PDn = ctx.get_params(NET_D)
+    big = np.abs(ref["gradD"]) > 1e-3 * np.abs(ref["gradD"]).max()
+    assert np.abs(PDn[big] - ref["state"]["PD"][big]).max() < 2e-5
+    ctx.close()
+
+
+def test_modules_equal_fused_step(fg):
+    """The nn.Module-level composition (fevalD / fevalG_on_D) and the fused fg_train_step are the same math."""
+    from face_generator_b200.lib import NET_D, NET_G
+    from face_generator_b200 import adversarial as A
+    B, C = 8, 3
+    case = PU.make_case(B, C, seed=61)
+    hyper = fg.hyper_default()
+    res = {}
+    for mode in ("fused", "modules"):
+        ctx = fg.Context(0, max_batch=B, channels=C)
+        ctx.set_params(NET_G, case["PG"])
+        ctx.set_params(NET_D, case["PD"])
+        if mode == "fused":
+            ctx.train_step(hyper, B, case["real"], case["noise_D"], case["noise_G"], case["masks_D"], case["masks_G"])
+        else:
+            A.train_batch_modules(ctx, hyper, case["real"], case["noise_D"], case["noise_G"], case["masks_D"],
+                                  case["masks_G"])
+        res[mode] = (ctx.get_params(NET_D), ctx.get_params(NET_G), ctx.get_grads(NET_D), ctx.get_grads(NET_G))
+        ctx.close()
+    for a, b in zip(res["fused"][2:], res["modules"][2:]):
+        assert PU.relerr(a, b) < 1e-5
+    for a, b in zip(res["fused"][:2], res["modules"][:2]):
+        assert np.abs(a - b).max() < 2.1e-3  # sign flips of noise-level gradients move a parameter by 2*lr
+
+
+def test_lop_layers(fg):
+    """L-op ABI (what the Lua b200.* nn.Modules call) against the oracle ops, NCHW in/out."""
+    import ctypes as Cc
+    from face_generator_b200.lib import _ptr
+    rng = np.random.default_rng(71)
+    ctx = fg.Context(0, max_batch=8, channels=3)
+    lib, h = ctx.lib, ctx.h
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    for (N, Cin, H, Cout, k) in [(3, 5, 8, 7, 3), (2, 16, 16, 32, 5), (2, 4, 32, 6, 7)]:
+        x, w, b = f(rng.standard_normal((N, Cin, H, H))), f(rng.standard_normal((Cout, Cin, k, k)) * 0.1), f(rng.standard_normal(Cout))
+        dy = f(rng.standard_normal((N, Cout, H, H)))
+        y = np.empty((N, Cout, H, H), np.float32)
+        assert lib.fg_conv2d_forward(h, _ptr(x), _ptr(w), _ptr(b), _ptr(y), N, Cin, H, H, Cout, k) == 0
+        assert PU.relerr(y, O.f64.conv_fwd(x, w, b)) < TOL
+        rdx, rdw, rdb = O.f64.conv_bwd(x, w, dy)
+        dx = np.empty_like(x)
+        assert lib.fg_conv2d_backward_data(h, _ptr(dy), _ptr(w), _ptr(dx), N, Cin, H, H, Cout, k) == 0
+        assert PU.relerr(dx, rdx) < TOL
+        dw, db = np.zeros_like(w), np.zeros_like(b)
+        assert lib.fg_conv2d_backward_filter(h, _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), N, Cin, H, H, Cout, k) == 0
+        assert PU.relerr(dw, rdw) < TOL and PU.relerr(db, rdb) < TOL
+    # Linear
+    N, fi, fo = 5, 100, 37
+    x, w, b, dy = f(rng.standard_normal((N, fi))), f(rng.standard_normal((fo, fi))), f(rng.standard_normal(fo)), f(rng.standard_normal((N, fo)))
+    y = np.empty((N, fo), np.float32)
+    assert lib.fg_linear_forward(h, _ptr(x), _ptr(w), _ptr(b), _ptr(y), N, fi, fo) == 0
+    assert PU.relerr(y, O.f64.linear_fwd(x, w, b)) < TOL
+    dx, dw, db = np.empty_like(x), np.zeros_like(w), np.zeros_like(b)
+    assert lib.fg_linear_backward(h, _ptr(x), _ptr(w), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), N, fi, fo) == 0
+    rdx, rdw, rdb = O.f64.linear_bwd(x, w, dy)
+    assert PU.relerr(dx, rdx) < TOL and PU.relerr(dw, rdw) < TOL and PU.relerr(db, rdb) < TOL
+    # BatchNorm (training) + backward
+    N, Cn, H = 4, 24, 6
+    x, g, be, dy = f(rng.standard_normal((N, Cn, H, H)) * 2 + 1), f(rng.uniform(0.5, 1.5, Cn)), f(rng.standard_normal(Cn)), f(rng.standard_normal((N, Cn, H, H)))
+    y, sm, si = np.empty_like(x), np.empty(Cn, np.float32), np.empty(Cn, np.float32)
+    rm, rv = np.zeros(Cn, np.float32), np.ones(Cn, np.float32)
+    assert lib.fg_bn_forward_train(h, _ptr(x), _ptr(g), _ptr(be), _ptr(y), _ptr(sm), _ptr(si), _ptr(rm), _ptr(rv), N, Cn, H * H) == 0
+    rrm, rrv = np.zeros(Cn), np.ones(Cn)
+    ry, rmean, ristd = O.f64.bn_fwd_train(x, g, be, rrm, rrv)
+    assert PU.relerr(y, ry) < TOL and PU.relerr(sm, rmean) < TOL and PU.relerr(si, ristd) < TOL
+    assert PU.relerr(rm, rrm) < TOL and PU.relerr(rv, rrv) < TOL
+    dx, dg, db = np.empty_like(x), np.zeros(Cn, np.float32), np.zeros(Cn, np.float32)
+    assert lib.fg_bn_backward(h, _ptr(x), _ptr(g), _ptr(sm), _ptr(si), _ptr(dy), _ptr(dx), _ptr(dg), _ptr(db), N, Cn, H * H) == 0
+    rdx, rdg, rdb = O.f64.bn_bwd(x, g, rmean, ristd, dy)
+    assert PU.relerr(dx, rdx) < TOL and PU.relerr(dg, rdg) < TOL and PU.relerr(db, rdb) < TOL
+    # PReLU
+    x, dy, a = f(rng.standard_normal(1000)), f(rng.standard_normal(1000)), np.array([0.25], np.float32)
+    y = np.empty_like(x)
+    assert lib.fg_prelu_forward(h, _ptr(x), _ptr(a), _ptr(y), 1000) == 0
+    assert PU.relerr(y, O.f64.prelu_fwd(x, 0.25)) < 1e-6
+    dx, da = np.empty_like(x), np.zeros(1, np.float32)
+    assert lib.fg_prelu_backward(h, _ptr(x), _ptr(a), _ptr(dy), _ptr(dx), _ptr(da), 1000) == 0
+    rdx, rda = O.f64.prelu_bwd(x, 0.25, dy)
+    assert PU.relerr(dx, rdx) < 1e-6 and abs(da[0] - rda) < TOL * abs(rda)
+    # BCE incl. saturation: composed gradient through a saturated sigmoid is exactly 0
+    xs, ts = f([1.0, 0.0, 0.3, 0.9]), f([0.0, 1.0, 1.0, 0.0])
+    assert abs(ctx.bce_forward(xs, ts) - O.f64.bce_fwd(xs, ts)) < 1e-4 * O.f64.bce_fwd(xs, ts)
+    gb = ctx.bce_backward(xs, ts)
+    assert PU.relerr(gb[2:], O.f64.bce_bwd(xs, ts)[2:]) < 1e-5
+    assert np.all(gb[:2] * xs[:2] * (1 - xs[:2]) == 0)
+    ctx.close()
+
+
+def test_adam_op_and_error_paths(fg):
+    from face_generator_b200.lib import _ptr, FGError
+    rng = np.random.default_rng(81)
+    ctx = fg.Context(0, max_batch=8, channels=3)
+    n = 100003
+    p, g = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    dp, dg, dm, dv = (ctx.dev_array(a) for a in (p, g, m, v))
+    p64, m64, v64 = p.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
+    for t in (1, 2, 3):
+        assert ctx.lib.fg_adam_step(ctx.h, dp, dg, dm, dv, n, 1e-3, 0.9, 0.999, 1e-8, t, 0.0, 1e-4, 1.0, 1.0) == 0
+        g64 = g.astype(np.float64)
+        O.f64.penalty_clamp(p64, g64, 0.0, 0.0, 1e-4, 1.0)
+        O.f64.adam(p64, g64, m64, v64, t)
+        # fg_adam_step rewrites g with the penalised/clamped gradient: restore the raw one
+        ctx.lib.fg_memcpy(ctx.h, dg, _ptr(g), g.nbytes)
+    out = np.empty(n, np.float32)
+    ctx.lib.fg_memcpy(ctx.h, _ptr(out), dp, out.nbytes)
+    assert np.abs(out - p64).max() < 1e-6
+    for d in (dp, dg, dm, dv):
+        ctx.dev_free(d)
+    # error behaviour: odd / too-large batches are rejected with a message, nothing crashes
+    case = PU.make_case(8, 3, seed=1)
+    hyper = fg.hyper_default()
+    with pytest.raises(FGError):
+        ctx.train_step(hyper, 6 + 1, case["real"], case["noise_D"], case["noise_G"])
+    with pytest.raises(FGError):
+        ctx.train_step(hyper, 16, case["real"], case["noise_D"], case["noise_G"])
+    with pytest.raises(FGError):
+        ctx.G_backward(np.zeros((4, 3, 32, 32), np.float32))  # backward before forward
+    with pytest.raises(FGError):
+        fg.Context(0, max_batch=8, channels=2)
+    ctx.close()
+
+
+def test_sample_chunked(fg):
+    """sample.lua:80: G forward in chunks with train-mode BN (per-chunk statistics)."""
+    from face_generator_b200.lib import NET_G
+    C, N, chunk = 3, 10, 4
+    case = PU.make_case(8, C, seed=91)
+    noise = np.random.default_rng(9).uniform(-1, 1, (N, 100)).astype(np.float32)
+    ctx = fg.Context(0, max_batch=8, channels=C)
+    ctx.set_params(NET_G, case["PG"])
+    out = ctx.sample(noise, chunk)
+    ref = np.concatenate([O.f64.G().forward(case["PG"], noise[s:s + chunk], C) for s in range(0, N, chunk)])
+    assert PU.relerr(out, ref) < TOL
+    ctx.close()
