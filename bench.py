@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the GAN train step (adversarial.lua loop body: 1 D iteration + 1 G iteration,
+both Adam updates) on synthetic 3x32x32 batches, batch 256 per GPU (BASELINE.json configs[1]; weak scaling).
+
+  python bench.py --gpus N --steps K --warmup W              our arm (libfg_b200.so through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...    the reference's CPU math (oracle fp32 port; Torch7
+                                                             itself cannot run in this image)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "32x32 GAN train images/sec (1 D-iter + 1 G-iter per batch, batch 256/GPU)"
+# algorithmic FLOPs: conv = 2*Cout*Cin*k*k*H*W per image per pass
+F_GC2 = 2 * 128 * 256 * 25 * 32 * 32      # 1677.72 MF
+F_GC1 = 2 * 256 * 128 * 25 * 16 * 16      # 419.43 MF
+F_ITER_PER_IMG = 8.087e9                  # reference-executed FLOPs per batch-image per iteration
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_inputs(B, C, seed):
+    rng = np.random.default_rng(seed)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    return (f(rng.random((B // 2, C, 32, 32))), f(rng.uniform(-1, 1, (B // 2, 100))), f(rng.uniform(-1, 1, (B, 100))))
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU path: Torch7 `nn` math (per-sample im2col + SGEMM, OpenMP batch-parallel) as
+    restated by the oracle's fp32 port, all host threads, same metric/config; each step is a bounded sample
+    (b images of the 256-image batch) so K steps end within minutes."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from face_generator_b200 import layouts as LY
+    C = 3
+    b = 16 if args.steps <= 24 else 8
+    O.set_num_threads(os.cpu_count())
+    rng = np.random.default_rng(1)
+    PG, PD = LY.trained_like_init(LY.G_layout(C), rng), LY.trained_like_init(LY.D_layout(C), rng, 1.4)
+    st = dict(PD=PD, PG=PG, mD=np.zeros_like(PD), vD=np.zeros_like(PD), mG=np.zeros_like(PG), vG=np.zeros_like(PG), tD=0,
+              tG=0, bnG=np.concatenate([np.zeros(256), np.ones(256), np.zeros(128), np.ones(128)]).astype(np.float32))
+    hyper = dict(lr_D=1e-3, lr_G=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, D_L1=0.0, D_L2=1e-4, G_L1=0.0, G_L2=0.0,
+                 D_clamp=1.0, G_clamp=5.0)
+    masks = (rng.random((b, O.MASK_PER_SAMPLE)) < 0.7).astype(np.float32)
+    real, nD, nG = synth_inputs(b, C, 7)
+    for _ in range(max(1, min(args.warmup, 2))):
+        O.f32.train_iteration(b, C, hyper, real, nD, nG, masks, masks, st, want_grads=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.f32.train_iteration(b, C, hyper, real, nD, nG, masks, masks, st, want_grads=False)
+    dt = time.perf_counter() - t0
+    v = b * args.steps / dt
+    sample = "%d-image sample of the 256-image batch per step, %d steps, fp32 oracle port (THNN algorithm), %d threads" % (
+        b, args.steps, O.num_threads())
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "train.lua color 3x32x32 batch=256 (configs[1]); reference arm runs a bounded sample",
+                   "global_batch": 256 * args.gpus, "parallelism": "cpu"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE configs[1]: 256)")
+    ap.add_argument("--conv-impl", type=int, default=-1, help="0 simt, 1 tcgen05 dense, 2 tcgen05 collapsed; -1 library default")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import face_generator_b200 as fg
+    from face_generator_b200 import layouts as LY
+    from face_generator_b200.lib import NET_D, NET_G, PinnedArray
+    B, C, K, W = args.batch, 3, args.steps, max(args.warmup, 3)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # plumbing only: rendezvous, barrier, max-over-ranks
+        dist.init_process_group("gloo")
+    ctx = fg.Context(local, max_batch=B, channels=C)
+    if args.conv_impl >= 0:
+        ctx.set_option("conv_impl", args.conv_impl)
+    rng = np.random.default_rng(1)  # identical initial parameters on every rank
+    ctx.set_params(NET_G, LY.trained_like_init(LY.G_layout(C), rng))
+    ctx.set_params(NET_D, LY.trained_like_init(LY.D_layout(C), rng, 1.4))
+    if world > 1:
+        ids = [ctx.dp_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.dp_init(ids[0], world, rank)
+        ctx.dp_broadcast_params()
+    hyper = fg.hyper_default()
+    real, nD, nG = synth_inputs(B, C, 100 + rank)  # rank-distinct shards
+    d_real, d_nD, d_nG = ctx.dev_array(real), ctx.dev_array(nD), ctx.dev_array(nG)
+    p_real, p_nD, p_nG = PinnedArray(real.shape), PinnedArray(nD.shape), PinnedArray(nG.shape)
+    p_real.array[:], p_nD.array[:], p_nG.array[:] = real, nD, nG
+
+    def barrier():
+        ctx.sync()
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    seed = [1000 * rank]
+
+    def step_resident():
+        seed[0] += 1
+        ctx.train_step(hyper, B, d_real, d_nD, d_nG, None, None, seed[0], want_stats=False)
+
+    def step_e2e():
+        seed[0] += 1
+        # H2D of this step's inputs from pinned memory + D2H of the step's result (losses/stats) inside the call
+        return ctx.train_step(hyper, B, p_real.addr, p_nD.addr, p_nG.addr, None, None, seed[0], want_stats=True)
+
+    def timed(fn, k):
+        barrier()
+        ctx.event_record(0)
+        for _ in range(k):
+            fn()
+        ctx.event_record(1)
+        barrier()
+        return max_over_ranks(ctx.event_elapsed_ms(0, 1))
+
+    for _ in range(W):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches()
+    ms = timed(step_resident, K)
+    launches = ctx.launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, K)
+    # dominant kernel family, timed live with CUDA events on the ctx stream (per launch)
+    ctx.timing_enable(True)
+    nprof = 3
+    for _ in range(nprof):
+        step_resident()
+    fam = {}
+    for name in ("G.C2.fwd", "G.C2.dgrad", "G.C2.wgrad", "G.C1", "G.C3", "G.L1", "D.", "nccl"):
+        t, n = ctx.timing_get(name)
+        fam[name] = (t / nprof, n // nprof)
+    t_all, _ = ctx.timing_get("*")
+    ctx.timing_enable(False)
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    value = B * world * K / (ms / 1e3)
+    e2e = B * world * K / (ms_e2e / 1e3)
+    # G.C2 forward runs at B/2 (D step) and B (G step) per iteration: 1.5*B images of algorithmic work
+    t_fwd = fam["G.C2.fwd"][0] / 1e3
+    tf_fwd = 1.5 * B * F_GC2 / t_fwd / 1e12 if t_fwd > 0 else 0.0
+    t_c2 = (fam["G.C2.fwd"][0] + fam["G.C2.dgrad"][0] + fam["G.C2.wgrad"][0]) / 1e3
+    tf_c2 = 3.5 * B * F_GC2 / t_c2 / 1e12 if t_c2 > 0 else 0.0
+    peak = peaks["bf16_sus"] / 2.0
+    out = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "train.lua color 3x32x32 batch=256 per GPU (BASELINE configs[1]), 1 D-iter + 1 G-iter, Adam",
+                   "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
+                   "conv_impl": ctx.get_option("conv_impl"), "dropout": "in-kernel RNG",
+                   "l2": "per-step working set (activations+grads ~1.5 GB) >> 126 MB L2, no explicit flush"},
+        "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": int(real.nbytes + nD.nbytes + nG.nbytes), "d2h_bytes_per_step": 40},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "G.C2 5x5 conv 256->128 @32x32 forward (implicit GEMM M=B*1024,N=128,K=6400)",
+                     "bound": "tensor", "achieved": tf_fwd, "peak": peak, "unit": "TFLOP/s",
+                     "frac": tf_fwd / peak, "traffic": None,
+                     "peak_source": "%s bf16 sustained %.1f TF / 2 (kind::tf32 is half rate); algorithmic fp32 FLOPs" % (
+                         peaks["src"], peaks["bf16_sus"]),
+                     "family_fwd_dgrad_wgrad_tflops": tf_c2,
+                     "step_algorithmic_tflops": F_ITER_PER_IMG * B * K / (ms / 1e3) / 1e12},
+        "kernel_ms_per_step": {k: round(v[0], 4) for k, v in fam.items()},
+        "conv_ms_per_step": round(t_all / nprof, 4),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O  # cpu_baseline leg: the checker timed as a reported baseline
+        O.set_num_threads(os.cpu_count())
+        b = 16
+        rng = np.random.default_rng(1)
+        PG, PD = LY.trained_like_init(LY.G_layout(C), rng), LY.trained_like_init(LY.D_layout(C), rng, 1.4)
+        st = dict(PD=PD, PG=PG, mD=np.zeros_like(PD), vD=np.zeros_like(PD), mG=np.zeros_like(PG), vG=np.zeros_like(PG),
+                  tD=0, tG=0, bnG=np.concatenate([np.zeros(256), np.ones(256), np.zeros(128), np.ones(128)]).astype(np.float32))
+        hp = dict(lr_D=1e-3, lr_G=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, D_L1=0.0, D_L2=1e-4, G_L1=0.0, G_L2=0.0,
+                  D_clamp=1.0, G_clamp=5.0)
+        masks = (rng.random((b, O.MASK_PER_SAMPLE)) < 0.7).astype(np.float32)
+        r, a, g = synth_inputs(b, C, 7)
+        O.f32.train_iteration(b, C, hp, r, a, g, masks, masks, st, want_grads=False)
+        t0, it = time.perf_counter(), 0
+        while it < 3 or (time.perf_counter() - t0 < 10 and it < 12):
+            O.f32.train_iteration(b, C, hp, r, a, g, masks, masks, st, want_grads=False)
+            it += 1
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": b * it / dt, "unit": "images/s", "cores": O.num_threads(), "kind": "port",
+                               "sample": "%d iterations at batch %d (colour) of the fp32 oracle port, %.1f s" % (it, b, dt)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,25 +1,72 @@
 // Data parallelism: one process per GPU, one NCCL communicator, one in-place sum-allreduce of the
 // flat gradient (+8 tail scalars) per optimizer step.  The reference has no
 // multi-GPU path at all; this is new functionality behind the same train-step call.
+//
+// NCCL is bound at run time (dlopen) instead of DT_NEEDED so that loading libfg_b200.so never pins a
+// libnccl.so.2 into a process that later imports another copy (e.g. the torch-bundled one used only
+// for test/bench plumbing): an already-loaded libnccl.so.2 is reused, else the system one is opened.
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include <cstring>
 
 #include "fg_internal.h"
 
-#define FG_NCCL(call)                                                                          \
-  do {                                                                                         \
-    ncclResult_t r__ = (call);                                                                 \
-    if (r__ != ncclSuccess) {                                                                  \
-      fg_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__));     \
-      return FG_ERR_NCCL;                                                                      \
-    }                                                                                          \
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+int nccl_load() {
+  if (g_nccl.handle) return FG_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    fg_set_error("cannot load libnccl.so.2: %s", dlerror());
+    return FG_ERR_NCCL;
+  }
+#define SYM(field, name)                                                 \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                             \
+  if (!g_nccl.field) {                                                   \
+    fg_set_error("libnccl.so.2 lacks %s", name);                         \
+    return FG_ERR_NCCL;                                                  \
+  }
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(Broadcast, "ncclBroadcast")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.handle = h;
+  return FG_OK;
+}
+}  // namespace
+
+#define FG_NCCL(call)                                                                                 \
+  do {                                                                                                \
+    ncclResult_t r__ = (call);                                                                        \
+    if (r__ != ncclSuccess) {                                                                         \
+      fg_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__));         \
+      return FG_ERR_NCCL;                                                                             \
+    }                                                                                                 \
   } while (0)
 
 int net_allreduce(fg_ctx* c, float* buf, int64_t n) {
   if (c->world <= 1) return FG_OK;
   ScopedTimer t(c, "nccl.allreduce");
-  FG_NCCL(ncclAllReduce(buf, buf, (size_t)n, ncclFloat, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+  FG_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
   return FG_OK;
 }
 
@@ -27,8 +74,9 @@ extern "C" {
 int fg_dp_unique_id(void* out128) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
   if (!out128) return FG_ERR_INVALID;
+  FG_TRY(nccl_load());
   ncclUniqueId id;
-  FG_NCCL(ncclGetUniqueId(&id));
+  FG_NCCL(g_nccl.GetUniqueId(&id));
   memcpy(out128, &id, sizeof(id));
   return FG_OK;
 }
@@ -39,16 +87,17 @@ int fg_dp_init(fg_ctx* c, const void* id128, int nranks, int rank) {
   }
   FG_CUDA(cudaSetDevice(c->device));
   if (c->nccl_comm) {
-    ncclCommDestroy((ncclComm_t)c->nccl_comm);
+    g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     c->nccl_comm = nullptr;
   }
   c->world = 1;
   c->rank = 0;
   if (nranks == 1) return FG_OK;
+  FG_TRY(nccl_load());
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   ncclComm_t comm;
-  FG_NCCL(ncclCommInitRank(&comm, nranks, id, rank));
+  FG_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
   c->nccl_comm = comm;
   c->world = nranks;
   c->rank = rank;
@@ -59,15 +108,15 @@ int fg_dp_broadcast_params(fg_ctx* c) {
   if (c->world <= 1) return FG_OK;
   FG_CUDA(cudaSetDevice(c->device));
   ncclComm_t comm = (ncclComm_t)c->nccl_comm;
-  FG_NCCL(ncclGroupStart());
-  FG_NCCL(ncclBroadcast(c->PG, c->PG, c->gl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(ncclBroadcast(c->PD, c->PD, c->dl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(ncclBroadcast(c->mG, c->mG, c->gl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(ncclBroadcast(c->vG, c->vG, c->gl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(ncclBroadcast(c->mD, c->mD, c->dl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(ncclBroadcast(c->vD, c->vD, c->dl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(ncclBroadcast(c->bnG, c->bnG, 768, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(ncclGroupEnd());
+  FG_NCCL(g_nccl.GroupStart());
+  FG_NCCL(g_nccl.Broadcast(c->PG, c->PG, c->gl.total, ncclFloat, 0, comm, c->stream));
+  FG_NCCL(g_nccl.Broadcast(c->PD, c->PD, c->dl.total, ncclFloat, 0, comm, c->stream));
+  FG_NCCL(g_nccl.Broadcast(c->mG, c->mG, c->gl.total, ncclFloat, 0, comm, c->stream));
+  FG_NCCL(g_nccl.Broadcast(c->vG, c->vG, c->gl.total, ncclFloat, 0, comm, c->stream));
+  FG_NCCL(g_nccl.Broadcast(c->mD, c->mD, c->dl.total, ncclFloat, 0, comm, c->stream));
+  FG_NCCL(g_nccl.Broadcast(c->vD, c->vD, c->dl.total, ncclFloat, 0, comm, c->stream));
+  FG_NCCL(g_nccl.Broadcast(c->bnG, c->bnG, 768, ncclFloat, 0, comm, c->stream));
+  FG_NCCL(g_nccl.GroupEnd());
   FG_CUDA(cudaStreamSynchronize(c->stream));
   c->G_packed = c->D_packed = false;
   return FG_OK;

@@ -312,8 +312,9 @@ __global__ void bn_prelu_apply_kernel(const float* __restrict__ z, const float* 
     const float4 v = z4[i];
     const float4 m = *reinterpret_cast<const float4*>(mean + ch);
     const float4 s = *reinterpret_cast<const float4*>(istd + ch);
-    const float4 g = *reinterpret_cast<const float4*>(gamma + ch);
-    const float4 b = *reinterpret_cast<const float4*>(beta + ch);
+    // gamma/beta live inside the flat parameter vector at arbitrary (unaligned) offsets: scalar loads
+    const float4 g = make_float4(gamma[ch], gamma[ch + 1], gamma[ch + 2], gamma[ch + 3]);
+    const float4 b = make_float4(beta[ch], beta[ch + 1], beta[ch + 2], beta[ch + 3]);
     float4 o;
     o.x = g.x * ((v.x - m.x) * s.x) + b.x;
     o.y = g.y * ((v.y - m.y) * s.y) + b.y;

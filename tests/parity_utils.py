@@ -2,7 +2,7 @@
 import numpy as np
 
 from oracle import oracle as O
-import torch_ref as R
+from face_generator_b200 import layouts as LY
 
 HYPER = dict(lr_D=1e-3, lr_G=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, D_L1=0.0, D_L2=1e-4, G_L1=0.0, G_L2=0.0,
              D_clamp=1.0, G_clamp=5.0)
@@ -14,22 +14,23 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
 
 
+def make_masks(B, rng):
+    m = np.zeros((B, O.MASK_PER_SAMPLE))
+    m[:, :960] = rng.random((B, 960)) < 0.8
+    m[:, 960:] = rng.random((B, 1024)) < 0.5
+    return m
+
+
 def make_case(B, C, seed, init="trained"):
     rng = np.random.default_rng(seed)
     if init == "trained":
-        PG, PD = R.trained_like_G(C, rng), R.trained_like_D(C, rng)
+        PG, PD = LY.trained_like_init(LY.G_layout(C), rng), LY.trained_like_init(LY.D_layout(C), rng, 1.4)
     else:  # the reference's own init: N(0, 0.005^2) weights (incl. BN gamma, PReLU slope), N(0, 0.001^2) biases
-        PG = rng.standard_normal(O.G_param_count(C)) * 0.005
-        PD = rng.standard_normal(O.D_param_count(C)) * 0.005
-        for lay, P in ((O.G_layout(C), PG), (O.D_layout(C), PD)):
-            for k, (o, s) in lay.items():
-                if k.endswith("b") or k.startswith("be"):
-                    n = int(np.prod(s))
-                    P[o:o + n] = rng.standard_normal(n) * 0.001
+        PG, PD = LY.reference_init(LY.G_layout(C), rng), LY.reference_init(LY.D_layout(C), rng)
     f = lambda a: np.ascontiguousarray(a, np.float32)
     return dict(PG=f(PG), PD=f(PD), real=f(rng.random((B // 2, C, 32, 32))),
                 noise_D=f(rng.uniform(-1, 1, (B // 2, 100))), noise_G=f(rng.uniform(-1, 1, (B, 100))),
-                masks_D=f(R.make_masks(B, rng)), masks_G=f(R.make_masks(B, rng)))
+                masks_D=f(make_masks(B, rng)), masks_G=f(make_masks(B, rng)))
 
 
 def fresh_state(case, dtype=np.float64):
