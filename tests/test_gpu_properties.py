@@ -52,7 +52,7 @@ def test_full_size_step_first_adam_update_is_lr(big):
     for net, P0 in ((NET_D, P0D), (NET_G, P0G)):
         P1, g = ctx.get_params(net), ctx.get_grads(net)
         assert np.isfinite(P1).all() and np.isfinite(g).all()
-        big_g = np.abs(g) > 1e-6
+        big_g = np.abs(g) > 1e-4  # eps/(sqrt(1-b2)|g|) < 0.4% there
         # interruptable_optimizers.lua:78-90 at t=1: |dx| = lr*|g|/(|g|+eps*sqrt(1-b2)...) ~= lr
         np.testing.assert_allclose(np.abs(P1 - P0)[big_g], 1e-3, rtol=2e-2)
         assert np.all(np.sign(P0 - P1)[big_g] == np.sign(g)[big_g])
