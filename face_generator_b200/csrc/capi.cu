@@ -146,6 +146,7 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
   if (!strcmp(key, "conv_impl")) {
     FG_REQUIRE(v >= 0 && v <= 2, "conv_impl must be 0 (simt), 1 (tc dense) or 2 (tc collapsed)");
     c->conv_impl = (int)v;
+    c->G_packed = c->D_packed = false;
     return FG_OK;
   }
   if (!strcmp(key, "params_dirty")) {

@@ -130,8 +130,17 @@ struct fg_ctx {
   cudaEvent_t events[16] = {};
   bool timing = false;
   std::map<std::string, TimerRec> timers;
-  // tcgen05 path state (k_conv_tc.cu)
-  void* tc = nullptr;
+  // tcgen05 path: TF32 hi/lo splits of activations / gradients / packed weights (k_conv_tc.cu)
+  struct TcBufs {
+    float *G_h0_hi = nullptr, *G_h0_lo = nullptr, *G_h1_hi = nullptr, *G_h1_lo = nullptr;  // conv inputs (fwd -> wgrad)
+    float *dy_hi = nullptr, *dy_lo = nullptr;                                             // current dY (dgrad + wgrad)
+    float *G_Wf_hi[2] = {nullptr, nullptr}, *G_Wf_lo[2] = {nullptr, nullptr};  // C1,C2 collapsed fwd [36][n][c]
+    float *G_Wd_hi[2] = {nullptr, nullptr}, *G_Wd_lo[2] = {nullptr, nullptr};  // collapsed dgrad [36][c][n]
+    float *G_Wx_hi[2] = {nullptr, nullptr}, *G_Wx_lo[2] = {nullptr, nullptr};  // dense fwd [25][n][c]
+    float *D_p_hi[3] = {nullptr, nullptr, nullptr}, *D_p_lo[3] = {nullptr, nullptr, nullptr};  // pooled inputs of c2..c4
+    float *D_Wf_hi[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Wf_lo[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *D_Wd_hi[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Wd_lo[4] = {nullptr, nullptr, nullptr, nullptr};
+  } tcb;
 };
 
 struct ScopedTimer {

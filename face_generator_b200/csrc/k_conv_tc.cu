@@ -1,4 +1,789 @@
-// tcgen05 / TMA implicit-GEMM convolution path (filled in below; stubs keep the library linkable).
+// tcgen05 / TMA implicit-GEMM convolutions for sm_100a with error-compensated 3xTF32
+// (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) so results stay within fp32 parity.
+//
+// Both kernels view a stride-1 "same" convolution as a sum over filter taps of shifted GEMMs and feed
+// the tensor cores with plain TILED TMA boxes of the NHWC activation tensors (out-of-image rows /
+// columns are zero-filled by TMA, which implements the zero padding for free):
+//
+//   tapconv (forward + dgrad):  D[pixel m][n]  = sum_taps A_tap[m][c] * W_tap[n][c]
+//       A_tap = box(32 ch, bw, bh, bb) of 128 pixels at spatial offset (dy,dx)  -> K-major operand
+//       W_tap = box(32 ch, BN rows) of the packed weights [tap][n][c]          -> K-major operand
+//   wgrad:                      D[n][c]        = sum_pixels dY[p][n] * X[p+off][c]
+//       dY, X boxes (32 ch, 32 pixels)                                          -> MN-major operands
+//
+// nn.SpatialUpSamplingNearest(2) -> conv5x5 is executed on the LOW-RES tensor: output phase (py,px)
+// only sees low-res offsets {-1,0,1}^2, either with the 25 original taps ("dense")
+// or with the weights pre-summed to 9 taps per phase ("collapsed", 2.78x fewer MMAs).
+//
+// Pipeline per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+// tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  3 smem stages of
+// {A_hi, A_lo, B_hi, B_lo}, 128B-swizzled, mbarrier full/empty rings, tcgen05.commit releases stages.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+
 #include "fg_internal.h"
-int tc_init(fg_ctx*) { return FG_OK; }
+#include "k_conv_tc.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 columns of 32-bit: thread i of the warp receives row (lane-quadrant*32 + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int kStages = 3;
+constexpr uint32_t kABytes = 128 * 128;  // 128 rows x 32 fp32
+
+// ------------------------------------------------------------------------------------------------
+// tapconv: forward / dgrad
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constant__ TcFwdParams p) {
+  constexpr uint32_t kBBytes = BN * 128;
+  constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+  constexpr uint32_t kIdesc = make_idesc(128, BN, 0, 0);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- tile decode ----
+  const int mt = blockIdx.x, n0 = blockIdx.y * BN;
+  const int ph = mt / p.tiles_per_phase;
+  int r = mt % p.tiles_per_phase;
+  int b0, y0, x0;
+  if (p.bb == 1) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    b0 = r / per_img;
+    r %= per_img;
+    y0 = (r / p.tiles_x) * p.bh;
+    x0 = (r % p.tiles_x) * p.bw;
+  } else {
+    b0 = r * p.bb;
+    y0 = 0;
+    x0 = 0;
+  }
+  const int nkb = p.ntaps * p.kpt;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&p.b_hi);
+      prefetch_tmap(&p.b_lo);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages, it = kb / kStages;
+        if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+        const int tap = kb / p.kpt, c0 = (kb - tap * p.kpt) * 32;
+        const int ti = ph * p.ntaps + tap;
+        const int am = p.amap[ti];
+        uint8_t* st = smem + s * kStageBytes;
+        mbar_expect_tx(full + s, kStageBytes);
+        tma_load_4d(st, &p.a_hi[am], full + s, c0, x0 + p.dx[ti], y0 + p.dy[ti], b0);
+        tma_load_4d(st + kABytes, &p.a_lo[am], full + s, c0, x0 + p.dx[ti], y0 + p.dy[ti], b0);
+        const int wrow = p.widx[ti] * p.Cout + n0;
+        tma_load_2d(st + 2 * kABytes, &p.b_hi, full + s, c0, wrow);
+        tma_load_2d(st + 2 * kABytes + kBBytes, &p.b_lo, full + s, c0, wrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages, it = kb / kStages;
+        mbar_wait(full + s, it & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * kStageBytes);
+        const uint64_t a_hi = make_desc(sa, 16, 1024), a_lo = make_desc(sa + kABytes, 16, 1024);
+        const uint64_t b_hi = make_desc(sa + 2 * kABytes, 16, 1024), b_lo = make_desc(sa + 2 * kABytes + kBBytes, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 fp32 of K) in the 16B-unit start-address field
+          umma_tf32(tmem_base, a_lo + ko, b_hi + ko, kIdesc, (kb | k) != 0);
+          umma_tf32(tmem_base, a_hi + ko, b_lo + ko, kIdesc, 1);
+          umma_tf32(tmem_base, a_hi + ko, b_hi + ko, kIdesc, 1);
+        }
+        umma_commit(empty + s);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ---- epilogue: 4 warps, warp%4 selects the TMEM lane quadrant ----
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // accumulator row == tile pixel
+    const int xi = m % p.bw, yi = (m / p.bw) % p.bh, bi = m / (p.bw * p.bh);
+    const int b = b0 + bi;
+    const int Y = p.out_scale * (y0 + yi) + (ph >> 1) * (p.out_scale - 1);
+    const int X = p.out_scale * (x0 + xi) + (ph & 1) * (p.out_scale - 1);
+    float* orow = p.out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + n0;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+      if (b < p.B) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 o;
+          o.x = __uint_as_float(v[i + 0]);
+          o.y = __uint_as_float(v[i + 1]);
+          o.z = __uint_as_float(v[i + 2]);
+          o.w = __uint_as_float(v[i + 3]);
+          if (p.bias) {
+            const float* bp = p.bias + n0 + j * 32 + i;
+            o.x += bp[0];
+            o.y += bp[1];
+            o.z += bp[2];
+            o.w += bp[3];
+          }
+          *reinterpret_cast<float4*>(orow + j * 32 + i) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: D[n (M=128 of Cout)][c (BN of Cin)] += sum over a pixel range of dY[p][n] * X[p+off][c]
+// grid: x = tile-tap, y = mtile * ntiles_n + ntile, z = K split.  Output accumulated with atomics.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ TcWgParams p) {
+  constexpr uint32_t kBox = 32 * 128;  // one (32 ch x 32 px) box = 4 KB
+  constexpr uint32_t kAB = 4 * kBox;   // M = 128 channels of dY
+  constexpr uint32_t kBB = (BN / 32) * kBox;
+  constexpr uint32_t kStageBytes = 2 * kAB + 2 * kBB;
+  constexpr uint32_t kIdesc = make_idesc(128, BN, 1, 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tt = blockIdx.x;
+  const int ntn = p.Cin / BN;
+  const int m0 = (blockIdx.y / ntn) * 128, c0 = (blockIdx.y % ntn) * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.kblocks, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const int ph = p.phase[tt], dyo = p.dy[tt], dxo = p.dx[tt];
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % kStages, it = i / kStages;
+          if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+          const int kb = kb_begin + i;
+          int b0, y0, x0;
+          if (p.bb == 1) {
+            const int per_img = p.tiles_x * p.tiles_y;
+            b0 = kb / per_img;
+            const int r = kb % per_img;
+            y0 = (r / p.tiles_x) * p.bh;
+            x0 = (r % p.tiles_x) * p.bw;
+          } else {
+            b0 = kb * p.bb;
+            y0 = 0;
+            x0 = 0;
+          }
+          uint8_t* st = smem + s * kStageBytes;
+          mbar_expect_tx(full + s, kStageBytes);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            tma_load_4d(st + g * kBox, &p.dy_hi[ph], full + s, m0 + g * 32, x0, y0, b0);
+            tma_load_4d(st + kAB + g * kBox, &p.dy_lo[ph], full + s, m0 + g * 32, x0, y0, b0);
+          }
+#pragma unroll
+          for (int g = 0; g < BN / 32; ++g) {
+            tma_load_4d(st + 2 * kAB + g * kBox, &p.x_hi, full + s, c0 + g * 32, x0 + dxo, y0 + dyo, b0);
+            tma_load_4d(st + 2 * kAB + kBB + g * kBox, &p.x_lo, full + s, c0 + g * 32, x0 + dxo, y0 + dyo, b0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % kStages, it = i / kStages;
+          mbar_wait(full + s, it & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * kStageBytes);
+          // MN-major, SWIZZLE_128B: 32 channels contiguous (128 B), 8 pixels per 1024 B atom;
+          // LBO = distance between 32-channel groups (one box), SBO = distance between 8-pixel groups
+          const uint64_t a_hi = make_desc(sa, kBox, 1024), a_lo = make_desc(sa + kAB, kBox, 1024);
+          const uint64_t b_hi = make_desc(sa + 2 * kAB, kBox, 1024), b_lo = make_desc(sa + 2 * kAB + kBB, kBox, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = (uint64_t)(k * 64);  // +1024 bytes = next 8 pixels
+            umma_tf32(tmem_base, a_lo + ko, b_hi + ko, kIdesc, (i | k) != 0);
+            umma_tf32(tmem_base, a_hi + ko, b_lo + ko, kIdesc, 1);
+            umma_tf32(tmem_base, a_hi + ko, b_hi + ko, kIdesc, 1);
+          }
+          umma_commit(empty + s);
+        }
+        umma_commit(tmem_full);
+      }
+    } else {
+      const int q = warp & 3;
+      const int n = m0 + q * 32 + lane;
+      float* orow = p.out + ((int64_t)tt * p.Cout + n) * p.Cin + c0;
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(orow + j * 32 + i, __uint_as_float(v[i]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise helpers of the tensor-core path
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  // hi: mantissa rounded to 10 bits (what kind::tf32 consumes exactly), lo: exact fp32 remainder
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
+}
+__global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n4) {
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* h4 = reinterpret_cast<float4*>(hi);
+  float4* l4 = reinterpret_cast<float4*>(lo);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = x4[i];
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x);
+    split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z);
+    split_tf32(v.w, h.w, l.w);
+    h4[i] = h;
+    l4[i] = l;
+  }
+}
+
+// up2 -> 5x5 collapses to 3x3 per output phase: 5x5 rows/cols {0,1}{2,3}{4} (even phase) or {0}{1,2}{3,4} (odd)
+__device__ __forceinline__ void group_range(int parity, int t, int& lo, int& hi) {
+  if (parity == 0) {
+    lo = t == 0 ? 0 : (t == 1 ? 2 : 4);
+    hi = t == 0 ? 1 : (t == 1 ? 3 : 4);
+  } else {
+    lo = t == 0 ? 0 : (t == 1 ? 1 : 3);
+    hi = t == 0 ? 0 : (t == 1 ? 2 : 4);
+  }
+}
+// W[N][Cc][5][5] -> fwd[ph][ty][tx][n][c] (hi/lo) and dgrad[ph][ty][tx][c][n] (hi/lo)
+__global__ void pack_collapsed_kernel(const float* __restrict__ W, float* __restrict__ f_hi, float* __restrict__ f_lo,
+                                      float* __restrict__ d_hi, float* __restrict__ d_lo, int N, int Cc) {
+  const int64_t total = (int64_t)36 * N * Cc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % Cc);
+    int64_t r = i / Cc;
+    const int n = (int)(r % N);
+    const int tp = (int)(r / N);  // ph*9 + ty*3 + tx
+    const int ph = tp / 9, ty = (tp % 9) / 3, tx = tp % 3;
+    int h0, h1, w0, w1;
+    group_range(ph >> 1, ty, h0, h1);
+    group_range(ph & 1, tx, w0, w1);
+    const float* w = W + ((int64_t)n * Cc + ch) * 25;
+    float s = 0.f;
+    for (int kh = h0; kh <= h1; ++kh)
+      for (int kw = w0; kw <= w1; ++kw) s += w[kh * 5 + kw];
+    float hi, lo;
+    split_tf32(s, hi, lo);
+    f_hi[i] = hi;
+    f_lo[i] = lo;
+    const int64_t j = ((int64_t)tp * Cc + ch) * N + n;
+    d_hi[j] = hi;
+    d_lo[j] = lo;
+  }
+}
+// generic: W[N][Cc][KK] -> fwd[t][n][c] hi/lo, dgrad[KK-1-t][c][n] hi/lo
+__global__ void pack_split_kernel(const float* __restrict__ W, float* __restrict__ f_hi, float* __restrict__ f_lo,
+                                  float* __restrict__ d_hi, float* __restrict__ d_lo, int N, int Cc, int KK) {
+  const int64_t total = (int64_t)N * Cc * KK;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % KK);
+    const int64_t r = i / KK;
+    const int ch = (int)(r % Cc);
+    const int n = (int)(r / Cc);
+    float hi, lo;
+    split_tf32(W[i], hi, lo);
+    const int64_t jf = ((int64_t)t * N + n) * Cc + ch;
+    f_hi[jf] = hi;
+    f_lo[jf] = lo;
+    if (d_hi) {
+      const int64_t jd = ((int64_t)(KK - 1 - t) * Cc + ch) * N + n;
+      d_hi[jd] = hi;
+      d_lo[jd] = lo;
+    }
+  }
+}
+// collapsed wgrad G[ph][ty][tx][n][c] -> dW[n][c][5][5] += sum over the 4 phases
+__global__ void combine_collapsed_wgrad_kernel(const float* __restrict__ G, float* __restrict__ dW, int N, int Cc) {
+  const int64_t total = (int64_t)N * Cc * 25;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % 25);
+    const int64_t r = i / 25;
+    const int ch = (int)(r % Cc);
+    const int n = (int)(r / Cc);
+    const int kh = t / 5, kw = t % 5;
+    float s = 0.f;
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      const int ty = py == 0 ? (kh < 2 ? 0 : (kh < 4 ? 1 : 2)) : (kh < 1 ? 0 : (kh < 3 ? 1 : 2));
+      const int tx = px == 0 ? (kw < 2 ? 0 : (kw < 4 ? 1 : 2)) : (kw < 1 ? 0 : (kw < 3 ? 1 : 2));
+      s += G[(((int64_t)(ph * 9 + ty * 3 + tx)) * N + n) * Cc + ch];
+    }
+    dW[i] += s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int get_encode() {
+  if (g_encode) return FG_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  FG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) {
+    fg_set_error("cuTensorMapEncodeTiled is not available in this driver");
+    return FG_ERR_UNSUPPORTED;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  return FG_OK;
+}
+
+// 4-D map over an NHWC fp32 tensor view: dims (C, W, H, B) with explicit byte strides
+int make_map4(CUtensorMap* m, const float* base, int C, int W, int H, int B, int64_t sW, int64_t sH, int64_t sB, int bc,
+              int bw, int bh, int bb) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sW, (cuuint64_t)sH, (cuuint64_t)sB};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fg_set_error("cuTensorMapEncodeTiled(4d) failed: %d (C=%d W=%d H=%d B=%d box %d,%d,%d,%d)", (int)r, C, W, H, B, bc, bw,
+                 bh, bb);
+    return FG_ERR_CUDA;
+  }
+  return FG_OK;
+}
+int make_map2(CUtensorMap* m, const float* base, int cols, int64_t rows, int bc, int br) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)bc, (cuuint32_t)br};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fg_set_error("cuTensorMapEncodeTiled(2d) failed: %d (cols=%d rows=%lld box %d,%d)", (int)r, cols, (long long)rows, bc, br);
+    return FG_ERR_CUDA;
+  }
+  return FG_OK;
+}
+
+// pixel box of `npix` pixels for a WxH image: returns false if no exact tiling exists
+bool pick_box(int H, int W, int npix, int* bw, int* bh, int* bb) {
+  if (W <= 0 || H <= 0) return false;
+  if (W >= npix) {
+    if (W % npix) return false;
+    *bw = npix; *bh = 1; *bb = 1;
+    return true;
+  }
+  if (npix % W) return false;
+  const int rows = npix / W;
+  if (rows <= H) {
+    if (H % rows) return false;
+    *bw = W; *bh = rows; *bb = 1;
+    return true;
+  }
+  if (rows % H) return false;
+  *bw = W; *bh = H; *bb = rows / H;
+  return true;
+}
+
+template <int BN>
+constexpr size_t fwd_smem() { return (size_t)kStages * (2 * kABytes + 2 * BN * 128) + 64 + 1024; }
+template <int BN>
+constexpr size_t wg_smem() { return (size_t)kStages * (2 * 4 * 4096 + 2 * (BN / 32) * 4096) + 64 + 1024; }
+
+#define LAUNCH_CHECK(c)                 \
+  do {                                  \
+    (c)->launches++;                    \
+    FG_CUDA(cudaGetLastError());        \
+  } while (0)
+
+}  // namespace
+
+int tc_init(fg_ctx* c) {
+  (void)c;
+  FG_TRY(get_encode());
+  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
+  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>()));
+  FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<64>()));
+  FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<128>()));
+  return FG_OK;
+}
 void tc_destroy(fg_ctx*) {}
+
+int tc_split(fg_ctx* c, const float* x, float* hi, float* lo, int64_t n) {
+  if (n % 4) {
+    fg_set_error("tc_split: element count must be a multiple of 4");
+    return FG_ERR_INVALID;
+  }
+  int64_t g = (n / 4 + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  split_kernel<<<(int)g, 256, 0, c->stream>>>(x, hi, lo, n / 4);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int tc_pack_split(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK) {
+  int64_t g = ((int64_t)N * Cc * KK + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  pack_split_kernel<<<(int)g, 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc, KK);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int tc_pack_collapsed(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc) {
+  int64_t g = ((int64_t)36 * N * Cc + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  pack_collapsed_kernel<<<(int)g, 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int tc_combine_collapsed_wgrad(fg_ctx* c, const float* G, float* dW, int N, int Cc) {
+  int64_t g = ((int64_t)N * Cc * 25 + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  combine_collapsed_wgrad_kernel<<<(int)g, 256, 0, c->stream>>>(G, dW, N, Cc);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+
+bool tc_conv_eligible(const ConvGeom& g) {
+  int bw, bh, bb;
+  const int Hl = g.H / g.ups, Wl = g.W / g.ups;
+  if (g.Cin % 32 || g.Cout % 64) return false;
+  if (g.ups == 2 && g.k != 5) return false;
+  if (g.k > 9 || !(g.k & 1)) return false;
+  return pick_box(Hl, Wl, 128, &bw, &bh, &bb) && pick_box(Hl, Wl, 32, &bw, &bh, &bb);
+}
+
+// Forward-type launch.  x_hi/x_lo: [B][H/ups][W/ups][Cin]; w_hi/w_lo: packed [tapw][Cout][Cin];
+// mode: 0 plain k x k conv (taps k*k, weights [t][n][c]);
+//       1 up2+5x5 dense (25 taps per output phase, weights [25][n][c]);
+//       2 up2+5x5 collapsed (9 taps per phase, weights [36][n][c])
+int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                const float* bias, float* out, ConvGeom g, int mode) {
+  TcFwdParams p;
+  memset(&p, 0, sizeof(p));
+  const int Hl = g.H / g.ups, Wl = g.W / g.ups;
+  if (!pick_box(Hl, Wl, 128, &p.bw, &p.bh, &p.bb)) {
+    fg_set_error("tc_conv_fwd: no 128-pixel box for %dx%d", Hl, Wl);
+    return FG_ERR_UNSUPPORTED;
+  }
+  const int64_t sW = (int64_t)g.Cin * 4, sH = sW * Wl, sB = sH * Hl;
+  FG_TRY(make_map4(&p.a_hi[0], x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+  FG_TRY(make_map4(&p.a_lo[0], x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+  const int BN = g.Cout % 128 == 0 ? 128 : 64;
+  int ntapw;
+  if (mode == 0) {
+    const int pad = (g.k - 1) / 2;
+    p.nphase = 1;
+    p.ntaps = g.k * g.k;
+    ntapw = p.ntaps;
+    for (int t = 0; t < p.ntaps; ++t) {
+      p.dy[t] = (int8_t)(t / g.k - pad);
+      p.dx[t] = (int8_t)(t % g.k - pad);
+      p.widx[t] = (int16_t)t;
+    }
+  } else if (mode == 1) {
+    p.nphase = 4;
+    p.ntaps = 25;
+    ntapw = 25;
+    for (int ph = 0; ph < 4; ++ph)
+      for (int t = 0; t < 25; ++t) {
+        const int kh = t / 5, kw = t % 5, py = ph >> 1, px = ph & 1;
+        // floor((py + kh - 2) / 2) without relying on negative division
+        p.dy[ph * 25 + t] = (int8_t)(((py + kh - 2) + 4) / 2 - 2);
+        p.dx[ph * 25 + t] = (int8_t)(((px + kw - 2) + 4) / 2 - 2);
+        p.widx[ph * 25 + t] = (int16_t)t;
+      }
+  } else {
+    p.nphase = 4;
+    p.ntaps = 9;
+    ntapw = 36;
+    for (int ph = 0; ph < 4; ++ph)
+      for (int t = 0; t < 9; ++t) {
+        p.dy[ph * 9 + t] = (int8_t)(t / 3 - 1);
+        p.dx[ph * 9 + t] = (int8_t)(t % 3 - 1);
+        p.widx[ph * 9 + t] = (int16_t)(ph * 9 + t);
+      }
+  }
+  FG_TRY(make_map2(&p.b_hi, w_hi, g.Cin, (int64_t)ntapw * g.Cout, 32, BN));
+  FG_TRY(make_map2(&p.b_lo, w_lo, g.Cin, (int64_t)ntapw * g.Cout, 32, BN));
+  p.kpt = g.Cin / 32;
+  p.Cout = g.Cout;
+  p.B = g.B; p.H = Hl; p.W = Wl;
+  p.tiles_x = Wl / p.bw;
+  p.tiles_y = Hl / p.bh;
+  p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
+  p.out = out;
+  p.bias = bias;
+  p.out_H = g.H; p.out_W = g.W;
+  p.out_scale = g.ups;
+  dim3 grid(p.tiles_per_phase * p.nphase, g.Cout / BN);
+  if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
+  else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+
+// dgrad of an up2+5x5 conv straight to the LOW-RES input gradient (the 2x2 sum of the upsample backward is
+// implicit: all 4 output phases accumulate into the same accumulator).  dy_hi/lo: [B][H][W][Cout] full-res;
+// wd_hi/lo: collapsed dgrad pack [36][Cin][Cout]; out: [B][H/2][W/2][Cin].
+int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const float* wd_hi, const float* wd_lo,
+                      float* out, ConvGeom g) {
+  TcFwdParams p;
+  memset(&p, 0, sizeof(p));
+  const int Hl = g.H / 2, Wl = g.W / 2;
+  if (!pick_box(Hl, Wl, 128, &p.bw, &p.bh, &p.bb)) return FG_ERR_UNSUPPORTED;
+  const int Cy = g.Cout;  // contraction runs over the forward conv's output channels
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    const int64_t off = ((int64_t)py * g.W + px) * Cy;
+    const int64_t sW = (int64_t)2 * Cy * 4, sH = (int64_t)2 * g.W * Cy * 4, sB = (int64_t)g.H * g.W * Cy * 4;
+    FG_TRY(make_map4(&p.a_hi[ph], dy_hi + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+    FG_TRY(make_map4(&p.a_lo[ph], dy_lo + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+  }
+  const int BN = g.Cin % 128 == 0 ? 128 : 64;
+  p.nphase = 1;
+  p.ntaps = 36;
+  for (int ph = 0; ph < 4; ++ph)
+    for (int t = 0; t < 9; ++t) {
+      // forward: out_ph[y,x] reads Xlow[y+ty-1, x+tx-1]  =>  dXlow[y,x] reads dY_ph[y-(ty-1), x-(tx-1)]
+      p.dy[ph * 9 + t] = (int8_t)(1 - t / 3);
+      p.dx[ph * 9 + t] = (int8_t)(1 - t % 3);
+      p.amap[ph * 9 + t] = (int8_t)ph;
+      p.widx[ph * 9 + t] = (int16_t)(ph * 9 + t);
+    }
+  FG_TRY(make_map2(&p.b_hi, wd_hi, Cy, (int64_t)36 * g.Cin, 32, BN));
+  FG_TRY(make_map2(&p.b_lo, wd_lo, Cy, (int64_t)36 * g.Cin, 32, BN));
+  p.kpt = Cy / 32;
+  p.Cout = g.Cin;
+  p.B = g.B; p.H = Hl; p.W = Wl;
+  p.tiles_x = Wl / p.bw;
+  p.tiles_y = Hl / p.bh;
+  p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
+  p.out = out;
+  p.bias = nullptr;
+  p.out_H = Hl; p.out_W = Wl;
+  p.out_scale = 1;
+  dim3 grid(p.tiles_per_phase, g.Cin / BN);
+  if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
+  else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+
+// wgrad.  x_hi/lo: [B][H/ups][W/ups][Cin]; dy_hi/lo: [B][H][W][Cout]; out (overwritten):
+//   ups==1: [k*k][Cout][Cin]          ups==2: collapsed [36][Cout][Cin]
+int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* out,
+                  ConvGeom g) {
+  TcWgParams p;
+  memset(&p, 0, sizeof(p));
+  const int Hl = g.H / g.ups, Wl = g.W / g.ups;
+  if (!pick_box(Hl, Wl, 32, &p.bw, &p.bh, &p.bb)) return FG_ERR_UNSUPPORTED;
+  {
+    const int64_t sW = (int64_t)g.Cin * 4, sH = sW * Wl, sB = sH * Hl;
+    FG_TRY(make_map4(&p.x_hi, x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+    FG_TRY(make_map4(&p.x_lo, x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+  }
+  int ntt;
+  if (g.ups == 1) {
+    const int64_t sW = (int64_t)g.Cout * 4, sH = sW * g.W, sB = sH * g.H;
+    FG_TRY(make_map4(&p.dy_hi[0], dy_hi, g.Cout, g.W, g.H, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+    FG_TRY(make_map4(&p.dy_lo[0], dy_lo, g.Cout, g.W, g.H, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+    const int pad = (g.k - 1) / 2;
+    ntt = g.k * g.k;
+    for (int t = 0; t < ntt; ++t) {
+      p.dy[t] = (int8_t)(t / g.k - pad);
+      p.dx[t] = (int8_t)(t % g.k - pad);
+      p.phase[t] = 0;
+    }
+  } else {
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      const int64_t off = ((int64_t)py * g.W + px) * g.Cout;
+      const int64_t sW = (int64_t)2 * g.Cout * 4, sH = (int64_t)2 * g.W * g.Cout * 4, sB = (int64_t)g.H * g.W * g.Cout * 4;
+      FG_TRY(make_map4(&p.dy_hi[ph], dy_hi + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+      FG_TRY(make_map4(&p.dy_lo[ph], dy_lo + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+    }
+    ntt = 36;
+    for (int ph = 0; ph < 4; ++ph)
+      for (int t = 0; t < 9; ++t) {
+        p.dy[ph * 9 + t] = (int8_t)(t / 3 - 1);
+        p.dx[ph * 9 + t] = (int8_t)(t % 3 - 1);
+        p.phase[ph * 9 + t] = (int8_t)ph;
+      }
+  }
+  const int BN = g.Cin % 128 == 0 ? 128 : 64;
+  p.Cout = g.Cout;
+  p.Cin = g.Cin;
+  p.tiles_x = Wl / p.bw;
+  p.tiles_y = Hl / p.bh;
+  p.kblocks = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
+  const int base = ntt * (g.Cout / 128) * (g.Cin / BN);
+  int splits = std::max(1, c->sm_count / base);
+  if (splits > p.kblocks) splits = p.kblocks;
+  p.kb_per_split = (p.kblocks + splits - 1) / splits;
+  splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
+  p.out = out;
+  FG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)ntt * g.Cout * g.Cin, c->stream));
+  dim3 grid(ntt, (g.Cout / 128) * (g.Cin / BN), splits);
+  if (BN == 128) wgrad_tc_kernel<128><<<grid, 192, wg_smem<128>(), c->stream>>>(p);
+  else wgrad_tc_kernel<64><<<grid, 192, wg_smem<64>(), c->stream>>>(p);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}

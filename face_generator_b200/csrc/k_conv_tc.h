@@ -1,0 +1,46 @@
+// Parameter blocks (passed as __grid_constant__) and host entry points of the tcgen05 conv path.
+#pragma once
+#include <cuda.h>
+
+#include <cstdint>
+
+#include "fg_internal.h"
+
+constexpr int kTcMaxTaps = 100;
+
+struct alignas(64) TcFwdParams {
+  CUtensorMap a_hi[4], a_lo[4];  // activation views (dgrad of an upsampled conv: one per output phase of dY)
+  CUtensorMap b_hi, b_lo;        // packed weights, 2-D (Cin, taps*Cout)
+  int8_t dy[kTcMaxTaps], dx[kTcMaxTaps], amap[kTcMaxTaps];  // indexed [phase*ntaps + tap]
+  int16_t widx[kTcMaxTaps];
+  int ntaps, nphase, kpt, Cout;
+  int B, H, W;         // tile-enumeration grid (the low-res grid for upsampled convs)
+  int bw, bh, bb;      // pixel box of one 128-row M tile
+  int tiles_x, tiles_y, tiles_per_phase;
+  float* out;
+  const float* bias;
+  int out_H, out_W, out_scale;
+};
+
+struct alignas(64) TcWgParams {
+  CUtensorMap dy_hi[4], dy_lo[4];
+  CUtensorMap x_hi, x_lo;
+  int8_t dy[kTcMaxTaps], dx[kTcMaxTaps], phase[kTcMaxTaps];  // per tile-tap
+  int Cout, Cin;
+  int bw, bh, bb;      // 32-pixel box of one K block
+  int tiles_x, tiles_y;
+  int kblocks, kb_per_split;
+  float* out;
+};
+
+bool tc_conv_eligible(const ConvGeom& g);
+int tc_split(fg_ctx* c, const float* x, float* hi, float* lo, int64_t n);
+int tc_pack_split(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK);
+int tc_pack_collapsed(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc);
+int tc_combine_collapsed_wgrad(fg_ctx* c, const float* G, float* dW, int N, int Cc);
+int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* bias,
+                float* out, ConvGeom g, int mode);
+int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const float* wd_hi, const float* wd_lo, float* out,
+                      ConvGeom g);
+int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* out,
+                  ConvGeom g);

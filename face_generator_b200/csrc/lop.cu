@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "fg_internal.h"
+#include "k_conv_tc.h"
 
 namespace {
 bool is_dev(const void* p) {
@@ -83,8 +84,18 @@ int fg_conv2d_forward(fg_ctx* c, const float* x, const float* w, const float* b,
   FG_TRY(scratch(c, 4, nw, &wp));
   FG_TRY(scratch(c, 5, ny, &yn));
   FG_TRY(k_nchw_to_nhwc(c, xd, xn, N, Cin, H * W));
-  FG_TRY(k_pack_weights(c, wd, wp, nullptr, Cout, Cin, k * k, 0, 0, 0, 0));
-  FG_TRY(k_conv_simt(c, xn, wp, bd, yn, ConvGeom{N, H, W, Cin, Cout, k, 1}));
+  const ConvGeom g{N, H, W, Cin, Cout, k, 1};
+  if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(g)) {
+    float *xs, *ws;
+    FG_TRY(scratch(c, 4, 2 * nx, &xs));
+    FG_TRY(scratch(c, 7, 2 * nw, &ws));
+    FG_TRY(tc_split(c, xn, xs, xs + nx, (int64_t)nx));
+    FG_TRY(tc_pack_split(c, wd, ws, ws + nw, nullptr, nullptr, Cout, Cin, k * k));
+    FG_TRY(tc_conv_fwd(c, xs, xs + nx, ws, ws + nw, bd, yn, g, 0));
+  } else {
+    FG_TRY(k_pack_weights(c, wd, wp, nullptr, Cout, Cin, k * k, 0, 0, 0, 0));
+    FG_TRY(k_conv_simt(c, xn, wp, bd, yn, g));
+  }
   FG_TRY(out_dev(c, y, ny, 6, &yd, false));
   FG_TRY(k_nhwc_to_nchw(c, yn, yd, N, Cout, H * W));
   return out_done(c, y, yd, ny);
@@ -103,8 +114,18 @@ int fg_conv2d_backward_data(fg_ctx* c, const float* dy, const float* w, float* d
   FG_TRY(scratch(c, 4, nw, &wpd));
   FG_TRY(scratch(c, 5, nx, &dxn));
   FG_TRY(k_nchw_to_nhwc(c, dyd, dyn, N, Cout, H * W));
-  FG_TRY(k_pack_weights(c, wd, nullptr, wpd, Cout, Cin, k * k, 0, 0, 0, 0));
-  FG_TRY(k_conv_simt(c, dyn, wpd, nullptr, dxn, ConvGeom{N, H, W, Cout, Cin, k, 1}));
+  const ConvGeom gd{N, H, W, Cout, Cin, k, 1};
+  if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(gd)) {
+    float *ys, *ws;
+    FG_TRY(scratch(c, 2, 2 * ny, &ys));
+    FG_TRY(scratch(c, 7, 4 * nw, &ws));
+    FG_TRY(tc_split(c, dyn, ys, ys + ny, (int64_t)ny));
+    FG_TRY(tc_pack_split(c, wd, ws, ws + nw, ws + 2 * nw, ws + 3 * nw, Cout, Cin, k * k));
+    FG_TRY(tc_conv_fwd(c, ys, ys + ny, ws + 2 * nw, ws + 3 * nw, nullptr, dxn, gd, 0));
+  } else {
+    FG_TRY(k_pack_weights(c, wd, nullptr, wpd, Cout, Cin, k * k, 0, 0, 0, 0));
+    FG_TRY(k_conv_simt(c, dyn, wpd, nullptr, dxn, gd));
+  }
   FG_TRY(out_dev(c, dx, nx, 6, &dxd, false));
   FG_TRY(k_nhwc_to_nchw(c, dxn, dxd, N, Cin, H * W));
   return out_done(c, dx, dxd, nx);
@@ -124,7 +145,17 @@ int fg_conv2d_backward_filter(fg_ctx* c, const float* x, const float* dy, float*
   FG_TRY(scratch(c, 5, nw, &ws));
   FG_TRY(k_nchw_to_nhwc(c, xd, xn, N, Cin, H * W));
   FG_TRY(k_nchw_to_nhwc(c, dyd, dyn, N, Cout, H * W));
-  FG_TRY(k_wgrad_simt(c, xn, dyn, ws, ConvGeom{N, H, W, Cin, Cout, k, 1}));
+  const ConvGeom gw{N, H, W, Cin, Cout, k, 1};
+  if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(gw) && Cout % 128 == 0 && Cin % 64 == 0) {
+    float *xs, *ys;
+    FG_TRY(scratch(c, 2, 2 * nx, &xs));
+    FG_TRY(scratch(c, 7, 2 * ny, &ys));
+    FG_TRY(tc_split(c, xn, xs, xs + nx, (int64_t)nx));
+    FG_TRY(tc_split(c, dyn, ys, ys + ny, (int64_t)ny));
+    FG_TRY(tc_conv_wgrad(c, xs, xs + nx, ys, ys + ny, ws, gw));
+  } else {
+    FG_TRY(k_wgrad_simt(c, xn, dyn, ws, gw));
+  }
   FG_TRY(out_dev(c, dw, nw, 6, &dwd, true));
   FG_TRY(k_unpack_wgrad(c, ws, dwd, Cout, Cin, k * k, 0, 0, 0, 0));
   if (db) {

@@ -3,6 +3,7 @@
 #include <algorithm>
 
 #include "fg_internal.h"
+#include "k_conv_tc.h"
 
 GLayout make_g_layout(int C) {
   GLayout L;
@@ -160,6 +161,35 @@ int net_alloc(fg_ctx* c) {
   c->io_dev_elems = std::max<size_t>(B * 1024 * C, B * kMaskPerSample);
   FG_TRY(dalloc(c, &c->io_dev, c->io_dev_elems));
   FG_TRY(dalloc(c, &c->io_dev2, c->io_dev_elems));
+  {  // tcgen05 path buffers
+    fg_ctx::TcBufs& t = c->tcb;
+    FG_TRY(dalloc(c, &t.G_h0_hi, B * 8192));
+    FG_TRY(dalloc(c, &t.G_h0_lo, B * 8192));
+    FG_TRY(dalloc(c, &t.G_h1_hi, B * 65536));
+    FG_TRY(dalloc(c, &t.G_h1_lo, B * 65536));
+    FG_TRY(dalloc(c, &t.dy_hi, B * 131072));
+    FG_TRY(dalloc(c, &t.dy_lo, B * 131072));
+    for (int i = 0; i < 2; ++i) {
+      FG_TRY(dalloc(c, &t.G_Wf_hi[i], 36 * 256 * 128));
+      FG_TRY(dalloc(c, &t.G_Wf_lo[i], 36 * 256 * 128));
+      FG_TRY(dalloc(c, &t.G_Wd_hi[i], 36 * 256 * 128));
+      FG_TRY(dalloc(c, &t.G_Wd_lo[i], 36 * 256 * 128));
+      FG_TRY(dalloc(c, &t.G_Wx_hi[i], 25 * 256 * 128));
+      FG_TRY(dalloc(c, &t.G_Wx_lo[i], 25 * 256 * 128));
+    }
+    for (int i = 0; i < 3; ++i) {
+      const size_t n = B * (size_t)kDhw[i + 1] * kDhw[i + 1] * kDcout[i];
+      FG_TRY(dalloc(c, &t.D_p_hi[i], n));
+      FG_TRY(dalloc(c, &t.D_p_lo[i], n));
+    }
+    for (int i = 1; i < 4; ++i) {
+      const size_t n = (size_t)9 * kDcout[i] * kDcin[i];
+      FG_TRY(dalloc(c, &t.D_Wf_hi[i], n));
+      FG_TRY(dalloc(c, &t.D_Wf_lo[i], n));
+      FG_TRY(dalloc(c, &t.D_Wd_hi[i], n));
+      FG_TRY(dalloc(c, &t.D_Wd_lo[i], n));
+    }
+  }
   FG_TRY(dalloc(c, &c->in_real, B * 1024 * C));
   FG_TRY(dalloc(c, &c->in_noiseD, B * kNoiseDim));
   FG_TRY(dalloc(c, &c->in_noiseG, B * kNoiseDim));
@@ -186,6 +216,15 @@ int net_pack_G(fg_ctx* c) {
   FG_TRY(k_pack_weights(c, c->PG + L.C1W, c->G_C1p, c->G_C1pd, 256, 128, 25, 0, 0, 0, 0));
   FG_TRY(k_pack_weights(c, c->PG + L.C2W, c->G_C2p, c->G_C2pd, 128, 256, 25, 0, 0, 0, 0));
   FG_TRY(k_pack_weights(c, c->PG + L.C3W, c->G_C3p, c->G_C3pd, c->C, 128, 9, 0, 0, 0, 0));
+  if (c->conv_impl != FG_CONV_SIMT) {
+    fg_ctx::TcBufs& t = c->tcb;
+    FG_TRY(tc_pack_collapsed(c, c->PG + L.C1W, t.G_Wf_hi[0], t.G_Wf_lo[0], t.G_Wd_hi[0], t.G_Wd_lo[0], 256, 128));
+    FG_TRY(tc_pack_collapsed(c, c->PG + L.C2W, t.G_Wf_hi[1], t.G_Wf_lo[1], t.G_Wd_hi[1], t.G_Wd_lo[1], 128, 256));
+    if (c->conv_impl == FG_CONV_TC_DENSE) {
+      FG_TRY(tc_pack_split(c, c->PG + L.C1W, t.G_Wx_hi[0], t.G_Wx_lo[0], nullptr, nullptr, 256, 128, 25));
+      FG_TRY(tc_pack_split(c, c->PG + L.C2W, t.G_Wx_hi[1], t.G_Wx_lo[1], nullptr, nullptr, 128, 256, 25));
+    }
+  }
   c->G_packed = true;
   return FG_OK;
 }
@@ -197,6 +236,11 @@ int net_pack_D(fg_ctx* c) {
   // View(2048) flattens [512][2][2] in (c,h,w) order; ours is NHWC (h,w,c): permute the columns
   FG_TRY(k_pack_weights(c, c->PD + L.L1W, c->D_L1p, c->D_L1pd, 512, 2048, 1, 0, 0, 512, 4));
   FG_TRY(k_pack_weights(c, c->PD + L.L2W, nullptr, c->D_L2pd, 512, 512, 1, 0, 0, 0, 0));
+  if (c->conv_impl != FG_CONV_SIMT) {
+    fg_ctx::TcBufs& t = c->tcb;
+    for (int i = 1; i < 4; ++i)
+      FG_TRY(tc_pack_split(c, c->PD + L.cW[i], t.D_Wf_hi[i], t.D_Wf_lo[i], t.D_Wd_hi[i], t.D_Wd_lo[i], kDcout[i], kDcin[i], 9));
+  }
   c->D_packed = true;
   return FG_OK;
 }
@@ -218,6 +262,46 @@ static int conv_wgrad(fg_ctx* c, const char* tag, const float* in, const float* 
   return k_unpack_wgrad(c, c->wgrad_ws, dW, g.Cout, g.Cin, g.k * g.k, nA, nS, cA, cS);
 }
 
+static inline bool use_tc(const fg_ctx* c, const ConvGeom& g) {
+  return c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(g);
+}
+static inline bool use_tc_wgrad(const fg_ctx* c, const ConvGeom& g) {
+  return use_tc(c, g) && g.Cout % 128 == 0 && g.Cin % 64 == 0;
+}
+
+// G's two nn.SpatialUpSamplingNearest(2) -> 5x5 convolutions (li = 0: C1, li = 1: C2), forward.
+// tcgen05 path: split the low-res input into TF32 hi/lo once (kept for wgrad), then the phase conv.
+static int g_ups_fwd(fg_ctx* c, int li, const char* tag, const float* h, float* h_hi, float* h_lo, const float* Wp,
+                     const float* bias, float* z, ConvGeom g) {
+  if (!use_tc(c, g)) return conv_fwd(c, tag, h, Wp, bias, z, g);
+  fg_ctx::TcBufs& t = c->tcb;
+  FG_TRY(tc_split(c, h, h_hi, h_lo, (int64_t)g.B * (g.H / 2) * (g.W / 2) * g.Cin));
+  ScopedTimer tm(c, tag);
+  if (c->conv_impl == FG_CONV_TC_DENSE) return tc_conv_fwd(c, h_hi, h_lo, t.G_Wx_hi[li], t.G_Wx_lo[li], bias, z, g, 1);
+  return tc_conv_fwd(c, h_hi, h_lo, t.G_Wf_hi[li], t.G_Wf_lo[li], bias, z, g, 2);
+}
+// backward of the same layer: dW += wgrad, dh = dgrad.  *pooled tells whether `dh` already is the gradient of
+// the LOW-RES input (tcgen05 path: the 2x2 sum of the upsample backward is folded into the dgrad GEMM) or the
+// full-resolution gradient that the consumer still has to sum 2x2 (SIMT path).
+static int g_ups_bwd(fg_ctx* c, int li, const char* wtag, const char* dtag, const float* h, const float* h_hi,
+                     const float* h_lo, const float* dz, const float* Wpd, ConvGeom g, float* dW, float* dh, bool* pooled) {
+  if (!use_tc_wgrad(c, g)) {
+    FG_TRY(conv_wgrad(c, wtag, h, dz, g, dW, 0, 0, 0, 0));
+    *pooled = false;
+    return conv_fwd(c, dtag, dz, Wpd, nullptr, dh, ConvGeom{g.B, g.H, g.W, g.Cout, g.Cin, g.k, 1});
+  }
+  fg_ctx::TcBufs& t = c->tcb;
+  FG_TRY(tc_split(c, dz, t.dy_hi, t.dy_lo, (int64_t)g.B * g.H * g.W * g.Cout));
+  {
+    ScopedTimer tm(c, wtag);
+    FG_TRY(tc_conv_wgrad(c, h_hi, h_lo, t.dy_hi, t.dy_lo, c->wgrad_ws, g));
+  }
+  FG_TRY(tc_combine_collapsed_wgrad(c, c->wgrad_ws, dW, g.Cout, g.Cin));
+  *pooled = true;
+  ScopedTimer tm(c, dtag);
+  return tc_conv_dgrad_ups(c, t.dy_hi, t.dy_lo, t.G_Wd_hi[li], t.G_Wd_lo[li], dh, g);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // G
 // ---------------------------------------------------------------------------------------------------
@@ -232,7 +316,8 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
   c->G_train = training;
   FG_TRY(conv_fwd(c, "G.L1.fwd", c->G_noise, c->G_L1p, c->G_L1p + 8192 * 100, c->G_z0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}));
   FG_TRY(k_prelu_fwd(c, c->G_z0, P + L.a1, c->G_h0, (int64_t)B * 8192));
-  FG_TRY(conv_fwd(c, "G.C1.fwd", c->G_h0, c->G_C1p, P + L.C1b, c->G_z1, ConvGeom{B, 16, 16, 128, 256, 5, 2}));
+  FG_TRY(g_ups_fwd(c, 0, "G.C1.fwd", c->G_h0, c->tcb.G_h0_hi, c->tcb.G_h0_lo, c->G_C1p, P + L.C1b, c->G_z1,
+                   ConvGeom{B, 16, 16, 128, 256, 5, 2}));
   if (training) {
     FG_TRY(k_bn_stats(c, c->G_z1, c->bn_acc, (int64_t)B * 256, 256));
     FG_TRY(k_bn_finalize(c, c->bn_acc, c->bn_mean1, c->bn_istd1, c->bnG, c->bnG + 256, (int64_t)B * 256, 256));
@@ -241,7 +326,8 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
   }
   FG_TRY(k_bn_prelu_apply(c, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->G_h1, (int64_t)B * 256,
                           256));
-  FG_TRY(conv_fwd(c, "G.C2.fwd", c->G_h1, c->G_C2p, P + L.C2b, c->G_z2, ConvGeom{B, 32, 32, 256, 128, 5, 2}));
+  FG_TRY(g_ups_fwd(c, 1, "G.C2.fwd", c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, c->G_C2p, P + L.C2b, c->G_z2,
+                   ConvGeom{B, 32, 32, 256, 128, 5, 2}));
   if (training) {
     FG_TRY(k_bn_stats(c, c->G_z2, c->bn_acc, (int64_t)B * 1024, 128));
     FG_TRY(k_bn_finalize(c, c->bn_acc, c->bn_mean2, c->bn_istd2, c->bnG + 512, c->bnG + 640, (int64_t)B * 1024, 128));
@@ -276,20 +362,21 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_mg,
                               c->G_dz2, B, 32, 32, 128, 0));
   // C2
-  FG_TRY(conv_wgrad(c, "G.C2.wgrad", c->G_h1, c->G_dz2, ConvGeom{B, 32, 32, 256, 128, 5, 2}, G + L.C2W, 0, 0, 0, 0));
+  bool pooled = false;
+  FG_TRY(g_ups_bwd(c, 1, "G.C2.wgrad", "G.C2.dgrad", c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, c->G_dz2, c->G_C2pd,
+                   ConvGeom{B, 32, 32, 256, 128, 5, 2}, G + L.C2W, c->G_dfull, &pooled));
   FG_TRY(k_colsum_add(c, c->G_dz2, G + L.C2b, (int64_t)B * 1024, 128, 0, 0));
-  FG_TRY(conv_fwd(c, "G.C2.dgrad", c->G_dz2, c->G_C2pd, nullptr, c->G_dfull, ConvGeom{B, 32, 32, 128, 256, 5, 1}));
   // BN1 + PReLU (the 2x2 sum = backward of the nearest upsample is folded into the loads)
   FG_TRY(k_bn_prelu_bwd_reduce(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_acc,
-                               G + L.a2, B, 16, 16, 256, 1));
+                               G + L.a2, B, 16, 16, 256, pooled ? 0 : 1));
   FG_TRY(k_bn_bwd_finalize(c, c->bn_acc, c->bn_mg, G + L.g1, G + L.be1, (int64_t)B * 256, 256));
   FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_mg,
-                              c->G_dz1, B, 16, 16, 256, 1));
+                              c->G_dz1, B, 16, 16, 256, pooled ? 0 : 1));
   // C1
-  FG_TRY(conv_wgrad(c, "G.C1.wgrad", c->G_h0, c->G_dz1, ConvGeom{B, 16, 16, 128, 256, 5, 2}, G + L.C1W, 0, 0, 0, 0));
+  FG_TRY(g_ups_bwd(c, 0, "G.C1.wgrad", "G.C1.dgrad", c->G_h0, c->tcb.G_h0_hi, c->tcb.G_h0_lo, c->G_dz1, c->G_C1pd,
+                   ConvGeom{B, 16, 16, 128, 256, 5, 2}, G + L.C1W, c->G_dfull, &pooled));
   FG_TRY(k_colsum_add(c, c->G_dz1, G + L.C1b, (int64_t)B * 256, 256, 0, 0));
-  FG_TRY(conv_fwd(c, "G.C1.dgrad", c->G_dz1, c->G_C1pd, nullptr, c->G_dfull, ConvGeom{B, 16, 16, 256, 128, 5, 1}));
-  FG_TRY(k_prelu_bwd(c, c->G_dfull, c->G_z0, P + L.a1, c->G_dz0, G + L.a1, B, 8, 8, 128, 1));
+  FG_TRY(k_prelu_bwd(c, c->G_dfull, c->G_z0, P + L.a1, c->G_dz0, G + L.a1, B, 8, 8, 128, pooled ? 0 : 1));
   // L1
   FG_TRY(conv_wgrad(c, "G.L1.wgrad", c->G_noise, c->G_dz0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}, G + L.L1W, 128, 64, 0, 0));
   FG_TRY(k_colsum_add(c, c->G_dz0, G + L.L1b, B, 8192, 128, 64));
@@ -315,7 +402,15 @@ int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hype
   static const char* tags[4] = {"D.C1.fwd", "D.C2.fwd", "D.C3.fwd", "D.C4.fwd"};
   for (int i = 0; i < 4; ++i) {
     const int H = kDhw[i];
-    FG_TRY(conv_fwd(c, tags[i], cur, c->D_cp[i], P + L.cb[i], c->D_z[i], ConvGeom{B, H, H, dcin(c, i), kDcout[i], 3, 1}));
+    const ConvGeom g{B, H, H, dcin(c, i), kDcout[i], 3, 1};
+    if (i > 0 && use_tc(c, g)) {
+      fg_ctx::TcBufs& t = c->tcb;
+      FG_TRY(tc_split(c, cur, t.D_p_hi[i - 1], t.D_p_lo[i - 1], (int64_t)B * H * H * g.Cin));
+      ScopedTimer tm(c, tags[i]);
+      FG_TRY(tc_conv_fwd(c, t.D_p_hi[i - 1], t.D_p_lo[i - 1], t.D_Wf_hi[i], t.D_Wf_lo[i], P + L.cb[i], c->D_z[i], g, 0));
+    } else {
+      FG_TRY(conv_fwd(c, tags[i], cur, c->D_cp[i], P + L.cb[i], c->D_z[i], g));
+    }
     FG_TRY(k_d_act_pool_fwd(c, c->D_z[i], P + L.ca[i], masks, kDmoff[i], 1.0f - h->p_spatial, c->D_p[i], B, H, H,
                             kDcout[i]));
     cur = c->D_p[i];
@@ -371,13 +466,30 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
     FG_TRY(k_d_act_pool_bwd(c, c->D_dp, c->D_z[i], P + L.ca[i], masks, kDmoff[i], eval_scale, c->D_dz,
                             want_wgrad ? G + L.ca[i] : nullptr, B, H, H, cout));
     const float* in = i == 0 ? c->D_x : c->D_p[i - 1];
+    const ConvGeom gf{B, H, H, cin, cout, 3, 1}, gd{B, H, H, cout, cin, 3, 1};
+    const bool tc = i > 0 && use_tc(c, gf) && use_tc(c, gd);
+    fg_ctx::TcBufs& t = c->tcb;
+    if (tc) FG_TRY(tc_split(c, c->D_dz, t.dy_hi, t.dy_lo, (int64_t)B * H * H * cout));
     if (want_wgrad) {
-      FG_TRY(conv_wgrad(c, wt[i], in, c->D_dz, ConvGeom{B, H, H, cin, cout, 3, 1}, G + L.cW[i], 0, 0, 0, 0));
+      if (tc && use_tc_wgrad(c, gf)) {
+        {
+          ScopedTimer tm(c, wt[i]);
+          FG_TRY(tc_conv_wgrad(c, t.D_p_hi[i - 1], t.D_p_lo[i - 1], t.dy_hi, t.dy_lo, c->wgrad_ws, gf));
+        }
+        FG_TRY(k_unpack_wgrad(c, c->wgrad_ws, G + L.cW[i], cout, cin, 9, 0, 0, 0, 0));
+      } else {
+        FG_TRY(conv_wgrad(c, wt[i], in, c->D_dz, gf, G + L.cW[i], 0, 0, 0, 0));
+      }
       FG_TRY(k_colsum_add(c, c->D_dz, G + L.cb[i], (int64_t)B * H * H, cout, 0, 0));
     }
-    if (i > 0 || want_dx)
-      FG_TRY(conv_fwd(c, dt[i], c->D_dz, c->D_cpd[i], nullptr, i == 0 ? c->D_dx : c->D_dp,
-                      ConvGeom{B, H, H, cout, cin, 3, 1}));
+    if (i > 0 || want_dx) {
+      if (tc) {
+        ScopedTimer tm(c, dt[i]);
+        FG_TRY(tc_conv_fwd(c, t.dy_hi, t.dy_lo, t.D_Wd_hi[i], t.D_Wd_lo[i], nullptr, c->D_dp, gd, 0));
+      } else {
+        FG_TRY(conv_fwd(c, dt[i], c->D_dz, c->D_cpd[i], nullptr, i == 0 ? c->D_dx : c->D_dp, gd));
+      }
+    }
   }
   return FG_OK;
 }

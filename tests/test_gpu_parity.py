@@ -35,7 +35,7 @@ def check_grads(layout, got, ref, skip=(), tol=TOL):
     return worst
 
 
-@pytest.mark.parametrize("C,B,impl", [(3, 4, 0), (1, 6, 0)])
+@pytest.mark.parametrize("C,B,impl", [(3, 4, 0), (1, 6, 0), (3, 4, 2), (3, 6, 1), (1, 8, 2)])
 def test_G_forward_backward(fg, C, B, impl):
     from face_generator_b200.lib import NET_G
     case = PU.make_case(2 * B, C, seed=31 + C)
@@ -66,8 +66,8 @@ def test_G_forward_backward(fg, C, B, impl):
     ctx.close()
 
 
-@pytest.mark.parametrize("C,B", [(3, 6), (1, 4)])
-def test_D_forward_backward(fg, C, B):
+@pytest.mark.parametrize("C,B,impl", [(3, 6, 0), (1, 4, 0), (3, 6, 2), (3, 8, 2)])
+def test_D_forward_backward(fg, C, B, impl):
     from face_generator_b200.lib import NET_D
     case = PU.make_case(B, C, seed=41 + C)
     rng = np.random.default_rng(8)
@@ -77,6 +77,7 @@ def test_D_forward_backward(fg, C, B):
     ref_out = d.forward(case["PD"], img, case["masks_D"])
     ref_dP, ref_dimg = d.backward(dout)
     ctx = fg.Context(0, max_batch=8, channels=C)
+    ctx.set_option("conv_impl", impl)
     ctx.set_params(NET_D, case["PD"])
     out = ctx.D_forward(img, masks=case["masks_D"])
     assert PU.relerr(out, ref_out) < TOL
@@ -90,12 +91,15 @@ def test_D_forward_backward(fg, C, B):
     ctx.close()
 
 
-@pytest.mark.parametrize("C,B,init", [(1, 16, "trained"), (3, 8, "trained"), (3, 8, "reference")])
-def test_train_step_matches_oracle(fg, C, B, init):
+@pytest.mark.parametrize("C,B,init,impl", [(1, 16, "trained", 0), (3, 8, "trained", 0), (3, 8, "reference", 0),
+                                           (1, 16, "trained", 2), (3, 8, "trained", 2), (3, 8, "reference", 2),
+                                           (3, 8, "trained", 1)])
+def test_train_step_matches_oracle(fg, C, B, init, impl):
     """BASELINE config 1 (gray, B=16: 8 real + 8 fake for D, 16 for G) and a colour case, two iterations."""
     from face_generator_b200.lib import NET_D, NET_G
     case = PU.make_case(B, C, seed=51 + C, init=init)
     ctx = fg.Context(0, max_batch=16, channels=C)
+    ctx.set_option("conv_impl", impl)
     ctx.set_params(NET_G, case["PG"])
     ctx.set_params(NET_D, case["PD"])
     hyper = fg.hyper_default()
@@ -145,6 +149,33 @@ def test_modules_equal_fused_step(fg):
         assert PU.relerr(a, b) < 1e-5
     for a, b in zip(res["fused"][:2], res["modules"][:2]):
         assert np.abs(a - b).max() < 2.1e-3  # sign flips of noise-level gradients move a parameter by 2*lr
+
+
+@pytest.mark.parametrize("N,Cin,H,Cout,k", [(8, 64, 16, 128, 3), (3, 128, 8, 256, 3), (5, 256, 4, 512, 3),
+                                            (2, 32, 32, 64, 5), (3, 64, 16, 128, 7), (1, 128, 32, 128, 1)])
+def test_tc_conv_lop(fg, N, Cin, H, Cout, k):
+    """tcgen05 3xTF32 implicit-GEMM kernels (fwd, dgrad, wgrad) in isolation through the L-op ABI; includes batch
+    tails that do not fill a 128-pixel tile (TMA zero fill + predicated epilogue)."""
+    from face_generator_b200.lib import _ptr
+    rng = np.random.default_rng(100 + N + Cin)
+    ctx = fg.Context(0, max_batch=8, channels=3)
+    ctx.set_option("conv_impl", 2)
+    lib, h = ctx.lib, ctx.h
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    x, w, b = f(rng.standard_normal((N, Cin, H, H))), f(rng.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k)), f(rng.standard_normal(Cout))
+    dy = f(rng.standard_normal((N, Cout, H, H)))
+    y = np.empty((N, Cout, H, H), np.float32)
+    assert lib.fg_conv2d_forward(h, _ptr(x), _ptr(w), _ptr(b), _ptr(y), N, Cin, H, H, Cout, k) == 0, lib.fg_last_error()
+    ref = O.f64.conv_fwd(x, w, b)
+    assert PU.relerr(y, ref) < 1e-5, PU.relerr(y, ref)  # 3xTF32 should be ~fp32 accurate
+    rdx, rdw, rdb = O.f64.conv_bwd(x, w, dy)
+    dx = np.empty_like(x)
+    assert lib.fg_conv2d_backward_data(h, _ptr(dy), _ptr(w), _ptr(dx), N, Cin, H, H, Cout, k) == 0, lib.fg_last_error()
+    assert PU.relerr(dx, rdx) < 1e-5, PU.relerr(dx, rdx)
+    dw, db = np.zeros_like(w), np.zeros_like(b)
+    assert lib.fg_conv2d_backward_filter(h, _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), N, Cin, H, H, Cout, k) == 0, lib.fg_last_error()
+    assert PU.relerr(dw, rdw) < 1e-5 and PU.relerr(db, rdb) < TOL, PU.relerr(dw, rdw)
+    ctx.close()
 
 
 def test_lop_layers(fg):
