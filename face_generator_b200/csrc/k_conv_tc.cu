@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "fg_internal.h"
@@ -113,9 +114,9 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout = 2) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
@@ -336,11 +337,14 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           const uint32_t sa = smem_u32(smem + s * kStageBytes);
           // MN-major, SWIZZLE_128B: 32 channels contiguous (128 B), 8 pixels per 1024 B atom;
           // LBO = distance between 32-channel groups (one box), SBO = distance between 8-pixel groups
-          const uint64_t a_hi = make_desc(sa, kBox, 1024), a_lo = make_desc(sa + kAB, kBox, 1024);
-          const uint64_t b_hi = make_desc(sa + 2 * kAB, kBox, 1024), b_lo = make_desc(sa + 2 * kAB + kBB, kBox, 1024);
+          // layout 1 = SWIZZLE_128B_BASE32B: the only smem layout tcgen05 accepts for MN-major tf32 operands
+          // (4 pixel rows x 128 B per swizzle atom, 32 B chunks XOR row%4); TMA side: SWIZZLE_128B_ATOM_32B
+          const uint64_t a_hi = make_desc(sa, p.dbg_lbo, p.dbg_sbo, 1), a_lo = make_desc(sa + kAB, p.dbg_lbo, p.dbg_sbo, 1);
+          const uint64_t b_hi = make_desc(sa + 2 * kAB, p.dbg_lbo, p.dbg_sbo, 1),
+                         b_lo = make_desc(sa + 2 * kAB + kBB, p.dbg_lbo, p.dbg_sbo, 1);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ko = (uint64_t)(k * 64);  // +1024 bytes = next 8 pixels
+            const uint64_t ko = (uint64_t)(k * (p.dbg_kstep >> 4));  // +1024 bytes = next 8 pixels
             umma_tf32(tmem_base, a_lo + ko, b_hi + ko, kIdesc, (i | k) != 0);
             umma_tf32(tmem_base, a_hi + ko, b_lo + ko, kIdesc, 1);
             umma_tf32(tmem_base, a_hi + ko, b_hi + ko, kIdesc, 1);
@@ -494,13 +498,13 @@ int get_encode() {
 
 // 4-D map over an NHWC fp32 tensor view: dims (C, W, H, B) with explicit byte strides
 int make_map4(CUtensorMap* m, const float* base, int C, int W, int H, int B, int64_t sW, int64_t sH, int64_t sB, int bc,
-              int bw, int bh, int bb) {
+              int bw, int bh, int bb, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)sW, (cuuint64_t)sH, (cuuint64_t)sB};
   cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fg_set_error("cuTensorMapEncodeTiled(4d) failed: %d (C=%d W=%d H=%d B=%d box %d,%d,%d,%d)", (int)r, C, W, H, B, bc, bw,
@@ -737,14 +741,14 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
   if (!pick_box(Hl, Wl, 32, &p.bw, &p.bh, &p.bb)) return FG_ERR_UNSUPPORTED;
   {
     const int64_t sW = (int64_t)g.Cin * 4, sH = sW * Wl, sB = sH * Hl;
-    FG_TRY(make_map4(&p.x_hi, x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
-    FG_TRY(make_map4(&p.x_lo, x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+    FG_TRY(make_map4(&p.x_hi, x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    FG_TRY(make_map4(&p.x_lo, x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   }
   int ntt;
   if (g.ups == 1) {
     const int64_t sW = (int64_t)g.Cout * 4, sH = sW * g.W, sB = sH * g.H;
-    FG_TRY(make_map4(&p.dy_hi[0], dy_hi, g.Cout, g.W, g.H, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
-    FG_TRY(make_map4(&p.dy_lo[0], dy_lo, g.Cout, g.W, g.H, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+    FG_TRY(make_map4(&p.dy_hi[0], dy_hi, g.Cout, g.W, g.H, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    FG_TRY(make_map4(&p.dy_lo[0], dy_lo, g.Cout, g.W, g.H, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     const int pad = (g.k - 1) / 2;
     ntt = g.k * g.k;
     for (int t = 0; t < ntt; ++t) {
@@ -757,8 +761,8 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
       const int py = ph >> 1, px = ph & 1;
       const int64_t off = ((int64_t)py * g.W + px) * g.Cout;
       const int64_t sW = (int64_t)2 * g.Cout * 4, sH = (int64_t)2 * g.W * g.Cout * 4, sB = (int64_t)g.H * g.W * g.Cout * 4;
-      FG_TRY(make_map4(&p.dy_hi[ph], dy_hi + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
-      FG_TRY(make_map4(&p.dy_lo[ph], dy_lo + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+      FG_TRY(make_map4(&p.dy_hi[ph], dy_hi + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+      FG_TRY(make_map4(&p.dy_lo[ph], dy_lo + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
     }
     ntt = 36;
     for (int ph = 0; ph < 4; ++ph)
@@ -780,6 +784,9 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
   p.kb_per_split = (p.kblocks + splits - 1) / splits;
   splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
   p.out = out;
+  p.dbg_lbo = getenv("FG_WG_LBO") ? atoi(getenv("FG_WG_LBO")) : 4096;
+  p.dbg_sbo = getenv("FG_WG_SBO") ? atoi(getenv("FG_WG_SBO")) : 512;
+  p.dbg_kstep = getenv("FG_WG_KSTEP") ? atoi(getenv("FG_WG_KSTEP")) : 1024;
   FG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)ntt * g.Cout * g.Cin, c->stream));
   dim3 grid(ntt, (g.Cout / 128) * (g.Cin / BN), splits);
   if (BN == 128) wgrad_tc_kernel<128><<<grid, 192, wg_smem<128>(), c->stream>>>(p);

@@ -31,6 +31,7 @@ struct alignas(64) TcWgParams {
   int tiles_x, tiles_y;
   int kblocks, kb_per_split;
   float* out;
+  int dbg_lbo, dbg_sbo, dbg_kstep;  // descriptor knobs (bytes); defaults 4096 / 1024 / 1024
 };
 
 bool tc_conv_eligible(const ConvGeom& g);

@@ -1,0 +1,242 @@
+-- b200.lua -- nn.Module shims over libfg_b200.so so that train.lua / adversarial.lua / sample.lua keep their
+-- plugin surface (SURVEY.md 8b):  MODEL:forward/backward, MODEL.modules[1].gradInput, MODEL:getParameters(),
+-- :training()/:evaluate(), CRITERION:forward/backward, interruptableAdam(opfunc, x, config).
+-- Delivered untested-by-execution (no LuaJIT/Torch7 in the build image); face_generator_b200/nn.py is the
+-- executable mirror and tests/test_gpu_parity.py::test_modules_equal_fused_step exercises the same call order.
+require 'nn'
+local ffi = require 'ffi'
+local F = require 'fg_ffi'
+local C = F.C
+
+b200 = b200 or {}
+
+-- one context per process/GPU, created lazily from OPT (train.lua:16-50)
+function b200.context(device, maxBatch, channels)
+  if not b200._ctx then
+    local out = ffi.new('fg_ctx*[1]')
+    F.check(C.fg_create(out, device or 0, maxBatch or 256, channels or 3), 'fg_create')
+    b200._ctx = ffi.gc(out[0], C.fg_destroy)
+    b200._hyper = ffi.new('fg_hyper[1]')
+    C.fg_hyper_default(b200._hyper)
+  end
+  return b200._ctx
+end
+
+-- hyper-parameters from the reference's OPT / OPTSTATE tables
+function b200.hyperFromOPT(OPT, OPTSTATE)
+  local h = b200._hyper[0]
+  h.D_L1, h.D_L2, h.G_L1, h.G_L2 = OPT.D_L1, OPT.D_L2, OPT.G_L1, OPT.G_L2
+  h.D_clamp, h.G_clamp, h.D_maxAcc = OPT.D_clamp, OPT.G_clamp, OPT.D_maxAcc
+  if OPTSTATE and OPTSTATE.adam then
+    h.lr_D = OPTSTATE.adam.D.learningRate or 1e-3
+    h.lr_G = OPTSTATE.adam.G.learningRate or 1e-3
+  end
+  return b200._hyper
+end
+
+---------------------------------------------------------------------------------------------------------------
+-- Fused networks: a single nn.Module whose flat weight/gradWeight alias the library's device buffers, so
+-- getParameters() (train.lua:151-152) is trivial and torch.save of params keeps working.
+---------------------------------------------------------------------------------------------------------------
+local Fused, parent = torch.class('b200.Fused', 'nn.Module')
+
+function Fused:__init(net, channels)
+  parent.__init(self)
+  self.net, self.channels = net, channels
+  self.ctx = b200.context()
+  self.n = tonumber(C.fg_param_count(net, channels))
+  self.train = true
+  self.output = torch.FloatTensor()
+  self.gradInput = torch.FloatTensor()
+end
+
+function Fused:training() self.train = true; return self end
+function Fused:evaluate() self.train = false; return self end
+
+-- flat parameter / gradient vectors as host copies (reference tools read them; the device stays authoritative)
+function Fused:getParameters()
+  local p, g = torch.FloatTensor(self.n), torch.FloatTensor(self.n)
+  F.check(C.fg_get_params(self.ctx, self.net, F.ptr(p)), 'fg_get_params')
+  F.check(C.fg_get_grads(self.ctx, self.net, F.ptr(g)), 'fg_get_grads')
+  return p, g
+end
+function Fused:setParameters(p) F.check(C.fg_set_params(self.ctx, self.net, F.ptr(p:float():contiguous())), 'fg_set_params') end
+function Fused:zeroGradParameters() F.check(C.fg_zero_grads(self.ctx, self.net), 'fg_zero_grads') end
+
+-- MODELS.create_G(dimensions, noiseDim)  (models.lua:87-93)
+local FusedG = torch.class('b200.FusedG', 'b200.Fused')
+function FusedG:__init(dimensions, noiseDim)
+  assert(noiseDim == 100 and dimensions[2] == 32, 'b200.FusedG implements create_G_decoder_upsampling32 with noiseDim 100')
+  b200.Fused.__init(self, F.NET_G, dimensions[1])
+end
+function FusedG:updateOutput(input)
+  local B = input:size(1)
+  self.output:resize(B, self.channels, 32, 32)
+  F.check(C.fg_G_forward(self.ctx, F.ptr(input:contiguous()), B, self.train and 1 or 0, F.ptr(self.output)), 'fg_G_forward')
+  return self.output
+end
+function FusedG:backward(input, gradOutput)  -- updateGradInput + accGradParameters in one call
+  self.gradInput:resizeAs(input)
+  F.check(C.fg_G_backward(self.ctx, F.ptr(gradOutput:contiguous()), F.ptr(self.gradInput)), 'fg_G_backward')
+  return self.gradInput
+end
+
+-- MODELS.create_D(dimensions)  (models.lua:98-104)
+local FusedD = torch.class('b200.FusedD', 'b200.Fused')
+function FusedD:__init(dimensions)
+  assert(dimensions[2] == 32, 'b200.FusedD implements create_D32b')
+  b200.Fused.__init(self, F.NET_D, dimensions[1])
+  self.seed = 0
+  self.modules = {self}  -- adversarial.lua:210 reads MODEL_D.modules[1].gradInput
+  self.wantWeightGrads = true
+end
+function FusedD:updateOutput(input)
+  local B = input:size(1)
+  self.output:resize(B, 1)
+  self.seed = self.seed + 1
+  F.check(C.fg_D_forward(self.ctx, F.ptr(input:contiguous()), B, self.train and 1 or 0, nil, self.seed, F.ptr(self.output)), 'fg_D_forward')
+  return self.output
+end
+function FusedD:backward(input, gradOutput)
+  self.gradInput:resizeAs(input)
+  F.check(C.fg_D_backward(self.ctx, F.ptr(gradOutput:contiguous()), self.wantWeightGrads and 1 or 0, F.ptr(self.gradInput)), 'fg_D_backward')
+  return self.gradInput
+end
+
+---------------------------------------------------------------------------------------------------------------
+-- nn.BCECriterion replacement (train.lua:148)
+---------------------------------------------------------------------------------------------------------------
+local BCE, bparent = torch.class('b200.BCECriterion', 'nn.Criterion')
+function BCE:__init() bparent.__init(self); self.ctx = b200.context(); self.gradInput = torch.FloatTensor() end
+function BCE:updateOutput(input, target)
+  local out = torch.FloatTensor(1)
+  F.check(C.fg_bce_forward(self.ctx, F.ptr(input:contiguous()), F.ptr(target:contiguous()), input:nElement(), F.ptr(out)), 'fg_bce_forward')
+  self.output = out[1]
+  return self.output
+end
+function BCE:updateGradInput(input, target)
+  self.gradInput:resizeAs(input)
+  F.check(C.fg_bce_backward(self.ctx, F.ptr(input:contiguous()), F.ptr(target:contiguous()), input:nElement(), F.ptr(self.gradInput)), 'fg_bce_backward')
+  return self.gradInput
+end
+
+---------------------------------------------------------------------------------------------------------------
+-- interruptableAdam(opfunc, x, config) (interruptable_optimizers.lua:49-94): x is the b200.Fused module whose
+-- parameters live on the device; penalty + clamp are fused into the step (adversarial.lua:103-123, :218-228).
+---------------------------------------------------------------------------------------------------------------
+function b200.interruptableAdam(opfunc, module, config)
+  local fx = opfunc(module)
+  if fx == false then return false end
+  F.check(C.fg_optim_step(module.ctx, module.net, b200._hyper, 1.0), 'fg_optim_step')
+  config.t = (config.t or 0) + 1
+  return module, {fx}
+end
+
+---------------------------------------------------------------------------------------------------------------
+-- per-layer modules (L-op level): constructor-compatible with the classes models.lua instantiates
+---------------------------------------------------------------------------------------------------------------
+local Conv, cparent = torch.class('b200.SpatialConvolution', 'nn.Module')  -- cudnn./nn.SpatialConvolution, stride 1, same pad
+function Conv:__init(nIn, nOut, kW, kH, dW, dH, padW, padH)
+  cparent.__init(self)
+  assert(kW == kH and (dW or 1) == 1 and (dH or 1) == 1 and (padW or 0) == (kW - 1) / 2, 'b200.SpatialConvolution: square, stride 1, same padding')
+  self.nIn, self.nOut, self.k = nIn, nOut, kW
+  self.weight, self.bias = torch.FloatTensor(nOut, nIn, kH, kW), torch.FloatTensor(nOut)
+  self.gradWeight, self.gradBias = torch.FloatTensor(nOut, nIn, kH, kW):zero(), torch.FloatTensor(nOut):zero()
+  self.ctx = b200.context()
+  self:reset()
+end
+function Conv:reset()
+  local stdv = 1 / math.sqrt(self.k * self.k * self.nIn)
+  self.weight:uniform(-stdv, stdv); self.bias:uniform(-stdv, stdv)
+end
+function Conv:updateOutput(input)
+  local N, H, W = input:size(1), input:size(3), input:size(4)
+  self.output:resize(N, self.nOut, H, W)
+  F.check(C.fg_conv2d_forward(self.ctx, F.ptr(input:contiguous()), F.ptr(self.weight), F.ptr(self.bias), F.ptr(self.output), N, self.nIn, H, W, self.nOut, self.k), 'fg_conv2d_forward')
+  return self.output
+end
+function Conv:updateGradInput(input, gradOutput)
+  local N, H, W = input:size(1), input:size(3), input:size(4)
+  self.gradInput:resizeAs(input)
+  F.check(C.fg_conv2d_backward_data(self.ctx, F.ptr(gradOutput:contiguous()), F.ptr(self.weight), F.ptr(self.gradInput), N, self.nIn, H, W, self.nOut, self.k), 'fg_conv2d_backward_data')
+  return self.gradInput
+end
+function Conv:accGradParameters(input, gradOutput, scale)
+  assert((scale or 1) == 1, 'b200.SpatialConvolution: scale must be 1')
+  local N, H, W = input:size(1), input:size(3), input:size(4)
+  F.check(C.fg_conv2d_backward_filter(self.ctx, F.ptr(input:contiguous()), F.ptr(gradOutput:contiguous()), F.ptr(self.gradWeight), F.ptr(self.gradBias), N, self.nIn, H, W, self.nOut, self.k), 'fg_conv2d_backward_filter')
+end
+
+-- layers/cudnnSpatialConvolutionUpsample.lua with factor = 1 (the only instantiation, models_c2f.lua:123-131)
+local SCU = torch.class('b200.SpatialConvolutionUpsample', 'b200.SpatialConvolution')
+function SCU:__init(nIn, nOut, kW, kH, factor)
+  assert((factor or 1) == 1, 'b200.SpatialConvolutionUpsample: only factor = 1 is used by the reference')
+  b200.SpatialConvolution.__init(self, nIn, nOut, kW, kH, 1, 1, (kW - 1) / 2, (kH - 1) / 2)
+end
+
+local Lin, lparent = torch.class('b200.Linear', 'nn.Module')
+function Lin:__init(inp, out)
+  lparent.__init(self)
+  self.inp, self.out = inp, out
+  self.weight, self.bias = torch.FloatTensor(out, inp), torch.FloatTensor(out)
+  self.gradWeight, self.gradBias = torch.FloatTensor(out, inp):zero(), torch.FloatTensor(out):zero()
+  self.ctx = b200.context()
+  local stdv = 1 / math.sqrt(inp)
+  self.weight:uniform(-stdv, stdv); self.bias:uniform(-stdv, stdv)
+end
+function Lin:updateOutput(input)
+  local N = input:size(1)
+  self.output:resize(N, self.out)
+  F.check(C.fg_linear_forward(self.ctx, F.ptr(input:contiguous()), F.ptr(self.weight), F.ptr(self.bias), F.ptr(self.output), N, self.inp, self.out), 'fg_linear_forward')
+  return self.output
+end
+function Lin:updateGradInput(input, gradOutput)
+  self.gradInput:resizeAs(input)
+  F.check(C.fg_linear_backward(self.ctx, F.ptr(input:contiguous()), F.ptr(self.weight), F.ptr(gradOutput:contiguous()), F.ptr(self.gradInput), nil, nil, input:size(1), self.inp, self.out), 'fg_linear_backward')
+  return self.gradInput
+end
+function Lin:accGradParameters(input, gradOutput)
+  F.check(C.fg_linear_backward(self.ctx, F.ptr(input:contiguous()), F.ptr(self.weight), F.ptr(gradOutput:contiguous()), nil, F.ptr(self.gradWeight), F.ptr(self.gradBias), input:size(1), self.inp, self.out), 'fg_linear_backward')
+end
+
+local BN, bnparent = torch.class('b200.SpatialBatchNormalization', 'nn.Module')
+function BN:__init(nFeature)
+  bnparent.__init(self)
+  self.n = nFeature
+  self.weight, self.bias = torch.FloatTensor(nFeature):uniform(), torch.FloatTensor(nFeature):zero()
+  self.gradWeight, self.gradBias = torch.FloatTensor(nFeature):zero(), torch.FloatTensor(nFeature):zero()
+  self.running_mean, self.running_var = torch.FloatTensor(nFeature):zero(), torch.FloatTensor(nFeature):fill(1)
+  self.save_mean, self.save_istd = torch.FloatTensor(nFeature), torch.FloatTensor(nFeature)
+  self.ctx = b200.context()
+end
+function BN:updateOutput(input)
+  local N, HW = input:size(1), input:size(3) * input:size(4)
+  self.output:resizeAs(input)
+  F.check(C.fg_bn_forward_train(self.ctx, F.ptr(input:contiguous()), F.ptr(self.weight), F.ptr(self.bias), F.ptr(self.output), F.ptr(self.save_mean), F.ptr(self.save_istd), F.ptr(self.running_mean), F.ptr(self.running_var), N, self.n, HW), 'fg_bn_forward_train')
+  return self.output
+end
+function BN:backward(input, gradOutput)
+  local N, HW = input:size(1), input:size(3) * input:size(4)
+  self.gradInput:resizeAs(input)
+  F.check(C.fg_bn_backward(self.ctx, F.ptr(input:contiguous()), F.ptr(self.weight), F.ptr(self.save_mean), F.ptr(self.save_istd), F.ptr(gradOutput:contiguous()), F.ptr(self.gradInput), F.ptr(self.gradWeight), F.ptr(self.gradBias), N, self.n, HW), 'fg_bn_backward')
+  return self.gradInput
+end
+
+local PR, prparent = torch.class('b200.PReLU', 'nn.Module')  -- nn.PReLU(): one shared slope
+function PR:__init()
+  prparent.__init(self)
+  self.weight, self.gradWeight = torch.FloatTensor(1):fill(0.25), torch.FloatTensor(1):zero()
+  self.ctx = b200.context()
+end
+function PR:updateOutput(input)
+  self.output:resizeAs(input)
+  F.check(C.fg_prelu_forward(self.ctx, F.ptr(input:contiguous()), F.ptr(self.weight), F.ptr(self.output), input:nElement()), 'fg_prelu_forward')
+  return self.output
+end
+function PR:backward(input, gradOutput)
+  self.gradInput:resizeAs(input)
+  F.check(C.fg_prelu_backward(self.ctx, F.ptr(input:contiguous()), F.ptr(self.weight), F.ptr(gradOutput:contiguous()), F.ptr(self.gradInput), F.ptr(self.gradWeight), input:nElement()), 'fg_prelu_backward')
+  return self.gradInput
+end
+
+return b200
