@@ -171,19 +171,42 @@ void col2im_add(const T* col, int Cin, int H, int W, int k, T* dx) {
         }
       }
 }
+// im2col of ONE sample, rows (c,kh,kw) distributed over the threads of the enclosing parallel region
+template <class T>
+void im2col_rows(const T* x, int Cin, int H, int W, int k, T* col) {
+  const int pad = (k - 1) / 2, KK = k * k;
+#pragma omp for schedule(static)
+  for (int r = 0; r < Cin * KK; ++r) {
+    const int c = r / KK, kh = (r % KK) / k, kw = r % k;
+    T* dst = col + (size_t)r * H * W;
+    for (int h = 0; h < H; ++h) {
+      const int ih = h + kh - pad;
+      if (ih < 0 || ih >= H) {
+        std::fill(dst + (size_t)h * W, dst + (size_t)(h + 1) * W, T(0));
+        continue;
+      }
+      const T* src = x + ((size_t)c * H + ih) * W;
+      for (int w = 0; w < W; ++w) {
+        const int iw = w + kw - pad;
+        dst[(size_t)h * W + w] = (iw < 0 || iw >= W) ? T(0) : src[iw];
+      }
+    }
+  }
+}
+// THNN SpatialConvolutionMM: loop over samples, im2col + GEMM per sample; the threads share one sample's
+// GEMM (rows of the output split across threads), so parallelism does not depend on the batch size.
 template <class T>
 void conv_fwd(int B, int Cin, int H, int W, int Cout, int k, const T* x, const T* Wt, const T* b, T* y) {
   const int K = Cin * k * k, HW = H * W;
+  std::vector<T> col((size_t)K * HW);
 #pragma omp parallel
-  {
-    std::vector<T> col((size_t)K * HW);
-#pragma omp for schedule(dynamic, 1)
-    for (int n = 0; n < B; ++n) {
-      im2col(x + (size_t)n * Cin * HW, Cin, H, W, k, col.data());
-      T* yn = y + (size_t)n * Cout * HW;
-      gemm_nn(Cout, HW, K, Wt, col.data(), yn, false);
-      for (int o = 0; o < Cout; ++o)
-        for (int p = 0; p < HW; ++p) yn[(size_t)o * HW + p] += b[o];
+  for (int n = 0; n < B; ++n) {
+    im2col_rows(x + (size_t)n * Cin * HW, Cin, H, W, k, col.data());  // implicit barrier after the omp for
+    T* yn = y + (size_t)n * Cout * HW;
+#pragma omp for schedule(static)
+    for (int o = 0; o < Cout; ++o) {
+      gemm_nn(1, HW, K, Wt + (size_t)o * K, col.data(), yn + (size_t)o * HW, false);
+      for (int p = 0; p < HW; ++p) yn[(size_t)o * HW + p] += b[o];
     }
   }
 }
@@ -191,47 +214,47 @@ void conv_fwd(int B, int Cin, int H, int W, int Cout, int k, const T* x, const T
 template <class T>
 void conv_bwd(int B, int Cin, int H, int W, int Cout, int k, const T* x, const T* Wt, const T* dy, T* dx,
               T* dW, T* db) {
-  const int K = Cin * k * k, HW = H * W;
-  if (dx) {
-#pragma omp parallel
-    {
-      std::vector<T> col((size_t)K * HW);
-#pragma omp for schedule(dynamic, 1)
-      for (int n = 0; n < B; ++n) {
-        gemm_tn(K, HW, Cout, Wt, dy + (size_t)n * Cout * HW, col.data(), false);
-        T* dxn = dx + (size_t)n * Cin * HW;
-        std::fill(dxn, dxn + (size_t)Cin * HW, T(0));
-        col2im_add(col.data(), Cin, H, W, k, dxn);
-      }
-    }
+  const int K = Cin * k * k, HW = H * W, KK = k * k, pad = (k - 1) / 2;
+  std::vector<T> col((size_t)K * HW);
+  std::vector<T> WtT;
+  if (dx) {  // W^T [K][Cout] so that column-gradient rows are independent dot products
+    WtT.resize((size_t)K * Cout);
+    for (int o = 0; o < Cout; ++o)
+      for (int r = 0; r < K; ++r) WtT[(size_t)r * Cout + o] = Wt[(size_t)o * K + r];
   }
-  if (dW) {
-    int nt = 1;
-#ifdef _OPENMP
-    nt = omp_get_max_threads();
-#endif
-    nt = std::min(nt, B);
-    std::vector<std::vector<T>> part(nt);
-#pragma omp parallel num_threads(nt)
-    {
-      int tid = 0;
-#ifdef _OPENMP
-      tid = omp_get_thread_num();
-#endif
-      std::vector<T>& acc = part[tid];
-      acc.assign((size_t)Cout * K, T(0));
-      std::vector<T> col((size_t)K * HW);
-#pragma omp for schedule(dynamic, 1)
-      for (int n = 0; n < B; ++n) {
-        im2col(x + (size_t)n * Cin * HW, Cin, H, W, k, col.data());
-        gemm_nt(Cout, K, HW, dy + (size_t)n * Cout * HW, col.data(), acc.data(), true);
+#pragma omp parallel
+  for (int n = 0; n < B; ++n) {
+    const T* dyn = dy + (size_t)n * Cout * HW;
+    if (dx) {
+#pragma omp for schedule(static)
+      for (int r = 0; r < K; ++r) gemm_nn(1, HW, Cout, WtT.data() + (size_t)r * Cout, dyn, col.data() + (size_t)r * HW, false);
+      T* dxn = dx + (size_t)n * Cin * HW;
+#pragma omp for schedule(static)
+      for (int c = 0; c < Cin; ++c) {  // col2im: each thread owns whole input channels
+        T* dst_c = dxn + (size_t)c * HW;
+        std::fill(dst_c, dst_c + HW, T(0));
+        for (int t = 0; t < KK; ++t) {
+          const int kh = t / k, kw = t % k;
+          const T* src = col.data() + ((size_t)c * KK + t) * HW;
+          for (int h = 0; h < H; ++h) {
+            const int ih = h + kh - pad;
+            if (ih < 0 || ih >= H) continue;
+            for (int w = 0; w < W; ++w) {
+              const int iw = w + kw - pad;
+              if (iw >= 0 && iw < W) dst_c[(size_t)ih * W + iw] += src[(size_t)h * W + w];
+            }
+          }
+        }
       }
     }
-    for (int t = 0; t < nt; ++t)
-      if (!part[t].empty())
-        for (size_t i = 0; i < (size_t)Cout * K; ++i) dW[i] += part[t][i];
+    if (dW) {
+      im2col_rows(x + (size_t)n * Cin * HW, Cin, H, W, k, col.data());
+#pragma omp for schedule(static)
+      for (int o = 0; o < Cout; ++o) gemm_nt(1, K, HW, dyn + (size_t)o * HW, col.data(), dW + (size_t)o * K, true);
+    }
   }
   if (db) {
+#pragma omp parallel for schedule(static)
     for (int o = 0; o < Cout; ++o) {
       T s = 0;
       for (int n = 0; n < B; ++n)
