@@ -221,6 +221,10 @@ int k_adam(fg_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, f
 int k_conv_simt(fg_ctx* c, const float* in, const float* Wp, const float* bias, float* out, ConvGeom g);
 // dWp[t][n][c] = sum_p dY[p][n] * in[pix(p,t)][c]   (dWp is overwritten)
 int k_wgrad_simt(fg_ctx* c, const float* in, const float* dY, float* dWp, ConvGeom g);
+// ---- k_conv_small.cu: 3-channel-side convolutions (G.C3, D.C1), bandwidth-shaped --------------------
+bool k_small_eligible(const ConvGeom& g);
+int k_conv_small(fg_ctx* c, const float* in, const float* Wp, const float* bias, float* out, ConvGeom g);
+int k_wgrad_small(fg_ctx* c, const float* in, const float* dY, float* dWp, ConvGeom g);
 
 // ---- k_conv_tc.cu ----------------------------------------------------------------------------------
 int tc_init(fg_ctx* c);

@@ -127,251 +127,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 constexpr int kStages = 3;
 constexpr uint32_t kABytes = 128 * 128;  // 128 rows x 32 fp32
 
-// ------------------------------------------------------------------------------------------------
-// tapconv: forward / dgrad
-// ------------------------------------------------------------------------------------------------
-template <int BN>
-__global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constant__ TcFwdParams p) {
-  constexpr uint32_t kBBytes = BN * 128;
-  constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
-  constexpr uint32_t kIdesc = make_idesc(128, BN, 0, 0);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* empty = full + kStages;
-  uint64_t* tmem_full = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // ---- tile decode ----
-  const int mt = blockIdx.x, n0 = blockIdx.y * BN;
-  const int ph = mt / p.tiles_per_phase;
-  int r = mt % p.tiles_per_phase;
-  int b0, y0, x0;
-  if (p.bb == 1) {
-    const int per_img = p.tiles_x * p.tiles_y;
-    b0 = r / per_img;
-    r %= per_img;
-    y0 = (r / p.tiles_x) * p.bh;
-    x0 = (r % p.tiles_x) * p.bw;
-  } else {
-    b0 = r * p.bb;
-    y0 = 0;
-    x0 = 0;
-  }
-  const int nkb = p.ntaps * p.kpt;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(empty + s, 1);
-    }
-    mbar_init(tmem_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      prefetch_tmap(&p.b_hi);
-      prefetch_tmap(&p.b_lo);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages, it = kb / kStages;
-        if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
-        const int tap = kb / p.kpt, c0 = (kb - tap * p.kpt) * 32;
-        const int ti = ph * p.ntaps + tap;
-        const int am = p.amap[ti];
-        uint8_t* st = smem + s * kStageBytes;
-        mbar_expect_tx(full + s, kStageBytes);
-        tma_load_4d(st, &p.a_hi[am], full + s, c0, x0 + p.dx[ti], y0 + p.dy[ti], b0);
-        tma_load_4d(st + kABytes, &p.a_lo[am], full + s, c0, x0 + p.dx[ti], y0 + p.dy[ti], b0);
-        const int wrow = p.widx[ti] * p.Cout + n0;
-        tma_load_2d(st + 2 * kABytes, &p.b_hi, full + s, c0, wrow);
-        tma_load_2d(st + 2 * kABytes + kBBytes, &p.b_lo, full + s, c0, wrow);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages, it = kb / kStages;
-        mbar_wait(full + s, it & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * kStageBytes);
-        const uint64_t a_hi = make_desc(sa, 16, 1024), a_lo = make_desc(sa + kABytes, 16, 1024);
-        const uint64_t b_hi = make_desc(sa + 2 * kABytes, 16, 1024), b_lo = make_desc(sa + 2 * kABytes + kBBytes, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 fp32 of K) in the 16B-unit start-address field
-          umma_tf32(tmem_base, a_lo + ko, b_hi + ko, kIdesc, (kb | k) != 0);
-          umma_tf32(tmem_base, a_hi + ko, b_lo + ko, kIdesc, 1);
-          umma_tf32(tmem_base, a_hi + ko, b_hi + ko, kIdesc, 1);
-        }
-        umma_commit(empty + s);
-      }
-      umma_commit(tmem_full);
-    }
-  } else {
-    // ---- epilogue: 4 warps, warp%4 selects the TMEM lane quadrant ----
-    const int q = warp & 3;
-    const int m = q * 32 + lane;  // accumulator row == tile pixel
-    const int xi = m % p.bw, yi = (m / p.bw) % p.bh, bi = m / (p.bw * p.bh);
-    const int b = b0 + bi;
-    const int Y = p.out_scale * (y0 + yi) + (ph >> 1) * (p.out_scale - 1);
-    const int X = p.out_scale * (x0 + xi) + (ph & 1) * (p.out_scale - 1);
-    float* orow = p.out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + n0;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int j = 0; j < BN / 32; ++j) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
-      if (b < p.B) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 o;
-          o.x = __uint_as_float(v[i + 0]);
-          o.y = __uint_as_float(v[i + 1]);
-          o.z = __uint_as_float(v[i + 2]);
-          o.w = __uint_as_float(v[i + 3]);
-          if (p.bias) {
-            const float* bp = p.bias + n0 + j * 32 + i;
-            o.x += bp[0];
-            o.y += bp[1];
-            o.z += bp[2];
-            o.w += bp[3];
-          }
-          *reinterpret_cast<float4*>(orow + j * 32 + i) = o;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------
-// wgrad: D[n (M=128 of Cout)][c (BN of Cin)] += sum over a pixel range of dY[p][n] * X[p+off][c]
-// grid: x = tile-tap, y = mtile * ntiles_n + ntile, z = K split.  Output accumulated with atomics.
-// ------------------------------------------------------------------------------------------------
-template <int BN>
-__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ TcWgParams p) {
-  constexpr uint32_t kBox = 32 * 128;  // one (32 ch x 32 px) box = 4 KB
-  constexpr uint32_t kAB = 4 * kBox;   // M = 128 channels of dY
-  constexpr uint32_t kBB = (BN / 32) * kBox;
-  constexpr uint32_t kStageBytes = 2 * kAB + 2 * kBB;
-  constexpr uint32_t kIdesc = make_idesc(128, BN, 1, 1);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* empty = full + kStages;
-  uint64_t* tmem_full = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tt = blockIdx.x;
-  const int ntn = p.Cin / BN;
-  const int m0 = (blockIdx.y / ntn) * 128, c0 = (blockIdx.y % ntn) * BN;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(p.kblocks, kb_begin + p.kb_per_split);
-  const int nkb = kb_end - kb_begin;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(empty + s, 1);
-    }
-    mbar_init(tmem_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (nkb > 0) {
-    if (warp == 0) {
-      if (lane == 0) {
-        const int ph = p.phase[tt], dyo = p.dy[tt], dxo = p.dx[tt];
-        for (int i = 0; i < nkb; ++i) {
-          const int s = i % kStages, it = i / kStages;
-          if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
-          const int kb = kb_begin + i;
-          int b0, y0, x0;
-          if (p.bb == 1) {
-            const int per_img = p.tiles_x * p.tiles_y;
-            b0 = kb / per_img;
-            const int r = kb % per_img;
-            y0 = (r / p.tiles_x) * p.bh;
-            x0 = (r % p.tiles_x) * p.bw;
-          } else {
-            b0 = kb * p.bb;
-            y0 = 0;
-            x0 = 0;
-          }
-          uint8_t* st = smem + s * kStageBytes;
-          mbar_expect_tx(full + s, kStageBytes);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            tma_load_4d(st + g * kBox, &p.dy_hi[ph], full + s, m0 + g * 32, x0, y0, b0);
-            tma_load_4d(st + kAB + g * kBox, &p.dy_lo[ph], full + s, m0 + g * 32, x0, y0, b0);
-          }
-#pragma unroll
-          for (int g = 0; g < BN / 32; ++g) {
-            tma_load_4d(st + 2 * kAB + g * kBox, &p.x_hi, full + s, c0 + g * 32, x0 + dxo, y0 + dyo, b0);
-            tma_load_4d(st + 2 * kAB + kBB + g * kBox, &p.x_lo, full + s, c0 + g * 32, x0 + dxo, y0 + dyo, b0);
-          }
-        }
-      }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        for (int i = 0; i < nkb; ++i) {
-          const int s = i % kStages, it = i / kStages;
-          mbar_wait(full + s, it & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * kStageBytes);
-          // MN-major, SWIZZLE_128B: 32 channels contiguous (128 B), 8 pixels per 1024 B atom;
-          // LBO = distance between 32-channel groups (one box), SBO = distance between 8-pixel groups
-          // layout 1 = SWIZZLE_128B_BASE32B: the only smem layout tcgen05 accepts for MN-major tf32 operands
-          // (4 pixel rows x 128 B per swizzle atom, 32 B chunks XOR row%4); TMA side: SWIZZLE_128B_ATOM_32B
-          const uint64_t a_hi = make_desc(sa, p.dbg_lbo, p.dbg_sbo, 1), a_lo = make_desc(sa + kAB, p.dbg_lbo, p.dbg_sbo, 1);
-          const uint64_t b_hi = make_desc(sa + 2 * kAB, p.dbg_lbo, p.dbg_sbo, 1),
-                         b_lo = make_desc(sa + 2 * kAB + kBB, p.dbg_lbo, p.dbg_sbo, 1);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ko = (uint64_t)(k * (p.dbg_kstep >> 4));  // +1024 bytes = next 8 pixels
-            umma_tf32(tmem_base, a_lo + ko, b_hi + ko, kIdesc, (i | k) != 0);
-            umma_tf32(tmem_base, a_hi + ko, b_lo + ko, kIdesc, 1);
-            umma_tf32(tmem_base, a_hi + ko, b_hi + ko, kIdesc, 1);
-          }
-          umma_commit(empty + s);
-        }
-        umma_commit(tmem_full);
-      }
-    } else {
-      const int q = warp & 3;
-      const int n = m0 + q * 32 + lane;
-      float* orow = p.out + ((int64_t)tt * p.Cout + n) * p.Cin + c0;
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(orow + j * 32 + i, __uint_as_float(v[i]));
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
-}
+#include "k_conv_tc_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // elementwise helpers of the tensor-core path
@@ -549,9 +309,9 @@ bool pick_box(int H, int W, int npix, int* bw, int* bh, int* bb) {
 }
 
 template <int BN>
-constexpr size_t fwd_smem() { return (size_t)kStages * (2 * kABytes + 2 * BN * 128) + 64 + 1024; }
+constexpr size_t fwd_smem() { return (size_t)kStages * (2 * kABytes + 2 * BN * 128) + 128 + 1024; }
 template <int BN>
-constexpr size_t wg_smem() { return (size_t)kStages * (2 * 4 * 4096 + 2 * (BN / 32) * 4096) + 64 + 1024; }
+constexpr size_t wg_smem() { return (size_t)kStages * (2 * 4 * 4096 + 2 * (BN / 32) * 4096) + 128 + 1024; }
 
 #define LAUNCH_CHECK(c)                 \
   do {                                  \
@@ -677,7 +437,8 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   p.bias = bias;
   p.out_H = g.H; p.out_W = g.W;
   p.out_scale = g.ups;
-  dim3 grid(p.tiles_per_phase * p.nphase, g.Cout / BN);
+  p.ntiles = p.tiles_per_phase * p.nphase * (g.Cout / BN);
+  dim3 grid(std::min(p.ntiles, c->sm_count));
   if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
   else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
   LAUNCH_CHECK(c);
@@ -724,7 +485,8 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
   p.bias = nullptr;
   p.out_H = Hl; p.out_W = Wl;
   p.out_scale = 1;
-  dim3 grid(p.tiles_per_phase, g.Cin / BN);
+  p.ntiles = p.tiles_per_phase * (g.Cin / BN);
+  dim3 grid(std::min(p.ntiles, c->sm_count));
   if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
   else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
   LAUNCH_CHECK(c);
@@ -784,9 +546,6 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
   p.kb_per_split = (p.kblocks + splits - 1) / splits;
   splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
   p.out = out;
-  p.dbg_lbo = getenv("FG_WG_LBO") ? atoi(getenv("FG_WG_LBO")) : 4096;
-  p.dbg_sbo = getenv("FG_WG_SBO") ? atoi(getenv("FG_WG_SBO")) : 512;
-  p.dbg_kstep = getenv("FG_WG_KSTEP") ? atoi(getenv("FG_WG_KSTEP")) : 1024;
   FG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)ntt * g.Cout * g.Cin, c->stream));
   dim3 grid(ntt, (g.Cout / 128) * (g.Cin / BN), splits);
   if (BN == 128) wgrad_tc_kernel<128><<<grid, 192, wg_smem<128>(), c->stream>>>(p);

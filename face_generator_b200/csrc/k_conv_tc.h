@@ -16,7 +16,7 @@ struct alignas(64) TcFwdParams {
   int ntaps, nphase, kpt, Cout;
   int B, H, W;         // tile-enumeration grid (the low-res grid for upsampled convs)
   int bw, bh, bb;      // pixel box of one 128-row M tile
-  int tiles_x, tiles_y, tiles_per_phase;
+  int tiles_x, tiles_y, tiles_per_phase, ntiles;
   float* out;
   const float* bias;
   int out_H, out_W, out_scale;
@@ -31,7 +31,6 @@ struct alignas(64) TcWgParams {
   int tiles_x, tiles_y;
   int kblocks, kb_per_split;
   float* out;
-  int dbg_lbo, dbg_sbo, dbg_kstep;  // descriptor knobs (bytes); defaults 4096 / 1024 / 1024
 };
 
 bool tc_conv_eligible(const ConvGeom& g);

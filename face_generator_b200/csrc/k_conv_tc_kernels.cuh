@@ -1,0 +1,321 @@
+// Device kernels of the tcgen05 convolution path (included by k_conv_tc.cu after the PTX wrappers).
+//
+// Numerics: the tensor core accumulates into TMEM with truncation, so a long K loop into ONE accumulator
+// drifts (measured 2-3e-5 relative at K = 2304, growing ~linearly with K).  Both kernels therefore
+// accumulate only kChunk K-blocks (4 x 32 channels or pixels, x3 MMAs) per TMEM buffer and let the epilogue
+// warps "promote" every chunk into fp32 registers with round-to-nearest adds (two TMEM buffers ping-pong, so
+// the promotion overlaps the next chunk's MMAs).  The same decoupling makes the forward kernel persistent:
+// while the epilogue stores tile i the MMA warp is already issuing tile i+1.
+#pragma once
+
+constexpr int kChunk = 4;  // K-blocks accumulated in the tensor core before promotion to registers
+
+struct FwdTile {
+  int ph, b0, y0, x0, n0;
+};
+template <int BN>
+__device__ __forceinline__ FwdTile fwd_decode(const TcFwdParams& p, int tile) {
+  const int ntn = p.Cout / BN;
+  FwdTile t;
+  const int mt = tile / ntn;
+  t.n0 = (tile - mt * ntn) * BN;  // n fastest: CTAs running together share the activation tile in L2
+  t.ph = mt / p.tiles_per_phase;
+  int r = mt - t.ph * p.tiles_per_phase;
+  if (p.bb == 1) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    t.b0 = r / per_img;
+    r -= t.b0 * per_img;
+    t.y0 = (r / p.tiles_x) * p.bh;
+    t.x0 = (r % p.tiles_x) * p.bw;
+  } else {
+    t.b0 = r * p.bb;
+    t.y0 = 0;
+    t.x0 = 0;
+  }
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tapconv: forward / dgrad.  Persistent: CTA i handles tiles i, i+gridDim.x, ...
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constant__ TcFwdParams p) {
+  constexpr uint32_t kBBytes = BN * 128;
+  constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+  constexpr uint32_t kIdesc = make_idesc(128, BN, 0, 0);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = p.ntaps * p.kpt;
+  const int nchunks = (nkb + kChunk - 1) / kChunk;
+  const int ntiles = p.ntiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + i, 1);
+      mbar_init(tmem_empty + i, 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&p.b_hi);
+      prefetch_tmap(&p.b_lo);
+      uint32_t kbg = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const FwdTile t = fwd_decode<BN>(p, tile);
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const uint32_t s = kbg % kStages, it = kbg / kStages;
+          if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+          const int tap = kb / p.kpt, c0 = (kb - tap * p.kpt) * 32;
+          const int ti = t.ph * p.ntaps + tap;
+          const int am = p.amap[ti];
+          uint8_t* st = smem + s * kStageBytes;
+          mbar_expect_tx(full + s, kStageBytes);
+          tma_load_4d(st, &p.a_hi[am], full + s, c0, t.x0 + p.dx[ti], t.y0 + p.dy[ti], t.b0);
+          tma_load_4d(st + kABytes, &p.a_lo[am], full + s, c0, t.x0 + p.dx[ti], t.y0 + p.dy[ti], t.b0);
+          const int wrow = p.widx[ti] * p.Cout + t.n0;
+          tma_load_2d(st + 2 * kABytes, &p.b_hi, full + s, c0, wrow);
+          tma_load_2d(st + 2 * kABytes + kBBytes, &p.b_lo, full + s, c0, wrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t kbg = 0, cg = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int ch = 0; ch < nchunks; ++ch, ++cg) {
+          const uint32_t buf = cg & 1, use = cg >> 1;
+          if (use > 0) mbar_wait(tmem_empty + buf, (use - 1) & 1);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + buf * BN;
+          const int nk = min(kChunk, nkb - ch * kChunk);
+          for (int j = 0; j < nk; ++j, ++kbg) {
+            const uint32_t s = kbg % kStages, it = kbg / kStages;
+            mbar_wait(full + s, it & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * kStageBytes);
+            const uint64_t a_hi = make_desc(sa, 16, 1024), a_lo = make_desc(sa + kABytes, 16, 1024);
+            const uint64_t b_hi = make_desc(sa + 2 * kABytes, 16, 1024),
+                           b_lo = make_desc(sa + 2 * kABytes + kBBytes, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 fp32 of K) in the 16B-unit start-address field
+              umma_tf32(tacc, a_lo + ko, b_hi + ko, kIdesc, (j | k) != 0);
+              umma_tf32(tacc, a_hi + ko, b_lo + ko, kIdesc, 1);
+              umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, 1);
+            }
+            umma_commit(empty + s);
+          }
+          umma_commit(tmem_full + buf);
+        }
+      }
+    }
+  } else {
+    // ---- epilogue: 4 warps, warp%4 selects the TMEM lane quadrant ----
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // accumulator row == tile pixel
+    const int xi = m % p.bw, yi = (m / p.bw) % p.bh, bi = m / (p.bw * p.bh);
+    uint32_t cg = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const FwdTile t = fwd_decode<BN>(p, tile);
+      float acc[BN];
+#pragma unroll
+      for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch, ++cg) {
+        const uint32_t buf = cg & 1, use = cg >> 1;
+        mbar_wait(tmem_full + buf, use & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(v[i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + buf);
+      }
+      const int b = t.b0 + bi;
+      if (b < p.B) {
+        const int Y = p.out_scale * (t.y0 + yi) + (t.ph >> 1) * (p.out_scale - 1);
+        const int X = p.out_scale * (t.x0 + xi) + (t.ph & 1) * (p.out_scale - 1);
+        float* orow = p.out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + t.n0;
+#pragma unroll
+        for (int i = 0; i < BN; i += 4) {
+          float4 o = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+          if (p.bias) {
+            const float* bp = p.bias + t.n0 + i;
+            o.x += bp[0];
+            o.y += bp[1];
+            o.z += bp[2];
+            o.w += bp[3];
+          }
+          *reinterpret_cast<float4*>(orow + i) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: D[n (M=128 of Cout)][c (BN of Cin)] += sum over a pixel range of dY[p][n] * X[p+off][c]
+// grid: x = tile-tap, y = mtile * ntiles_n + ntile, z = K split.  Output accumulated with atomics.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ TcWgParams p) {
+  constexpr uint32_t kBox = 32 * 128;  // one (32 ch x 32 px) box = 4 KB
+  constexpr uint32_t kAB = 4 * kBox;   // M = 128 channels of dY
+  constexpr uint32_t kBB = (BN / 32) * kBox;
+  constexpr uint32_t kStageBytes = 2 * kAB + 2 * kBB;
+  constexpr uint32_t kIdesc = make_idesc(128, BN, 1, 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tt = blockIdx.x;
+  const int ntn = p.Cin / BN;
+  const int m0 = (blockIdx.y / ntn) * 128, c0 = (blockIdx.y % ntn) * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.kblocks, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+  const int nchunks = (nkb + kChunk - 1) / kChunk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + i, 1);
+      mbar_init(tmem_empty + i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const int ph = p.phase[tt], dyo = p.dy[tt], dxo = p.dx[tt];
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % kStages, it = i / kStages;
+          if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+          const int kb = kb_begin + i;
+          int b0, y0, x0;
+          if (p.bb == 1) {
+            const int per_img = p.tiles_x * p.tiles_y;
+            b0 = kb / per_img;
+            const int r = kb % per_img;
+            y0 = (r / p.tiles_x) * p.bh;
+            x0 = (r % p.tiles_x) * p.bw;
+          } else {
+            b0 = kb * p.bb;
+            y0 = 0;
+            x0 = 0;
+          }
+          uint8_t* st = smem + s * kStageBytes;
+          mbar_expect_tx(full + s, kStageBytes);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            tma_load_4d(st + g * kBox, &p.dy_hi[ph], full + s, m0 + g * 32, x0, y0, b0);
+            tma_load_4d(st + kAB + g * kBox, &p.dy_lo[ph], full + s, m0 + g * 32, x0, y0, b0);
+          }
+#pragma unroll
+          for (int g = 0; g < BN / 32; ++g) {
+            tma_load_4d(st + 2 * kAB + g * kBox, &p.x_hi, full + s, c0 + g * 32, x0 + dxo, y0 + dyo, b0);
+            tma_load_4d(st + 2 * kAB + kBB + g * kBox, &p.x_lo, full + s, c0 + g * 32, x0 + dxo, y0 + dyo, b0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        int i = 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const uint32_t buf = ch & 1, use = ch >> 1;
+          if (use > 0) mbar_wait(tmem_empty + buf, (use - 1) & 1);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + buf * BN;
+          const int nk = min(kChunk, nkb - ch * kChunk);
+          for (int j = 0; j < nk; ++j, ++i) {
+            const int s = i % kStages, it = i / kStages;
+            mbar_wait(full + s, it & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * kStageBytes);
+            // MN-major operands.  layout 1 = SWIZZLE_128B_BASE32B: the only smem layout tcgen05 accepts for
+            // MN-major tf32 (4 pixel rows x 128 B per swizzle atom, 32 B chunks XOR row%4; TMA side
+            // SWIZZLE_128B_ATOM_32B).  LBO = distance between 32-channel groups (one 4 KB box),
+            // SBO = distance between 4-pixel groups (512 B).
+            const uint64_t a_hi = make_desc(sa, kBox, 512, 1), a_lo = make_desc(sa + kAB, kBox, 512, 1);
+            const uint64_t b_hi = make_desc(sa + 2 * kAB, kBox, 512, 1), b_lo = make_desc(sa + 2 * kAB + kBB, kBox, 512, 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ko = (uint64_t)(k * 64);  // +1024 bytes = next 8 pixels
+              umma_tf32(tacc, a_lo + ko, b_hi + ko, kIdesc, (j | k) != 0);
+              umma_tf32(tacc, a_hi + ko, b_lo + ko, kIdesc, 1);
+              umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, 1);
+            }
+            umma_commit(empty + s);
+          }
+          umma_commit(tmem_full + buf);
+        }
+      }
+    } else {
+      const int q = warp & 3;
+      const int n = m0 + q * 32 + lane;
+      float acc[BN];
+#pragma unroll
+      for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const uint32_t buf = ch & 1, use = ch >> 1;
+        mbar_wait(tmem_full + buf, use & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(v[i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + buf);
+      }
+      float* orow = p.out + ((int64_t)tt * p.Cout + n) * p.Cin + c0;
+#pragma unroll
+      for (int i = 0; i < BN; ++i) atomicAdd(orow + i, acc[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+}

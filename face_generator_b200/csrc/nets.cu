@@ -251,13 +251,13 @@ int net_pack_D(fg_ctx* c) {
 static int conv_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp, const float* bias, float* out,
                     ConvGeom g) {
   ScopedTimer t(c, tag);
-  return k_conv_simt(c, in, Wp, bias, out, g);
+  return k_small_eligible(g) ? k_conv_small(c, in, Wp, bias, out, g) : k_conv_simt(c, in, Wp, bias, out, g);
 }
 static int conv_wgrad(fg_ctx* c, const char* tag, const float* in, const float* dY, ConvGeom g, float* dW, int nA, int nS,
                       int cA, int cS) {
   {
     ScopedTimer t(c, tag);
-    FG_TRY(k_wgrad_simt(c, in, dY, c->wgrad_ws, g));
+    FG_TRY(k_small_eligible(g) ? k_wgrad_small(c, in, dY, c->wgrad_ws, g) : k_wgrad_simt(c, in, dY, c->wgrad_ws, g));
   }
   return k_unpack_wgrad(c, c->wgrad_ws, dW, g.Cout, g.Cin, g.k * g.k, nA, nS, cA, cS);
 }
