@@ -134,6 +134,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE configs[1]: 256)")
     ap.add_argument("--conv-impl", type=int, default=-1, help="0 simt, 1 tcgen05 dense, 2 tcgen05 collapsed; -1 library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="per-layer kernel timings in kernel_ms_per_step")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -216,7 +217,11 @@ def main():
     for _ in range(nprof):
         step_resident()
     fam = {}
-    for name in ("G.C2.fwd", "G.C2.dgrad", "G.C2.wgrad", "G.C1", "G.C3", "G.L1", "D.", "nccl"):
+    names = ["G.C2.fwd", "G.C2.dgrad", "G.C2.wgrad", "G.C1", "G.C3", "G.L1", "D.", "nccl"]
+    if args.breakdown:
+        names += ["G.C1.fwd", "G.C1.dgrad", "G.C1.wgrad", "G.C3.fwd", "G.C3.dgrad", "G.C3.wgrad"]
+        names += ["D.%s.%s" % (l, k) for l in ("C1", "C2", "C3", "C4", "L1", "L2", "L3") for k in ("fwd", "dgrad", "wgrad")]
+    for name in names:
         t, n = ctx.timing_get(name)
         fam[name] = (t / nprof, n // nprof)
     t_all, _ = ctx.timing_get("*")

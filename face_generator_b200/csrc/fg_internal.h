@@ -35,6 +35,7 @@ void fg_set_error(const char* fmt, ...);
 
 constexpr int kMaskPerSample = 1984;  // 64+128+256+512 SpatialDropout + 512+512 Dropout keep flags
 constexpr int kNoiseDim = 100;
+constexpr int kSmallMaxParts = 2048;  // partial rows of the small-channel wgrad workspace
 constexpr int kGradTail = 8;          // extra floats behind each flat gradient (DP-reduced scalars)
 
 // Geometry of one stride-1 "same" convolution seen as a sum over taps of shifted GEMMs.
@@ -95,6 +96,7 @@ struct fg_ctx {
   float *D_cp[4] = {nullptr, nullptr, nullptr, nullptr}, *D_cpd[4] = {nullptr, nullptr, nullptr, nullptr};
   float *D_L1p = nullptr, *D_L1pd = nullptr, *D_L2pd = nullptr, *D_L3pd = nullptr;
   bool G_packed = false, D_packed = false;
+  float* small_ws = nullptr;  // per-block partials of the small-channel wgrad (k_conv_small.cu)
   float* wgrad_ws = nullptr;  // packed weight-gradient workspace (largest layer)
   size_t wgrad_ws_elems = 0;
   // G activations (NHWC)
@@ -140,6 +142,8 @@ struct fg_ctx {
     float *D_p_hi[3] = {nullptr, nullptr, nullptr}, *D_p_lo[3] = {nullptr, nullptr, nullptr};  // pooled inputs of c2..c4
     float *D_Wf_hi[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Wf_lo[4] = {nullptr, nullptr, nullptr, nullptr};
     float *D_Wd_hi[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Wd_lo[4] = {nullptr, nullptr, nullptr, nullptr};
+    // D's Linear layers: [0] L1 fwd [512][2048'], [1] L1 dgrad [2048'][512], [2] L2 fwd, [3] L2 dgrad
+    float *D_Lw_hi[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Lw_lo[4] = {nullptr, nullptr, nullptr, nullptr};
   } tcb;
 };
 

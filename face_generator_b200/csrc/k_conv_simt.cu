@@ -104,6 +104,83 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict_
   }
 }
 
+// Same tiling for a TINY input-channel count (D.C1: Cin = 3, G.C3 dgrad: 3 "input" channels): the
+// contraction index is flattened to k = t*Cin + c so that K = k*k*Cin = 27 fills two BK=16 steps instead
+// of padding every tap to 16.
+template <int TM, int TN>
+__global__ void __launch_bounds__(256) conv_simt_flatk_kernel(const float* __restrict__ in, const float* __restrict__ Wp,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              ConvGeom g) {
+  constexpr int BM = 16 * TM, BN = 16 * TN;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int P = g.B * g.H * g.W;
+  const int p0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int KK = g.k * g.k, pad = (g.k - 1) / 2, Ktot = KK * g.Cin;
+  int pb[TM], py[TM], px[TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int p = p0 + ty + 16 * i;
+    if (p < P) {
+      const int r = p % (g.H * g.W);
+      pb[i] = p / (g.H * g.W);
+      py[i] = r / g.W;
+      px[i] = r % g.W;
+    } else {
+      pb[i] = 0;
+      py[i] = -100000;
+      px[i] = 0;
+    }
+  }
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < Ktot; k0 += BK) {
+    const int kk = k0 + tx;
+    const bool kok = kk < Ktot;
+    const int t = kok ? kk / g.Cin : 0, cc = kok ? kk - t * g.Cin : 0;
+    const int kh = t / g.k, kw = t - kh * g.k;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int iy = py[i] + kh - pad, ix = px[i] + kw - pad;
+      const bool ok = kok && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+      As[tx][ty + 16 * i] = ok ? __ldg(in + ((int64_t)(pb[i] * g.H + iy) * g.W + ix) * g.Cin + cc) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + ty + 16 * j;
+      Bs[tx][ty + 16 * j] = (kok && n < g.Cout) ? __ldg(Wp + ((int64_t)t * g.Cout + n) * g.Cin + cc) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < BK; ++q) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[q][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[q][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int p = p0 + ty * TM + i;
+    if (p >= P) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n < g.Cout) out[(int64_t)p * g.Cout + n] = acc[i][j] + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
 // grid: x = n-tile, y = c-tile, z = tap * splits + split
 template <int TM, int TN>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(const float* __restrict__ in, const float* __restrict__ dY,
@@ -185,6 +262,20 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const float* __restrict
 
 int k_conv_simt(fg_ctx* c, const float* in, const float* Wp, const float* bias, float* out, ConvGeom g) {
   const int P = g.B * g.H * g.W;
+  if (g.Cin < 16 && g.ups == 1 && g.k > 1) {
+    if (g.Cout > 64) {
+      dim3 grid((P + 127) / 128, (g.Cout + 127) / 128);
+      conv_simt_flatk_kernel<8, 8><<<grid, 256, 0, c->stream>>>(in, Wp, bias, out, g);
+    } else if (g.Cout > 16) {
+      dim3 grid((P + 127) / 128, (g.Cout + 63) / 64);
+      conv_simt_flatk_kernel<8, 4><<<grid, 256, 0, c->stream>>>(in, Wp, bias, out, g);
+    } else {
+      dim3 grid((P + 127) / 128, (g.Cout + 15) / 16);
+      conv_simt_flatk_kernel<8, 1><<<grid, 256, 0, c->stream>>>(in, Wp, bias, out, g);
+    }
+    LAUNCH_CHECK(c);
+    return FG_OK;
+  }
   if (g.Cout > 64) {
     dim3 grid((P + 127) / 128, (g.Cout + 127) / 128);
     conv_simt_kernel<8, 8><<<grid, 256, 0, c->stream>>>(in, Wp, bias, out, g);

@@ -105,52 +105,93 @@ __global__ void __launch_bounds__(256) conv_smalln_kernel(const float* __restric
 }
 
 // ---- weight gradient with one small and one big side ----------------------------------------------------
-//   acc[t][cs] (per thread = per big channel cb) += big[p][cb] * small[p + sign*off_t][cs]
-//   out index: transposed ? (t*Cb + cb)*CS + cs : (t*CS + cs)*Cb + cb      (accumulated with atomics)
+//   G.C3:  dW[n<Cs][c][t] = sum_p dY[p][n] * X[p+off_t][c]      big = X  (Cb = 128), small = dY, sign = -1
+//   D.C1:  dW[n][c<Cs][t] = sum_p dY[p][n] * X[p+off_t][c]      big = dY (Cb = 64),  small = X,  sign = +1
+// One thread per big channel walks along image rows with a 3x3 sliding window of the small tensor held in
+// registers (staged per row through shared memory as float4): 3 broadcast LDS.128 + 1 coalesced LDG per
+// 9*Cs FMAs.  Blocks write per-block partial sums; a second tiny kernel reduces them in a fixed order
+// (deterministic, no atomics).
+//   window index idx = r*3 + c holds small[y+r-1][x+c-1];  tap t = idx (sign +1) or 8 - idx (sign -1)
 template <int CS>
 __global__ void __launch_bounds__(128) wgrad_smallbig_kernel(const float* __restrict__ big, const float* __restrict__ small,
-                                                             float* __restrict__ out, int B, int H, int W, int Cb, int k,
-                                                             int sign, int transposed, int pix_per_block) {
-  const int KK = k * k, pad = (k - 1) / 2;
-  const int lanes = blockDim.x / Cb;  // pixel lanes per block (Cb = 64 -> 2, 128 -> 1)
+                                                             float* __restrict__ part, int B, int H, int W, int Cb,
+                                                             int rows_per_block) {
+  __shared__ float4 sm[3][68];
+  const int lanes = 128 / Cb;
   const int cb = threadIdx.x % Cb, pl = threadIdx.x / Cb;
-  const int64_t P = (int64_t)B * H * W;
-  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
+  const int xs = W / lanes, x_begin = pl * xs, x_end = x_begin + xs;
   float acc[9][CS];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int c = 0; c < CS; ++c) acc[t][c] = 0.f;
-  for (int64_t p = p0 + pl; p < p1; p += lanes) {
-    const int x = (int)(p % W);
-    const int y = (int)((p / W) % H);
-    const int b = (int)(p / ((int64_t)W * H));
-    const float bv = big[p * Cb + cb];
+  const int BH = B * H;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(BH, r0 + rows_per_block);
+  for (int r = r0; r < r1; ++r) {
+    const int b = r / H, y = r - b * H;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * (W + 2); i += 128) {
+      const int rr = i / (W + 2), cc = i - rr * (W + 2);
+      const int yy = y + rr - 1, xx = cc - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const float* sp = small + (((int64_t)b * H + yy) * W + xx) * CS;
+        v.x = sp[0];
+        if (CS > 1) v.y = sp[1 % CS];
+        if (CS > 2) v.z = sp[2 % CS];
+        if (CS > 3) v.w = sp[3 % CS];
+      }
+      sm[rr][cc] = v;
+    }
+    __syncthreads();
+    const float* bp = big + (int64_t)r * W * Cb + cb;
+    float4 w0[3], w1[3], w2[3];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      if (t >= KK) break;
-      const int iy = y + sign * (t / k - pad), ix = x + sign * (t % k - pad);
-      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-      const float* sp = small + (((int64_t)b * H + iy) * W + ix) * CS;
+    for (int rr = 0; rr < 3; ++rr) {
+      w0[rr] = sm[rr][x_begin];
+      w1[rr] = sm[rr][x_begin + 1];
+    }
+    for (int x = x_begin; x < x_end; ++x) {
+      const float bv = bp[(int64_t)x * Cb];
 #pragma unroll
-      for (int c = 0; c < CS; ++c) acc[t][c] = fmaf(bv, __ldg(sp + c), acc[t][c]);
+      for (int rr = 0; rr < 3; ++rr) {
+        w2[rr] = sm[rr][x + 2];
+        const float4 q[3] = {w0[rr], w1[rr], w2[rr]};
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          acc[rr * 3 + cc][0] = fmaf(bv, q[cc].x, acc[rr * 3 + cc][0]);
+          if (CS > 1) acc[rr * 3 + cc][1 % CS] = fmaf(bv, q[cc].y, acc[rr * 3 + cc][1 % CS]);
+          if (CS > 2) acc[rr * 3 + cc][2 % CS] = fmaf(bv, q[cc].z, acc[rr * 3 + cc][2 % CS]);
+          if (CS > 3) acc[rr * 3 + cc][3 % CS] = fmaf(bv, q[cc].w, acc[rr * 3 + cc][3 % CS]);
+        }
+        w0[rr] = w1[rr];
+        w1[rr] = w2[rr];
+      }
     }
   }
+  float* dst = part + ((int64_t)blockIdx.x * lanes + pl) * (9 * CS * Cb);
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    if (t >= KK) break;
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int c = 0; c < CS; ++c) {
-      float* dst = transposed ? out + ((int64_t)t * Cb + cb) * CS + c : out + ((int64_t)t * CS + c) * Cb + cb;
-      atomicAdd(dst, acc[t][c]);
-    }
-  }
+    for (int c = 0; c < CS; ++c) dst[(t * CS + c) * Cb + cb] = acc[t][c];
+}
+// out (overwritten) = sum over partial rows, mapped to the packed [t][n][c] layout
+__global__ void wgrad_small_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int CS, int Cb,
+                                          int sign, int transposed) {
+  const int total = 9 * CS * Cb;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= total) return;
+  float s = 0.f;
+  for (int i = 0; i < nparts; ++i) s += part[(int64_t)i * total + j];
+  const int idx = j / (CS * Cb), cs = (j / Cb) % CS, cb = j % Cb;
+  const int t = sign > 0 ? idx : 8 - idx;
+  out[transposed ? ((int64_t)t * Cb + cb) * CS + cs : ((int64_t)t * CS + cs) * Cb + cb] = s;
 }
 }  // namespace
 
 bool k_small_eligible(const ConvGeom& g) {
   const int cs = g.Cin < g.Cout ? g.Cin : g.Cout, cb = g.Cin < g.Cout ? g.Cout : g.Cin;
-  return g.ups == 1 && g.k == 3 && cs >= 1 && cs <= 4 && (cb == 32 || cb == 64 || cb == 128);
+  return g.ups == 1 && g.k == 3 && cs >= 1 && cs <= 4 && (cb == 32 || cb == 64 || cb == 128) && g.W <= 64 && g.W % 4 == 0;
 }
 
 // forward-type conv (also used for dgrad with the flipped/transposed pack): picks small-K or small-N
@@ -184,19 +225,20 @@ int k_conv_small(fg_ctx* c, const float* in, const float* Wp, const float* bias,
 
 // dWp[t][n][c] (overwritten) = sum_p dY[p][n] * X[pix(p,t)][c]   with min(Cin,Cout) <= 4
 int k_wgrad_small(fg_ctx* c, const float* in, const float* dY, float* dWp, ConvGeom g) {
-  const int64_t P = (int64_t)g.B * g.H * g.W;
-  FG_CUDA(cudaMemsetAsync(dWp, 0, sizeof(float) * (size_t)9 * g.Cout * g.Cin, c->stream));
-  const bool small_out = g.Cout <= 4;  // G.C3: small = dY (at p), big = X (at p+off)  => iterate big pixels, sign -1
+  const bool small_out = g.Cout <= 4;  // G.C3: small = dY, big = X (window read mirrored: sign -1)
   const float* big = small_out ? in : dY;
   const float* small = small_out ? dY : in;
   const int Cb = small_out ? g.Cin : g.Cout, Cs = small_out ? g.Cout : g.Cin;
-  int grid = c->sm_count * 8;
-  int ppb = (int)((P + grid - 1) / grid);
-  if (ppb < 32) ppb = 32;
-  grid = (int)((P + ppb - 1) / ppb);
-  const int sign = small_out ? -1 : 1;
-  const int transposed = small_out ? 0 : 1;  // layout [t][n][c]: n is the small side for G.C3, the big side for D.C1
-#define WG(CS_) wgrad_smallbig_kernel<CS_><<<grid, 128, 0, c->stream>>>(big, small, dWp, g.B, g.H, g.W, Cb, g.k, sign, transposed, ppb)
+  const int lanes = 128 / Cb;
+  const int BH = g.B * g.H;
+  int rpb = 8;
+  int nblocks = (BH + rpb - 1) / rpb;
+  while (nblocks * lanes > kSmallMaxParts) {
+    rpb *= 2;
+    nblocks = (BH + rpb - 1) / rpb;
+  }
+  const int sign = small_out ? -1 : 1, transposed = small_out ? 0 : 1;
+#define WG(CS_) wgrad_smallbig_kernel<CS_><<<nblocks, 128, 0, c->stream>>>(big, small, c->small_ws, g.B, g.H, g.W, Cb, rpb)
   switch (Cs) {
     case 1: WG(1); break;
     case 2: WG(2); break;
@@ -204,6 +246,9 @@ int k_wgrad_small(fg_ctx* c, const float* in, const float* dY, float* dWp, ConvG
     default: WG(4); break;
   }
 #undef WG
+  LAUNCH_CHECK(c);
+  const int total = 9 * Cs * Cb;
+  wgrad_small_reduce_kernel<<<(total + 127) / 128, 128, 0, c->stream>>>(c->small_ws, dWp, nblocks * lanes, Cs, Cb, sign, transposed);
   LAUNCH_CHECK(c);
   return FG_OK;
 }

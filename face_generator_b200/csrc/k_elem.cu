@@ -372,11 +372,15 @@ __global__ void bn_prelu_bwd_reduce_kernel(const float* __restrict__ dh, const f
   const float m = mean[ch], is = istd[ch], ga = gamma[ch], be = beta[ch];
   double sg = 0, sgx = 0, ss = 0;
   for (int64_t r = r0 + lane; r < r1; r += lanes) {
-    const int x = (int)(r % W);
-    const int64_t q = r / W;
-    const int y = (int)(q % H);
-    const int b = (int)(q / H);
-    const float d = load_dh(dh, b, y, x, ch, H, W, C, pool);
+    float d;
+    if (pool) {
+      const uint32_t ru = (uint32_t)r;
+      const int x = (int)(ru % (uint32_t)W);
+      const uint32_t q = ru / (uint32_t)W;
+      d = load_dh(dh, (int)(q / (uint32_t)H), (int)(q % (uint32_t)H), x, ch, H, W, C, 1);
+    } else {
+      d = dh[r * C + ch];
+    }
     const float xh = (z[r * C + ch] - m) * is;
     float g = d;
     if (act) {
@@ -462,10 +466,47 @@ __global__ void bn_prelu_bwd_apply_kernel(const float* __restrict__ dh, const fl
     dz[i] = ga * is * (g - mg[ch] - xh * mg[C + ch]);
   }
 }
+// pool == 0 fast path: float4 along channels, no pixel decode
+__global__ void bn_prelu_bwd_apply4_kernel(const float* __restrict__ dh, const float* __restrict__ z,
+                                           const float* __restrict__ mean, const float* __restrict__ istd,
+                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           const float* __restrict__ slope, const float* __restrict__ mg,
+                                           float* __restrict__ dz, int64_t n4, int C) {
+  const bool act = slope != nullptr;
+  const float a = act ? *slope : 1.f;
+  const float4* dh4 = reinterpret_cast<const float4*>(dh);
+  const float4* z4 = reinterpret_cast<const float4*>(z);
+  float4* dz4 = reinterpret_cast<float4*>(dz);
+  const int C4 = C / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % C4) * 4;
+    const float4 d = dh4[i], v = z4[i];
+    const float dv[4] = {d.x, d.y, d.z, d.w}, zv[4] = {v.x, v.y, v.z, v.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float is = istd[ch + j], ga = gamma[ch + j];
+      const float xh = (zv[j] - mean[ch + j]) * is;
+      float g = dv[j];
+      if (act) {
+        const float u = ga * xh + beta[ch + j];
+        if (!(u > 0.f)) g = a * g;
+      }
+      o[j] = ga * is * (g - mg[ch + j] - xh * mg[C + ch + j]);
+    }
+    dz4[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
 int k_bn_prelu_bwd_apply(fg_ctx* c, const float* dh, const float* z, const float* mean, const float* istd,
                          const float* gamma, const float* beta, const float* slope, const float* mg, float* dz, int B,
                          int H, int W, int C, int pool) {
   const int64_t n = (int64_t)B * H * W * C;
+  if (!pool && C % 4 == 0) {
+    bn_prelu_bwd_apply4_kernel<<<grid_for(n / 4, 256), 256, 0, c->stream>>>(dh, z, mean, istd, gamma, beta, slope, mg, dz,
+                                                                           n / 4, C);
+    LAUNCH_CHECK(c);
+    return FG_OK;
+  }
   bn_prelu_bwd_apply_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(dh, z, mean, istd, gamma, beta, slope, mg, dz, B, H,
                                                                     W, C, pool);
   LAUNCH_CHECK(c);
@@ -529,33 +570,48 @@ int k_masks_generate(fg_ctx* c, float* masks, int B, uint64_t seed, float p_spat
 // ------------------------------------------------------------------------------------------------
 // D conv blocks: PReLU -> SpatialDropout (channel mask, NO rescale) -> SpatialAveragePooling(2,2,2,2)
 // ------------------------------------------------------------------------------------------------
+// float4 along channels, 32-bit index math (all D tensors have < 2^31 elements and C % 4 == 0)
+__device__ __forceinline__ float4 prelu4(float4 v, float a) {
+  v.x = v.x > 0.f ? v.x : a * v.x;
+  v.y = v.y > 0.f ? v.y : a * v.y;
+  v.z = v.z > 0.f ? v.z : a * v.z;
+  v.w = v.w > 0.f ? v.w : a * v.w;
+  return v;
+}
 __global__ void d_act_pool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ slope,
                                       const float* __restrict__ masks, int moff, float eval_scale, float* __restrict__ p,
                                       int B, int H, int W, int C) {
   const float a = *slope;
-  const int Ho = H / 2, Wo = W / 2;
-  const int64_t n = (int64_t)B * Ho * Wo * C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % C);
-    int64_t r = i / C;
-    const int xo = (int)(r % Wo);
+  const uint32_t Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const uint32_t n = (uint32_t)B * Ho * Wo * C4;
+  const float4* z4 = reinterpret_cast<const float4*>(z);
+  float4* p4 = reinterpret_cast<float4*>(p);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t c4 = i % C4;
+    uint32_t r = i / C4;
+    const uint32_t xo = r % Wo;
     r /= Wo;
-    const int yo = (int)(r % Ho);
-    const int b = (int)(r / Ho);
-    const float m = masks ? masks[(int64_t)b * kMaskPerSample + moff + ch] : eval_scale;
-    const int64_t base = (((int64_t)b * H + 2 * yo) * W + 2 * xo) * C + ch;
-    const int64_t rs = (int64_t)W * C;
-    float v0 = z[base], v1 = z[base + C], v2 = z[base + rs], v3 = z[base + rs + C];
-    v0 = (v0 > 0.f ? v0 : a * v0) * m;
-    v1 = (v1 > 0.f ? v1 : a * v1) * m;
-    v2 = (v2 > 0.f ? v2 : a * v2) * m;
-    v3 = (v3 > 0.f ? v3 : a * v3) * m;
-    p[i] = (v0 + v1 + v2 + v3) * 0.25f;
+    const uint32_t yo = r % Ho, b = r / Ho;
+    float4 m = make_float4(eval_scale, eval_scale, eval_scale, eval_scale);
+    if (masks) m = *reinterpret_cast<const float4*>(masks + (size_t)b * kMaskPerSample + moff + c4 * 4);
+    const uint32_t base = ((b * H + 2 * yo) * W + 2 * xo) * C4 + c4, rs = (uint32_t)W * C4;
+    const float4 v0 = prelu4(z4[base], a), v1 = prelu4(z4[base + C4], a), v2 = prelu4(z4[base + rs], a),
+                 v3 = prelu4(z4[base + rs + C4], a);
+    float4 o;
+    o.x = (v0.x * m.x + v1.x * m.x + v2.x * m.x + v3.x * m.x) * 0.25f;
+    o.y = (v0.y * m.y + v1.y * m.y + v2.y * m.y + v3.y * m.y) * 0.25f;
+    o.z = (v0.z * m.z + v1.z * m.z + v2.z * m.z + v3.z * m.z) * 0.25f;
+    o.w = (v0.w * m.w + v1.w * m.w + v2.w * m.w + v3.w * m.w) * 0.25f;
+    p4[i] = o;
   }
 }
 int k_d_act_pool_fwd(fg_ctx* c, const float* z, const float* slope, const float* masks, int moff, float eval_scale,
                      float* p, int B, int H, int W, int C) {
-  const int64_t n = (int64_t)B * (H / 2) * (W / 2) * C;
+  const int64_t n = (int64_t)B * (H / 2) * (W / 2) * C / 4;
+  if (C % 4 || (moff % 4) || (int64_t)B * H * W * C >= ((int64_t)1 << 31)) {
+    fg_set_error("d_act_pool_fwd: unsupported shape (C %% 4, size)");
+    return FG_ERR_UNSUPPORTED;
+  }
   d_act_pool_fwd_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(z, slope, masks, moff, eval_scale, p, B, H, W, C);
   LAUNCH_CHECK(c);
   return FG_OK;
@@ -564,33 +620,54 @@ __global__ void d_act_pool_bwd_kernel(const float* __restrict__ dp, const float*
                                       const float* __restrict__ slope, const float* __restrict__ masks, int moff,
                                       float eval_scale, float* __restrict__ dz, float* __restrict__ dslope, int B, int H,
                                       int W, int C) {
+  // one thread = one pooled pixel x 4 channels: reads dp once, handles its 2x2 window of z / dz
   const float a = *slope;
-  const int Ho = H / 2, Wo = W / 2;
-  const int64_t n = (int64_t)B * H * W * C;
-  double s = 0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % C);
-    int64_t r = i / C;
-    const int x = (int)(r % W);
-    r /= W;
-    const int y = (int)(r % H);
-    const int b = (int)(r / H);
-    const float m = masks ? masks[(int64_t)b * kMaskPerSample + moff + ch] : eval_scale;
-    const float g = dp[(((int64_t)b * Ho + y / 2) * Wo + x / 2) * C + ch] * 0.25f * m;
-    const float v = z[i];
-    if (v > 0.f) {
-      dz[i] = g;
-    } else {
-      dz[i] = a * g;
-      s += (double)g * (double)v;
+  const uint32_t Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const uint32_t n = (uint32_t)B * Ho * Wo * C4;
+  const float4* z4 = reinterpret_cast<const float4*>(z);
+  const float4* dp4 = reinterpret_cast<const float4*>(dp);
+  float4* dz4 = reinterpret_cast<float4*>(dz);
+  float s = 0.f;  // per-thread partial over a handful of elements; summed in double across the block
+  double sd = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t c4 = i % C4;
+    uint32_t r = i / C4;
+    const uint32_t xo = r % Wo;
+    r /= Wo;
+    const uint32_t yo = r % Ho, b = r / Ho;
+    float4 m = make_float4(eval_scale, eval_scale, eval_scale, eval_scale);
+    if (masks) m = *reinterpret_cast<const float4*>(masks + (size_t)b * kMaskPerSample + moff + c4 * 4);
+    const float4 d = dp4[i];
+    const float4 g = make_float4(d.x * 0.25f * m.x, d.y * 0.25f * m.y, d.z * 0.25f * m.z, d.w * 0.25f * m.w);
+    const uint32_t base = ((b * H + 2 * yo) * W + 2 * xo) * C4 + c4, rs = (uint32_t)W * C4;
+    s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t idx = base + (q & 1) * C4 + (q >> 1) * rs;
+      const float4 v = z4[idx];
+      float4 o;
+      o.x = v.x > 0.f ? g.x : a * g.x;
+      o.y = v.y > 0.f ? g.y : a * g.y;
+      o.z = v.z > 0.f ? g.z : a * g.z;
+      o.w = v.w > 0.f ? g.w : a * g.w;
+      if (!(v.x > 0.f)) s = fmaf(g.x, v.x, s);
+      if (!(v.y > 0.f)) s = fmaf(g.y, v.y, s);
+      if (!(v.z > 0.f)) s = fmaf(g.z, v.z, s);
+      if (!(v.w > 0.f)) s = fmaf(g.w, v.w, s);
+      dz4[idx] = o;
     }
+    sd += (double)s;
   }
-  s = block_sum(s);
-  if (threadIdx.x == 0 && dslope) atomicAdd(dslope, (float)s);
+  sd = block_sum(sd);
+  if (threadIdx.x == 0 && dslope) atomicAdd(dslope, (float)sd);
 }
 int k_d_act_pool_bwd(fg_ctx* c, const float* dp, const float* z, const float* slope, const float* masks, int moff,
                      float eval_scale, float* dz, float* dslope, int B, int H, int W, int C) {
-  const int64_t n = (int64_t)B * H * W * C;
+  const int64_t n = (int64_t)B * (H / 2) * (W / 2) * C / 4;
+  if (C % 4 || (moff % 4) || (int64_t)B * H * W * C >= ((int64_t)1 << 31)) {
+    fg_set_error("d_act_pool_bwd: unsupported shape (C %% 4, size)");
+    return FG_ERR_UNSUPPORTED;
+  }
   d_act_pool_bwd_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, c->stream>>>(dp, z, slope, masks, moff, eval_scale, dz, dslope,
                                                                          B, H, W, C);
   LAUNCH_CHECK(c);

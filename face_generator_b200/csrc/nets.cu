@@ -115,6 +115,7 @@ int net_alloc(fg_ctx* c) {
   FG_TRY(dalloc(c, &c->D_L2pd, 512 * 512));
   c->wgrad_ws_elems = 9 * 512 * 256;
   FG_TRY(dalloc(c, &c->wgrad_ws, c->wgrad_ws_elems));
+  FG_TRY(dalloc(c, &c->small_ws, (size_t)kSmallMaxParts * 9 * 4 * 128));
   // G activations
   FG_TRY(dalloc(c, &c->G_noise, B * kNoiseDim));
   FG_TRY(dalloc(c, &c->G_z0, B * 8192));
@@ -182,6 +183,10 @@ int net_alloc(fg_ctx* c) {
       FG_TRY(dalloc(c, &t.D_p_hi[i], n));
       FG_TRY(dalloc(c, &t.D_p_lo[i], n));
     }
+    for (int i = 0; i < 4; ++i) {
+      FG_TRY(dalloc(c, &t.D_Lw_hi[i], i < 2 ? 512 * 2048 : 512 * 512));
+      FG_TRY(dalloc(c, &t.D_Lw_lo[i], i < 2 ? 512 * 2048 : 512 * 512));
+    }
     for (int i = 1; i < 4; ++i) {
       const size_t n = (size_t)9 * kDcout[i] * kDcin[i];
       FG_TRY(dalloc(c, &t.D_Wf_hi[i], n));
@@ -240,6 +245,10 @@ int net_pack_D(fg_ctx* c) {
     fg_ctx::TcBufs& t = c->tcb;
     for (int i = 1; i < 4; ++i)
       FG_TRY(tc_pack_split(c, c->PD + L.cW[i], t.D_Wf_hi[i], t.D_Wf_lo[i], t.D_Wd_hi[i], t.D_Wd_lo[i], kDcout[i], kDcin[i], 9));
+    FG_TRY(tc_split(c, c->D_L1p, t.D_Lw_hi[0], t.D_Lw_lo[0], 512 * 2048));
+    FG_TRY(tc_split(c, c->D_L1pd, t.D_Lw_hi[1], t.D_Lw_lo[1], 512 * 2048));
+    FG_TRY(tc_split(c, c->PD + L.L2W, t.D_Lw_hi[2], t.D_Lw_lo[2], 512 * 512));
+    FG_TRY(tc_split(c, c->D_L2pd, t.D_Lw_hi[3], t.D_Lw_lo[3], 512 * 512));
   }
   c->D_packed = true;
   return FG_OK;
@@ -251,7 +260,8 @@ int net_pack_D(fg_ctx* c) {
 static int conv_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp, const float* bias, float* out,
                     ConvGeom g) {
   ScopedTimer t(c, tag);
-  return k_small_eligible(g) ? k_conv_small(c, in, Wp, bias, out, g) : k_conv_simt(c, in, Wp, bias, out, g);
+  // small OUTPUT channel count -> warp-per-pixel kernel; small INPUT channel count -> flat-K SIMT tiles
+  return (k_small_eligible(g) && g.Cout <= 4) ? k_conv_small(c, in, Wp, bias, out, g) : k_conv_simt(c, in, Wp, bias, out, g);
 }
 static int conv_wgrad(fg_ctx* c, const char* tag, const float* in, const float* dY, ConvGeom g, float* dW, int nA, int nS,
                       int cA, int cS) {
@@ -267,6 +277,17 @@ static inline bool use_tc(const fg_ctx* c, const ConvGeom& g) {
 }
 static inline bool use_tc_wgrad(const fg_ctx* c, const ConvGeom& g) {
   return use_tc(c, g) && g.Cout % 128 == 0 && g.Cin % 64 == 0;
+}
+
+// nn.Linear as a 1x1 convolution on a 1x1 image.  With only B rows the fp32 SIMT tiling leaves the GPU
+// idle (8 CTAs at B=256); the tcgen05 path splits the input on the fly and uses the pre-split weights.
+static int lin_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp, int wi, const float* bias, float* out,
+                   ConvGeom g) {
+  if (!use_tc(c, g)) return conv_fwd(c, tag, in, Wp, bias, out, g);
+  fg_ctx::TcBufs& t = c->tcb;
+  FG_TRY(tc_split(c, in, t.dy_hi, t.dy_lo, (int64_t)g.B * g.Cin));
+  ScopedTimer tm(c, tag);
+  return tc_conv_fwd(c, t.dy_hi, t.dy_lo, t.D_Lw_hi[wi], t.D_Lw_lo[wi], bias, out, g, 0);
 }
 
 // G's two nn.SpatialUpSamplingNearest(2) -> 5x5 convolutions (li = 0: C1, li = 1: C2), forward.
@@ -418,9 +439,9 @@ int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hype
   const float scale = 1.0f / (1.0f - h->p_drop);
   c->D_drop_scale = scale;
   c->D_spatial_eval = 1.0f - h->p_spatial;
-  FG_TRY(conv_fwd(c, "D.L1.fwd", c->D_p[3], c->D_L1p, P + L.L1b, c->D_zl1, ConvGeom{B, 1, 1, 2048, 512, 1, 1}));
+  FG_TRY(lin_fwd(c, "D.L1.fwd", c->D_p[3], c->D_L1p, 0, P + L.L1b, c->D_zl1, ConvGeom{B, 1, 1, 2048, 512, 1, 1}));
   FG_TRY(k_lin_act_drop_fwd(c, c->D_zl1, P + L.a5, masks, 960, scale, c->D_hl1, B, 512));
-  FG_TRY(conv_fwd(c, "D.L2.fwd", c->D_hl1, P + L.L2W, P + L.L2b, c->D_zl2, ConvGeom{B, 1, 1, 512, 512, 1, 1}));
+  FG_TRY(lin_fwd(c, "D.L2.fwd", c->D_hl1, P + L.L2W, 2, P + L.L2b, c->D_zl2, ConvGeom{B, 1, 1, 512, 512, 1, 1}));
   FG_TRY(k_lin_act_drop_fwd(c, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_hl2, B, 512));
   FG_TRY(conv_fwd(c, "D.L3.fwd", c->D_hl2, P + L.L3W, P + L.L3b, c->D_logit, ConvGeom{B, 1, 1, 512, 1, 1, 1}));
   c->D_fwd_valid = true;
@@ -450,7 +471,7 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
     FG_TRY(conv_wgrad(c, "D.L2.wgrad", c->D_hl1, c->D_dzl, ConvGeom{B, 1, 1, 512, 512, 1, 1}, G + L.L2W, 0, 0, 0, 0));
     FG_TRY(k_colsum_add(c, c->D_dzl, G + L.L2b, B, 512, 0, 0));
   }
-  FG_TRY(conv_fwd(c, "D.L2.dgrad", c->D_dzl, c->D_L2pd, nullptr, c->D_dh, ConvGeom{B, 1, 1, 512, 512, 1, 1}));
+  FG_TRY(lin_fwd(c, "D.L2.dgrad", c->D_dzl, c->D_L2pd, 3, nullptr, c->D_dh, ConvGeom{B, 1, 1, 512, 512, 1, 1}));
   FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl1, P + L.a5, masks, 960, scale, c->D_dzl, want_wgrad ? G + L.a5 : nullptr, B,
                             512));
   // L1
@@ -458,7 +479,7 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
     FG_TRY(conv_wgrad(c, "D.L1.wgrad", c->D_p[3], c->D_dzl, ConvGeom{B, 1, 1, 2048, 512, 1, 1}, G + L.L1W, 0, 0, 512, 4));
     FG_TRY(k_colsum_add(c, c->D_dzl, G + L.L1b, B, 512, 0, 0));
   }
-  FG_TRY(conv_fwd(c, "D.L1.dgrad", c->D_dzl, c->D_L1pd, nullptr, c->D_dp, ConvGeom{B, 1, 1, 512, 2048, 1, 1}));
+  FG_TRY(lin_fwd(c, "D.L1.dgrad", c->D_dzl, c->D_L1pd, 1, nullptr, c->D_dp, ConvGeom{B, 1, 1, 512, 2048, 1, 1}));
   static const char* wt[4] = {"D.C1.wgrad", "D.C2.wgrad", "D.C3.wgrad", "D.C4.wgrad"};
   static const char* dt[4] = {"D.C1.dgrad", "D.C2.dgrad", "D.C3.dgrad", "D.C4.dgrad"};
   for (int i = 3; i >= 0; --i) {

@@ -24,7 +24,7 @@ class GradMismatch(AssertionError):
     """A gradient comparison failed.  Forward outputs are continuous in the inputs, but PReLU's derivative is
     not: when two fp32 implementations round a pre-activation of ~1e-7 to different signs the gradient of that
     element changes by (1-a), which at batch 4..16 is visible at the 1e-3 level in the batch-summed gradients
-    (DESIGN.md section 6).  Gradient parity is therefore asserted at 1e-4 on the first seed of a short list whose
+    (DESIGN.md section 5).  Gradient parity is therefore asserted at 1e-4 on the first seed of a short list whose
     branch pattern agrees; forward outputs / losses must match at 1e-4 for EVERY seed."""
 
 
