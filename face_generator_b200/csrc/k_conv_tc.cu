@@ -141,12 +141,13 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
   lo = x - hi;
 }
+template <bool ALIGNED>
 __global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n4) {
   const float4* x4 = reinterpret_cast<const float4*>(x);
   float4* h4 = reinterpret_cast<float4*>(hi);
   float4* l4 = reinterpret_cast<float4*>(lo);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 v = x4[i];
+    const float4 v = ALIGNED ? x4[i] : make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
     float4 h, l;
     split_tf32(v.x, h.x, l.x);
     split_tf32(v.y, h.y, l.y);
@@ -339,7 +340,8 @@ int tc_split(fg_ctx* c, const float* x, float* hi, float* lo, int64_t n) {
   }
   int64_t g = (n / 4 + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  split_kernel<<<(int)g, 256, 0, c->stream>>>(x, hi, lo, n / 4);
+  if (reinterpret_cast<uintptr_t>(x) % 16 == 0) split_kernel<true><<<(int)g, 256, 0, c->stream>>>(x, hi, lo, n / 4);
+  else split_kernel<false><<<(int)g, 256, 0, c->stream>>>(x, hi, lo, n / 4);  // e.g. a weight block inside the flat parameter vector
   LAUNCH_CHECK(c);
   return FG_OK;
 }

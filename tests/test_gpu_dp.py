@@ -1,0 +1,108 @@
+"""Data-parallel parity on real GPUs (needs >= 2 B200s: run under `gpurun --gpus 2`; skipped on one GPU).
+Two processes, one per GPU, NCCL all-reduce inside fg_train_step; checked against the oracle-based DP
+restatement (tests/dp_ref.py) and for replica equality."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_count():
+    try:
+        import subprocess
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
+        return sum(1 for l in out.splitlines() if l.startswith("GPU "))
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, impl, q):
+    import torch.distributed as dist
+    import parity_utils as PU
+    import face_generator_b200 as fg
+    from face_generator_b200.lib import NET_D, NET_G
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, C = 8, 3
+    base = PU.make_case(B, C, seed=700)
+    case = PU.make_case(B, C, seed=701 + rank)
+    ctx = fg.Context(rank, max_batch=B, channels=C)
+    ctx.set_option("conv_impl", impl)
+    # rank 1 starts from garbage on purpose: fg_dp_broadcast_params must overwrite it with rank 0's
+    ctx.set_params(NET_G, base["PG"] if rank == 0 else base["PG"] * 0 + 0.123)
+    ctx.set_params(NET_D, base["PD"] if rank == 0 else base["PD"] * 0 - 0.321)
+    ids = [ctx.dp_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.dp_init(ids[0], world, rank)
+    ctx.dp_broadcast_params()
+    st = ctx.train_step(fg.hyper_default(), B, case["real"], case["noise_D"], case["noise_G"], case["masks_D"], case["masks_G"])
+    q.put((rank, ctx.get_params(NET_D), ctx.get_params(NET_G), ctx.get_grads(NET_D), ctx.get_grads(NET_G), st))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("impl", [0, 2])
+def test_dp_two_gpus_match_oracle_and_each_other(impl):
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import threading
+    import torch.multiprocessing as mp
+    import parity_utils as PU
+    import dp_ref
+    world, port = 2, 29741 + impl
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_worker, args=(r, world, port, impl, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r = q.get(timeout=600)
+        got[r[0]] = r
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    # replicas bit-identical after the step
+    np.testing.assert_array_equal(got[0][1], got[1][1])
+    np.testing.assert_array_equal(got[0][2], got[1][2])
+    np.testing.assert_array_equal(got[0][3], got[1][3])
+    assert got[0][5]["conf"] == got[1][5]["conf"] and sum(got[0][5]["conf"]) == 16  # global confusion counts
+    # oracle emulation of the two ranks
+    B, C = 8, 3
+    base = PU.make_case(B, C, seed=700)
+    cases, states = [], []
+    for r in range(world):
+        cs = PU.make_case(B, C, seed=701 + r)
+        cs["PG"], cs["PD"] = base["PG"], base["PD"]
+        cases.append(cs)
+        states.append(PU.fresh_state(cs))
+    bufs, lock, bar, out = {}, threading.Lock(), threading.Barrier(world), [None, None]
+
+    def make_ar(rank):
+        def ar(a):
+            with lock:
+                bufs[rank] = np.array(a, np.float64)
+            bar.wait()
+            tot = bufs[0] + bufs[1]
+            bar.wait()
+            return tot
+        return ar
+
+    ths = [threading.Thread(target=lambda r=r: out.__setitem__(r, dp_ref.rank_step(cases[r], states[r], B, C, world, make_ar(r))))
+           for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    # gradients after all-reduce + 1/N + penalty + clamp (kink flips possible: 2e-2 bar)
+    assert PU.relerr(got[0][3], out[0]["gradD"]) < 2e-2
+    assert PU.relerr(got[0][4], out[0]["gradG"]) < 2e-2
+    assert abs(got[0][5]["loss_D"] - out[0]["lossD"]) < 1e-4 * max(1, abs(out[0]["lossD"]))
