@@ -79,7 +79,7 @@ struct fg_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   int64_t launches = 0;
-  int conv_impl = FG_CONV_SIMT;
+  int conv_impl = FG_CONV_TC_COLLAPSED;  // default: tcgen05 path; FG_CONV_SIMT is the fp32 FFMA cross-check
   int sm_count = 148;
   GLayout gl;
   DLayout dl;
@@ -216,6 +216,9 @@ int k_sigmoid_grad_mul(fg_ctx* c, const float* dout, const float* out, float* dl
 // optimizer
 int k_penalty_loss(fg_ctx* c, const float* p, int64_t n, float l1, float l2, float* loss_inout);
 int k_gate_and_prep(fg_ctx* c, int net, const fg_hyper* h, const float* tail4, int B, float world);
+int k_gemv_fwd(fg_ctx* c, const float* x, const float* w, const float* bias, float* out, int B, int K);
+int k_gemv_dgrad(fg_ctx* c, const float* dy, const float* w, float* dx, int B, int K);
+int k_gemv_wgrad_add(fg_ctx* c, const float* x, const float* dy, float* dw, float* db, int B, int K);
 int k_adam(fg_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
            float l1_grad, float l2, float clampv, float grad_scale, const float* step_dev, const int* flag_dev,
            float step_host, float* g_out);

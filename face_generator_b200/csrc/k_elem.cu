@@ -876,6 +876,56 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
     }
   }
 }
+// ------------------------------------------------------------------------------------------------
+// nn.Linear(K, 1) (D's last layer, models.lua:412): a GEMV, one warp per batch row
+// ------------------------------------------------------------------------------------------------
+__global__ void gemv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                float* __restrict__ out, int B, int K) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(x[(size_t)row * K + k], w[k], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s + (bias ? bias[0] : 0.f);
+}
+// dx[b][k] = dy[b] * w[k]
+__global__ void gemv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B,
+                                  int K) {
+  const int n = B * K;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dx[i] = dy[i / K] * w[i % K];
+}
+// dw[k] += sum_b dy[b] * x[b][k] ; db[0] += sum_b dy[b]
+__global__ void gemv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                  float* __restrict__ db, int B, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(dy[b], x[(size_t)b * K + k], s);
+    dw[k] += s;
+  }
+  if (k == 0 && db) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dy[b];
+    db[0] += s;
+  }
+}
+int k_gemv_fwd(fg_ctx* c, const float* x, const float* w, const float* bias, float* out, int B, int K) {
+  gemv_fwd_kernel<<<(B * 32 + 255) / 256, 256, 0, c->stream>>>(x, w, bias, out, B, K);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int k_gemv_dgrad(fg_ctx* c, const float* dy, const float* w, float* dx, int B, int K) {
+  gemv_dgrad_kernel<<<grid_for((int64_t)B * K, 256), 256, 0, c->stream>>>(dy, w, dx, B, K);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int k_gemv_wgrad_add(fg_ctx* c, const float* x, const float* dy, float* dw, float* db, int B, int K) {
+  gemv_wgrad_kernel<<<(K + 127) / 128, 128, 0, c->stream>>>(x, dy, dw, db, B, K);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+
 int k_adam(fg_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
            float l1_grad, float l2, float clampv, float grad_scale, const float* step_dev, const int* flag_dev,
            float step_host, float* g_out) {

@@ -443,7 +443,10 @@ int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hype
   FG_TRY(k_lin_act_drop_fwd(c, c->D_zl1, P + L.a5, masks, 960, scale, c->D_hl1, B, 512));
   FG_TRY(lin_fwd(c, "D.L2.fwd", c->D_hl1, P + L.L2W, 2, P + L.L2b, c->D_zl2, ConvGeom{B, 1, 1, 512, 512, 1, 1}));
   FG_TRY(k_lin_act_drop_fwd(c, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_hl2, B, 512));
-  FG_TRY(conv_fwd(c, "D.L3.fwd", c->D_hl2, P + L.L3W, P + L.L3b, c->D_logit, ConvGeom{B, 1, 1, 512, 1, 1, 1}));
+  {
+    ScopedTimer tm(c, "D.L3.fwd");
+    FG_TRY(k_gemv_fwd(c, c->D_hl2, P + L.L3W, P + L.L3b, c->D_logit, B, 512));
+  }
   c->D_fwd_valid = true;
   return FG_OK;
 }
@@ -460,10 +463,13 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
   const float scale = c->D_drop_scale, eval_scale = c->D_spatial_eval;
   // L3
   if (want_wgrad) {
-    FG_TRY(conv_wgrad(c, "D.L3.wgrad", c->D_hl2, dlogit, ConvGeom{B, 1, 1, 512, 1, 1, 1}, G + L.L3W, 0, 0, 0, 0));
-    FG_TRY(k_colsum_add(c, dlogit, G + L.L3b, B, 1, 0, 0));
+    ScopedTimer tm(c, "D.L3.wgrad");
+    FG_TRY(k_gemv_wgrad_add(c, c->D_hl2, dlogit, G + L.L3W, G + L.L3b, B, 512));
   }
-  FG_TRY(conv_fwd(c, "D.L3.dgrad", dlogit, P + L.L3W, nullptr, c->D_dh, ConvGeom{B, 1, 1, 1, 512, 1, 1}));
+  {
+    ScopedTimer tm(c, "D.L3.dgrad");
+    FG_TRY(k_gemv_dgrad(c, dlogit, P + L.L3W, c->D_dh, B, 512));
+  }
   FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_dzl, want_wgrad ? G + L.a6 : nullptr, B,
                             512));
   // L2
