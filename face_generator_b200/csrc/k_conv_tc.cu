@@ -60,6 +60,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -270,6 +277,24 @@ int make_map4(CUtensorMap* m, const float* base, int C, int W, int H, int B, int
   if (r != CUDA_SUCCESS) {
     fg_set_error("cuTensorMapEncodeTiled(4d) failed: %d (C=%d W=%d H=%d B=%d box %d,%d,%d,%d)", (int)r, C, W, H, B, bc, bw,
                  bh, bb);
+    return FG_ERR_CUDA;
+  }
+  return FG_OK;
+}
+// 5-D map for the MN-major wgrad operands: dims (32 ch-in-group, W, H, B, C/32 groups); the box takes `ngroups`
+// channel groups of one 32-pixel box so the tile lands as [group][pixel][32 ch] (SWIZZLE_128B_ATOM_32B)
+int make_map5(CUtensorMap* m, const float* base, int C, int W, int H, int B, int64_t sW, int64_t sH, int64_t sB, int bw,
+              int bh, int bb, int ngroups) {
+  cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(C / 32)};
+  cuuint64_t strides[4] = {(cuuint64_t)sW, (cuuint64_t)sH, (cuuint64_t)sB, 128};
+  cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb, (cuuint32_t)ngroups};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fg_set_error("cuTensorMapEncodeTiled(5d) failed: %d (C=%d W=%d H=%d B=%d box %d,%d,%d x%d)", (int)r, C, W, H, B, bw, bh,
+                 bb, ngroups);
     return FG_ERR_CUDA;
   }
   return FG_OK;
@@ -505,14 +530,15 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
   if (!pick_box(Hl, Wl, 32, &p.bw, &p.bh, &p.bb)) return FG_ERR_UNSUPPORTED;
   {
     const int64_t sW = (int64_t)g.Cin * 4, sH = sW * Wl, sB = sH * Hl;
-    FG_TRY(make_map4(&p.x_hi, x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    FG_TRY(make_map4(&p.x_lo, x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    const int ngx = (g.Cin % 128 == 0 ? 128 : 64) / 32;
+    FG_TRY(make_map5(&p.x_hi, x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, ngx));
+    FG_TRY(make_map5(&p.x_lo, x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, ngx));
   }
   int ntt;
   if (g.ups == 1) {
     const int64_t sW = (int64_t)g.Cout * 4, sH = sW * g.W, sB = sH * g.H;
-    FG_TRY(make_map4(&p.dy_hi[0], dy_hi, g.Cout, g.W, g.H, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-    FG_TRY(make_map4(&p.dy_lo[0], dy_lo, g.Cout, g.W, g.H, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    FG_TRY(make_map5(&p.dy_hi[0], dy_hi, g.Cout, g.W, g.H, g.B, sW, sH, sB, p.bw, p.bh, p.bb, 4));
+    FG_TRY(make_map5(&p.dy_lo[0], dy_lo, g.Cout, g.W, g.H, g.B, sW, sH, sB, p.bw, p.bh, p.bb, 4));
     const int pad = (g.k - 1) / 2;
     ntt = g.k * g.k;
     for (int t = 0; t < ntt; ++t) {
@@ -525,8 +551,8 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
       const int py = ph >> 1, px = ph & 1;
       const int64_t off = ((int64_t)py * g.W + px) * g.Cout;
       const int64_t sW = (int64_t)2 * g.Cout * 4, sH = (int64_t)2 * g.W * g.Cout * 4, sB = (int64_t)g.H * g.W * g.Cout * 4;
-      FG_TRY(make_map4(&p.dy_hi[ph], dy_hi + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-      FG_TRY(make_map4(&p.dy_lo[ph], dy_lo + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+      FG_TRY(make_map5(&p.dy_hi[ph], dy_hi + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, 4));
+      FG_TRY(make_map5(&p.dy_lo[ph], dy_lo + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, 4));
     }
     ntt = 36;
     for (int ph = 0; ph < 4; ++ph)

@@ -19,8 +19,8 @@ __device__ __forceinline__ FwdTile fwd_decode(const TcFwdParams& p, int tile) {
   FwdTile t;
   const int mt = tile / ntn;
   t.n0 = (tile - mt * ntn) * BN;  // n fastest: CTAs running together share the activation tile in L2
-  t.ph = mt / p.tiles_per_phase;
-  int r = mt - t.ph * p.tiles_per_phase;
+  int r = mt / p.nphase;  // the 4 output phases of one pixel tile run back to back: they share the input boxes in L2
+  t.ph = mt - r * p.nphase;
   if (p.bb == 1) {
     const int per_img = p.tiles_x * p.tiles_y;
     t.b0 = r / per_img;
@@ -43,13 +43,16 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   constexpr uint32_t kBBytes = BN * 128;
   constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
   constexpr uint32_t kIdesc = make_idesc(128, BN, 0, 0);
+  // accumulator ring in TMEM: 4 buffers so the MMA warp can run 4 chunks ahead of the epilogue warps while
+  // those write a finished tile to global memory (with 2 buffers ~12k cycles/tile were lost waiting there)
+  constexpr uint32_t kAcc = 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty = full + kStages;
-  uint64_t* tmem_full = empty + kStages;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_full = empty + kStages;      // [kAcc]
+  uint64_t* tmem_empty = tmem_full + kAcc;    // [kAcc]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAcc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.ntaps * p.kpt;
@@ -61,13 +64,13 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < (int)kAcc; ++i) {
       mbar_init(tmem_full + i, 1);
       mbar_init(tmem_empty + i, 4);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<kAcc * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
       uint32_t kbg = 0, cg = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int ch = 0; ch < nchunks; ++ch, ++cg) {
-          const uint32_t buf = cg & 1, use = cg >> 1;
+          const uint32_t buf = cg % kAcc, use = cg / kAcc;
           if (use > 0) mbar_wait(tmem_empty + buf, (use - 1) & 1);
           tc_fence_after();
           const uint32_t tacc = tmem_base + buf * BN;
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
 #pragma unroll
       for (int i = 0; i < BN; ++i) acc[i] = 0.f;
       for (int ch = 0; ch < nchunks; ++ch, ++cg) {
-        const uint32_t buf = cg & 1, use = cg >> 1;
+        const uint32_t buf = cg % kAcc, use = cg / kAcc;
         mbar_wait(tmem_full + buf, use & 1);
         tc_fence_after();
 #pragma unroll
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<kAcc * BN>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -245,16 +248,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           }
           uint8_t* st = smem + s * kStageBytes;
           mbar_expect_tx(full + s, kStageBytes);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            tma_load_4d(st + g * kBox, &p.dy_hi[ph], full + s, m0 + g * 32, x0, y0, b0);
-            tma_load_4d(st + kAB + g * kBox, &p.dy_lo[ph], full + s, m0 + g * 32, x0, y0, b0);
-          }
-#pragma unroll
-          for (int g = 0; g < BN / 32; ++g) {
-            tma_load_4d(st + 2 * kAB + g * kBox, &p.x_hi, full + s, c0 + g * 32, x0 + dxo, y0 + dyo, b0);
-            tma_load_4d(st + 2 * kAB + kBB + g * kBox, &p.x_lo, full + s, c0 + g * 32, x0 + dxo, y0 + dyo, b0);
-          }
+          // 5-D maps (32 ch, w, h, b, channel-group): ONE bulk copy lands [group][pixel][32 ch] = all the 4 KB
+          // boxes of an operand (16 single-box copies per stage made the kernel TMA-issue bound)
+          tma_load_5d(st, &p.dy_hi[ph], full + s, 0, x0, y0, b0, m0 / 32);
+          tma_load_5d(st + kAB, &p.dy_lo[ph], full + s, 0, x0, y0, b0, m0 / 32);
+          tma_load_5d(st + 2 * kAB, &p.x_hi, full + s, 0, x0 + dxo, y0 + dyo, b0, c0 / 32);
+          tma_load_5d(st + 2 * kAB + kBB, &p.x_lo, full + s, 0, x0 + dxo, y0 + dyo, b0, c0 / 32);
         }
       }
     } else if (warp == 1) {
