@@ -147,17 +147,27 @@ __global__ void __launch_bounds__(128) wgrad_smallbig_kernel(const float* __rest
 #pragma unroll
     for (int c = 0; c < CS; ++c) dst[(t * CS + c) * Cb + cb] = acc[t][c];
 }
-// out (overwritten) = sum over partial rows, mapped to the packed [t][n][c] layout
+// out (zeroed by the caller) += sum over a slice of the partial rows, mapped to the packed [t][n][c] layout.
+// grid.y slices the partial rows so the loads are not one long dependent chain per thread.
 __global__ void wgrad_small_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int CS, int Cb,
                                           int sign, int transposed) {
   const int total = 9 * CS * Cb;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= total) return;
-  float s = 0.f;
-  for (int i = 0; i < nparts; ++i) s += part[(size_t)i * total + j];
+  const int per = (nparts + gridDim.y - 1) / gridDim.y;
+  const int i0 = blockIdx.y * per, i1 = min(nparts, i0 + per);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = i0;
+  for (; i + 3 < i1; i += 4) {
+    s0 += part[(size_t)i * total + j];
+    s1 += part[(size_t)(i + 1) * total + j];
+    s2 += part[(size_t)(i + 2) * total + j];
+    s3 += part[(size_t)(i + 3) * total + j];
+  }
+  for (; i < i1; ++i) s0 += part[(size_t)i * total + j];
   const int idx = j / (CS * Cb), cs = (j / Cb) % CS, cb = j % Cb;
   const int t = sign > 0 ? idx : 8 - idx;
-  out[transposed ? ((size_t)t * Cb + cb) * CS + cs : ((size_t)t * CS + cs) * Cb + cb] = s;
+  atomicAdd(out + (transposed ? ((size_t)t * Cb + cb) * CS + cs : ((size_t)t * CS + cs) * Cb + cb), (s0 + s1) + (s2 + s3));
 }
 }  // namespace
 
@@ -224,8 +234,9 @@ int k_wgrad_small(fg_ctx* c, const float* in, const float* dY, float* dWp, ConvG
 #undef WG
   LAUNCH_CHECK(c);
   const int total = 9 * Cs * Cb;
-  wgrad_small_reduce_kernel<<<(total + 127) / 128, 128, 0, c->stream>>>(c->small_ws, dWp, nblocks * lanes, Cs, Cb, sign,
-                                                                        transposed);
+  FG_CUDA(cudaMemsetAsync(dWp, 0, sizeof(float) * total, c->stream));
+  wgrad_small_reduce_kernel<<<dim3((total + 127) / 128, 32), 128, 0, c->stream>>>(c->small_ws, dWp, nblocks * lanes, Cs, Cb,
+                                                                                sign, transposed);
   LAUNCH_CHECK(c);
   return FG_OK;
 }

@@ -119,6 +119,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// two 32x32 loads in flight, one wait: halves the exposed TMEM-load latency of the promotion loop
+__device__ __forceinline__ void tmem_ld_32x32_x2(uint32_t taddr_a, uint32_t taddr_b, uint32_t* a, uint32_t* b) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31]),
+        "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]), "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]), "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
+      : "r"(taddr_a), "r"(taddr_b)
+      : "memory");
+}
+
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout, version 1 = Blackwell):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout = 2) {
@@ -465,6 +477,7 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   p.out_H = g.H; p.out_W = g.W;
   p.out_scale = g.ups;
   p.ntiles = p.tiles_per_phase * p.nphase * (g.Cout / BN);
+  p.dbg = getenv("FG_TC_DBG") ? atoi(getenv("FG_TC_DBG")) : 0;
   dim3 grid(std::min(p.ntiles, c->sm_count));
   if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
   else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
@@ -513,6 +526,7 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
   p.out_H = Hl; p.out_W = Wl;
   p.out_scale = 1;
   p.ntiles = p.tiles_per_phase * (g.Cin / BN);
+  p.dbg = getenv("FG_TC_DBG") ? atoi(getenv("FG_TC_DBG")) : 0;
   dim3 grid(std::min(p.ntiles, c->sm_count));
   if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
   else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);

@@ -20,6 +20,7 @@ struct alignas(64) TcFwdParams {
   float* out;
   const float* bias;
   int out_H, out_W, out_scale;
+  int dbg;  // experiment switches (FG_TC_DBG): 1 = skip MMAs, 2 = skip TMA data movement
 };
 
 struct alignas(64) TcWgParams {

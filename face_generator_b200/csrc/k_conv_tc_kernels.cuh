@@ -8,7 +8,7 @@
 // while the epilogue stores tile i the MMA warp is already issuing tile i+1.
 #pragma once
 
-constexpr int kChunk = 4;  // K-blocks accumulated in the tensor core before promotion to registers
+constexpr int kChunk = 8;  // K-blocks accumulated in the tensor core before promotion to registers
 
 struct FwdTile {
   int ph, b0, y0, x0, n0;
@@ -90,6 +90,10 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
           const int ti = t.ph * p.ntaps + tap;
           const int am = p.amap[ti];
           uint8_t* st = smem + s * kStageBytes;
+          if (p.dbg & 2) {  // experiment: no data movement, only the barrier protocol
+            mbar_arrive(full + s);
+            continue;
+          }
           mbar_expect_tx(full + s, kStageBytes);
           tma_load_4d(st, &p.a_hi[am], full + s, c0, t.x0 + p.dx[ti], t.y0 + p.dy[ti], t.b0);
           tma_load_4d(st + kABytes, &p.a_lo[am], full + s, c0, t.x0 + p.dx[ti], t.y0 + p.dy[ti], t.b0);
@@ -117,12 +121,14 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
             const uint64_t a_hi = make_desc(sa, 16, 1024), a_lo = make_desc(sa + kABytes, 16, 1024);
             const uint64_t b_hi = make_desc(sa + 2 * kABytes, 16, 1024),
                            b_lo = make_desc(sa + 2 * kABytes + kBBytes, 16, 1024);
+            if (!(p.dbg & 1)) {  // (dbg bit 0: experiment without MMAs)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 fp32 of K) in the 16B-unit start-address field
-              umma_tf32(tacc, a_lo + ko, b_hi + ko, kIdesc, (j | k) != 0);
-              umma_tf32(tacc, a_hi + ko, b_lo + ko, kIdesc, 1);
-              umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, 1);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 fp32 of K) in the 16B-unit start-address field
+                umma_tf32(tacc, a_lo + ko, b_hi + ko, kIdesc, (j | k) != 0);
+                umma_tf32(tacc, a_hi + ko, b_lo + ko, kIdesc, 1);
+                umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, 1);
+              }
             }
             umma_commit(empty + s);
           }
@@ -146,11 +152,15 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
         mbar_wait(tmem_full + buf, use & 1);
         tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32), v);
+        for (int j = 0; j < BN / 32; j += 2) {
+          uint32_t va[32], vb[32];
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32);
+          tmem_ld_32x32_x2(ta, ta + 32, va, vb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i) {
+            acc[j * 32 + i] += __uint_as_float(va[i]);
+            acc[j * 32 + 32 + i] += __uint_as_float(vb[i]);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -299,11 +309,15 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         mbar_wait(tmem_full + buf, use & 1);
         tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32), v);
+        for (int j = 0; j < BN / 32; j += 2) {
+          uint32_t va[32], vb[32];
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32);
+          tmem_ld_32x32_x2(ta, ta + 32, va, vb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i) {
+            acc[j * 32 + i] += __uint_as_float(va[i]);
+            acc[j * 32 + 32 + i] += __uint_as_float(vb[i]);
+          }
         }
         tc_fence_before();
         __syncwarp();
