@@ -42,10 +42,10 @@ template <int BN>
 __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constant__ TcFwdParams p) {
   constexpr uint32_t kBBytes = BN * 128;
   constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
-  constexpr uint32_t kIdesc = make_idesc(128, BN, 0, 0);
+  constexpr uint32_t kIdesc = make_idesc(128, BN, 0, 0), kIdesc2 = make_idesc(128, 2 * BN, 0, 0);
   // accumulator ring in TMEM: 4 buffers so the MMA warp can run 4 chunks ahead of the epilogue warps while
   // those write a finished tile to global memory (with 2 buffers ~12k cycles/tile were lost waiting there)
-  constexpr uint32_t kAcc = 4;
+  constexpr uint32_t kAcc = 256 / BN;  // 2 x (2*BN columns) for BN = 128, 4 for BN = 64: always all 512 TMEM columns
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<kAcc * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<kAcc * 2 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
           const uint32_t buf = cg % kAcc, use = cg / kAcc;
           if (use > 0) mbar_wait(tmem_empty + buf, (use - 1) & 1);
           tc_fence_after();
-          const uint32_t tacc = tmem_base + buf * BN;
+          const uint32_t tacc = tmem_base + buf * 2 * BN;
           const int nk = min(kChunk, nkb - ch * kChunk);
           for (int j = 0; j < nk; ++j, ++kbg) {
             const uint32_t s = kbg % kStages, it = kbg / kStages;
@@ -125,9 +125,11 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 fp32 of K) in the 16B-unit start-address field
-                umma_tf32(tacc, a_lo + ko, b_hi + ko, kIdesc, (j | k) != 0);
-                umma_tf32(tacc, a_hi + ko, b_lo + ko, kIdesc, 1);
-                umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, 1);
+                // [b_hi | b_lo] are adjacent in the stage, so ONE N = 2*BN instruction computes a_hi*b_hi -> columns
+                // [0,BN) and a_hi*b_lo -> [BN,2BN): the tensor core's operand fetch from shared memory (the binding
+                // resource of 128x128 tf32 tiles) drops from 24 KB to 20 KB per K step; the epilogue adds the halves
+                umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc2, (j | k) != 0);
+                umma_tf32(tacc, a_lo + ko, b_hi + ko, kIdesc, 1);
               }
             }
             umma_commit(empty + s);
@@ -152,15 +154,12 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
         mbar_wait(tmem_full + buf, use & 1);
         tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < BN / 32; j += 2) {
+        for (int j = 0; j < BN / 32; ++j) {
           uint32_t va[32], vb[32];
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32);
-          tmem_ld_32x32_x2(ta, ta + 32, va, vb);
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * BN + (uint32_t)(j * 32);
+          tmem_ld_32x32_x2(ta, ta + BN, va, vb);  // same 32 outputs: hi*hi + lo*hi block and hi*lo block
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            acc[j * 32 + i] += __uint_as_float(va[i]);
-            acc[j * 32 + 32 + i] += __uint_as_float(vb[i]);
-          }
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(va[i]) + __uint_as_float(vb[i]);
         }
         tc_fence_before();
         __syncwarp();
@@ -188,7 +187,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<kAcc * BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<kAcc * 2 * BN>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   constexpr uint32_t kAB = 4 * kBox;   // M = 128 channels of dY
   constexpr uint32_t kBB = (BN / 32) * kBox;
   constexpr uint32_t kStageBytes = 2 * kAB + 2 * kBB;
-  constexpr uint32_t kIdesc = make_idesc(128, BN, 1, 1);
+  constexpr uint32_t kIdesc = make_idesc(128, BN, 1, 1), kIdesc2 = make_idesc(128, 2 * BN, 1, 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -230,7 +229,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<4 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -273,7 +272,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           const uint32_t buf = ch & 1, use = ch >> 1;
           if (use > 0) mbar_wait(tmem_empty + buf, (use - 1) & 1);
           tc_fence_after();
-          const uint32_t tacc = tmem_base + buf * BN;
+          const uint32_t tacc = tmem_base + buf * 2 * BN;
           const int nk = min(kChunk, nkb - ch * kChunk);
           for (int j = 0; j < nk; ++j, ++i) {
             const int s = i % kStages, it = i / kStages;
@@ -289,9 +288,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t ko = (uint64_t)(k * 64);  // +1024 bytes = next 8 pixels
-              umma_tf32(tacc, a_lo + ko, b_hi + ko, kIdesc, (j | k) != 0);
-              umma_tf32(tacc, a_hi + ko, b_lo + ko, kIdesc, 1);
-              umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, 1);
+              umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc2, (j | k) != 0);  // x_hi | x_lo groups are adjacent
+              umma_tf32(tacc, a_lo + ko, b_hi + ko, kIdesc, 1);
             }
             umma_commit(empty + s);
           }
@@ -309,15 +307,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         mbar_wait(tmem_full + buf, use & 1);
         tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < BN / 32; j += 2) {
+        for (int j = 0; j < BN / 32; ++j) {
           uint32_t va[32], vb[32];
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32);
-          tmem_ld_32x32_x2(ta, ta + 32, va, vb);
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * BN + (uint32_t)(j * 32);
+          tmem_ld_32x32_x2(ta, ta + BN, va, vb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            acc[j * 32 + i] += __uint_as_float(va[i]);
-            acc[j * 32 + 32 + i] += __uint_as_float(vb[i]);
-          }
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(va[i]) + __uint_as_float(vb[i]);
         }
         tc_fence_before();
         __syncwarp();
@@ -330,5 +325,5 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<4 * BN>(tmem_base);
 }

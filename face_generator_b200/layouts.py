@@ -41,7 +41,7 @@ def reference_init(layout_total, rng):
     return P
 
 
-def trained_like_init(layout_total, rng, gain=1.0):
+def trained_like_init(layout_total, rng, gain=1.0, slope=0.25):
     """Non-degenerate synthetic weights (fan-in scaled, gamma~U(0.5,1.5), slopes 0.25) so activations,
     BatchNorm statistics and gradients look like a network in training."""
     layout, total = layout_total
@@ -49,7 +49,7 @@ def trained_like_init(layout_total, rng, gain=1.0):
     for k, (o, s) in layout.items():
         n = int(np.prod(s))
         if k[0] == "a":
-            P[o:o + n] = 0.25
+            P[o:o + n] = slope
         elif k in ("g1", "g2"):
             P[o:o + n] = rng.uniform(0.5, 1.5, n)
         elif k.endswith("W"):

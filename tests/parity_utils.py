@@ -23,8 +23,12 @@ def make_masks(B, rng):
 
 def make_case(B, C, seed, init="trained"):
     rng = np.random.default_rng(seed)
-    if init == "trained":
-        PG, PD = LY.trained_like_init(LY.G_layout(C), rng), LY.trained_like_init(LY.D_layout(C), rng, 1.4)
+    if init in ("trained", "smooth"):
+        # "smooth": all PReLU slopes = 1 (identity) -> the loss is differentiable everywhere, so gradients can be
+        # compared strictly; with real slopes a pre-activation within fp32 noise of 0 may take the other branch
+        sl = 1.0 if init == "smooth" else 0.25
+        PG = LY.trained_like_init(LY.G_layout(C), rng, slope=sl)
+        PD = LY.trained_like_init(LY.D_layout(C), rng, 1.4, slope=sl)
     else:  # the reference's own init: N(0, 0.005^2) weights (incl. BN gamma, PReLU slope), N(0, 0.001^2) biases
         PG, PD = LY.reference_init(LY.G_layout(C), rng), LY.reference_init(LY.D_layout(C), rng)
     f = lambda a: np.ascontiguousarray(a, np.float32)
