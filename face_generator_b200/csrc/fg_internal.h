@@ -183,6 +183,10 @@ int k_prelu_fwd(fg_ctx* c, const float* z, const float* slope, float* h, int64_t
 int k_prelu_bwd(fg_ctx* c, const float* dh, const float* z, const float* slope, float* dz, float* dslope, int B, int H,
                 int W, int C, int pool);
 int k_bn_stats(fg_ctx* c, const float* z, double* acc2C, int64_t P, int C);
+bool k_bn4_ok(int C);  // k_bn.cu: float4, multi-row versions of the two BatchNorm reductions
+int k_bn_stats4(fg_ctx* c, const float* z, double* acc, int64_t P, int C);
+int k_bn_bwd_reduce4(fg_ctx* c, const float* dh, const float* z, const float* mean, const float* istd, const float* gamma,
+                     const float* beta, const float* slope, double* acc, float* dslope, int64_t P, int C);
 int k_bn_finalize(fg_ctx* c, double* acc2C, float* mean, float* istd, float* run_mean, float* run_var, int64_t P,
                   int C);
 int k_bn_eval_prep(fg_ctx* c, const float* run_mean, const float* run_var, float* mean, float* istd, int C);

@@ -404,6 +404,16 @@ int tc_combine_collapsed_wgrad(fg_ctx* c, const float* G, float* dW, int N, int 
   return FG_OK;
 }
 
+static int tc_chunk() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FG_TC_CHUNK");
+    v = e ? atoi(e) : 4;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
 bool tc_conv_eligible(const ConvGeom& g) {
   int bw, bh, bb;
   const int Hl = g.H / g.ups, Wl = g.W / g.ups;
@@ -478,6 +488,7 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   p.out_scale = g.ups;
   p.ntiles = p.tiles_per_phase * p.nphase * (g.Cout / BN);
   p.dbg = getenv("FG_TC_DBG") ? atoi(getenv("FG_TC_DBG")) : 0;
+  p.chunk = tc_chunk();
   dim3 grid(std::min(p.ntiles, c->sm_count));
   if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
   else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
@@ -527,6 +538,7 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
   p.out_scale = 1;
   p.ntiles = p.tiles_per_phase * (g.Cin / BN);
   p.dbg = getenv("FG_TC_DBG") ? atoi(getenv("FG_TC_DBG")) : 0;
+  p.chunk = tc_chunk();
   dim3 grid(std::min(p.ntiles, c->sm_count));
   if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
   else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
@@ -588,6 +600,7 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
   p.kb_per_split = (p.kblocks + splits - 1) / splits;
   splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
   p.out = out;
+  p.chunk = tc_chunk();
   FG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)ntt * g.Cout * g.Cin, c->stream));
   dim3 grid(ntt, (g.Cout / 128) * (g.Cin / BN), splits);
   if (BN == 128) wgrad_tc_kernel<128><<<grid, 192, wg_smem<128>(), c->stream>>>(p);

@@ -20,7 +20,8 @@ struct alignas(64) TcFwdParams {
   float* out;
   const float* bias;
   int out_H, out_W, out_scale;
-  int dbg;  // experiment switches (FG_TC_DBG): 1 = skip MMAs, 2 = skip TMA data movement
+  int dbg;    // experiment switches (FG_TC_DBG): 1 = skip MMAs, 2 = skip TMA data movement
+  int chunk;  // K-blocks accumulated in TMEM before the epilogue promotes them to fp32 registers
 };
 
 struct alignas(64) TcWgParams {
@@ -32,6 +33,7 @@ struct alignas(64) TcWgParams {
   int tiles_x, tiles_y;
   int kblocks, kb_per_split;
   float* out;
+  int chunk;
 };
 
 bool tc_conv_eligible(const ConvGeom& g);

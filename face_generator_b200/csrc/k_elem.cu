@@ -255,6 +255,7 @@ static inline int bn_block(int C) {
   return C * lanes;
 }
 int k_bn_stats(fg_ctx* c, const float* z, double* acc, int64_t P, int C) {
+  if (k_bn4_ok(C)) return k_bn_stats4(c, z, acc, P, C);  // float4 / multi-row version (k_bn.cu)
   if (C > 1024) {
     fg_set_error("BatchNorm with C=%d > 1024 unsupported", C);
     return FG_ERR_UNSUPPORTED;
@@ -412,6 +413,8 @@ __global__ void bn_prelu_bwd_reduce_kernel(const float* __restrict__ dh, const f
 int k_bn_prelu_bwd_reduce(fg_ctx* c, const float* dh, const float* z, const float* mean, const float* istd,
                           const float* gamma, const float* beta, const float* slope, double* acc, float* dslope, int B,
                           int H, int W, int C, int pool) {
+  if (!pool && k_bn4_ok(C))
+    return k_bn_bwd_reduce4(c, dh, z, mean, istd, gamma, beta, slope, acc, dslope, (int64_t)B * H * W, C);
   if (C > 1024) return FG_ERR_UNSUPPORTED;
   FG_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, c->stream));
   const int64_t P = (int64_t)B * H * W;
