@@ -27,48 +27,65 @@ __global__ void __launch_bounds__(256) conv_smalln_kernel(const float* __restric
   __shared__ __align__(16) float ws[9 * NS * C];  // [t][n][c]
   for (int i = threadIdx.x; i < 9 * NS * C; i += blockDim.x) ws[i] = Wp[i];
   __syncthreads();
+  // A warp walks a run of RL = 8 pixels of one image row with a 3-column sliding window in registers:
+  // 3 new vector loads per pixel instead of 9 (the 3x3 neighbourhoods of adjacent pixels overlap 6/9).
+  constexpr int RL = 8;
   const int lane = threadIdx.x & 31;
-  const uint32_t P = (uint32_t)B * H * W;
+  const uint32_t runs_per_row = (uint32_t)W / RL;
+  const uint32_t nruns = (uint32_t)B * H * runs_per_row;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < P; p += warps) {
-    const int x = (int)(p % (uint32_t)W);
-    const int y = (int)((p / (uint32_t)W) % (uint32_t)H);
-    const float* base = in + (size_t)p * C + lane * VEC;
-    float v[9][VEC];
+  for (uint32_t run = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; run < nruns; run += warps) {
+    const int x0 = (int)(run % runs_per_row) * RL;
+    const uint32_t row = run / runs_per_row;  // b*H + y
+    const int y = (int)(row % (uint32_t)H);
+    const float* rowbase = in + (size_t)row * W * C + lane * VEC;
+    float col[3][3][VEC];  // [column slot][dy][vec]
+    auto load_col = [&](int slot, int xx) {
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int dy = t / 3 - 1, dx = t % 3 - 1;
-      const bool ok = (unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W;
-      const float* ip = base + (dy * W + dx) * C;
-      if (VEC == 4) {
-        const float4 q = ok ? *reinterpret_cast<const float4*>(ip) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[t][0] = q.x; v[t][1 % VEC] = q.y; v[t][2 % VEC] = q.z; v[t][3 % VEC] = q.w;
-      } else if (VEC == 2) {
-        const float2 q = ok ? *reinterpret_cast<const float2*>(ip) : make_float2(0.f, 0.f);
-        v[t][0] = q.x; v[t][1 % VEC] = q.y;
-      } else {
-        v[t][0] = ok ? ip[0] : 0.f;
+      for (int dy = 0; dy < 3; ++dy) {
+        const bool ok = (unsigned)(y + dy - 1) < (unsigned)H && (unsigned)xx < (unsigned)W;
+        const float* ip = rowbase + ((dy - 1) * W + xx) * C;
+        if (VEC == 4) {
+          const float4 q = ok ? *reinterpret_cast<const float4*>(ip) : make_float4(0.f, 0.f, 0.f, 0.f);
+          col[slot][dy][0] = q.x; col[slot][dy][1 % VEC] = q.y; col[slot][dy][2 % VEC] = q.z; col[slot][dy][3 % VEC] = q.w;
+        } else if (VEC == 2) {
+          const float2 q = ok ? *reinterpret_cast<const float2*>(ip) : make_float2(0.f, 0.f);
+          col[slot][dy][0] = q.x; col[slot][dy][1 % VEC] = q.y;
+        } else {
+          col[slot][dy][0] = ok ? ip[0] : 0.f;
+        }
       }
-    }
-    float acc[NS];
+    };
+    load_col(0, x0 - 1);
+    load_col(1, x0);
 #pragma unroll
-    for (int n = 0; n < NS; ++n) acc[n] = 0.f;
+    for (int i = 0; i < RL; ++i) {
+      load_col((i + 2) % 3, x0 + i + 1);
+      float acc[NS];
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+      for (int n = 0; n < NS; ++n) acc[n] = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int t = dy * 3 + dx, slot = (i + dx) % 3;
+#pragma unroll
+          for (int n = 0; n < NS; ++n) {
+            const float* wp = ws + (t * NS + n) * C + lane * VEC;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[n] = fmaf(col[slot][dy][j], wp[j], acc[n]);
+          }
+        }
 #pragma unroll
       for (int n = 0; n < NS; ++n) {
-        const float* wp = ws + (t * NS + n) * C + lane * VEC;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[n] = fmaf(v[t][j], wp[j], acc[n]);
+        for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
       }
+      if (lane == 0) {
+        float* op = out + ((size_t)row * W + x0 + i) * NS;
 #pragma unroll
-    for (int n = 0; n < NS; ++n) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int n = 0; n < NS; ++n) out[(size_t)p * NS + n] = acc[n] + (bias ? bias[n] : 0.f);
+        for (int n = 0; n < NS; ++n) op[n] = acc[n] + (bias ? bias[n] : 0.f);
+      }
     }
   }
 }
@@ -186,7 +203,11 @@ int k_conv_small(fg_ctx* c, const float* in, const float* Wp, const float* bias,
     fg_set_error("k_conv_small: expects Cout <= 4");
     return FG_ERR_UNSUPPORTED;
   }
-  int grid = (int)std::min<int64_t>((P + 7) / 8, c->sm_count * 8);
+  if (g.W % 8) {
+    fg_set_error("k_conv_small: W must be a multiple of 8");
+    return FG_ERR_UNSUPPORTED;
+  }
+  int grid = (int)std::min<int64_t>((P / 8 * 32 + 255) / 256, c->sm_count * 8);  // one warp per run of 8 pixels
 #define SN(NS_, VEC_) conv_smalln_kernel<NS_, VEC_><<<grid, 256, 0, c->stream>>>(in, Wp, bias, out, g.B, g.H, g.W)
   const int vec = g.Cin / 32;
   if (vec == 4) {

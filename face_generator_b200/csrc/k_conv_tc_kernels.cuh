@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
                 // [0,BN) and a_hi*b_lo -> [BN,2BN): the tensor core's operand fetch from shared memory (the binding
                 // resource of 128x128 tf32 tiles) drops from 24 KB to 20 KB per K step; the epilogue adds the halves
                 umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc2, (j | k) != 0);
-                umma_tf32(tacc, a_lo + ko, b_hi + ko, kIdesc, 1);
+                // the two small cross terms share the SECOND column block, so the first one only ever accumulates
+                // hi*hi: half as many truncating accumulations on the block that carries the magnitude
+                umma_tf32(tacc + BN, a_lo + ko, b_hi + ko, kIdesc, 1);
               }
             }
             umma_commit(empty + s);
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
             for (int k = 0; k < 4; ++k) {
               const uint64_t ko = (uint64_t)(k * 64);  // +1024 bytes = next 8 pixels
               umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc2, (j | k) != 0);  // x_hi | x_lo groups are adjacent
-              umma_tf32(tacc, a_lo + ko, b_hi + ko, kIdesc, 1);
+              umma_tf32(tacc + BN, a_lo + ko, b_hi + ko, kIdesc, 1);  // cross terms share the second block
             }
             umma_commit(empty + s);
           }

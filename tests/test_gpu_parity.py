@@ -68,7 +68,10 @@ def check_grads(layout, got, ref, skip=(), tol=TOL):
             continue
         e = np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
         worst = max(worst, e)
-        gcheck(e < (max(tol, KINK_TOL) if _kinked[0] else tol), "%s: relerr %.3e" % (k, e))
+        # the ONE shared PReLU slope per layer has a gradient that is a sum of ~1e6 terms with heavy cancellation:
+        # its conditioning amplifies rounding by ~100x, so it gets a 3e-4 bar (everything else: 1e-4)
+        t = 3 * tol if (k[0] == "a" and k[1:].isdigit()) else tol
+        gcheck(e < (max(t, KINK_TOL) if _kinked[0] else t), "%s: relerr %.3e" % (k, e))
     return worst
 
 
@@ -146,8 +149,7 @@ def _D_forward_backward(fg, C, B, impl, seed, init="trained"):
     assert PU.relerr(ctx.D_forward(img, training=False), ref_eval) < TOL
     ctx.close()
     # the shared PReLU slopes' gradients are sums with heavy cancellation: 3e-4 bar
-    check_grads({k: v for k, v in O.D_layout(C).items() if not k.startswith("a")}, gD, ref_dP)
-    check_grads({k: v for k, v in O.D_layout(C).items() if k.startswith("a")}, gD, ref_dP, tol=3e-4)
+    check_grads(O.D_layout(C), gD, ref_dP)
     gcheck(PU.relerr(dimg, ref_dimg) < (KINK_TOL if _kinked[0] else TOL), "dimg")
 
 
