@@ -90,6 +90,46 @@ __global__ void __launch_bounds__(256) conv_smalln_kernel(const float* __restric
   }
 }
 
+// ---- small contraction: out[p][n] = bias[n] + sum_{t,c<CS} in[pix(p,t)][c] * Wp[t][n][c]  (D.C1 fwd, G.C3 dgrad)
+// one thread per (pixel, 4 consecutive output channels): the 9*CS inputs of a pixel are broadcast loads shared by
+// the N/4 threads of that pixel, the weights come from shared memory as float4, the output is one float4 store.
+template <int CS>
+__global__ void __launch_bounds__(256) conv_smallk4_kernel(const float* __restrict__ in, const float* __restrict__ Wp,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                           int H, int W, int N) {
+  __shared__ __align__(16) float ws[9 * CS * 128];  // [t][c][n]
+  for (int i = threadIdx.x; i < 9 * CS * N; i += blockDim.x) {
+    const int n = i % N, c = (i / N) % CS, t = i / (N * CS);
+    ws[i] = Wp[((size_t)t * N + n) * CS + c];
+  }
+  __syncthreads();
+  const uint32_t N4 = (uint32_t)N >> 2;
+  const uint32_t total = (uint32_t)B * H * W * N4;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t n4 = i % N4, p = i / N4;
+    const int x = (int)(p % (uint32_t)W), y = (int)((p / (uint32_t)W) % (uint32_t)H);
+    float4 acc = bias ? make_float4(bias[n4 * 4], bias[n4 * 4 + 1], bias[n4 * 4 + 2], bias[n4 * 4 + 3])
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* base = in + (size_t)p * CS;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3 - 1, dx = t % 3 - 1;
+      if ((unsigned)(y + dy) >= (unsigned)H || (unsigned)(x + dx) >= (unsigned)W) continue;
+      const float* ip = base + (dy * W + dx) * CS;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) {
+        const float v = __ldg(ip + c);
+        const float4 w = *reinterpret_cast<const float4*>(ws + (t * CS + c) * N + n4 * 4);
+        acc.x = fmaf(v, w.x, acc.x);
+        acc.y = fmaf(v, w.y, acc.y);
+        acc.z = fmaf(v, w.z, acc.z);
+        acc.w = fmaf(v, w.w, acc.w);
+      }
+    }
+    *reinterpret_cast<float4*>(out + (size_t)i * 4) = acc;
+  }
+}
+
 // ---- weight gradient with one small and one big side ----------------------------------------------------
 //   G.C3:  dW[n<Cs][c][t] = sum_p dY[p][n] * X[p+off_t][c]      big = X  (Cb = 128), small = dY, sign = -1
 //   D.C1:  dW[n][c<Cs][t] = sum_p dY[p][n] * X[p+off_t][c]      big = dY (Cb = 64),  small = X,  sign = +1
@@ -196,9 +236,22 @@ bool k_small_eligible(const ConvGeom& g) {
          (int64_t)g.B * g.H * g.W * cb < ((int64_t)1 << 31);
 }
 
-// forward-type conv with a small OUTPUT channel count (also D.C1's dgrad with the flipped/transposed pack)
+// forward-type conv: small OUTPUT channel count (G.C3 fwd, D.C1 dgrad) or small INPUT channel count
+// (D.C1 fwd, G.C3 dgrad), both with the tap-major pack [t][n][c]
 int k_conv_small(fg_ctx* c, const float* in, const float* Wp, const float* bias, float* out, ConvGeom g) {
   const int64_t P = (int64_t)g.B * g.H * g.W;
+  if (g.Cin <= 4) {
+    const int64_t total = P * (g.Cout / 4);
+    int grid = (int)std::min<int64_t>((total + 255) / 256, c->sm_count * 16);
+    switch (g.Cin) {
+      case 1: conv_smallk4_kernel<1><<<grid, 256, 0, c->stream>>>(in, Wp, bias, out, g.B, g.H, g.W, g.Cout); break;
+      case 2: conv_smallk4_kernel<2><<<grid, 256, 0, c->stream>>>(in, Wp, bias, out, g.B, g.H, g.W, g.Cout); break;
+      case 3: conv_smallk4_kernel<3><<<grid, 256, 0, c->stream>>>(in, Wp, bias, out, g.B, g.H, g.W, g.Cout); break;
+      default: conv_smallk4_kernel<4><<<grid, 256, 0, c->stream>>>(in, Wp, bias, out, g.B, g.H, g.W, g.Cout); break;
+    }
+    LAUNCH_CHECK(c);
+    return FG_OK;
+  }
   if (g.Cout > 4 || 9 * g.Cout * g.Cin > kMaxSmallW) {
     fg_set_error("k_conv_small: expects Cout <= 4");
     return FG_ERR_UNSUPPORTED;

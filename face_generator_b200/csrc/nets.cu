@@ -260,8 +260,8 @@ int net_pack_D(fg_ctx* c) {
 static int conv_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp, const float* bias, float* out,
                     ConvGeom g) {
   ScopedTimer t(c, tag);
-  // small OUTPUT channel count -> warp-per-pixel kernel; small INPUT channel count -> flat-K SIMT tiles
-  return (k_small_eligible(g) && g.Cout <= 4) ? k_conv_small(c, in, Wp, bias, out, g) : k_conv_simt(c, in, Wp, bias, out, g);
+  // 3-channel-side 3x3 convolutions get bandwidth-shaped kernels (k_conv_small.cu)
+  return k_small_eligible(g) ? k_conv_small(c, in, Wp, bias, out, g) : k_conv_simt(c, in, Wp, bias, out, g);
 }
 static int conv_wgrad(fg_ctx* c, const char* tag, const float* in, const float* dY, ConvGeom g, float* dW, int nA, int nS,
                       int cA, int cS) {
