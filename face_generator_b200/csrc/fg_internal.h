@@ -144,6 +144,7 @@ struct fg_ctx {
     float *D_Wd_hi[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Wd_lo[4] = {nullptr, nullptr, nullptr, nullptr};
     // D's Linear layers: [0] L1 fwd [512][2048'], [1] L1 dgrad [2048'][512], [2] L2 fwd, [3] L2 dgrad
     float *D_Lw_hi[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Lw_lo[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *D_lin_hi[2] = {nullptr, nullptr}, *D_lin_lo[2] = {nullptr, nullptr};  // splits of p4 / hl1 kept for wgrad
   } tcb;
 };
 
@@ -191,14 +192,15 @@ int k_bn_finalize(fg_ctx* c, double* acc2C, float* mean, float* istd, float* run
                   int C);
 int k_bn_eval_prep(fg_ctx* c, const float* run_mean, const float* run_var, float* mean, float* istd, int C);
 int k_bn_prelu_apply(fg_ctx* c, const float* z, const float* mean, const float* istd, const float* gamma,
-                     const float* beta, const float* slope, float* h, int64_t P, int C);
+                     const float* beta, const float* slope, float* h, int64_t P, int C, float* hi = nullptr,
+                     float* lo = nullptr);  // h may be nullptr when only the TF32 hi/lo split is wanted
 int k_bn_prelu_bwd_reduce(fg_ctx* c, const float* dh, const float* z, const float* mean, const float* istd,
                           const float* gamma, const float* beta, const float* slope, double* acc2C, float* dslope,
                           int B, int H, int W, int C, int pool);
 int k_bn_bwd_finalize(fg_ctx* c, double* acc2C, float* mg2C, float* dgamma, float* dbeta, int64_t P, int C);
 int k_bn_prelu_bwd_apply(fg_ctx* c, const float* dh, const float* z, const float* mean, const float* istd,
                          const float* gamma, const float* beta, const float* slope, const float* mg2C, float* dz,
-                         int B, int H, int W, int C, int pool);
+                         int B, int H, int W, int C, int pool, float* hi = nullptr, float* lo = nullptr);
 int k_sigmoid_fwd(fg_ctx* c, const float* z, float* y, int64_t n);
 int k_sigmoid_bwd(fg_ctx* c, const float* dy, const float* y, float* dz, int64_t n);
 int k_masks_generate(fg_ctx* c, float* masks, int B, uint64_t seed, float p_spatial, float p_drop);

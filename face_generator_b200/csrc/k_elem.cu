@@ -303,11 +303,14 @@ int k_bn_eval_prep(fg_ctx* c, const float* rm, const float* rv, float* mean, flo
 __global__ void bn_prelu_apply_kernel(const float* __restrict__ z, const float* __restrict__ mean,
                                       const float* __restrict__ istd, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, const float* __restrict__ slope,
-                                      float* __restrict__ h, int64_t n4, int C) {
+                                      float* __restrict__ h, float* __restrict__ hi, float* __restrict__ lo, int64_t n4,
+                                      int C) {
   const bool act = slope != nullptr;
   const float a = act ? *slope : 1.f;
   const float4* z4 = reinterpret_cast<const float4*>(z);
   float4* h4 = reinterpret_cast<float4*>(h);
+  float4* hi4 = reinterpret_cast<float4*>(hi);
+  float4* lo4 = reinterpret_cast<float4*>(lo);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)((i * 4) % C);
     const float4 v = z4[i];
@@ -327,7 +330,17 @@ __global__ void bn_prelu_apply_kernel(const float* __restrict__ z, const float* 
       o.z = o.z > 0.f ? o.z : a * o.z;
       o.w = o.w > 0.f ? o.w : a * o.w;
     }
-    h4[i] = o;
+    if (h) h4[i] = o;
+    if (hi) {  // TF32 hi/lo split for the tensor-core consumer, written here instead of by a separate pass
+      float4 vh, vl;
+      vh.x = __uint_as_float((__float_as_uint(o.x) + 0x1000u) & 0xFFFFE000u);
+      vh.y = __uint_as_float((__float_as_uint(o.y) + 0x1000u) & 0xFFFFE000u);
+      vh.z = __uint_as_float((__float_as_uint(o.z) + 0x1000u) & 0xFFFFE000u);
+      vh.w = __uint_as_float((__float_as_uint(o.w) + 0x1000u) & 0xFFFFE000u);
+      vl = make_float4(o.x - vh.x, o.y - vh.y, o.z - vh.z, o.w - vh.w);
+      hi4[i] = vh;
+      lo4[i] = vl;
+    }
   }
 }
 __global__ void bn_prelu_apply_scalar_kernel(const float* __restrict__ z, const float* __restrict__ mean,
@@ -344,11 +357,15 @@ __global__ void bn_prelu_apply_scalar_kernel(const float* __restrict__ z, const 
   }
 }
 int k_bn_prelu_apply(fg_ctx* c, const float* z, const float* mean, const float* istd, const float* gamma,
-                     const float* beta, const float* slope, float* h, int64_t P, int C) {
+                     const float* beta, const float* slope, float* h, int64_t P, int C, float* hi, float* lo) {
   const int64_t n = P * C;
   if (C % 4 == 0) {
-    bn_prelu_apply_kernel<<<grid_for(n / 4, 256), 256, 0, c->stream>>>(z, mean, istd, gamma, beta, slope, h, n / 4, C);
+    bn_prelu_apply_kernel<<<grid_for(n / 4, 256), 256, 0, c->stream>>>(z, mean, istd, gamma, beta, slope, h, hi, lo, n / 4, C);
   } else {
+    if (hi || !h) {
+      fg_set_error("bn_prelu_apply: hi/lo outputs need C %% 4 == 0");
+      return FG_ERR_UNSUPPORTED;
+    }
     bn_prelu_apply_scalar_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(z, mean, istd, gamma, beta, slope, h, n, C);
   }
   LAUNCH_CHECK(c);
@@ -474,12 +491,15 @@ __global__ void bn_prelu_bwd_apply4_kernel(const float* __restrict__ dh, const f
                                            const float* __restrict__ mean, const float* __restrict__ istd,
                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                            const float* __restrict__ slope, const float* __restrict__ mg,
-                                           float* __restrict__ dz, int64_t n4, int C) {
+                                           float* __restrict__ dz, float* __restrict__ hi, float* __restrict__ lo,
+                                           int64_t n4, int C) {
   const bool act = slope != nullptr;
   const float a = act ? *slope : 1.f;
   const float4* dh4 = reinterpret_cast<const float4*>(dh);
   const float4* z4 = reinterpret_cast<const float4*>(z);
   float4* dz4 = reinterpret_cast<float4*>(dz);
+  float4* hi4 = reinterpret_cast<float4*>(hi);
+  float4* lo4 = reinterpret_cast<float4*>(lo);
   const int C4 = C / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i % C4) * 4;
@@ -498,17 +518,28 @@ __global__ void bn_prelu_bwd_apply4_kernel(const float* __restrict__ dh, const f
       o[j] = ga * is * (g - mg[ch + j] - xh * mg[C + ch + j]);
     }
     dz4[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (hi) {  // TF32 hi/lo split of dz for the tensor-core dgrad / wgrad, written by the producer
+      float h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __uint_as_float((__float_as_uint(o[j]) + 0x1000u) & 0xFFFFE000u);
+      hi4[i] = make_float4(h[0], h[1], h[2], h[3]);
+      lo4[i] = make_float4(o[0] - h[0], o[1] - h[1], o[2] - h[2], o[3] - h[3]);
+    }
   }
 }
 int k_bn_prelu_bwd_apply(fg_ctx* c, const float* dh, const float* z, const float* mean, const float* istd,
                          const float* gamma, const float* beta, const float* slope, const float* mg, float* dz, int B,
-                         int H, int W, int C, int pool) {
+                         int H, int W, int C, int pool, float* hi, float* lo) {
   const int64_t n = (int64_t)B * H * W * C;
   if (!pool && C % 4 == 0) {
     bn_prelu_bwd_apply4_kernel<<<grid_for(n / 4, 256), 256, 0, c->stream>>>(dh, z, mean, istd, gamma, beta, slope, mg, dz,
-                                                                           n / 4, C);
+                                                                           hi, lo, n / 4, C);
     LAUNCH_CHECK(c);
     return FG_OK;
+  }
+  if (hi) {
+    fg_set_error("bn_prelu_bwd_apply: hi/lo outputs need the un-pooled float4 path");
+    return FG_ERR_UNSUPPORTED;
   }
   bn_prelu_bwd_apply_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(dh, z, mean, istd, gamma, beta, slope, mg, dz, B, H,
                                                                     W, C, pool);

@@ -183,6 +183,10 @@ int net_alloc(fg_ctx* c) {
       FG_TRY(dalloc(c, &t.D_p_hi[i], n));
       FG_TRY(dalloc(c, &t.D_p_lo[i], n));
     }
+    for (int i = 0; i < 2; ++i) {
+      FG_TRY(dalloc(c, &t.D_lin_hi[i], B * (i == 0 ? 2048 : 512)));
+      FG_TRY(dalloc(c, &t.D_lin_lo[i], B * (i == 0 ? 2048 : 512)));
+    }
     for (int i = 0; i < 4; ++i) {
       FG_TRY(dalloc(c, &t.D_Lw_hi[i], i < 2 ? 512 * 2048 : 512 * 512));
       FG_TRY(dalloc(c, &t.D_Lw_lo[i], i < 2 ? 512 * 2048 : 512 * 512));
@@ -282,12 +286,25 @@ static inline bool use_tc_wgrad(const fg_ctx* c, const ConvGeom& g) {
 // nn.Linear as a 1x1 convolution on a 1x1 image.  With only B rows the fp32 SIMT tiling leaves the GPU
 // idle (8 CTAs at B=256); the tcgen05 path splits the input on the fly and uses the pre-split weights.
 static int lin_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp, int wi, const float* bias, float* out,
-                   ConvGeom g) {
+                   ConvGeom g, float* keep_hi = nullptr, float* keep_lo = nullptr) {
   if (!use_tc(c, g)) return conv_fwd(c, tag, in, Wp, bias, out, g);
   fg_ctx::TcBufs& t = c->tcb;
-  FG_TRY(tc_split(c, in, t.dy_hi, t.dy_lo, (int64_t)g.B * g.Cin));
+  float* hi = keep_hi ? keep_hi : t.dy_hi;  // forward keeps the split of its input for the tensor-core wgrad
+  float* lo = keep_lo ? keep_lo : t.dy_lo;
+  FG_TRY(tc_split(c, in, hi, lo, (int64_t)g.B * g.Cin));
   ScopedTimer tm(c, tag);
-  return tc_conv_fwd(c, t.dy_hi, t.dy_lo, t.D_Lw_hi[wi], t.D_Lw_lo[wi], bias, out, g, 0);
+  return tc_conv_fwd(c, hi, lo, t.D_Lw_hi[wi], t.D_Lw_lo[wi], bias, out, g, 0);
+}
+// weight gradient of a Linear layer on the tensor cores: x split kept by the forward, dY split left in
+// tcb.dy_* by the dgrad call that must precede this one
+static int lin_wgrad_tc(fg_ctx* c, const char* tag, const float* x_hi, const float* x_lo, ConvGeom g, float* dW, int cA,
+                        int cS) {
+  fg_ctx::TcBufs& t = c->tcb;
+  {
+    ScopedTimer tm(c, tag);
+    FG_TRY(tc_conv_wgrad(c, x_hi, x_lo, t.dy_hi, t.dy_lo, c->wgrad_ws, g));
+  }
+  return k_unpack_wgrad(c, c->wgrad_ws, dW, g.Cout, g.Cin, 1, 0, 0, cA, cS);
 }
 
 // G's two nn.SpatialUpSamplingNearest(2) -> 5x5 convolutions (li = 0: C1, li = 1: C2), forward.
@@ -296,7 +313,7 @@ static int g_ups_fwd(fg_ctx* c, int li, const char* tag, const float* h, float* 
                      const float* bias, float* z, ConvGeom g) {
   if (!use_tc(c, g)) return conv_fwd(c, tag, h, Wp, bias, z, g);
   fg_ctx::TcBufs& t = c->tcb;
-  FG_TRY(tc_split(c, h, h_hi, h_lo, (int64_t)g.B * (g.H / 2) * (g.W / 2) * g.Cin));
+  if (h) FG_TRY(tc_split(c, h, h_hi, h_lo, (int64_t)g.B * (g.H / 2) * (g.W / 2) * g.Cin));  // nullptr: producer wrote hi/lo
   ScopedTimer tm(c, tag);
   if (c->conv_impl == FG_CONV_TC_DENSE) return tc_conv_fwd(c, h_hi, h_lo, t.G_Wx_hi[li], t.G_Wx_lo[li], bias, z, g, 1);
   return tc_conv_fwd(c, h_hi, h_lo, t.G_Wf_hi[li], t.G_Wf_lo[li], bias, z, g, 2);
@@ -312,7 +329,7 @@ static int g_ups_bwd(fg_ctx* c, int li, const char* wtag, const char* dtag, cons
     return conv_fwd(c, dtag, dz, Wpd, nullptr, dh, ConvGeom{g.B, g.H, g.W, g.Cout, g.Cin, g.k, 1});
   }
   fg_ctx::TcBufs& t = c->tcb;
-  FG_TRY(tc_split(c, dz, t.dy_hi, t.dy_lo, (int64_t)g.B * g.H * g.W * g.Cout));
+  if (dz) FG_TRY(tc_split(c, dz, t.dy_hi, t.dy_lo, (int64_t)g.B * g.H * g.W * g.Cout));  // nullptr: producer wrote hi/lo
   {
     ScopedTimer tm(c, wtag);
     FG_TRY(tc_conv_wgrad(c, h_hi, h_lo, t.dy_hi, t.dy_lo, c->wgrad_ws, g));
@@ -345,10 +362,13 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
   } else {
     FG_TRY(k_bn_eval_prep(c, c->bnG, c->bnG + 256, c->bn_mean1, c->bn_istd1, 256));
   }
-  FG_TRY(k_bn_prelu_apply(c, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->G_h1, (int64_t)B * 256,
-                          256));
-  FG_TRY(g_ups_fwd(c, 1, "G.C2.fwd", c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, c->G_C2p, P + L.C2b, c->G_z2,
-                   ConvGeom{B, 32, 32, 256, 128, 5, 2}));
+  const ConvGeom gC2{B, 32, 32, 256, 128, 5, 2};
+  const bool h1_split = training && use_tc(c, gC2);  // tcgen05 path consumes h1 only as TF32 hi/lo
+  FG_TRY(k_bn_prelu_apply(c, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2,
+                          c->G_h1, (int64_t)B * 256, 256, h1_split ? c->tcb.G_h1_hi : nullptr,
+                          h1_split ? c->tcb.G_h1_lo : nullptr));
+  FG_TRY(g_ups_fwd(c, 1, "G.C2.fwd", h1_split ? nullptr : c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, c->G_C2p, P + L.C2b,
+                   c->G_z2, gC2));
   if (training) {
     FG_TRY(k_bn_stats(c, c->G_z2, c->bn_acc, (int64_t)B * 1024, 128));
     FG_TRY(k_bn_finalize(c, c->bn_acc, c->bn_mean2, c->bn_istd2, c->bnG + 512, c->bnG + 640, (int64_t)B * 1024, 128));
@@ -380,21 +400,27 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   FG_TRY(k_bn_prelu_bwd_reduce(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_acc,
                                G + L.a3, B, 32, 32, 128, 0));
   FG_TRY(k_bn_bwd_finalize(c, c->bn_acc, c->bn_mg, G + L.g2, G + L.be2, (int64_t)B * 1024, 128));
+  // in tcgen05 mode the BN-backward kernels also emit the TF32 hi/lo split of dz (no separate split pass)
+  const ConvGeom gC2{B, 32, 32, 256, 128, 5, 2}, gC1{B, 16, 16, 128, 256, 5, 2};
+  const bool tc2 = use_tc_wgrad(c, gC2), tc1 = use_tc_wgrad(c, gC1);
   FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_mg,
-                              c->G_dz2, B, 32, 32, 128, 0));
+                              c->G_dz2, B, 32, 32, 128, 0, tc2 ? c->tcb.dy_hi : nullptr, tc2 ? c->tcb.dy_lo : nullptr));
   // C2
   bool pooled = false;
-  FG_TRY(g_ups_bwd(c, 1, "G.C2.wgrad", "G.C2.dgrad", c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, c->G_dz2, c->G_C2pd,
-                   ConvGeom{B, 32, 32, 256, 128, 5, 2}, G + L.C2W, c->G_dfull, &pooled));
+  FG_TRY(g_ups_bwd(c, 1, "G.C2.wgrad", "G.C2.dgrad", c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, tc2 ? nullptr : c->G_dz2,
+                   c->G_C2pd, gC2, G + L.C2W, c->G_dfull, &pooled));
   FG_TRY(k_colsum_add(c, c->G_dz2, G + L.C2b, (int64_t)B * 1024, 128, 0, 0));
   // BN1 + PReLU (the 2x2 sum = backward of the nearest upsample is folded into the loads)
   FG_TRY(k_bn_prelu_bwd_reduce(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_acc,
                                G + L.a2, B, 16, 16, 256, pooled ? 0 : 1));
   FG_TRY(k_bn_bwd_finalize(c, c->bn_acc, c->bn_mg, G + L.g1, G + L.be1, (int64_t)B * 256, 256));
+  const bool split1 = tc1 && pooled;
   FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_mg,
-                              c->G_dz1, B, 16, 16, 256, pooled ? 0 : 1));
+                              c->G_dz1, B, 16, 16, 256, pooled ? 0 : 1, split1 ? c->tcb.dy_hi : nullptr,
+                              split1 ? c->tcb.dy_lo : nullptr));
   // C1
-  FG_TRY(g_ups_bwd(c, 0, "G.C1.wgrad", "G.C1.dgrad", c->G_h0, c->tcb.G_h0_hi, c->tcb.G_h0_lo, c->G_dz1, c->G_C1pd,
+  FG_TRY(g_ups_bwd(c, 0, "G.C1.wgrad", "G.C1.dgrad", c->G_h0, c->tcb.G_h0_hi, c->tcb.G_h0_lo, split1 ? nullptr : c->G_dz1,
+                   c->G_C1pd,
                    ConvGeom{B, 16, 16, 128, 256, 5, 2}, G + L.C1W, c->G_dfull, &pooled));
   FG_TRY(k_colsum_add(c, c->G_dz1, G + L.C1b, (int64_t)B * 256, 256, 0, 0));
   FG_TRY(k_prelu_bwd(c, c->G_dfull, c->G_z0, P + L.a1, c->G_dz0, G + L.a1, B, 8, 8, 128, pooled ? 0 : 1));
@@ -439,9 +465,11 @@ int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hype
   const float scale = 1.0f / (1.0f - h->p_drop);
   c->D_drop_scale = scale;
   c->D_spatial_eval = 1.0f - h->p_spatial;
-  FG_TRY(lin_fwd(c, "D.L1.fwd", c->D_p[3], c->D_L1p, 0, P + L.L1b, c->D_zl1, ConvGeom{B, 1, 1, 2048, 512, 1, 1}));
+  FG_TRY(lin_fwd(c, "D.L1.fwd", c->D_p[3], c->D_L1p, 0, P + L.L1b, c->D_zl1, ConvGeom{B, 1, 1, 2048, 512, 1, 1},
+                 c->tcb.D_lin_hi[0], c->tcb.D_lin_lo[0]));
   FG_TRY(k_lin_act_drop_fwd(c, c->D_zl1, P + L.a5, masks, 960, scale, c->D_hl1, B, 512));
-  FG_TRY(lin_fwd(c, "D.L2.fwd", c->D_hl1, P + L.L2W, 2, P + L.L2b, c->D_zl2, ConvGeom{B, 1, 1, 512, 512, 1, 1}));
+  FG_TRY(lin_fwd(c, "D.L2.fwd", c->D_hl1, P + L.L2W, 2, P + L.L2b, c->D_zl2, ConvGeom{B, 1, 1, 512, 512, 1, 1},
+                 c->tcb.D_lin_hi[1], c->tcb.D_lin_lo[1]));
   FG_TRY(k_lin_act_drop_fwd(c, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_hl2, B, 512));
   {
     ScopedTimer tm(c, "D.L3.fwd");
@@ -473,19 +501,23 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
   FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_dzl, want_wgrad ? G + L.a6 : nullptr, B,
                             512));
   // L2
+  const ConvGeom gL2{B, 1, 1, 512, 512, 1, 1}, gL1{B, 1, 1, 2048, 512, 1, 1};
+  const bool tcw2 = want_wgrad && use_tc_wgrad(c, gL2), tcw1 = want_wgrad && use_tc_wgrad(c, gL1);
   if (want_wgrad) {
-    FG_TRY(conv_wgrad(c, "D.L2.wgrad", c->D_hl1, c->D_dzl, ConvGeom{B, 1, 1, 512, 512, 1, 1}, G + L.L2W, 0, 0, 0, 0));
+    if (!tcw2) FG_TRY(conv_wgrad(c, "D.L2.wgrad", c->D_hl1, c->D_dzl, gL2, G + L.L2W, 0, 0, 0, 0));
     FG_TRY(k_colsum_add(c, c->D_dzl, G + L.L2b, B, 512, 0, 0));
   }
   FG_TRY(lin_fwd(c, "D.L2.dgrad", c->D_dzl, c->D_L2pd, 3, nullptr, c->D_dh, ConvGeom{B, 1, 1, 512, 512, 1, 1}));
+  if (tcw2) FG_TRY(lin_wgrad_tc(c, "D.L2.wgrad", c->tcb.D_lin_hi[1], c->tcb.D_lin_lo[1], gL2, G + L.L2W, 0, 0));
   FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl1, P + L.a5, masks, 960, scale, c->D_dzl, want_wgrad ? G + L.a5 : nullptr, B,
                             512));
   // L1
   if (want_wgrad) {
-    FG_TRY(conv_wgrad(c, "D.L1.wgrad", c->D_p[3], c->D_dzl, ConvGeom{B, 1, 1, 2048, 512, 1, 1}, G + L.L1W, 0, 0, 512, 4));
+    if (!tcw1) FG_TRY(conv_wgrad(c, "D.L1.wgrad", c->D_p[3], c->D_dzl, gL1, G + L.L1W, 0, 0, 512, 4));
     FG_TRY(k_colsum_add(c, c->D_dzl, G + L.L1b, B, 512, 0, 0));
   }
   FG_TRY(lin_fwd(c, "D.L1.dgrad", c->D_dzl, c->D_L1pd, 1, nullptr, c->D_dp, ConvGeom{B, 1, 1, 512, 2048, 1, 1}));
+  if (tcw1) FG_TRY(lin_wgrad_tc(c, "D.L1.wgrad", c->tcb.D_lin_hi[0], c->tcb.D_lin_lo[0], gL1, G + L.L1W, 512, 4));
   static const char* wt[4] = {"D.C1.wgrad", "D.C2.wgrad", "D.C3.wgrad", "D.C4.wgrad"};
   static const char* dt[4] = {"D.C1.dgrad", "D.C2.dgrad", "D.C3.dgrad", "D.C4.dgrad"};
   for (int i = 3; i >= 0; --i) {
