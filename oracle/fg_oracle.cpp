@@ -46,7 +46,28 @@ namespace {
 // C[M,N] (+)= A[M,K] * B[K,N]            (row-major, "NN")
 template <class T>
 void gemm_nn(int M, int N, int K, const T* A, const T* B, T* C, bool acc) {
-  for (int i = 0; i < M; ++i) {
+  int i = 0;
+  // 4 output rows at a time share every streamed row of B (4x less memory traffic than one row at a time)
+  for (; i + 3 < M; i += 4) {
+    T* c0 = C + (size_t)i * N;
+    T *c1 = c0 + N, *c2 = c1 + N, *c3 = c2 + N;
+    if (!acc) std::fill(c0, c0 + (size_t)4 * N, T(0));
+    const T* a0 = A + (size_t)i * K;
+    const T *a1 = a0 + K, *a2 = a1 + K, *a3 = a2 + K;
+    for (int k = 0; k < K; ++k) {
+      const T v0 = a0[k], v1 = a1[k], v2 = a2[k], v3 = a3[k];
+      const T* b = B + (size_t)k * N;
+#pragma omp simd
+      for (int j = 0; j < N; ++j) {
+        const T bj = b[j];
+        c0[j] += v0 * bj;
+        c1[j] += v1 * bj;
+        c2[j] += v2 * bj;
+        c3[j] += v3 * bj;
+      }
+    }
+  }
+  for (; i < M; ++i) {
     T* c = C + (size_t)i * N;
     if (!acc) std::fill(c, c + N, T(0));
     const T* a = A + (size_t)i * K;
@@ -76,7 +97,29 @@ void gemm_tn(int M, int N, int K, const T* A, const T* B, T* C, bool acc) {
 // C[M,N] (+)= A[M,K] * B[N,K]^T           ("NT")
 template <class T>
 void gemm_nt(int M, int N, int K, const T* A, const T* B, T* C, bool acc) {
-  for (int i = 0; i < M; ++i) {
+  int i = 0;
+  for (; i + 3 < M; i += 4) {  // 4 rows of A share each streamed row of B
+    const T* a0 = A + (size_t)i * K;
+    const T *a1 = a0 + K, *a2 = a1 + K, *a3 = a2 + K;
+    for (int j = 0; j < N; ++j) {
+      const T* b = B + (size_t)j * K;
+      T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma omp simd reduction(+ : s0, s1, s2, s3)
+      for (int k = 0; k < K; ++k) {
+        const T bk = b[k];
+        s0 += a0[k] * bk;
+        s1 += a1[k] * bk;
+        s2 += a2[k] * bk;
+        s3 += a3[k] * bk;
+      }
+      T* c = C + (size_t)i * N + j;
+      c[0] = acc ? c[0] + s0 : s0;
+      c[(size_t)N] = acc ? c[(size_t)N] + s1 : s1;
+      c[(size_t)2 * N] = acc ? c[(size_t)2 * N] + s2 : s2;
+      c[(size_t)3 * N] = acc ? c[(size_t)3 * N] + s3 : s3;
+    }
+  }
+  for (; i < M; ++i) {
     const T* a = A + (size_t)i * K;
     for (int j = 0; j < N; ++j) {
       const T* b = B + (size_t)j * K;
@@ -204,9 +247,11 @@ void conv_fwd(int B, int Cin, int H, int W, int Cout, int k, const T* x, const T
     im2col_rows(x + (size_t)n * Cin * HW, Cin, H, W, k, col.data());  // implicit barrier after the omp for
     T* yn = y + (size_t)n * Cout * HW;
 #pragma omp for schedule(static)
-    for (int o = 0; o < Cout; ++o) {
-      gemm_nn(1, HW, K, Wt + (size_t)o * K, col.data(), yn + (size_t)o * HW, false);
-      for (int p = 0; p < HW; ++p) yn[(size_t)o * HW + p] += b[o];
+    for (int ob = 0; ob < (Cout + 3) / 4; ++ob) {
+      const int o0 = ob * 4, no = std::min(4, Cout - o0);
+      gemm_nn(no, HW, K, Wt + (size_t)o0 * K, col.data(), yn + (size_t)o0 * HW, false);
+      for (int o = o0; o < o0 + no; ++o)
+        for (int p = 0; p < HW; ++p) yn[(size_t)o * HW + p] += b[o];
     }
   }
 }
@@ -227,7 +272,10 @@ void conv_bwd(int B, int Cin, int H, int W, int Cout, int k, const T* x, const T
     const T* dyn = dy + (size_t)n * Cout * HW;
     if (dx) {
 #pragma omp for schedule(static)
-      for (int r = 0; r < K; ++r) gemm_nn(1, HW, Cout, WtT.data() + (size_t)r * Cout, dyn, col.data() + (size_t)r * HW, false);
+      for (int rb = 0; rb < (K + 3) / 4; ++rb) {
+        const int r0 = rb * 4, nr = std::min(4, K - r0);
+        gemm_nn(nr, HW, Cout, WtT.data() + (size_t)r0 * Cout, dyn, col.data() + (size_t)r0 * HW, false);
+      }
       T* dxn = dx + (size_t)n * Cin * HW;
 #pragma omp for schedule(static)
       for (int c = 0; c < Cin; ++c) {  // col2im: each thread owns whole input channels
@@ -250,7 +298,10 @@ void conv_bwd(int B, int Cin, int H, int W, int Cout, int k, const T* x, const T
     if (dW) {
       im2col_rows(x + (size_t)n * Cin * HW, Cin, H, W, k, col.data());
 #pragma omp for schedule(static)
-      for (int o = 0; o < Cout; ++o) gemm_nt(1, K, HW, dyn + (size_t)o * HW, col.data(), dW + (size_t)o * K, true);
+      for (int ob = 0; ob < (Cout + 3) / 4; ++ob) {
+        const int o0 = ob * 4, no = std::min(4, Cout - o0);
+        gemm_nt(no, K, HW, dyn + (size_t)o0 * HW, col.data(), dW + (size_t)o0 * K, true);
+      }
     }
   }
   if (db) {
