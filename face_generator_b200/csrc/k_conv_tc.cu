@@ -347,7 +347,7 @@ bool pick_box(int H, int W, int npix, int* bw, int* bh, int* bb) {
 }
 
 template <int BN>
-constexpr size_t fwd_smem() { return (size_t)kStages * (2 * kABytes + 2 * BN * 128) + 128 + 1024; }
+constexpr size_t fwd_smem() { return (size_t)kStages * (2 * kABytes + 2 * BN * 128) + 256 + 1024; }
 template <int BN>
 constexpr size_t wg_smem() { return (size_t)kStages * (2 * 4 * 4096 + 2 * (BN / 32) * 4096) + 128 + 1024; }
 
@@ -439,7 +439,15 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   const int64_t sW = (int64_t)g.Cin * 4, sH = sW * Wl, sB = sH * Hl;
   FG_TRY(make_map4(&p.a_hi[0], x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
   FG_TRY(make_map4(&p.a_lo[0], x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
-  const int BN = g.Cout % 128 == 0 ? 128 : 64;
+  // N tile: 128 unless halving it keeps the same number of waves on the 148 SMs (few-tile layers such as
+  // D.C4's dgrad or the Linear layers): a BN=64 tile costs ~0.6 of a BN=128 tile
+  int BN = g.Cout % 128 == 0 ? 128 : 64;
+  if (BN == 128) {
+    const int mt = (mode == 0 ? 1 : 4) * (p.bb == 1 ? g.B * (Wl / p.bw) * (Hl / p.bh) : (g.B + p.bb - 1) / p.bb);
+    const int t128 = mt * (g.Cout / 128), t64 = mt * (g.Cout / 64);
+    const int w128 = (t128 + c->sm_count - 1) / c->sm_count, w64 = (t64 + c->sm_count - 1) / c->sm_count;
+    if (w64 * 6 < w128 * 10) BN = 64;
+  }
   int ntapw;
   if (mode == 0) {
     const int pad = (g.k - 1) / 2;

@@ -43,17 +43,23 @@ template <int BN>
 __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constant__ TcFwdParams p) {
   constexpr uint32_t kBBytes = BN * 128;
   constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
-  constexpr uint32_t kIdesc = make_idesc(128, BN, 0, 0), kIdesc2 = make_idesc(128, 2 * BN, 0, 0);
-  // accumulator ring in TMEM: 4 buffers so the MMA warp can run 4 chunks ahead of the epilogue warps while
-  // those write a finished tile to global memory (with 2 buffers ~12k cycles/tile were lost waiting there)
-  constexpr uint32_t kAcc = 256 / BN;  // 2 x (2*BN columns) for BN = 128, 4 for BN = 64: always all 512 TMEM columns
+  constexpr uint32_t kIdesc = make_idesc(128, BN, 0, 0);
+  // TMEM layout (all 512 columns): [0,256) a ring of kAcc buffers for the MAIN term hi*hi -- the MMA warp
+  // accumulates `chunk` K-blocks into one buffer, the epilogue promotes it to fp32 registers and frees it;
+  // [256, 256+2*BN) two buffers (tile parity) for the CROSS terms hi*lo + lo*hi, which are 2^-11 smaller, so
+  // their truncation drift is irrelevant and they stay in TMEM for the whole tile (read once at the end).
+  // Promotion cost is bounded by the TMEM read rate (~64 B/clk): reading only the main block per chunk is what
+  // makes a short chunk affordable.
+  constexpr uint32_t kAcc = 256 / BN;
+  constexpr uint32_t kCrossCol = 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty = full + kStages;
   uint64_t* tmem_full = empty + kStages;      // [kAcc]
   uint64_t* tmem_empty = tmem_full + kAcc;    // [kAcc]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAcc);
+  uint64_t* cross_empty = tmem_empty + kAcc;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cross_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.ntaps * p.kpt;
@@ -70,9 +76,11 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
       mbar_init(tmem_full + i, 1);
       mbar_init(tmem_empty + i, 4);  // one arrive per epilogue warp
     }
+    mbar_init(cross_empty + 0, 4);
+    mbar_init(cross_empty + 1, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<kAcc * 2 * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -107,13 +115,15 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t kbg = 0, cg = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      uint32_t kbg = 0, cg = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+        const uint32_t tcross = tmem_base + kCrossCol + (tl & 1) * BN;
+        if (tl >= 2) mbar_wait(cross_empty + (tl & 1), ((tl >> 1) - 1) & 1);  // epilogue has read tile tl-2's cross block
         for (int ch = 0; ch < nchunks; ++ch, ++cg) {
           const uint32_t buf = cg % kAcc, use = cg / kAcc;
           if (use > 0) mbar_wait(tmem_empty + buf, (use - 1) & 1);
           tc_fence_after();
-          const uint32_t tacc = tmem_base + buf * 2 * BN;
+          const uint32_t tacc = tmem_base + buf * BN;
           const int nk = min(kChunk, nkb - ch * kChunk);
           for (int j = 0; j < nk; ++j, ++kbg) {
             const uint32_t s = kbg % kStages, it = kbg / kStages;
@@ -127,13 +137,9 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 fp32 of K) in the 16B-unit start-address field
-                // [b_hi | b_lo] are adjacent in the stage, so ONE N = 2*BN instruction computes a_hi*b_hi -> columns
-                // [0,BN) and a_hi*b_lo -> [BN,2BN): the tensor core's operand fetch from shared memory (the binding
-                // resource of 128x128 tf32 tiles) drops from 24 KB to 20 KB per K step; the epilogue adds the halves
-                umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc2, (j | k) != 0);
-                // the two small cross terms share the SECOND column block, so the first one only ever accumulates
-                // hi*hi: half as many truncating accumulations on the block that carries the magnitude
-                umma_tf32(tacc + BN, a_lo + ko, b_hi + ko, kIdesc, 1);
+                umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, (j | k) != 0);        // main term -> ring buffer
+                umma_tf32(tcross, a_hi + ko, b_lo + ko, kIdesc, (ch | j | k) != 0);  // cross terms -> per-tile block
+                umma_tf32(tcross, a_lo + ko, b_hi + ko, kIdesc, 1);
               }
             }
             umma_commit(empty + s);
@@ -147,8 +153,8 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
     const int q = warp & 3;
     const int m = q * 32 + lane;  // accumulator row == tile pixel
     const int xi = m % p.bw, yi = (m / p.bw) % p.bh, bi = m / (p.bw * p.bh);
-    uint32_t cg = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    uint32_t cg = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
       const FwdTile t = fwd_decode<BN>(p, tile);
       float acc[BN];
 #pragma unroll
@@ -158,16 +164,35 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
         mbar_wait(tmem_full + buf, use & 1);
         tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
+        for (int j = 0; j < BN / 32; j += 2) {
           uint32_t va[32], vb[32];
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * BN + (uint32_t)(j * 32);
-          tmem_ld_32x32_x2(ta, ta + BN, va, vb);  // same 32 outputs: hi*hi + lo*hi block and hi*lo block
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32);
+          tmem_ld_32x32_x2(ta, ta + 32, va, vb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(va[i]) + __uint_as_float(vb[i]);
+          for (int i = 0; i < 32; ++i) {
+            acc[j * 32 + i] += __uint_as_float(va[i]);
+            acc[j * 32 + 32 + i] += __uint_as_float(vb[i]);
+          }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + buf);
+      }
+      {  // the last chunk's commit also covers every cross-term MMA of this tile: add the cross block once
+#pragma unroll
+        for (int j = 0; j < BN / 32; j += 2) {
+          uint32_t va[32], vb[32];
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kCrossCol + (tl & 1) * BN + (uint32_t)(j * 32);
+          tmem_ld_32x32_x2(ta, ta + 32, va, vb);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            acc[j * 32 + i] += __uint_as_float(va[i]);
+            acc[j * 32 + 32 + i] += __uint_as_float(vb[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cross_empty + (tl & 1));
       }
       const int b = t.b0 + bi;
       if (b < p.B) {
@@ -191,7 +216,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<kAcc * 2 * BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -204,7 +229,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   constexpr uint32_t kAB = 4 * kBox;   // M = 128 channels of dY
   constexpr uint32_t kBB = (BN / 32) * kBox;
   constexpr uint32_t kStageBytes = 2 * kAB + 2 * kBB;
-  constexpr uint32_t kIdesc = make_idesc(128, BN, 1, 1), kIdesc2 = make_idesc(128, 2 * BN, 1, 1);
+  constexpr uint32_t kIdesc = make_idesc(128, BN, 1, 1);
+  constexpr uint32_t kCrossCol = 256;  // main ring: 2 buffers at [0, 2*BN); cross terms: [256, 256+BN) for the whole tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -234,7 +260,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<4 * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -277,7 +303,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           const uint32_t buf = ch & 1, use = ch >> 1;
           if (use > 0) mbar_wait(tmem_empty + buf, (use - 1) & 1);
           tc_fence_after();
-          const uint32_t tacc = tmem_base + buf * 2 * BN;
+          const uint32_t tacc = tmem_base + buf * BN, tcross = tmem_base + kCrossCol;
           const int nk = min(kChunk, nkb - ch * kChunk);
           for (int j = 0; j < nk; ++j, ++i) {
             const int s = i % kStages, it = i / kStages;
@@ -293,8 +319,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t ko = (uint64_t)(k * 64);  // +1024 bytes = next 8 pixels
-              umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc2, (j | k) != 0);  // x_hi | x_lo groups are adjacent
-              umma_tf32(tacc + BN, a_lo + ko, b_hi + ko, kIdesc, 1);  // cross terms share the second block
+              umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, (j | k) != 0);        // main term -> ring buffer
+              umma_tf32(tcross, a_hi + ko, b_lo + ko, kIdesc, (ch | j | k) != 0);  // cross terms stay in TMEM
+              umma_tf32(tcross, a_lo + ko, b_hi + ko, kIdesc, 1);
             }
             umma_commit(empty + s);
           }
@@ -312,16 +339,30 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         mbar_wait(tmem_full + buf, use & 1);
         tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
+        for (int j = 0; j < BN / 32; j += 2) {
           uint32_t va[32], vb[32];
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * BN + (uint32_t)(j * 32);
-          tmem_ld_32x32_x2(ta, ta + BN, va, vb);
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32);
+          tmem_ld_32x32_x2(ta, ta + 32, va, vb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(va[i]) + __uint_as_float(vb[i]);
+          for (int i = 0; i < 32; ++i) {
+            acc[j * 32 + i] += __uint_as_float(va[i]);
+            acc[j * 32 + 32 + i] += __uint_as_float(vb[i]);
+          }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + buf);
+      }
+#pragma unroll
+      for (int j = 0; j < BN / 32; j += 2) {  // cross terms: complete once the last chunk has been committed
+        uint32_t va[32], vb[32];
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kCrossCol + (uint32_t)(j * 32);
+        tmem_ld_32x32_x2(ta, ta + 32, va, vb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          acc[j * 32 + i] += __uint_as_float(va[i]);
+          acc[j * 32 + 32 + i] += __uint_as_float(vb[i]);
+        }
       }
       float* orow = p.out + ((int64_t)tt * p.Cout + n) * p.Cin + c0;
 #pragma unroll
@@ -330,5 +371,5 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<4 * BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
