@@ -799,6 +799,8 @@ void train_iteration(int B, int C, const Hyper& hp, const T* real, const T* nois
   stats[6] = 0; stats[7] = 0;
 }
 
+#include "fg_oracle_c2f.h"  // coarse-to-fine nets + loop (models_c2f.lua, adversarial_c2f.lua)
+
 }  // namespace
 
 // ==============================================================================================
@@ -897,10 +899,57 @@ void train_iteration(int B, int C, const Hyper& hp, const T* real, const T* nois
 FG_EXPORTS(f64, double)
 FG_EXPORTS(f32, float)
 
+#define FG_C2F_EXPORTS(SFX, T)                                                                                   \
+  extern "C" {                                                                                                   \
+  void fgo_maxpool2_fwd_##SFX(int BC, int H, int W, const T* x, T* y, unsigned char* arg) {                      \
+    maxpool2_fwd<T>(BC, H, W, x, y, arg);                                                                        \
+  }                                                                                                              \
+  void fgo_maxpool2_bwd_##SFX(int BC, int H, int W, const T* dy, const unsigned char* arg, T* dx) {              \
+    maxpool2_bwd<T>(BC, H, W, dy, arg, dx);                                                                      \
+  }                                                                                                              \
+  void* fgo_c2f_G_new_##SFX() { return new C2fGNet<T>(); }                                                       \
+  void fgo_c2f_G_free_##SFX(void* h) { delete (C2fGNet<T>*)h; }                                                  \
+  void fgo_c2f_G_forward_##SFX(void* h, const T* P, const T* noise, const T* cond, int B, int C, T* out) {       \
+    C2fGNet<T>* g = (C2fGNet<T>*)h;                                                                              \
+    g->forward(P, noise, cond, B, C);                                                                            \
+    std::copy(g->z[4].begin(), g->z[4].end(), out);                                                              \
+  }                                                                                                              \
+  void fgo_c2f_G_backward_##SFX(void* h, const T* P, const T* dout, T* dP) {                                     \
+    ((C2fGNet<T>*)h)->backward(P, dout, dP);                                                                     \
+  }                                                                                                              \
+  void* fgo_c2f_D_new_##SFX() { return new C2fDNet<T>(); }                                                       \
+  void fgo_c2f_D_free_##SFX(void* h) { delete (C2fDNet<T>*)h; }                                                  \
+  void fgo_c2f_D_forward_##SFX(void* h, const T* P, const T* diff, const T* cond, int B, int C, int training,    \
+                               const T* masks, T* out) {                                                         \
+    C2fDNet<T>* d = (C2fDNet<T>*)h;                                                                              \
+    d->forward(P, diff, cond, B, C, training != 0, masks);                                                       \
+    std::copy(d->out.begin(), d->out.end(), out);                                                                \
+  }                                                                                                              \
+  void fgo_c2f_D_backward_##SFX(void* h, const T* P, const T* dout, T* dP, T* ddiff) {                           \
+    ((C2fDNet<T>*)h)->backward(P, dout, dP, ddiff);                                                              \
+  }                                                                                                              \
+  void fgo_c2f_train_iteration_##SFX(int B, int C, const double* hp11, const T* real_diff, const T* condD,       \
+                                     const T* noiseD, const T* condG, const T* noiseG, const T* masksD,          \
+                                     const T* masksG, T* PD, T* PG, T* mD, T* vD, T* mG, T* vG, int* tD,         \
+                                     int* tG, double* stats, T* gradD_out, T* gradG_out, T* fake_out,            \
+                                     T* outD_out) {                                                              \
+    Hyper hp{hp11[0], hp11[1], hp11[2], hp11[3], hp11[4], hp11[5], hp11[6], hp11[7], hp11[8], hp11[9],           \
+             hp11[10]};                                                                                          \
+    c2f_train_iteration<T>(B, C, hp, real_diff, condD, noiseD, condG, noiseG, masksD, masksG, PD, PG, mD, vD,    \
+                           mG, vG, tD, tG, stats, gradD_out, gradG_out, fake_out, outD_out);                     \
+  }                                                                                                              \
+  }
+
+FG_C2F_EXPORTS(f64, double)
+FG_C2F_EXPORTS(f32, float)
+
 extern "C" {
 long fgo_G_param_count(int C) { return (long)GLayout(C).total; }
 long fgo_D_param_count(int C) { return (long)DLayout(C).total; }
 int fgo_mask_per_sample() { return kMaskPerSample; }
+long fgo_c2f_G_param_count(int C) { return (long)C2fGLayout(C).total; }
+long fgo_c2f_D_param_count(int C) { return (long)C2fDLayout(C).total; }
+int fgo_c2f_mask_per_sample() { return kC2fMaskPerSample; }
 int fgo_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -15,8 +15,8 @@ _SO = os.path.join(_HERE, "libfg_oracle.so")
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "fg_oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("fg_oracle.cpp", "fg_oracle_c2f.h")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
