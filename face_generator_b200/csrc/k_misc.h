@@ -1,0 +1,21 @@
+// Host entry points of k_misc.cu (table ops, max pooling, dropout, NCHW pooling/upsampling).
+#pragma once
+#include "fg_internal.h"
+
+// NHWC (fused nets)
+int k_join_to_nhwc(fg_ctx* c, const float* noise_nchw, const float* cond_nchw, float* out_nhwc, int B, int C, int HW);
+int k_add(fg_ctx* c, const float* a, const float* b, float* out, int64_t n);
+int k_maxpool2_fwd(fg_ctx* c, const float* h, float* p, int B, int H, int W, int C);                  // H,W: input size
+int k_maxpool2_bwd(fg_ctx* c, const float* dp, const float* h, float* dh, int B, int H, int W, int C);
+// y = x * mask * scale; mask element order is the reference's NCHW flattening: masks[b*stride + moff + ch*HW + q]
+int k_dropout_nhwc(fg_ctx* c, const float* x, const float* masks, int64_t stride, int moff, int HW, int C, float scale,
+                   float* y, int B);
+int k_bernoulli_keep(fg_ctx* c, float* out, int64_t n, uint64_t seed, float p_drop);  // 1 with probability 1-p_drop
+// NCHW (L-op boundary); H,W are the sizes of the layer INPUT
+int k_up2_fwd_nchw(fg_ctx* c, const float* x, float* y, int64_t BC, int H, int W);
+int k_up2_bwd_nchw(fg_ctx* c, const float* dy, float* dx, int64_t BC, int H, int W);
+int k_avgpool2_fwd_nchw(fg_ctx* c, const float* x, float* y, int64_t BC, int H, int W);
+int k_avgpool2_bwd_nchw(fg_ctx* c, const float* dy, float* dx, int64_t BC, int H, int W);
+int k_maxpool2_fwd_nchw(fg_ctx* c, const float* x, float* y, int64_t BC, int H, int W);
+int k_maxpool2_bwd_nchw(fg_ctx* c, const float* x, const float* dy, float* dx, int64_t BC, int H, int W);
+int k_dropout_nchw(fg_ctx* c, const float* x, const float* mask, float scale, int inner, float* y, int64_t n);

@@ -6,6 +6,7 @@
 
 #include "fg_internal.h"
 #include "k_conv_tc.h"
+#include "k_misc.h"
 
 namespace {
 bool is_dev(const void* p) {
@@ -309,6 +310,103 @@ int fg_prelu_backward(fg_ctx* c, const float* x, const float* slope, const float
   FG_TRY(out_done(c, dx, dxd, n));
   if (dslope) FG_TRY(out_done(c, dslope, dsd, 1));
   return FG_OK;
+}
+
+// ---- resampling / pooling / dropout / sigmoid: NCHW kernels, no layout round trip --------------------
+// shared shape: one input of nin floats, one output of nout floats
+#define UNARY_LOP(NAME, IN, OUT, NIN, NOUT, CALL)                                   \
+  ENTER(c);                                                                         \
+  FG_REQUIRE(IN && OUT && N > 0 && C > 0 && H > 0 && W > 0, NAME ": bad arguments"); \
+  const size_t nin = (NIN), nout = (NOUT);                                          \
+  const float* ind;                                                                 \
+  float* outd;                                                                      \
+  FG_TRY(in_dev(c, IN, nin, 0, &ind));                                              \
+  FG_TRY(out_dev(c, OUT, nout, 6, &outd, false));                                   \
+  FG_TRY(CALL);                                                                     \
+  return out_done(c, OUT, outd, nout)
+
+int fg_upsample2_forward(fg_ctx* c, const float* x, float* y, int N, int C, int H, int W) {
+  UNARY_LOP("fg_upsample2_forward", x, y, (size_t)N * C * H * W, (size_t)N * C * H * W * 4,
+            k_up2_fwd_nchw(c, ind, outd, (int64_t)N * C, H, W));
+}
+int fg_upsample2_backward(fg_ctx* c, const float* dy, float* dx, int N, int C, int H, int W) {
+  UNARY_LOP("fg_upsample2_backward", dy, dx, (size_t)N * C * H * W * 4, (size_t)N * C * H * W,
+            k_up2_bwd_nchw(c, ind, outd, (int64_t)N * C, H, W));
+}
+int fg_avgpool2_forward(fg_ctx* c, const float* x, float* y, int N, int C, int H, int W) {
+  UNARY_LOP("fg_avgpool2_forward", x, y, (size_t)N * C * H * W, (size_t)N * C * (H / 2) * (W / 2),
+            k_avgpool2_fwd_nchw(c, ind, outd, (int64_t)N * C, H, W));
+}
+int fg_avgpool2_backward(fg_ctx* c, const float* dy, float* dx, int N, int C, int H, int W) {
+  UNARY_LOP("fg_avgpool2_backward", dy, dx, (size_t)N * C * (H / 2) * (W / 2), (size_t)N * C * H * W,
+            k_avgpool2_bwd_nchw(c, ind, outd, (int64_t)N * C, H, W));
+}
+int fg_maxpool2_forward(fg_ctx* c, const float* x, float* y, int N, int C, int H, int W) {
+  UNARY_LOP("fg_maxpool2_forward", x, y, (size_t)N * C * H * W, (size_t)N * C * (H / 2) * (W / 2),
+            k_maxpool2_fwd_nchw(c, ind, outd, (int64_t)N * C, H, W));
+}
+#undef UNARY_LOP
+int fg_maxpool2_backward(fg_ctx* c, const float* x, const float* dy, float* dx, int N, int C, int H, int W) {
+  ENTER(c);
+  FG_REQUIRE(x && dy && dx && N > 0 && C > 0 && H > 0 && W > 0, "fg_maxpool2_backward: bad arguments");
+  const size_t nx = (size_t)N * C * H * W, ny = (size_t)N * C * (H / 2) * (W / 2);
+  const float *xd, *dyd;
+  float* dxd;
+  FG_TRY(in_dev(c, x, nx, 0, &xd));
+  FG_TRY(in_dev(c, dy, ny, 1, &dyd));
+  FG_TRY(out_dev(c, dx, nx, 6, &dxd, false));
+  FG_TRY(k_maxpool2_bwd_nchw(c, xd, dyd, dxd, (int64_t)N * C, H, W));
+  return out_done(c, dx, dxd, nx);
+}
+
+static int dropout_apply(fg_ctx* c, const char* who, const float* x, const float* mask, float p, int spatial, float* y, int N,
+                         int C, int HW) {
+  ENTER(c);
+  FG_REQUIRE(x && y && N > 0 && C > 0 && HW > 0 && p >= 0.f && p < 1.f, "%s: bad arguments", who);
+  const size_t n = (size_t)N * C * HW, nm = spatial ? (size_t)N * C : n;
+  const float *xd, *md = nullptr;
+  float* yd;
+  FG_TRY(in_dev(c, x, n, 0, &xd));
+  if (mask) FG_TRY(in_dev(c, mask, nm, 1, &md));
+  FG_TRY(out_dev(c, y, n, 6, &yd, false));
+  // training: nn.Dropout rescales by 1/(1-p), nn.SpatialDropout does not; evaluate(): identity resp. (1-p)
+  const float scale = mask ? (spatial ? 1.f : 1.f / (1.f - p)) : (spatial ? 1.f - p : 1.f);
+  FG_TRY(k_dropout_nchw(c, xd, md, scale, spatial ? HW : 1, yd, (int64_t)n));
+  return out_done(c, y, yd, n);
+}
+int fg_dropout_forward(fg_ctx* c, const float* x, const float* mask, float p, int spatial, float* y, int N, int C, int HW) {
+  return dropout_apply(c, "fg_dropout_forward", x, mask, p, spatial, y, N, C, HW);
+}
+int fg_dropout_backward(fg_ctx* c, const float* dy, const float* mask, float p, int spatial, float* dx, int N, int C,
+                        int HW) {
+  return dropout_apply(c, "fg_dropout_backward", dy, mask, p, spatial, dx, N, C, HW);
+}
+int fg_dropout_mask(fg_ctx* c, float* mask_dev, int64_t n, float p, uint64_t seed) {
+  ENTER(c);
+  FG_REQUIRE(mask_dev && n > 0 && is_dev(mask_dev), "fg_dropout_mask: needs a device buffer");
+  return k_bernoulli_keep(c, mask_dev, n, seed, p);
+}
+
+int fg_sigmoid_forward(fg_ctx* c, const float* x, float* y, int64_t n) {
+  ENTER(c);
+  FG_REQUIRE(x && y && n > 0, "fg_sigmoid_forward: bad arguments");
+  const float* xd;
+  float* yd;
+  FG_TRY(in_dev(c, x, n, 0, &xd));
+  FG_TRY(out_dev(c, y, n, 6, &yd, false));
+  FG_TRY(k_sigmoid_fwd(c, xd, yd, n));
+  return out_done(c, y, yd, n);
+}
+int fg_sigmoid_backward(fg_ctx* c, const float* y, const float* dy, float* dx, int64_t n) {
+  ENTER(c);
+  FG_REQUIRE(y && dy && dx && n > 0, "fg_sigmoid_backward: bad arguments");
+  const float *yd, *dyd;
+  float* dxd;
+  FG_TRY(in_dev(c, y, n, 0, &yd));
+  FG_TRY(in_dev(c, dy, n, 1, &dyd));
+  FG_TRY(out_dev(c, dx, n, 6, &dxd, false));
+  FG_TRY(k_sigmoid_bwd(c, dyd, yd, dxd, n));
+  return out_done(c, dx, dxd, n);
 }
 
 }  // extern "C"

@@ -57,3 +57,40 @@ def trained_like_init(layout_total, rng, gain=1.0, slope=0.25):
         else:
             P[o:o + n] = rng.standard_normal(n) * 0.05
     return P
+
+
+def c2f_G_layout(c):
+    """create_G_d (models_c2f.lua:113-145): 5 SpatialConvolutionUpsample(factor 1) with 4 shared-slope PReLUs."""
+    cin, cout, k = [c + 1, 64, 64, 128, 256], [64, 64, 128, 256, c], [3, 3, 5, 5, 7]
+    out, o = {}, 0
+    for i in range(5):
+        items = [("c%dW" % (i + 1), (cout[i], cin[i], k[i], k[i])), ("c%db" % (i + 1), (cout[i],))]
+        if i < 4:
+            items.append(("a%d" % (i + 1), (1,)))
+        for name, shape in items:
+            out[name] = (o, shape)
+            o += int(np.prod(shape))
+    return out, o
+
+
+def c2f_D_layout(c):
+    """create_D_c (models_c2f.lua:237-278)."""
+    cin, cout = [c, 64, 64, 128], [64, 64, 128, 256]
+    items = []
+    for i in range(4):
+        items += [("c%dW" % (i + 1), (cout[i], cin[i], 3, 3)), ("c%db" % (i + 1), (cout[i],)), ("a%d" % (i + 1), (1,))]
+    items += [("L1W", (512, 16384)), ("L1b", (512,)), ("a5", (1,)), ("L2W", (1, 512)), ("L2b", (1,))]
+    out, o = {}, 0
+    for name, shape in items:
+        out[name] = (o, shape)
+        o += int(np.prod(shape))
+    return out, o
+
+
+def c2f_pairs(B, c, rng):
+    """Synthetic stand-in for dataset_c2f.lua:54-60: fine ~ U[0,1), coarse = 2x average-down then 2x nearest-up,
+    diff = fine - coarse.  Returns (diff, coarse), both [B][c][32][32] float32."""
+    fine = rng.random((B, c, 32, 32))
+    small = fine.reshape(B, c, 16, 2, 16, 2).mean(axis=(3, 5))
+    coarse = np.repeat(np.repeat(small, 2, axis=2), 2, axis=3)
+    return (fine - coarse).astype(np.float32), coarse.astype(np.float32)

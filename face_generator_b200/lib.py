@@ -72,6 +72,34 @@ SYMBOLS = {
     "fg_bn_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
     "fg_prelu_forward": (_I, [_P, _P, _P, _P, _L]),
     "fg_prelu_backward": (_I, [_P, _P, _P, _P, _P, _P, _L]),
+    "fg_upsample2_forward": (_I, [_P, _P, _P, _I, _I, _I, _I]),
+    "fg_upsample2_backward": (_I, [_P, _P, _P, _I, _I, _I, _I]),
+    "fg_avgpool2_forward": (_I, [_P, _P, _P, _I, _I, _I, _I]),
+    "fg_avgpool2_backward": (_I, [_P, _P, _P, _I, _I, _I, _I]),
+    "fg_maxpool2_forward": (_I, [_P, _P, _P, _I, _I, _I, _I]),
+    "fg_maxpool2_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I]),
+    "fg_dropout_forward": (_I, [_P, _P, _P, _F, _I, _P, _I, _I, _I]),
+    "fg_dropout_backward": (_I, [_P, _P, _P, _F, _I, _P, _I, _I, _I]),
+    "fg_dropout_mask": (_I, [_P, _P, _L, _F, _U64]),
+    "fg_sigmoid_forward": (_I, [_P, _P, _P, _L]),
+    "fg_sigmoid_backward": (_I, [_P, _P, _P, _P, _L]),
+    "fg_c2f_create": (_I, [_P, C.POINTER(_P)]),
+    "fg_c2f_destroy": (_I, [_P]),
+    "fg_c2f_param_count": (_L, [_I, _I]),
+    "fg_c2f_mask_per_sample": (_I, []),
+    "fg_c2f_set_params": (_I, [_P, _I, _P]),
+    "fg_c2f_get_params": (_I, [_P, _I, _P]),
+    "fg_c2f_get_grads": (_I, [_P, _I, _P]),
+    "fg_c2f_zero_grads": (_I, [_P, _I]),
+    "fg_c2f_params_ptr": (_P, [_P, _I]),
+    "fg_c2f_grads_ptr": (_P, [_P, _I]),
+    "fg_c2f_set_adam_state": (_I, [_P, _I, _P, _P, _I]),
+    "fg_c2f_get_adam_state": (_I, [_P, _I, _P, _P, C.POINTER(_I)]),
+    "fg_c2f_G_forward": (_I, [_P, _P, _P, _I, _P]),
+    "fg_c2f_G_backward": (_I, [_P, _P]),
+    "fg_c2f_D_forward": (_I, [_P, _P, _P, _I, _I, _P, _U64, _P]),
+    "fg_c2f_D_backward": (_I, [_P, _P, _I, _P]),
+    "fg_c2f_train_step": (_I, [_P, C.POINTER(Hyper), _I, _P, _P, _P, _P, _P, _P, _P, _U64, C.POINTER(StepStats)]),
     "fg_train_step": (_I, [_P, C.POINTER(Hyper), _I, _P, _P, _P, _P, _P, _U64, C.POINTER(StepStats)]),
     "fg_sample": (_I, [_P, _P, _I, _I, _P]),
     "fg_dp_unique_id": (_I, [_P]),
@@ -343,3 +371,185 @@ class Context:
 
     def dp_broadcast_params(self):
         _check(self.lib.fg_dp_broadcast_params(self.h), "fg_dp_broadcast_params")
+
+    # ---- L-op: resampling / pooling / dropout / sigmoid at the nn.Module boundary (NCHW numpy in/out) ----
+    def upsample2_forward(self, x):
+        x = f32(x)
+        N, Cc, H, W = x.shape
+        y = np.empty((N, Cc, 2 * H, 2 * W), np.float32)
+        _check(self.lib.fg_upsample2_forward(self.h, _ptr(x), _ptr(y), N, Cc, H, W), "fg_upsample2_forward")
+        return y
+
+    def upsample2_backward(self, dy):
+        dy = f32(dy)
+        N, Cc, H2, W2 = dy.shape
+        dx = np.empty((N, Cc, H2 // 2, W2 // 2), np.float32)
+        _check(self.lib.fg_upsample2_backward(self.h, _ptr(dy), _ptr(dx), N, Cc, H2 // 2, W2 // 2), "fg_upsample2_backward")
+        return dx
+
+    def avgpool2_forward(self, x):
+        x = f32(x)
+        N, Cc, H, W = x.shape
+        y = np.empty((N, Cc, H // 2, W // 2), np.float32)
+        _check(self.lib.fg_avgpool2_forward(self.h, _ptr(x), _ptr(y), N, Cc, H, W), "fg_avgpool2_forward")
+        return y
+
+    def avgpool2_backward(self, dy):
+        dy = f32(dy)
+        N, Cc, Ho, Wo = dy.shape
+        dx = np.empty((N, Cc, 2 * Ho, 2 * Wo), np.float32)
+        _check(self.lib.fg_avgpool2_backward(self.h, _ptr(dy), _ptr(dx), N, Cc, 2 * Ho, 2 * Wo), "fg_avgpool2_backward")
+        return dx
+
+    def maxpool2_forward(self, x):
+        x = f32(x)
+        N, Cc, H, W = x.shape
+        y = np.empty((N, Cc, H // 2, W // 2), np.float32)
+        _check(self.lib.fg_maxpool2_forward(self.h, _ptr(x), _ptr(y), N, Cc, H, W), "fg_maxpool2_forward")
+        return y
+
+    def maxpool2_backward(self, x, dy):
+        x, dy = f32(x), f32(dy)
+        N, Cc, H, W = x.shape
+        dx = np.empty_like(x)
+        _check(self.lib.fg_maxpool2_backward(self.h, _ptr(x), _ptr(dy), _ptr(dx), N, Cc, H, W), "fg_maxpool2_backward")
+        return dx
+
+    def dropout_forward(self, x, mask, p, spatial=False):
+        """x [N][C][H][W] (or [N][F]); mask: keep flags (same shape as x, or [N][C] when spatial) / None = evaluate()."""
+        x = f32(x)
+        N, Cc = x.shape[0], x.shape[1]
+        HW = int(np.prod(x.shape[2:])) if x.ndim > 2 else 1
+        mask = f32(mask) if mask is not None else None
+        y = np.empty_like(x)
+        _check(self.lib.fg_dropout_forward(self.h, _ptr(x), _ptr(mask), p, int(spatial), _ptr(y), N, Cc, HW),
+               "fg_dropout_forward")
+        return y
+
+    def dropout_backward(self, dy, mask, p, spatial=False):
+        dy = f32(dy)
+        N, Cc = dy.shape[0], dy.shape[1]
+        HW = int(np.prod(dy.shape[2:])) if dy.ndim > 2 else 1
+        mask = f32(mask) if mask is not None else None
+        dx = np.empty_like(dy)
+        _check(self.lib.fg_dropout_backward(self.h, _ptr(dy), _ptr(mask), p, int(spatial), _ptr(dx), N, Cc, HW),
+               "fg_dropout_backward")
+        return dx
+
+    def dropout_mask(self, n, p, seed):
+        """keep flags drawn on the device (throughput mode), returned as a host array for inspection."""
+        dev = self.lib.fg_dev_alloc(n * 4)
+        if not dev:
+            raise FGError("fg_dev_alloc failed")
+        try:
+            _check(self.lib.fg_dropout_mask(self.h, dev, n, p, seed), "fg_dropout_mask")
+            out = np.empty(n, np.float32)
+            _check(self.lib.fg_memcpy(self.h, _ptr(out), dev, n * 4), "fg_memcpy")
+            self.sync()
+        finally:
+            self.lib.fg_dev_free(dev)
+        return out
+
+    def sigmoid_forward(self, x):
+        x = f32(x)
+        y = np.empty_like(x)
+        _check(self.lib.fg_sigmoid_forward(self.h, _ptr(x), _ptr(y), x.size), "fg_sigmoid_forward")
+        return y
+
+    def sigmoid_backward(self, y, dy):
+        y, dy = f32(y), f32(dy)
+        dx = np.empty_like(y)
+        _check(self.lib.fg_sigmoid_backward(self.h, _ptr(y), _ptr(dy), _ptr(dx), y.size), "fg_sigmoid_backward")
+        return dx
+
+
+C2F_MASK_PER_SAMPLE = 16384 + 512
+
+
+class C2f:
+    """Coarse-to-fine nets + loop (train_c2f.lua) on a Context.  Mirrors lua/adversarial_c2f_b200.lua."""
+
+    def __init__(self, ctx):
+        self.ctx, self.lib, self.C = ctx, ctx.lib, ctx.C
+        h = C.c_void_p()
+        _check(self.lib.fg_c2f_create(ctx.h, C.byref(h)), "fg_c2f_create")
+        self.h = h
+        self.nG = int(self.lib.fg_c2f_param_count(NET_G, self.C))
+        self.nD = int(self.lib.fg_c2f_param_count(NET_D, self.C))
+
+    def close(self):
+        if self.h:
+            self.lib.fg_c2f_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.close()
+        except Exception:
+            pass
+
+    def count(self, net):
+        return self.nD if net == NET_D else self.nG
+
+    def set_params(self, net, p):
+        p = f32(p)
+        assert p.size == self.count(net)
+        _check(self.lib.fg_c2f_set_params(self.h, net, _ptr(p)), "fg_c2f_set_params")
+
+    def get_params(self, net):
+        out = np.empty(self.count(net), np.float32)
+        _check(self.lib.fg_c2f_get_params(self.h, net, _ptr(out)), "fg_c2f_get_params")
+        return out
+
+    def get_grads(self, net):
+        out = np.empty(self.count(net), np.float32)
+        _check(self.lib.fg_c2f_get_grads(self.h, net, _ptr(out)), "fg_c2f_get_grads")
+        return out
+
+    def zero_grads(self, net):
+        _check(self.lib.fg_c2f_zero_grads(self.h, net), "fg_c2f_zero_grads")
+
+    def set_adam_state(self, net, m, v, t):
+        _check(self.lib.fg_c2f_set_adam_state(self.h, net, _ptr(f32(m)), _ptr(f32(v)), int(t)), "fg_c2f_set_adam_state")
+
+    def get_adam_state(self, net):
+        m, v, t = np.empty(self.count(net), np.float32), np.empty(self.count(net), np.float32), C.c_int(0)
+        _check(self.lib.fg_c2f_get_adam_state(self.h, net, _ptr(m), _ptr(v), C.byref(t)), "fg_c2f_get_adam_state")
+        return m, v, t.value
+
+    def G_forward(self, noise, cond, want_diff=True):
+        noise, cond = f32(noise), f32(cond)
+        B = cond.shape[0]
+        out = np.empty((B, self.C, 32, 32), np.float32) if want_diff else None
+        _check(self.lib.fg_c2f_G_forward(self.h, _ptr(noise), _ptr(cond), B, _ptr(out)), "fg_c2f_G_forward")
+        return out
+
+    def G_backward(self, d_diff):
+        _check(self.lib.fg_c2f_G_backward(self.h, _ptr(f32(d_diff))), "fg_c2f_G_backward")
+
+    def D_forward(self, diff, cond, masks=None, training=True, seed=0):
+        diff, cond = f32(diff), f32(cond)
+        B = diff.shape[0]
+        masks = f32(masks) if masks is not None else None
+        out = np.empty(B, np.float32)
+        _check(self.lib.fg_c2f_D_forward(self.h, _ptr(diff), _ptr(cond), B, int(training), _ptr(masks), seed, _ptr(out)),
+               "fg_c2f_D_forward")
+        return out
+
+    def D_backward(self, d_out, want_wgrad=True, want_ddiff=True):
+        d_out = f32(d_out)
+        dd = np.empty((d_out.shape[0], self.C, 32, 32), np.float32) if want_ddiff else None
+        _check(self.lib.fg_c2f_D_backward(self.h, _ptr(d_out), int(want_wgrad), _ptr(dd)), "fg_c2f_D_backward")
+        return dd
+
+    def train_step(self, hyper, B, real_diff, cond_D, noise_D, cond_G, noise_G, masks_D=None, masks_G=None, seed=0,
+                   want_stats=True):
+        """Pointers may be numpy float32 arrays (host) or raw addresses (device / pinned)."""
+        st = StepStats() if want_stats else None
+        _check(self.lib.fg_c2f_train_step(self.h, C.byref(hyper), B, _ptr(real_diff), _ptr(cond_D), _ptr(noise_D),
+                                          _ptr(cond_G), _ptr(noise_G), _ptr(masks_D), _ptr(masks_G), seed,
+                                          C.byref(st) if st is not None else None), "fg_c2f_train_step")
+        if st is None:
+            return None
+        return dict(loss_D=st.loss_D, loss_G=st.loss_G, conf=list(st.conf), t_D=st.t_D, t_G=st.t_G, acc_D=st.acc_D)

@@ -140,6 +140,30 @@ int fg_bn_backward(fg_ctx* ctx, const float* x, const float* gamma, const float*
 int fg_prelu_forward(fg_ctx* ctx, const float* x, const float* slope, float* y, int64_t n);
 int fg_prelu_backward(fg_ctx* ctx, const float* x, const float* slope, const float* dy, float* dx, float* dslope,
                       int64_t n);
+/* nn.SpatialUpSamplingNearest(2) (models.lua:63,68): x [N][C][H][W] -> y [N][C][2H][2W];
+ * backward sums each 2x2 block of dy.                                                            */
+int fg_upsample2_forward(fg_ctx* ctx, const float* x, float* y, int N, int C, int H, int W);
+int fg_upsample2_backward(fg_ctx* ctx, const float* dy, float* dx, int N, int C, int H, int W);
+/* nn.SpatialAveragePooling(2,2,2,2) (models.lua:388,...): x [N][C][H][W] -> y [N][C][H/2][W/2]   */
+int fg_avgpool2_forward(fg_ctx* ctx, const float* x, float* y, int N, int C, int H, int W);
+int fg_avgpool2_backward(fg_ctx* ctx, const float* dy, float* dx, int N, int C, int H, int W);
+/* nn.SpatialMaxPooling(2,2) (models_c2f.lua:251,256): first strict maximum in row-major window
+ * order wins (THNN); the backward recomputes the arg-max from x.                                 */
+int fg_maxpool2_forward(fg_ctx* ctx, const float* x, float* y, int N, int C, int H, int W);
+int fg_maxpool2_backward(fg_ctx* ctx, const float* x, const float* dy, float* dx, int N, int C, int H, int W);
+/* nn.Dropout (spatial=0: one keep flag per element, y = x*mask/(1-p), models.lua:408,411) and
+ * nn.SpatialDropout (spatial=1: one flag per (n,c) plane, NO rescale, models.lua:387,...).
+ * mask holds 0/1 keep flags (n elements resp. N*C); mask == NULL means evaluate(): Dropout is the
+ * identity, SpatialDropout multiplies by (1-p).  The backward is the same map applied to dy.     */
+int fg_dropout_forward(fg_ctx* ctx, const float* x, const float* mask, float p, int spatial, float* y, int N, int C,
+                       int HW);
+int fg_dropout_backward(fg_ctx* ctx, const float* dy, const float* mask, float p, int spatial, float* dx, int N,
+                        int C, int HW);
+/* draws keep flags (1 with probability 1-p) for the two layers above into a DEVICE buffer        */
+int fg_dropout_mask(fg_ctx* ctx, float* mask_dev, int64_t n, float p, uint64_t seed);
+/* nn.Sigmoid (models.lua:74,413)                                                                 */
+int fg_sigmoid_forward(fg_ctx* ctx, const float* x, float* y, int64_t n);
+int fg_sigmoid_backward(fg_ctx* ctx, const float* y, const float* dy, float* dx, int64_t n);
 
 /* ---- L-step: the adversarial.lua:54-300 loop body -------------------------------------------- */
 /* real [B/2][C][32][32] in [0,1]; noise_D [B/2][100], noise_G [B][100] ~ U(-1,1)
@@ -151,6 +175,44 @@ int fg_train_step(fg_ctx* ctx, const fg_hyper* h, int B, const float* real, cons
                   fg_step_stats* stats);
 /* sample.lua:80 / nn_utils.lua:45-69: G forward over N noise vectors in chunks (train-mode BN). */
 int fg_sample(fg_ctx* ctx, const float* noise, int N, int chunk, float* images_out);
+
+/* ---- coarse-to-fine GAN (train_c2f.lua; BASELINE configs[3]) --------------------------------- */
+/* G = models_c2f.lua:113-145 create_G_d, D = models_c2f.lua:237-278 create_D_c, both at 32x32 on
+ * the ctx's channel count; cudnn.SpatialConvolutionUpsample with factor 1
+ * (layers/cudnnSpatialConvolutionUpsample.lua) is a "same" convolution.  The object borrows the
+ * ctx (stream, device, DP communicator, "conv_impl"); destroy it before the ctx.  Flat parameter
+ * vectors follow getParameters() order: G [c1W c1b a1 ... c4W c4b a4 c5W c5b], D [c1W c1b a1 ...
+ * c4W c4b a4 L1W L1b a5 L2W L2b].                                                                 */
+typedef struct fg_c2f fg_c2f;
+int fg_c2f_create(fg_ctx* ctx, fg_c2f** out);
+int fg_c2f_destroy(fg_c2f* n);
+int64_t fg_c2f_param_count(int net, int channels);        /* 1 101 319 / 8 797 382 for colour      */
+int fg_c2f_mask_per_sample(void);                         /* 16896 = [256][8][8] + [512] nn.Dropout */
+int fg_c2f_set_params(fg_c2f* n, int net, const float* src);
+int fg_c2f_get_params(fg_c2f* n, int net, float* dst);
+int fg_c2f_get_grads(fg_c2f* n, int net, float* dst);
+int fg_c2f_zero_grads(fg_c2f* n, int net);
+float* fg_c2f_params_ptr(fg_c2f* n, int net);
+float* fg_c2f_grads_ptr(fg_c2f* n, int net);
+int fg_c2f_set_adam_state(fg_c2f* n, int net, const float* m, const float* v, int t);
+int fg_c2f_get_adam_state(fg_c2f* n, int net, float* m, float* v, int* t);
+/* MODEL_G:forward({noise, cond}): noise [B][1][32][32], cond (coarse image) [B][C][32][32]
+ * -> generated diff [B][C][32][32] (may be NULL).  backward accumulates into G's grad buffer.    */
+int fg_c2f_G_forward(fg_c2f* n, const float* noise, const float* cond, int B, float* diff_out);
+int fg_c2f_G_backward(fg_c2f* n, const float* d_diff);
+/* MODEL_D:forward({diff, cond}) -> [B] sigmoid outputs; masks [B][16896] nn.Dropout keep flags
+ * or NULL (drawn from seed); training=0 => evaluate().  d_diff = MODEL_D.gradInput[1].           */
+int fg_c2f_D_forward(fg_c2f* n, const float* diff, const float* cond, int B, int training, const float* masks,
+                     uint64_t seed, float* out);
+int fg_c2f_D_backward(fg_c2f* n, const float* d_out, int want_wgrad, float* d_diff);
+/* one adversarial_c2f.lua:121-187 loop body (1 D iteration + 1 G iteration, optim.adam for both):
+ * real_diff [B/2][C][32][32] (fine - coarse of the real half), cond_D [B][C][32][32] (rows < B/2
+ * go with the real half, the rest feed G), noise_D [B/2][1][32][32], cond_G / noise_G [B] redrawn
+ * for the G step, masks_* [B][16896] or NULL.  h->D_maxAcc / accs_interval are ignored (the c2f
+ * loop has no accuracy gate).                                                                     */
+int fg_c2f_train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_diff, const float* cond_D,
+                      const float* noise_D, const float* cond_G, const float* noise_G, const float* masks_D,
+                      const float* masks_G, uint64_t seed, fg_step_stats* stats);
 
 /* ---- data parallel: one process per GPU, NCCL over NVLink (new functionality) ----- */
 int fg_dp_unique_id(void* out128);                        /* ncclGetUniqueId, 128 bytes           */

@@ -1,0 +1,216 @@
+"""Coarse-to-fine path (BASELINE.json configs[3]: train_c2f.lua, SpatialConvolutionUpsample nets).
+
+CPU: the oracle reproduces the committed golden vectors; the C ABI reports the reference's parameter counts.
+GPU (-m gpu): fg_c2f_* through the C ABI against the fp64 oracle on the same seeded inputs.
+Tolerances: 1e-4 relative (BASELINE.json north_star) on everything continuous; gradients are held to 1e-4 on the
+"smooth" cases (PReLU slopes 1 => no kinks) and to KINK_TOL on cases with real slopes."""
+import os
+
+import numpy as np
+import pytest
+
+import c2f_utils as CU
+import parity_utils as PU
+from oracle import oracle_c2f as OC
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STRIDE = 1009
+TOL = 1e-4
+KINK_TOL = 2e-2
+
+
+def load(name):
+    return np.load(os.path.join(G, name + ".npz"), allow_pickle=False)
+
+
+# ------------------------------------------------------------------------------------------ CPU
+@pytest.mark.parametrize("name", ["c2f_train_color_b8", "c2f_train_gray_b4_smooth"])
+def test_oracle_reproduces_c2f_golden(name):
+    g = load(name)
+    B, C = int(g["B"]), int(g["C"])
+    case = CU.make_case(B, C, seed=int(g["seed"]), init=str(g["init"]))
+    assert abs(sum(np.abs(case[k]).sum() for k in sorted(case)) - float(g["input_checksum"])) < 1e-5
+    res = CU.oracle_iteration(case, B, C)
+    assert abs(res["lossD"] - float(g["lossD"])) < 1e-10 and abs(res["lossG"] - float(g["lossG"])) < 1e-10
+    np.testing.assert_array_equal(res["conf"], g["conf"])
+    assert PU.relerr(res["gradD"][::STRIDE], g["gradD"]) < 1e-9
+    assert PU.relerr(res["gradG"][::STRIDE], g["gradG"]) < 1e-9
+    assert PU.relerr(res["state"]["PD"][::STRIDE], g["PD"]) < 1e-12
+
+
+def test_c2f_param_counts_match_reference_models():
+    from face_generator_b200.lib import load_library, C2F_MASK_PER_SAMPLE
+    from face_generator_b200 import layouts as LY
+    lib = load_library()
+    for C in (1, 3):
+        assert lib.fg_c2f_param_count(0, C) == OC.G_param_count(C) == LY.c2f_G_layout(C)[1]
+        assert lib.fg_c2f_param_count(1, C) == OC.D_param_count(C) == LY.c2f_D_layout(C)[1]
+    assert lib.fg_c2f_param_count(0, 3) == 1101319 and lib.fg_c2f_param_count(1, 3) == 8797382
+    assert lib.fg_c2f_mask_per_sample() == OC.MASK_PER_SAMPLE == C2F_MASK_PER_SAMPLE
+
+
+# ------------------------------------------------------------------------------------------ GPU
+def _ctx(B, C, impl):
+    import face_generator_b200 as fg
+    ctx = fg.Context(0, max_batch=B, channels=C)
+    ctx.set_option("conv_impl", impl)
+    return ctx, fg.C2f(ctx)
+
+
+def _layer_errs(got, ref, layout):
+    out = {}
+    for k, (o, s) in layout.items():
+        n = int(np.prod(s))
+        out[k] = PU.relerr(got[o:o + n], ref[o:o + n])
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C", [3, 1])
+@pytest.mark.parametrize("impl", [0, 2])
+def test_gpu_c2f_nets_forward_backward(C, impl):
+    from face_generator_b200.lib import NET_D, NET_G
+    B = 6
+    case = CU.make_case(2 * B, C, seed=510 + C, init="smooth")
+    rng = np.random.default_rng(7)
+    noise, cond = case["noise_G"][:B], case["cond_G"][:B]
+    dout = rng.standard_normal((B, C, 32, 32)).astype(np.float32)
+    g = OC.f64.G()
+    ref_out = g.forward(case["PG"], noise, cond)
+    ref_dP = g.backward(dout)
+    ctx, net = _ctx(2 * B, C, impl)
+    net.set_params(NET_G, case["PG"])
+    net.set_params(NET_D, case["PD"])
+    assert PU.relerr(net.G_forward(noise, cond), ref_out) < TOL
+    net.zero_grads(NET_G)
+    net.G_backward(dout)
+    errs = _layer_errs(net.get_grads(NET_G), ref_dP, OC.G_layout(C))
+    assert max(errs.values()) < TOL, errs
+    # D: training mode with given masks, then evaluate()
+    diff, condD, masks = case["real_diff"][:B], case["cond_D"][:B], case["masks_D"][:B]
+    dd = rng.standard_normal(B).astype(np.float32)
+    d = OC.f64.D()
+    ref_o = d.forward(case["PD"], diff, condD, masks)
+    ref_dPD, ref_dd = d.backward(dd)
+    assert PU.relerr(net.D_forward(diff, condD, masks=masks), ref_o) < TOL
+    net.zero_grads(NET_D)
+    got_dd = net.D_backward(dd)
+    assert PU.relerr(got_dd, ref_dd) < TOL
+    errs = _layer_errs(net.get_grads(NET_D), ref_dPD, OC.D_layout(C))
+    assert max(errs.values()) < TOL, errs
+    ref_eval = d.forward(case["PD"], diff, condD, None, training=False)
+    assert PU.relerr(net.D_forward(diff, condD, training=False), ref_eval) < TOL
+    # want_wgrad=0 leaves D's gradient buffer untouched and still returns gradInput[1]
+    net.D_forward(diff, condD, masks=masks)
+    net.zero_grads(NET_D)
+    got2 = net.D_backward(dd, want_wgrad=False)
+    assert np.abs(net.get_grads(NET_D)).max() == 0.0
+    assert PU.relerr(got2, ref_dd) < TOL
+    net.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,C,init,impl", [(8, 3, "smooth", 2), (8, 3, "smooth", 0), (4, 1, "smooth", 2), (8, 3, "trained", 2),
+                                           (16, 1, "trained", 2)])
+def test_gpu_c2f_train_step_matches_oracle(B, C, init, impl):
+    import face_generator_b200 as fg
+    from face_generator_b200.lib import NET_D, NET_G
+    case = CU.make_case(B, C, seed=520 + B + C, init=init)
+    ref = CU.oracle_iteration(case, B, C)
+    ctx, net = _ctx(B, C, impl)
+    net.set_params(NET_G, case["PG"])
+    net.set_params(NET_D, case["PD"])
+    hyper = fg.hyper_default(**{k: v for k, v in CU.HYPER.items()})
+    st = net.train_step(hyper, B, case["real_diff"], case["cond_D"], case["noise_D"], case["cond_G"], case["noise_G"],
+                        case["masks_D"], case["masks_G"])
+    assert abs(st["loss_D"] - ref["lossD"]) < TOL * max(1.0, abs(ref["lossD"]))
+    assert abs(st["loss_G"] - ref["lossG"]) < TOL * max(1.0, abs(ref["lossG"]))
+    assert st["conf"] == [int(v) for v in ref["conf"]]
+    assert st["t_D"] == 1 and st["t_G"] == 1
+    gtol = TOL if init == "smooth" else KINK_TOL
+    assert PU.relerr(net.get_grads(NET_D), ref["gradD"]) < gtol
+    assert PU.relerr(net.get_grads(NET_G), ref["gradG"]) < gtol
+    # first Adam step: |dp| = lr wherever |g| >> eps, so parameters are compared where the gradient is not ~0
+    for netid, key, gkey in ((NET_D, "PD", "gradD"), (NET_G, "PG", "gradG")):
+        big = np.abs(ref[gkey]) > 1e-4 * np.abs(ref[gkey]).max()
+        got = net.get_params(netid)
+        assert np.abs(got[big] - ref["state"][key][big]).max() < 2e-5, key
+        m, v, t = net.get_adam_state(netid)
+        assert t == 1
+        assert PU.relerr(m, ref["state"]["m" + key[1]]) < gtol
+    net.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c2f_train_color_b8", "c2f_train_gray_b4_smooth"])
+def test_gpu_c2f_matches_golden(name):
+    import face_generator_b200 as fg
+    from face_generator_b200.lib import NET_D, NET_G
+    g = load(name)
+    B, C, init = int(g["B"]), int(g["C"]), str(g["init"])
+    case = CU.make_case(B, C, seed=int(g["seed"]), init=init)
+    ctx, net = _ctx(B, C, 2)
+    net.set_params(NET_G, case["PG"])
+    net.set_params(NET_D, case["PD"])
+    st = net.train_step(fg.hyper_default(**CU.HYPER), B, case["real_diff"], case["cond_D"], case["noise_D"], case["cond_G"],
+                        case["noise_G"], case["masks_D"], case["masks_G"])
+    assert abs(st["loss_D"] - float(g["lossD"])) < TOL and abs(st["loss_G"] - float(g["lossG"])) < TOL * max(1, float(g["lossG"]))
+    assert st["conf"] == [int(v) for v in g["conf"]]
+    gtol = TOL if init == "smooth" else KINK_TOL
+    assert np.abs(net.get_grads(NET_D)[::STRIDE] - g["gradD"]).max() < gtol * float(g["gradD_absmax"])
+    assert np.abs(net.get_grads(NET_G)[::STRIDE] - g["gradG"]).max() < gtol * float(g["gradG_absmax"])
+    net.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_c2f_modules_equal_fused_step():
+    """fevalD / fevalG_on_D composed from the L-net calls == the fused fg_c2f_train_step (same kernels underneath)."""
+    import face_generator_b200 as fg
+    from face_generator_b200 import adversarial_c2f as A
+    from face_generator_b200.lib import NET_D, NET_G
+    B, C = 8, 3
+    case = CU.make_case(B, C, seed=530, init="smooth")
+    # lr = 0 keeps D's parameters fixed between the D and the G step, so both compositions see the same D
+    hyper = fg.hyper_default(**dict(CU.HYPER, lr_D=0.0, lr_G=0.0, D_L1=0.0, D_clamp=0.0, G_clamp=0.0))
+    ctx, net = _ctx(B, C, 2)
+    net.set_params(NET_G, case["PG"])
+    net.set_params(NET_D, case["PD"])
+    A.train_batch(net, hyper, case["real_diff"], case["cond_D"], case["noise_D"], case["cond_G"], case["noise_G"],
+                  case["masks_D"], case["masks_G"])
+    fused = net.get_grads(NET_D), net.get_grads(NET_G)
+    mod = A.train_batch_modules(net, case["real_diff"], case["cond_D"], case["noise_D"], case["cond_G"], case["noise_G"],
+                                case["masks_D"], case["masks_G"])
+    assert PU.relerr(mod["grad_D"], fused[0]) < 2e-5
+    assert PU.relerr(mod["grad_G"], fused[1]) < 2e-5
+    net.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_c2f_seeded_dropout_is_reproducible_and_trains():
+    """Throughput mode: masks == NULL => keep flags drawn on the device from `seed`."""
+    import face_generator_b200 as fg
+    from face_generator_b200.lib import NET_D, NET_G
+    B, C = 8, 3
+    case = CU.make_case(B, C, seed=540)
+    hyper = fg.hyper_default(**CU.HYPER)
+    grads = []
+    for rep in range(2):
+        ctx, net = _ctx(B, C, 2)
+        net.set_params(NET_G, case["PG"])
+        net.set_params(NET_D, case["PD"])
+        losses = []
+        for it in range(3):
+            st = net.train_step(hyper, B, case["real_diff"], case["cond_D"], case["noise_D"], case["cond_G"],
+                                case["noise_G"], None, None, seed=99 + it)
+            losses.append((st["loss_D"], st["loss_G"]))
+            assert np.isfinite(st["loss_D"]) and np.isfinite(st["loss_G"]) and st["t_D"] == it + 1
+        grads.append((net.get_grads(NET_D), losses))
+        net.close()
+        ctx.close()
+    # split-K atomics are the only run-to-run difference
+    assert np.allclose(np.array(grads[0][1]), np.array(grads[1][1]), rtol=1e-4, atol=1e-6)
+    assert PU.relerr(grads[0][0], grads[1][0]) < KINK_TOL
