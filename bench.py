@@ -36,6 +36,22 @@ def load_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
 
 
+def ncu_traffic(profile="r1_ncu_tapconv_v12.md"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the G.C2 forward launch at batch 256 (the first kernel of the
+    committed `ncu --set full` summary; a number taken under the profiler, quoted only as traffic, never as time)."""
+    import re
+    try:
+        txt = open(os.path.join(ROOT, "profiles", profile)).read().split("\n## ")[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = re.search(r"\| %s \| ([0-9.,]+) \| (\w+) \|" % re.escape(key), txt)
+            tot += float(m.group(1).replace(",", "")) * scale[m.group(2)]
+        return tot, "profiles/" + profile
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -243,6 +259,7 @@ def main():
     t_c2 = (fam["G.C2.fwd"][0] + fam["G.C2.dgrad"][0] + fam["G.C2.wgrad"][0]) / 1e3
     tf_c2 = 3.5 * B * F_GC2 / t_c2 / 1e12 if t_c2 > 0 else 0.0
     peak = peaks["bf16_sus"] / 2.0
+    traffic, traffic_src = ncu_traffic()
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -257,7 +274,9 @@ def main():
         "clocks": clocks,
         "roofline": {"kernel": "G.C2 5x5 conv 256->128 @32x32 forward (implicit GEMM M=B*1024,N=128,K=6400)",
                      "bound": "tensor", "achieved": tf_fwd, "peak": peak, "unit": "TFLOP/s",
-                     "frac": tf_fwd / peak, "traffic": None,
+                     "frac": tf_fwd / peak, "traffic": traffic,
+                     "traffic_note": "DRAM bytes of the batch-%d launch (%s); algorithmic bytes of that launch: "
+                                     "input hi+lo 2x67.1 MB + output 134.2 MB + weights 9.4 MB" % (256, traffic_src),
                      "peak_source": "%s bf16 sustained %.1f TF / 2 (kind::tf32 is half rate); algorithmic fp32 FLOPs" % (
                          peaks["src"], peaks["bf16_sus"]),
                      "family_fwd_dgrad_wgrad_tflops": tf_c2,

@@ -54,6 +54,37 @@ int fg_bn_backward(fg_ctx* ctx, const float* x, const float* gamma, const float*
                    const float* dy, float* dx, float* dgamma, float* dbeta, int N, int C, int HW);
 int fg_prelu_forward(fg_ctx* ctx, const float* x, const float* slope, float* y, int64_t n);
 int fg_prelu_backward(fg_ctx* ctx, const float* x, const float* slope, const float* dy, float* dx, float* dslope, int64_t n);
+int fg_upsample2_forward(fg_ctx* ctx, const float* x, float* y, int N, int C, int H, int W);
+int fg_upsample2_backward(fg_ctx* ctx, const float* dy, float* dx, int N, int C, int H, int W);
+int fg_avgpool2_forward(fg_ctx* ctx, const float* x, float* y, int N, int C, int H, int W);
+int fg_avgpool2_backward(fg_ctx* ctx, const float* dy, float* dx, int N, int C, int H, int W);
+int fg_maxpool2_forward(fg_ctx* ctx, const float* x, float* y, int N, int C, int H, int W);
+int fg_maxpool2_backward(fg_ctx* ctx, const float* x, const float* dy, float* dx, int N, int C, int H, int W);
+int fg_dropout_forward(fg_ctx* ctx, const float* x, const float* mask, float p, int spatial, float* y, int N, int C, int HW);
+int fg_dropout_backward(fg_ctx* ctx, const float* dy, const float* mask, float p, int spatial, float* dx, int N, int C, int HW);
+int fg_dropout_mask(fg_ctx* ctx, float* mask_dev, int64_t n, float p, uint64_t seed);
+int fg_sigmoid_forward(fg_ctx* ctx, const float* x, float* y, int64_t n);
+int fg_sigmoid_backward(fg_ctx* ctx, const float* y, const float* dy, float* dx, int64_t n);
+typedef struct fg_c2f fg_c2f;
+int fg_c2f_create(fg_ctx* ctx, fg_c2f** out);
+int fg_c2f_destroy(fg_c2f* n);
+int64_t fg_c2f_param_count(int net, int channels);
+int fg_c2f_mask_per_sample(void);
+int fg_c2f_set_params(fg_c2f* n, int net, const float* src);
+int fg_c2f_get_params(fg_c2f* n, int net, float* dst);
+int fg_c2f_get_grads(fg_c2f* n, int net, float* dst);
+int fg_c2f_zero_grads(fg_c2f* n, int net);
+float* fg_c2f_params_ptr(fg_c2f* n, int net);
+float* fg_c2f_grads_ptr(fg_c2f* n, int net);
+int fg_c2f_set_adam_state(fg_c2f* n, int net, const float* m, const float* v, int t);
+int fg_c2f_get_adam_state(fg_c2f* n, int net, float* m, float* v, int* t);
+int fg_c2f_G_forward(fg_c2f* n, const float* noise, const float* cond, int B, float* diff_out);
+int fg_c2f_G_backward(fg_c2f* n, const float* d_diff);
+int fg_c2f_D_forward(fg_c2f* n, const float* diff, const float* cond, int B, int training, const float* masks, uint64_t seed, float* out);
+int fg_c2f_D_backward(fg_c2f* n, const float* d_out, int want_wgrad, float* d_diff);
+int fg_c2f_train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_diff, const float* cond_D, const float* noise_D,
+                      const float* cond_G, const float* noise_G, const float* masks_D, const float* masks_G, uint64_t seed,
+                      fg_step_stats* stats);
 int fg_train_step(fg_ctx* ctx, const fg_hyper* h, int B, const float* real, const float* noise_D, const float* noise_G,
                   const float* masks_D, const float* masks_G, uint64_t seed, fg_step_stats* stats);
 int fg_sample(fg_ctx* ctx, const float* noise, int N, int chunk, float* images_out);
