@@ -204,7 +204,98 @@ __global__ void dropout_nchw_kernel(const float* __restrict__ x, const float* __
 __global__ void scale_kernel(const float* __restrict__ x, float scale, float* __restrict__ y, int64_t n) {
   GRID_STRIDE(i, n) y[i] = x[i] * scale;
 }
+
+// ---- channel padding around the tensor-core kernels (layers whose small side has < 64 channels) ----------
+// x = hi + lo with hi exactly representable in TF32 (round to nearest on the 13 dropped mantissa bits)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  const uint32_t b = __float_as_uint(x);
+  hi = __uint_as_float((b + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
+}
+// src [P][Cs] -> hi/lo [P][Cp], channels >= Cs are zero
+__global__ void pad_split_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t P,
+                                 int Cs, int Cp) {
+  const int64_t n = P * Cp;
+  GRID_STRIDE(i, n) {
+    const int ch = (int)(i % Cp);
+    float h = 0.f, l = 0.f;
+    if (ch < Cs) split_tf32(src[(i / Cp) * Cs + ch], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+// dst[p][n] = src[p][n] + bias[n] for n < Cs  (src rows are Cp wide)
+__global__ void compact_bias_kernel(const float* __restrict__ src, const float* __restrict__ bias, float* __restrict__ dst,
+                                    int64_t P, int Cs, int Cp) {
+  const int64_t n = P * Cs;
+  GRID_STRIDE(i, n) {
+    const int ch = (int)(i % Cs);
+    dst[i] = src[(i / Cs) * Cp + ch] + (bias ? bias[ch] : 0.f);
+  }
+}
+// W [N][Cc][KK] -> TF32 hi/lo of the tap-major pack [t][Np][Cc] (rows >= N are never written: keep them zero)
+__global__ void pack_pad_split_kernel(const float* __restrict__ W, float* __restrict__ hi, float* __restrict__ lo, int N,
+                                      int Np, int Cc, int KK) {
+  const int64_t n = (int64_t)N * Cc * KK;
+  GRID_STRIDE(i, n) {
+    const int t = (int)(i % KK);
+    const int64_t r = i / KK;
+    const int ch = (int)(r % Cc), row = (int)(r / Cc);
+    float h, l;
+    split_tf32(W[i], h, l);
+    const int64_t j = ((int64_t)t * Np + row) * Cc + ch;
+    hi[j] = h;
+    lo[j] = l;
+  }
+}
+// dW[n][c][t] += G[t][n][c] for n < N, G rows padded to Np
+__global__ void unpack_wgrad_pad_kernel(const float* __restrict__ G, float* __restrict__ dW, int N, int Np, int Cc, int KK) {
+  const int64_t n = (int64_t)N * Cc * KK;
+  GRID_STRIDE(i, n) {
+    const int t = (int)(i % KK);
+    const int64_t r = i / KK;
+    const int ch = (int)(r % Cc), row = (int)(r / Cc);
+    dW[i] += G[((int64_t)t * Np + row) * Cc + ch];
+  }
+}
+// roles swapped (big channel count on the M side): dW[n][c][t] += Gt[KK-1-t][c][n], Gt = [KK][Cc][Np]
+__global__ void unpack_wgrad_swapped_kernel(const float* __restrict__ Gt, float* __restrict__ dW, int N, int Np, int Cc,
+                                            int KK) {
+  const int64_t n = (int64_t)N * Cc * KK;
+  GRID_STRIDE(i, n) {
+    const int t = (int)(i % KK);
+    const int64_t r = i / KK;
+    const int ch = (int)(r % Cc), row = (int)(r / Cc);
+    dW[i] += Gt[((int64_t)(KK - 1 - t) * Cc + ch) * Np + row];
+  }
+}
 }  // namespace
+
+int k_pad_split(fg_ctx* c, const float* src, float* hi, float* lo, int64_t P, int Cs, int Cp) {
+  pad_split_kernel<<<grid_for(P * Cp, 256), 256, 0, c->stream>>>(src, hi, lo, P, Cs, Cp);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int k_compact_bias(fg_ctx* c, const float* src, const float* bias, float* dst, int64_t P, int Cs, int Cp) {
+  compact_bias_kernel<<<grid_for(P * Cs, 256), 256, 0, c->stream>>>(src, bias, dst, P, Cs, Cp);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int k_pack_pad_split(fg_ctx* c, const float* W, float* hi, float* lo, int N, int Np, int Cc, int KK) {
+  pack_pad_split_kernel<<<grid_for((int64_t)N * Cc * KK, 256), 256, 0, c->stream>>>(W, hi, lo, N, Np, Cc, KK);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int k_unpack_wgrad_pad(fg_ctx* c, const float* G, float* dW, int N, int Np, int Cc, int KK) {
+  unpack_wgrad_pad_kernel<<<grid_for((int64_t)N * Cc * KK, 256), 256, 0, c->stream>>>(G, dW, N, Np, Cc, KK);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int k_unpack_wgrad_swapped(fg_ctx* c, const float* Gt, float* dW, int N, int Np, int Cc, int KK) {
+  unpack_wgrad_swapped_kernel<<<grid_for((int64_t)N * Cc * KK, 256), 256, 0, c->stream>>>(Gt, dW, N, Np, Cc, KK);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
 
 int k_join_to_nhwc(fg_ctx* c, const float* noise, const float* cond, float* out, int B, int C, int HW) {
   join_to_nhwc_kernel<<<grid_for((int64_t)B * HW * (C + 1), 256), 256, 0, c->stream>>>(noise, cond, out, B, C, HW);

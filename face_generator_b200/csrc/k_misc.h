@@ -11,6 +11,12 @@ int k_maxpool2_bwd(fg_ctx* c, const float* dp, const float* h, float* dh, int B,
 int k_dropout_nhwc(fg_ctx* c, const float* x, const float* masks, int64_t stride, int moff, int HW, int C, float scale,
                    float* y, int B);
 int k_bernoulli_keep(fg_ctx* c, float* out, int64_t n, uint64_t seed, float p_drop);  // 1 with probability 1-p_drop
+// channel padding around the tensor-core kernels (layers with a narrow output side)
+int k_pad_split(fg_ctx* c, const float* src, float* hi, float* lo, int64_t P, int Cs, int Cp);       // [P][Cs] -> TF32 hi/lo [P][Cp]
+int k_compact_bias(fg_ctx* c, const float* src, const float* bias, float* dst, int64_t P, int Cs, int Cp);
+int k_pack_pad_split(fg_ctx* c, const float* W, float* hi, float* lo, int N, int Np, int Cc, int KK);  // W[N][Cc][KK] -> [t][Np][Cc]
+int k_unpack_wgrad_pad(fg_ctx* c, const float* G, float* dW, int N, int Np, int Cc, int KK);          // dW += G[t][n<N][c]
+int k_unpack_wgrad_swapped(fg_ctx* c, const float* Gt, float* dW, int N, int Np, int Cc, int KK);     // dW += Gt[KK-1-t][c][n<N]
 // NCHW (L-op boundary); H,W are the sizes of the layer INPUT
 int k_up2_fwd_nchw(fg_ctx* c, const float* x, float* y, int64_t BC, int H, int W);
 int k_up2_bwd_nchw(fg_ctx* c, const float* dy, float* dx, int64_t BC, int H, int W);

@@ -27,6 +27,12 @@ struct ConvL {  // one convolution / Linear layer (NHWC, stride 1, same padding)
   float *Wp = nullptr, *Wpd = nullptr;                                            // fp32 packs [t][n][c], [t'][c][n]
   float *Wf_hi = nullptr, *Wf_lo = nullptr, *Wd_hi = nullptr, *Wd_lo = nullptr;   // TF32 splits of the packs
   float *x_hi = nullptr, *x_lo = nullptr;                                         // split of the input (fwd -> wgrad)
+  // Layers whose output side is too narrow for a tensor-core tile still run there with zero-padded channels:
+  //   pad_out (Cout <= 4, e.g. the 256->C 7x7 output layer): forward with the weights padded to pad_out rows;
+  //           wgrad with the roles swapped (big channel count on the 128-row M side, padded dY on the N side)
+  //   pad_dy  (Cout == 64): wgrad with dY padded to the 128 rows the M side needs
+  int pad_out = 0, pad_dy = 0;
+  float *Wq_hi = nullptr, *Wq_lo = nullptr;  // [t][pad_out][Cin] TF32 hi/lo
   bool need_dgrad = true;
   const char *tf = "", *td = "", *tw = "";
   ConvGeom geom(int B) const { return ConvGeom{B, H, H, Cin, Cout, k, 1}; }
@@ -50,6 +56,7 @@ struct fg_c2f {
   float *D_zl1 = nullptr, *D_al1 = nullptr, *D_hl1 = nullptr, *D_logit = nullptr, *D_out = nullptr, *D_masks = nullptr,
         *D_dlogit = nullptr, *D_dx = nullptr;
   float *ga = nullptr, *gb = nullptr, *dy_hi = nullptr, *dy_lo = nullptr, *ws = nullptr;
+  float *pad_hi = nullptr, *pad_lo = nullptr;  // channel-padded TF32 split of dY (ConvL::pad_out / pad_dy)
   float *in_a = nullptr, *in_b = nullptr, *in_c = nullptr, *in_d = nullptr, *in_e = nullptr, *in_m1 = nullptr,
         *in_m2 = nullptr, *io = nullptr;
   int G_B = 0, D_B = 0;
@@ -111,6 +118,21 @@ int convl_alloc(fg_c2f* n, ConvL& L) {
     FG_TRY(dalloc(n, &L.Wd_hi, nw));
     FG_TRY(dalloc(n, &L.Wd_lo, nw));
   }
+  // padded tensor-core variants (see ConvL)
+  const int B = n->maxB;
+  if (L.pad_out && !(tc_conv_eligible(ConvGeom{B, L.H, L.H, L.Cin, L.pad_out, L.k, 1}) &&
+                     tc_conv_eligible(ConvGeom{B, L.H, L.H, L.pad_out, L.Cin, L.k, 1}) && L.Cin % 128 == 0))
+    L.pad_out = 0;
+  if (L.pad_dy && !(L.x_hi && tc_conv_eligible(ConvGeom{B, L.H, L.H, L.Cin, L.pad_dy, L.k, 1}) && L.Cin % 64 == 0))
+    L.pad_dy = 0;
+  if (L.pad_out) {
+    const size_t nq = (size_t)L.k * L.k * L.pad_out * L.Cin;
+    FG_TRY(dalloc(n, &L.Wq_hi, nq));  // zero-initialised: the padding rows stay zero
+    FG_TRY(dalloc(n, &L.Wq_lo, nq));
+    const size_t nx = (size_t)B * L.H * L.H * L.Cin;
+    FG_TRY(dalloc(n, &L.x_hi, nx));
+    FG_TRY(dalloc(n, &L.x_lo, nx));
+  }
   return FG_OK;
 }
 int convl_pack(fg_ctx* c, ConvL& L, const float* P) {
@@ -120,10 +142,20 @@ int convl_pack(fg_ctx* c, ConvL& L, const float* P) {
   const int64_t nw = (int64_t)KK * L.Cout * L.Cin;
   if (L.Wf_hi) FG_TRY(tc_split(c, L.Wp, L.Wf_hi, L.Wf_lo, nw));
   if (L.Wd_hi) FG_TRY(tc_split(c, L.Wpd, L.Wd_hi, L.Wd_lo, nw));
+  if (L.pad_out) FG_TRY(k_pack_pad_split(c, P + L.w_off, L.Wq_hi, L.Wq_lo, L.Cout, L.pad_out, L.Cin, KK));
   return FG_OK;
 }
-int convl_fwd(fg_ctx* c, ConvL& L, const float* in, const float* P, float* out, int B) {
+int convl_fwd(fg_c2f* n, ConvL& L, const float* in, const float* P, float* out, int B) {
+  fg_ctx* c = n->c;
   const ConvGeom g = L.geom(B);
+  if (L.pad_out && c->conv_impl != FG_CONV_SIMT) {
+    FG_TRY(tc_split(c, in, L.x_hi, L.x_lo, (int64_t)B * L.H * L.H * L.Cin));
+    {
+      ScopedTimer t(c, L.tf);
+      FG_TRY(tc_conv_fwd(c, L.x_hi, L.x_lo, L.Wq_hi, L.Wq_lo, nullptr, n->ga, ConvGeom{B, L.H, L.H, L.Cin, L.pad_out, L.k, 1}, 0));
+    }
+    return k_compact_bias(c, n->ga, P + L.b_off, out, (int64_t)B * L.H * L.H, L.Cout, L.pad_out);
+  }
   if (tc_f(c, L, B)) {
     FG_TRY(tc_split(c, in, L.x_hi, L.x_lo, (int64_t)B * L.H * L.H * L.Cin));
     ScopedTimer t(c, L.tf);
@@ -138,7 +170,26 @@ int convl_bwd(fg_c2f* n, ConvL& L, const float* in, const float* dy, float* G, f
   const ConvGeom g = L.geom(B), gd = L.geom_d(B);
   const bool w_tc = G && tc_w(c, L, B), d_tc = din && tc_d(c, L, B);
   if (w_tc || d_tc) FG_TRY(tc_split(c, dy, n->dy_hi, n->dy_lo, (int64_t)B * L.H * L.H * L.Cout));
-  if (G) {
+  const bool tc_on = c->conv_impl != FG_CONV_SIMT;
+  const int64_t P = (int64_t)B * L.H * L.H;
+  if (G && tc_on && L.pad_out) {
+    // swapped roles: Gt[t'][c][n] = sum_p X[p][c] * dYpad[p + off(t')][n]  ==  dW[KK-1-t'][n][c]
+    FG_TRY(k_pad_split(c, dy, n->pad_hi, n->pad_lo, P, L.Cout, L.pad_out));
+    {
+      ScopedTimer t(c, L.tw);
+      FG_TRY(tc_conv_wgrad(c, n->pad_hi, n->pad_lo, L.x_hi, L.x_lo, n->ws, ConvGeom{B, L.H, L.H, L.pad_out, L.Cin, L.k, 1}));
+    }
+    FG_TRY(k_unpack_wgrad_swapped(c, n->ws, G + L.w_off, L.Cout, L.pad_out, L.Cin, L.k * L.k));
+    FG_TRY(k_colsum_add(c, dy, G + L.b_off, P, L.Cout, 0, 0));
+  } else if (G && tc_on && L.pad_dy && !w_tc) {
+    FG_TRY(k_pad_split(c, dy, n->pad_hi, n->pad_lo, P, L.Cout, L.pad_dy));
+    {
+      ScopedTimer t(c, L.tw);
+      FG_TRY(tc_conv_wgrad(c, L.x_hi, L.x_lo, n->pad_hi, n->pad_lo, n->ws, ConvGeom{B, L.H, L.H, L.Cin, L.pad_dy, L.k, 1}));
+    }
+    FG_TRY(k_unpack_wgrad_pad(c, n->ws, G + L.w_off, L.Cout, L.pad_dy, L.Cin, L.k * L.k));
+    FG_TRY(k_colsum_add(c, dy, G + L.b_off, P, L.Cout, 0, 0));
+  } else if (G) {
     {
       ScopedTimer t(c, L.tw);
       if (w_tc) FG_TRY(tc_conv_wgrad(c, L.x_hi, L.x_lo, n->dy_hi, n->dy_lo, n->ws, g));
@@ -146,7 +197,7 @@ int convl_bwd(fg_c2f* n, ConvL& L, const float* in, const float* dy, float* G, f
       else FG_TRY(k_wgrad_simt(c, in, dy, n->ws, g));
     }
     FG_TRY(k_unpack_wgrad(c, n->ws, G + L.w_off, L.Cout, L.Cin, L.k * L.k, 0, 0, L.cA, L.cS));
-    FG_TRY(k_colsum_add(c, dy, G + L.b_off, (int64_t)B * L.H * L.H, L.Cout, 0, 0));
+    FG_TRY(k_colsum_add(c, dy, G + L.b_off, P, L.Cout, 0, 0));
   }
   if (din) {
     ScopedTimer t(c, L.td);
@@ -172,6 +223,8 @@ void make_layouts(fg_c2f* n) {
       if (i < 4) { n->Gca[i] = o; o += 1; }
       L.need_dgrad = i > 0;
       L.tf = tf[i]; L.td = td[i]; L.tw = tw[i];
+      if (co[i] <= 4 && ci[i] % 128 == 0) L.pad_out = 64;  // c5: 256 -> C, 7x7
+      if (co[i] == 64 && ci[i] % 64 == 0) L.pad_dy = 128;  // c2: 64 -> 64
     }
     n->nG = o;
   }
@@ -188,6 +241,7 @@ void make_layouts(fg_c2f* n) {
       L.b_off = o; o += co[i];
       n->Dca[i] = o; o += 1;
       L.tf = tf[i]; L.td = td[i]; L.tw = tw[i];
+      if (co[i] == 64 && ci[i] % 64 == 0) L.pad_dy = 128;  // c2: 64 -> 64
     }
     ConvL& L = n->DL1;
     L.Cin = 16384; L.Cout = 512; L.k = 1; L.H = 1;
@@ -250,6 +304,8 @@ int c2f_alloc(fg_c2f* n) {
   FG_TRY(dalloc(n, &n->gb, big));
   FG_TRY(dalloc(n, &n->dy_hi, big));
   FG_TRY(dalloc(n, &n->dy_lo, big));
+  FG_TRY(dalloc(n, &n->pad_hi, big / 2));  // up to 128 padded channels at 32x32
+  FG_TRY(dalloc(n, &n->pad_lo, big / 2));
   FG_TRY(dalloc(n, &n->ws, std::max<size_t>((size_t)512 * 16384, (size_t)25 * 256 * 128)));
   FG_TRY(dalloc(n, &n->in_a, B * 1024 * C));
   FG_TRY(dalloc(n, &n->in_b, B * 1024 * C));
@@ -285,7 +341,7 @@ int G_forward(fg_c2f* n, const float* noise, const float* cond, int B) {
   FG_TRY(k_join_to_nhwc(c, noise, cond, n->G_x, B, n->C, 1024));
   const float* cur = n->G_x;
   for (int i = 0; i < 5; ++i) {
-    FG_TRY(convl_fwd(c, n->Gc[i], cur, n->PG, n->G_z[i], B));
+    FG_TRY(convl_fwd(n, n->Gc[i], cur, n->PG, n->G_z[i], B));
     if (i < 4) {
       FG_TRY(k_prelu_fwd(c, n->G_z[i], n->PG + n->Gca[i], n->G_h[i], (int64_t)B * 1024 * n->Gc[i].Cout));
       cur = n->G_h[i];
@@ -326,7 +382,7 @@ int D_forward(fg_c2f* n, const float* diff, const float* cond, int B, bool train
   const float* cur = n->D_x;
   for (int i = 0; i < 4; ++i) {
     const ConvL& L = n->Dc[i];
-    FG_TRY(convl_fwd(c, n->Dc[i], cur, P, n->D_z[i], B));
+    FG_TRY(convl_fwd(n, n->Dc[i], cur, P, n->D_z[i], B));
     FG_TRY(k_prelu_fwd(c, n->D_z[i], P + n->Dca[i], n->D_h[i], (int64_t)B * L.H * L.H * L.Cout));
     cur = n->D_h[i];
     if (i == 1) {
@@ -342,7 +398,7 @@ int D_forward(fg_c2f* n, const float* diff, const float* cond, int B, bool train
     FG_TRY(k_dropout_nhwc(c, n->D_p4, n->D_masks, kC2fMask, 0, 64, 256, n->D_scale, n->D_d4, B));
     d4 = n->D_d4;
   }
-  FG_TRY(convl_fwd(c, n->DL1, d4, P, n->D_zl1, B));
+  FG_TRY(convl_fwd(n, n->DL1, d4, P, n->D_zl1, B));
   FG_TRY(k_prelu_fwd(c, n->D_zl1, P + n->Da5, n->D_al1, (int64_t)B * 512));
   const float* hl1 = n->D_al1;
   if (training) {

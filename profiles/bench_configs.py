@@ -146,7 +146,10 @@ def train_small(B, C, steps):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only", default="", help="c2f | sample | small")
     a = ap.parse_args()
-    for job in (lambda: c2f(32, a.steps), lambda: c2f(256, a.steps), lambda: sample(16, a.steps), lambda: sample(1024, a.steps),
-                lambda: train_small(16, 1, a.steps)):
-        print(json.dumps(job()), flush=True)
+    jobs = [("c2f", lambda: c2f(32, a.steps)), ("c2f", lambda: c2f(256, a.steps)), ("sample", lambda: sample(16, a.steps)),
+            ("sample", lambda: sample(1024, a.steps)), ("small", lambda: train_small(16, 1, a.steps))]
+    for kind, job in jobs:
+        if not a.only or a.only == kind:
+            print(json.dumps(job()), flush=True)
