@@ -100,6 +100,20 @@ SYMBOLS = {
     "fg_c2f_D_forward": (_I, [_P, _P, _P, _I, _I, _P, _U64, _P]),
     "fg_c2f_D_backward": (_I, [_P, _P, _I, _P]),
     "fg_c2f_train_step": (_I, [_P, C.POINTER(Hyper), _I, _P, _P, _P, _P, _P, _P, _P, _U64, C.POINTER(StepStats)]),
+    "fg_t7_open": (_I, [C.c_char_p, C.POINTER(_P)]),
+    "fg_t7_close": (_I, [_P]),
+    "fg_t7_kind": (_I, [_P, C.c_char_p]),
+    "fg_t7_number": (_I, [_P, C.c_char_p, C.POINTER(C.c_double)]),
+    "fg_t7_string": (_L, [_P, C.c_char_p, _P, _L]),
+    "fg_t7_tensor": (_L, [_P, C.c_char_p, _P, _L, C.POINTER(_L)]),
+    "fg_t7_net_params": (_L, [_P, C.c_char_p, _P, _L]),
+    "fg_t7_net_bn_state": (_L, [_P, C.c_char_p, _P, _L]),
+    "fg_t7_net_describe": (_L, [_P, C.c_char_p, _P, _L]),
+    "fg_t7_writer_open": (_I, [C.c_char_p, C.POINTER(_P)]),
+    "fg_t7_writer_add_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(_L), _I]),
+    "fg_t7_writer_add_number": (_I, [_P, C.c_char_p, C.c_double]),
+    "fg_t7_writer_add_string": (_I, [_P, C.c_char_p, C.c_char_p]),
+    "fg_t7_writer_close": (_I, [_P]),
     "fg_train_step": (_I, [_P, C.POINTER(Hyper), _I, _P, _P, _P, _P, _P, _U64, C.POINTER(StepStats)]),
     "fg_sample": (_I, [_P, _P, _I, _I, _P]),
     "fg_dp_unique_id": (_I, [_P]),

@@ -214,6 +214,43 @@ int fg_c2f_train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_dif
                       const float* noise_D, const float* cond_G, const float* noise_G, const float* masks_D,
                       const float* masks_G, uint64_t seed, fg_step_stats* stats);
 
+/* ---- Torch7 checkpoint files (host only, no GPU needed) --------------------------------------- */
+/* Reads the binary torch.save format of the reference's checkpoints -- torch.save(filename,
+ * {D=MODEL_D, G=MODEL_G, opt=OPT, epoch=EPOCH}) at adversarial.lua:328 / adversarial_c2f.lua:216,
+ * read back by sample.lua:251-258 and train.lua:104-124 -- and writes files stock torch.load
+ * reads.  `path` arguments are dotted keys from the root table ("G", "opt.batchSize", "epoch",
+ * "G.modules.2"); numeric segments index array parts.  CudaTensor/CudaStorage are read as float. */
+typedef struct fg_t7 fg_t7;
+int fg_t7_open(const char* path, fg_t7** out);
+int fg_t7_close(fg_t7* f);
+/* 0 nil, 1 number, 2 string, 3 table, 4 torch object (nn module ...), 5 boolean, 6 function,
+ * 16 tensor, 17 storage; -1 when the path does not exist                                         */
+int fg_t7_kind(fg_t7* f, const char* path);
+int fg_t7_number(fg_t7* f, const char* path, double* out);
+/* string value, or the class name of a torch object ("nn.Sequential"); returns its length or -1  */
+int64_t fg_t7_string(fg_t7* f, const char* path, char* dst, int64_t cap);
+/* tensor as row-major floats (strides/offset honoured); dst may be NULL (count only); dims8 may
+ * be NULL or receives up to 8 sizes (0-terminated).  Returns the element count or -1.            */
+int64_t fg_t7_tensor(fg_t7* f, const char* path, float* dst, int64_t cap, int64_t* dims8);
+/* flat parameter vector of the nn module tree at `path` in MODEL:getParameters() order
+ * (train.lua:151-152: module order, weight then bias; containers incl. the nn.Copy wrappers of
+ * NN_UTILS.activateCuda are walked through) -- ready for fg_set_params / fg_c2f_set_params.      */
+int64_t fg_t7_net_params(fg_t7* f, const char* path, float* dst, int64_t cap);
+/* BatchNorm running statistics per BN layer in module order: running_mean[C], running_var[C]
+ * (a 2015-era running_std is converted) -- for G this is the fg_set_bn_state layout.             */
+int64_t fg_t7_net_bn_state(fg_t7* f, const char* path, float* dst, int64_t cap);
+/* class-name skeleton, e.g. "nn.Sequential{nn.Copy,nn.Sequential{nn.Linear,...},nn.Copy}"       */
+int64_t fg_t7_net_describe(fg_t7* f, const char* path, char* dst, int64_t cap);
+/* writer: ONE root table {key = torch.FloatTensor | number | string}.  Used to export flat
+ * parameter / Adam-state vectors (the reference drops its optimizer state, train.lua:122); a
+ * Torch host restores them with PARAMETERS_G:copy(file.G) after MODELS.create_G().               */
+typedef struct fg_t7_writer fg_t7_writer;
+int fg_t7_writer_open(const char* path, fg_t7_writer** out);
+int fg_t7_writer_add_tensor(fg_t7_writer* w, const char* key, const float* data, const int64_t* dims, int ndim);
+int fg_t7_writer_add_number(fg_t7_writer* w, const char* key, double v);
+int fg_t7_writer_add_string(fg_t7_writer* w, const char* key, const char* s);
+int fg_t7_writer_close(fg_t7_writer* w);                  /* writes the file and frees the writer   */
+
 /* ---- data parallel: one process per GPU, NCCL over NVLink (new functionality) ----- */
 int fg_dp_unique_id(void* out128);                        /* ncclGetUniqueId, 128 bytes           */
 int fg_dp_init(fg_ctx* ctx, const void* id128, int nranks, int rank);
