@@ -100,6 +100,14 @@ SYMBOLS = {
     "fg_c2f_D_forward": (_I, [_P, _P, _P, _I, _I, _P, _U64, _P]),
     "fg_c2f_D_backward": (_I, [_P, _P, _I, _P]),
     "fg_c2f_train_step": (_I, [_P, C.POINTER(Hyper), _I, _P, _P, _P, _P, _P, _P, _P, _U64, C.POINTER(StepStats)]),
+    "fg_dataset_create": (_I, [_P, _L, _I, _I, _I, C.POINTER(_P)]),
+    "fg_dataset_destroy": (_I, [_P]),
+    "fg_dataset_size": (_L, [_P]),
+    "fg_dataset_upload": (_I, [_P, _L, _L, _P]),
+    "fg_dataset_gather": (_I, [_P, _P, _I, _P]),
+    "fg_dataset_draw": (_I, [_P, _U64, _I, _P]),
+    "fg_noise_uniform": (_I, [_P, _U64, _L, _P]),
+    "fg_train_step_dataset": (_I, [_P, _P, C.POINTER(Hyper), _I, _U64, C.POINTER(StepStats)]),
     "fg_t7_open": (_I, [C.c_char_p, C.POINTER(_P)]),
     "fg_t7_close": (_I, [_P]),
     "fg_t7_kind": (_I, [_P, C.c_char_p]),

@@ -85,6 +85,31 @@ int fg_c2f_D_backward(fg_c2f* n, const float* d_out, int want_wgrad, float* d_di
 int fg_c2f_train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_diff, const float* cond_D, const float* noise_D,
                       const float* cond_G, const float* noise_G, const float* masks_D, const float* masks_G, uint64_t seed,
                       fg_step_stats* stats);
+typedef struct fg_dataset fg_dataset;
+int fg_dataset_create(fg_ctx* ctx, int64_t N, int Cs, int Hs, int Ws, fg_dataset** out);
+int fg_dataset_destroy(fg_dataset* d);
+int64_t fg_dataset_size(fg_dataset* d);
+int fg_dataset_upload(fg_dataset* d, int64_t first, int64_t count, const uint8_t* images);
+int fg_dataset_gather(fg_dataset* d, const int32_t* idx, int B, float* out);
+int fg_dataset_draw(fg_dataset* d, uint64_t seed, int B, int32_t* idx_out);
+int fg_noise_uniform(fg_ctx* ctx, uint64_t seed, int64_t n, float* out);
+int fg_train_step_dataset(fg_ctx* ctx, fg_dataset* d, const fg_hyper* h, int B, uint64_t seed, fg_step_stats* stats);
+typedef struct fg_t7 fg_t7;
+int fg_t7_open(const char* path, fg_t7** out);
+int fg_t7_close(fg_t7* f);
+int fg_t7_kind(fg_t7* f, const char* path);
+int fg_t7_number(fg_t7* f, const char* path, double* out);
+int64_t fg_t7_string(fg_t7* f, const char* path, char* dst, int64_t cap);
+int64_t fg_t7_tensor(fg_t7* f, const char* path, float* dst, int64_t cap, int64_t* dims8);
+int64_t fg_t7_net_params(fg_t7* f, const char* path, float* dst, int64_t cap);
+int64_t fg_t7_net_bn_state(fg_t7* f, const char* path, float* dst, int64_t cap);
+int64_t fg_t7_net_describe(fg_t7* f, const char* path, char* dst, int64_t cap);
+typedef struct fg_t7_writer fg_t7_writer;
+int fg_t7_writer_open(const char* path, fg_t7_writer** out);
+int fg_t7_writer_add_tensor(fg_t7_writer* w, const char* key, const float* data, const int64_t* dims, int ndim);
+int fg_t7_writer_add_number(fg_t7_writer* w, const char* key, double v);
+int fg_t7_writer_add_string(fg_t7_writer* w, const char* key, const char* s);
+int fg_t7_writer_close(fg_t7_writer* w);
 int fg_train_step(fg_ctx* ctx, const fg_hyper* h, int B, const float* real, const float* noise_D, const float* noise_G,
                   const float* masks_D, const float* masks_G, uint64_t seed, fg_step_stats* stats);
 int fg_sample(fg_ctx* ctx, const float* noise, int N, int chunk, float* images_out);

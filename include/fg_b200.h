@@ -214,6 +214,28 @@ int fg_c2f_train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_dif
                       const float* noise_D, const float* cond_G, const float* noise_G, const float* masks_D,
                       const float* masks_G, uint64_t seed, fg_step_stats* stats);
 
+/* ---- device-resident dataset and on-GPU batch assembly ---------------------------------------- */
+/* Replaces dataset.lua:80-117 (image.load(path, nbChannels, "float") + image.scale(img, 32, 32)) and
+ * the per-sample batch loop of adversarial.lua:244-249 for the train step's input side: the DECODED
+ * images stay on the GPU as uint8 [N][Cs][Hs][Ws] (planar, 0..255; dataset.originalScale = 64) and
+ * one kernel produces the normalised, re-scaled fp32 batch.  Cs = 3 with a 1-channel ctx applies
+ * image.rgb2y.  Scaling follows image.scale's default mode (area average when shrinking, linear
+ * interpolation when enlarging).                                                                  */
+typedef struct fg_dataset fg_dataset;
+int fg_dataset_create(fg_ctx* ctx, int64_t N, int Cs, int Hs, int Ws, fg_dataset** out);
+int fg_dataset_destroy(fg_dataset* d);
+int64_t fg_dataset_size(fg_dataset* d);
+int fg_dataset_upload(fg_dataset* d, int64_t first, int64_t count, const uint8_t* images);
+/* out [B][C][32][32] (host or device) for B 0-based indices (host or device int32)              */
+int fg_dataset_gather(fg_dataset* d, const int32_t* idx, int B, float* out);
+/* the counter-based streams fg_train_step_dataset draws from: B indices in [0,N) / n floats in
+ * [-1,1) (NN_UTILS.createNoiseInputs, utils/nn_utils.lua:35-39); outputs host or device           */
+int fg_dataset_draw(fg_dataset* d, uint64_t seed, int B, int32_t* idx_out);
+int fg_noise_uniform(fg_ctx* ctx, uint64_t seed, int64_t n, float* out);
+/* fg_train_step with every input produced on the device: real = gather(draw(4*seed, B/2)),
+ * noise_D = uniform(4*seed+1), noise_G = uniform(4*seed+2), dropout masks from `seed`             */
+int fg_train_step_dataset(fg_ctx* ctx, fg_dataset* d, const fg_hyper* h, int B, uint64_t seed, fg_step_stats* stats);
+
 /* ---- Torch7 checkpoint files (host only, no GPU needed) --------------------------------------- */
 /* Reads the binary torch.save format of the reference's checkpoints -- torch.save(filename,
  * {D=MODEL_D, G=MODEL_G, opt=OPT, epoch=EPOCH}) at adversarial.lua:328 / adversarial_c2f.lua:216,

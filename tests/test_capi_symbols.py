@@ -58,3 +58,11 @@ def test_param_counts_match_reference_models():
         assert lib.fg_param_count(1, C) == O.D_param_count(C)
     assert lib.fg_param_count(0, 3) == 2470406
     assert lib.fg_param_count(1, 3) == 2863239  # 2 863 233 w+b + 6 PReLU slopes (models.lua:382-416)
+
+
+def test_lua_ffi_cdef_declares_every_symbol():
+    """face_generator_b200/lua/fg_ffi.lua (the binding a Torch maintainer loads) must cdef the whole header."""
+    lua = open(os.path.join(ROOT, "face_generator_b200", "lua", "fg_ffi.lua")).read()
+    declared = set(re.findall(r"\b(fg_[a-zA-Z0-9_]+)\s*\(", lua))
+    missing = [n for n in header_symbols() if n not in declared]
+    assert not missing, missing
