@@ -146,6 +146,80 @@ __global__ void uniform_pm1_kernel(float* __restrict__ out, int64_t n, uint64_t 
     out[i] = (float)(r >> 40) * (2.0f / 16777216.0f) - 1.0f;  // 24-bit uniform in [-1, 1)
   }
 }
+// ---- nearest neighbour by torch.dist (2-norm), brute force, HBM-bound ------------------------------------
+// sample.lua:141-159 findClosestNeighboursOf: for every query the training image with the smallest torch.dist;
+// adversarial_c2f.lua:305-325 approxParzen: the smallest distance between one ground truth and K generations.
+// One warp per candidate, kQG queries staged in shared memory per pass; best[q] = (dist^2 bits << 32 | index),
+// reduced with 64-bit atomicMin: non-negative floats order like their bit patterns, ties go to the lowest index
+// (the reference keeps the first strict minimum).
+constexpr int kQG = 4;
+template <bool U8>
+__global__ void __launch_bounds__(256) nearest_kernel(const float* __restrict__ cands, const uint8_t* __restrict__ data, int64_t N,
+                                                      int D, int C, int Cs, int Hs, int Ws, const float* __restrict__ queries, int Q,
+                                                      unsigned long long* __restrict__ best) {
+  extern __shared__ float qs[];  // [kQG][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool gray = Cs == 3 && C == 1;
+  for (int q0 = 0; q0 < Q; q0 += kQG) {
+    const int nq = min(kQG, Q - q0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nq * D; i += blockDim.x) qs[i] = queries[(int64_t)q0 * D + i];
+    __syncthreads();
+    for (int64_t cand = (int64_t)blockIdx.x * nwarps + warp; cand < N; cand += (int64_t)gridDim.x * nwarps) {
+      float acc[kQG] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = lane; i < D; i += 32) {
+        float v;
+        if (!U8) {
+          v = cands[cand * D + i];
+        } else {  // the 32x32 view of the cached image, same arithmetic as gather_kernel
+          const int x = i & 31, y = (i >> 5) & 31, ch = i >> 10;
+          const Span sy = axis_span(y, Hs, 32), sx = axis_span(x, Ws, 32);
+          const uint8_t* base = data + cand * (int64_t)Cs * Hs * Ws;
+          float acc_y = 0.f;
+          for (int yy = sy.i0; yy <= sy.i1; ++yy) {
+            float acc_x = 0.f;
+            for (int xx = sx.i0; xx <= sx.i1; ++xx) {
+              float p;
+              if (gray) {
+                p = 0.299f * (base[(0 * Hs + yy) * Ws + xx] * (1.f / 255.f)) + 0.587f * (base[(1 * Hs + yy) * Ws + xx] * (1.f / 255.f)) +
+                    0.114f * (base[(2 * Hs + yy) * Ws + xx] * (1.f / 255.f));
+              } else {
+                p = base[((int64_t)ch * Hs + yy) * Ws + xx] * (1.f / 255.f);
+              }
+              acc_x += span_w(sx, xx) * p;
+            }
+            acc_y += span_w(sy, yy) * (acc_x / sx.norm);
+          }
+          v = acc_y / sy.norm;
+        }
+#pragma unroll
+        for (int g = 0; g < kQG; ++g) {
+          if (g < nq) {
+            const float d = v - qs[g * D + i];
+            acc[g] += d * d;
+          }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < kQG; ++g) {
+        float s = acc[g];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && g < nq)
+          atomicMin(best + q0 + g, ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(uint32_t)cand);
+      }
+    }
+  }
+}
+__global__ void nearest_unpack_kernel(const unsigned long long* __restrict__ best, int Q, int32_t* __restrict__ idx,
+                                      float* __restrict__ dist) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < Q) {
+    idx[q] = (int32_t)(uint32_t)(best[q] & 0xffffffffull);
+    dist[q] = sqrtf(__uint_as_float((uint32_t)(best[q] >> 32)));
+  }
+}
+
 bool is_dev(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -161,9 +235,65 @@ int gather(fg_dataset* d, const int32_t* idx_dev, int B, float* out_dev) {
   LAUNCH_CHECK(c);
   return FG_OK;
 }
+// queries [Q][D] (host or device); candidates either fp32 [N][D] (host or device) or the dataset cache.
+// idx_out / dist_out: host or device, Q entries each.
+int nearest_run(fg_ctx* c, const float* cands, const fg_dataset* d, int64_t N, int D, const float* queries, int Q,
+                int32_t* idx_out, float* dist_out) {
+  FG_REQUIRE(queries && idx_out && dist_out && Q >= 1 && N >= 1 && D >= 1 && D <= 3072 && N < ((int64_t)1 << 32),
+             "nearest: need 1 <= D <= 3072 (3x32x32), Q >= 1, 1 <= N < 2^32");
+  float *q_dev = nullptr, *c_dev = nullptr, *dist_dev = nullptr;
+  int32_t* idx_dev = nullptr;
+  unsigned long long* best = nullptr;
+  int rc = FG_OK;
+  auto fail = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == FG_OK) {
+      fg_set_error("nearest: %s -> %s", what, cudaGetErrorString(e));
+      rc = FG_ERR_CUDA;
+    }
+    return e != cudaSuccess;
+  };
+  do {
+    const float* qd = queries;
+    if (!is_dev(queries)) {
+      if (fail(cudaMalloc((void**)&q_dev, sizeof(float) * (size_t)Q * D), "cudaMalloc")) break;
+      if (fail(cudaMemcpyAsync(q_dev, queries, sizeof(float) * (size_t)Q * D, cudaMemcpyHostToDevice, c->stream), "H2D")) break;
+      qd = q_dev;
+    }
+    const float* cd = cands;
+    if (cands && !is_dev(cands)) {
+      if (fail(cudaMalloc((void**)&c_dev, sizeof(float) * (size_t)N * D), "cudaMalloc")) break;
+      if (fail(cudaMemcpyAsync(c_dev, cands, sizeof(float) * (size_t)N * D, cudaMemcpyHostToDevice, c->stream), "H2D")) break;
+      cd = c_dev;
+    }
+    if (fail(cudaMalloc((void**)&best, sizeof(unsigned long long) * Q), "cudaMalloc")) break;
+    if (fail(cudaMalloc((void**)&idx_dev, sizeof(int32_t) * Q), "cudaMalloc")) break;
+    if (fail(cudaMalloc((void**)&dist_dev, sizeof(float) * Q), "cudaMalloc")) break;
+    if (fail(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * Q, c->stream), "memset")) break;
+    const int warps = 8;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((N + warps - 1) / warps, (int64_t)c->sm_count * 4));
+    const size_t smem = sizeof(float) * kQG * D;
+    if (d)
+      nearest_kernel<true><<<grid, 32 * warps, smem, c->stream>>>(nullptr, d->data, N, D, c->C, d->Cs, d->Hs, d->Ws, qd, Q, best);
+    else
+      nearest_kernel<false><<<grid, 32 * warps, smem, c->stream>>>(cd, nullptr, N, D, 0, 0, 0, 0, qd, Q, best);
+    c->launches++;
+    if (fail(cudaGetLastError(), "nearest_kernel")) break;
+    nearest_unpack_kernel<<<(Q + 127) / 128, 128, 0, c->stream>>>(best, Q, idx_dev, dist_dev);
+    c->launches++;
+    if (fail(cudaMemcpyAsync(idx_out, idx_dev, sizeof(int32_t) * Q, cudaMemcpyDefault, c->stream), "copy")) break;
+    if (fail(cudaMemcpyAsync(dist_out, dist_dev, sizeof(float) * Q, cudaMemcpyDefault, c->stream), "copy")) break;
+    fail(cudaStreamSynchronize(c->stream), "sync");
+  } while (0);
+  cudaFree(q_dev);
+  cudaFree(c_dev);
+  cudaFree(best);
+  cudaFree(idx_dev);
+  cudaFree(dist_dev);
+  return rc;
+}
 }  // namespace
 
-#define ENTER(d)                                         \
+#define ENTER(d)                                      \
   do {                                                   \
     if (!(d) || !(d)->c) {                               \
       fg_set_error("null fg_dataset");                   \
@@ -282,6 +412,40 @@ int fg_noise_uniform(fg_ctx* c, uint64_t seed, int64_t n, float* out) {
   }
   return FG_OK;
 }
+// ---- scoring helpers of sample.lua / adversarial_c2f.lua ------------------------------------
+// NN_UTILS.sortImagesByPrediction's device part (utils/nn_utils.lua:90-98): D's prediction for N images in chunks
+// of `chunk` (OPT.batchSize).  sample.lua never calls evaluate(), so training = 1 reproduces its live dropout
+// (masks drawn from seed + chunk start); training = 0 is the deterministic evaluate() score.
+int fg_D_score(fg_ctx* c, const float* images, int64_t N, int chunk, int training, uint64_t seed, float* preds_out) {
+  if (!c) {
+    fg_set_error("null fg_ctx");
+    return FG_ERR_INVALID;
+  }
+  FG_REQUIRE(images && preds_out && N >= 1 && chunk >= 1 && chunk <= c->maxB, "fg_D_score: bad arguments (chunk %d, max %d)", chunk,
+             c->maxB);
+  const size_t img = (size_t)c->C * 1024;
+  for (int64_t s = 0; s < N; s += chunk) {
+    const int b = (int)std::min<int64_t>(chunk, N - s);
+    FG_TRY(fg_D_forward(c, images + (size_t)s * img, b, training, nullptr, seed + (uint64_t)s, preds_out + s));
+  }
+  return FG_OK;
+}
+// for each of Q queries [Q][D] the candidate [N][D] with the smallest torch.dist (2-norm) and that distance
+int fg_nearest(fg_ctx* c, const float* queries, int Q, const float* cands, int64_t N, int D, int32_t* idx_out, float* dist_out) {
+  if (!c) {
+    fg_set_error("null fg_ctx");
+    return FG_ERR_INVALID;
+  }
+  FG_CUDA(cudaSetDevice(c->device));
+  FG_REQUIRE(cands, "fg_nearest: null candidates");
+  return nearest_run(c, cands, nullptr, N, D, queries, Q, idx_out, dist_out);
+}
+// sample.lua:141-159 findClosestNeighboursOf against the device-resident training set (32x32 view of every image)
+int fg_dataset_nearest(fg_dataset* d, const float* queries, int Q, int32_t* idx_out, float* dist_out) {
+  ENTER(d);
+  return nearest_run(d->c, nullptr, d, d->N, d->c->C * 1024, queries, Q, idx_out, dist_out);
+}
+
 // One adversarial.lua loop body fed entirely on the device: real half-batch = gather(draw(4*seed)), noise for the
 // D step = uniform(4*seed+1), for the G step = uniform(4*seed+2), dropout masks from `seed` as in fg_train_step.
 int fg_train_step_dataset(fg_ctx* c, fg_dataset* d, const fg_hyper* h, int B, uint64_t seed, fg_step_stats* stats) {

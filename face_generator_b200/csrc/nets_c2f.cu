@@ -689,6 +689,28 @@ int fg_c2f_D_backward(fg_c2f* n, const float* d_out, int want_wgrad, float* d_di
   return FG_OK;
 }
 
+// adversarial_c2f.lua:305-325 approxParzen, one sample: K generations G({noise_k, coarse}) + coarse for the SAME
+// coarse image, the smallest torch.dist to the ground-truth fine image.  noise [K][1][32][32], coarse / fine
+// [C][32][32] (host or device); *dist_out (host).
+int fg_c2f_parzen_dist(fg_c2f* n, const float* noise, const float* coarse, const float* fine, int K, float* dist_out) {
+  ENTER(n);
+  FG_REQUIRE(noise && coarse && fine && dist_out && K >= 1 && K <= n->maxB, "fg_c2f_parzen_dist: bad arguments (K %d, max %d)", K,
+             n->maxB);
+  fg_ctx* c = n->c;
+  const size_t img = (size_t)n->C * 1024;
+  const float *nd, *fd;
+  FG_TRY(to_dev(c, noise, (size_t)K * 1024, n->in_c, &nd));
+  for (int k = 0; k < K; ++k)  // condInputs[i] = condInput:clone()  (:318-320)
+    FG_CUDA(cudaMemcpyAsync(n->in_b + (size_t)k * img, coarse, img * sizeof(float), cudaMemcpyDefault, c->stream));
+  FG_TRY(G_forward(n, nd, n->in_b, K));
+  FG_TRY(k_nchw_to_nhwc(c, n->in_b, n->D_cond, K, n->C, 1024));
+  FG_TRY(k_add(c, n->G_z[4], n->D_cond, n->io, (int64_t)K * img));  // neighbors:add(condInputs)  (:322)
+  FG_TRY(to_dev(c, fine, img, n->in_a, &fd));
+  FG_TRY(k_nchw_to_nhwc(c, fd, n->in_d, 1, n->C, 1024));
+  int32_t idx = 0;
+  return fg_nearest(c, n->in_d, 1, n->io, K, (int)img, &idx, dist_out);
+}
+
 int fg_c2f_train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_diff, const float* cond_D,
                       const float* noise_D, const float* cond_G, const float* noise_G, const float* masks_D,
                       const float* masks_G, uint64_t seed, fg_step_stats* stats) {

@@ -108,6 +108,10 @@ SYMBOLS = {
     "fg_dataset_draw": (_I, [_P, _U64, _I, _P]),
     "fg_noise_uniform": (_I, [_P, _U64, _L, _P]),
     "fg_train_step_dataset": (_I, [_P, _P, C.POINTER(Hyper), _I, _U64, C.POINTER(StepStats)]),
+    "fg_D_score": (_I, [_P, _P, _L, _I, _I, _U64, _P]),
+    "fg_nearest": (_I, [_P, _P, _I, _P, _L, _I, _P, _P]),
+    "fg_dataset_nearest": (_I, [_P, _P, _I, _P, _P]),
+    "fg_c2f_parzen_dist": (_I, [_P, _P, _P, _P, _I, _P]),
     "fg_t7_open": (_I, [C.c_char_p, C.POINTER(_P)]),
     "fg_t7_close": (_I, [_P]),
     "fg_t7_kind": (_I, [_P, C.c_char_p]),

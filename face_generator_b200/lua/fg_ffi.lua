@@ -94,6 +94,10 @@ int fg_dataset_gather(fg_dataset* d, const int32_t* idx, int B, float* out);
 int fg_dataset_draw(fg_dataset* d, uint64_t seed, int B, int32_t* idx_out);
 int fg_noise_uniform(fg_ctx* ctx, uint64_t seed, int64_t n, float* out);
 int fg_train_step_dataset(fg_ctx* ctx, fg_dataset* d, const fg_hyper* h, int B, uint64_t seed, fg_step_stats* stats);
+int fg_D_score(fg_ctx* ctx, const float* images, int64_t N, int chunk, int training, uint64_t seed, float* preds_out);
+int fg_nearest(fg_ctx* ctx, const float* queries, int Q, const float* cands, int64_t N, int D, int32_t* idx_out, float* dist_out);
+int fg_dataset_nearest(fg_dataset* d, const float* queries, int Q, int32_t* idx_out, float* dist_out);
+int fg_c2f_parzen_dist(fg_c2f* n, const float* noise, const float* coarse, const float* fine, int K, float* dist_out);
 typedef struct fg_t7 fg_t7;
 int fg_t7_open(const char* path, fg_t7** out);
 int fg_t7_close(fg_t7* f);

@@ -236,6 +236,21 @@ int fg_noise_uniform(fg_ctx* ctx, uint64_t seed, int64_t n, float* out);
  * noise_D = uniform(4*seed+1), noise_G = uniform(4*seed+2), dropout masks from `seed`             */
 int fg_train_step_dataset(fg_ctx* ctx, fg_dataset* d, const fg_hyper* h, int B, uint64_t seed, fg_step_stats* stats);
 
+/* ---- scoring helpers of the sampler / the c2f trainer ------------------------------------------ */
+/* device part of NN_UTILS.sortImagesByPrediction (utils/nn_utils.lua:90-98; sample.lua:84-85):
+ * D's prediction for N images [N][C][32][32], `chunk` (= OPT.batchSize) at a time.  training=1 is
+ * what sample.lua does (it never calls evaluate(): dropout live, masks from seed), 0 = evaluate(). */
+int fg_D_score(fg_ctx* ctx, const float* images, int64_t N, int chunk, int training, uint64_t seed, float* preds_out);
+/* brute-force nearest neighbour by torch.dist (2-norm): for each of Q queries [Q][D] the index of
+ * the closest of N candidates [N][D] and the distance (D <= 3072); ties -> lowest index            */
+int fg_nearest(fg_ctx* ctx, const float* queries, int Q, const float* cands, int64_t N, int D, int32_t* idx_out,
+               float* dist_out);
+/* findClosestNeighboursOf (sample.lua:141-159) against the device-resident training set            */
+int fg_dataset_nearest(fg_dataset* d, const float* queries, int Q, int32_t* idx_out, float* dist_out);
+/* one sample of adversarial_c2f.lua:305-325 approxParzen: min_k || G({noise_k, coarse}) + coarse - fine ||,
+ * noise [K][1][32][32], coarse / fine [C][32][32]                                                   */
+int fg_c2f_parzen_dist(fg_c2f* n, const float* noise, const float* coarse, const float* fine, int K, float* dist_out);
+
 /* ---- Torch7 checkpoint files (host only, no GPU needed) --------------------------------------- */
 /* Reads the binary torch.save format of the reference's checkpoints -- torch.save(filename,
  * {D=MODEL_D, G=MODEL_G, opt=OPT, epoch=EPOCH}) at adversarial.lua:328 / adversarial_c2f.lua:216,
