@@ -153,7 +153,22 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
     c->G_packed = c->D_packed = false;
     return FG_OK;
   }
+  if (!strcmp(key, "optimizer_D") || !strcmp(key, "optimizer_G")) {  // OPT.D_optmethod / OPT.G_optmethod (train.lua:38-39)
+    FG_REQUIRE(v >= FG_OPT_ADAM && v <= FG_OPT_SGD, "%s must be 0 (adam), 1 (adagrad) or 2 (sgd)", key);
+    (key[10] == 'D' ? c->opt_D : c->opt_G) = (int)v;
+    return FG_OK;
+  }
   fg_set_error("fg_set_option: unknown key '%s'", key);
+  return FG_ERR_INVALID;
+}
+int fg_set_option_f(fg_ctx* c, const char* key, double v) {
+  ENTER(c);
+  if (!strcmp(key, "sgd_momentum_D") || !strcmp(key, "sgd_momentum_G")) {  // OPT.D_SGD_momentum / G_SGD_momentum (train.lua:23,25)
+    FG_REQUIRE(v >= 0.0 && v < 1.0, "%s must be in [0, 1)", key);
+    (key[13] == 'D' ? c->sgd_mom_D : c->sgd_mom_G) = (float)v;
+    return FG_OK;
+  }
+  fg_set_error("fg_set_option_f: unknown key '%s'", key);
   return FG_ERR_INVALID;
 }
 int64_t fg_get_option(fg_ctx* c, const char* key) {
@@ -162,6 +177,8 @@ int64_t fg_get_option(fg_ctx* c, const char* key) {
   if (!strcmp(key, "max_batch")) return c->maxB;
   if (!strcmp(key, "channels")) return c->C;
   if (!strcmp(key, "sm_count")) return c->sm_count;
+  if (!strcmp(key, "optimizer_D")) return c->opt_D;
+  if (!strcmp(key, "optimizer_G")) return c->opt_G;
   return -1;
 }
 

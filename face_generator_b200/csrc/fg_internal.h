@@ -81,6 +81,9 @@ struct fg_ctx {
   int64_t launches = 0;
   int conv_impl = FG_CONV_TC_COLLAPSED;  // default: tcgen05 path; FG_CONV_SIMT is the fp32 FFMA cross-check
   int sm_count = 148;
+  // OPT.D_optmethod / OPT.G_optmethod (train.lua:38-39): FG_OPT_ADAM | FG_OPT_ADAGRAD | FG_OPT_SGD, and SGD momentum
+  int opt_D = 0, opt_G = 0;
+  float sgd_mom_D = 0.f, sgd_mom_G = 0.f;
   GLayout gl;
   DLayout dl;
   // flat buffers (owned)
@@ -228,6 +231,11 @@ int k_gemv_wgrad_add(fg_ctx* c, const float* x, const float* dy, float* dw, floa
 int k_adam(fg_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
            float l1_grad, float l2, float clampv, float grad_scale, const float* step_dev, const int* flag_dev,
            float step_host, float* g_out);
+// same pass with the update rule selected: mode FG_OPT_ADAM (as k_adam) | FG_OPT_ADAGRAD (variance in v) |
+// FG_OPT_SGD (momentum buffer in m, `mom` = momentum = dampening; *t_dev == 1 marks the first step)
+int k_optim_update(fg_ctx* c, int mode, float* p, float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                   float mom, float l1_grad, float l2, float clampv, float grad_scale, const float* step_dev,
+                   const int* flag_dev, const int* t_dev);
 
 // ---- k_conv_simt.cu --------------------------------------------------------------------------------
 // out[p][n] = bias[n] + sum_{t,c} in[pix(p,t)][c] * Wp[t][n][c]

@@ -848,7 +848,13 @@ int k_penalty_loss(fg_ctx* c, const float* p, int64_t n, float l1, float l2, flo
 }
 // D: accuracy history + "doTrainD" gate (adversarial.lua:126-178); both nets: t += 1 and
 // stepSize = lr*sqrt(1-beta2^t)/(1-beta1^t) in double (interruptable_optimizers.lua:75-87)
-__global__ void gate_prep_kernel(DeviceStats* st, float* acc_hist, int net, fg_hyper h, const float* tail4, float total) {
+// Adagrad / SGD (interruptable_optimizers.lua:7-46, :97-167) use clr = lr / (1 + nevals*lrd) with lrd = 0 (train.lua
+// never sets learningRateDecay) => the step size is the learning rate; t counts evaluations (state.evalCounter).
+__device__ __forceinline__ float step_size(const fg_hyper& h, int opt, float lr, double t) {
+  if (opt != FG_OPT_ADAM) return lr;
+  return (float)((double)lr * sqrt(1.0 - pow((double)h.beta2, t)) / (1.0 - pow((double)h.beta1, t)));
+}
+__global__ void gate_prep_kernel(DeviceStats* st, float* acc_hist, int net, fg_hyper h, const float* tail4, float total, int opt) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (net == FG_NET_D) {
     int interval = h.accs_interval;
@@ -869,18 +875,17 @@ __global__ void gate_prep_kernel(DeviceStats* st, float* acc_hist, int net, fg_h
     st->trained_D = go;
     if (go) {
       st->t_D += 1;
-      const double t = st->t_D;
-      st->step_D = (float)((double)h.lr_D * sqrt(1.0 - pow((double)h.beta2, t)) / (1.0 - pow((double)h.beta1, t)));
+      st->step_D = step_size(h, opt, h.lr_D, (double)st->t_D);
     }
   } else {
     st->do_train_G = 1;
     st->t_G += 1;
-    const double t = st->t_G;
-    st->step_G = (float)((double)h.lr_G * sqrt(1.0 - pow((double)h.beta2, t)) / (1.0 - pow((double)h.beta1, t)));
+    st->step_G = step_size(h, opt, h.lr_G, (double)st->t_G);
   }
 }
 int k_gate_and_prep(fg_ctx* c, int net, const fg_hyper* h, const float* tail4, int B, float world) {
-  gate_prep_kernel<<<1, 32, 0, c->stream>>>(c->dstats, c->acc_hist, net, *h, tail4, (float)B * world);
+  gate_prep_kernel<<<1, 32, 0, c->stream>>>(c->dstats, c->acc_hist, net, *h, tail4, (float)B * world,
+                                            net == FG_NET_D ? c->opt_D : c->opt_G);
   LAUNCH_CHECK(c);
   return FG_OK;
 }
@@ -888,9 +893,10 @@ int k_gate_and_prep(fg_ctx* c, int net, const fg_hyper* h, const float* tail4, i
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             int64_t n, float beta1, float beta2, float eps, float l1_grad, float l2, float clampv,
                             float grad_scale, const float* __restrict__ step_dev, const int* __restrict__ flag_dev,
-                            float step_host, int update) {
+                            float step_host, int update, int mode, float mom, const int* __restrict__ t_dev) {
   if (flag_dev && *flag_dev == 0) update = 0;
   const float step = step_dev ? *step_dev : step_host;
+  const bool first = t_dev ? *t_dev == 1 : false;
   const bool pen = (l1_grad != 0.f) || (l2 != 0.f);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float pv = p[i];
@@ -901,12 +907,24 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
     }
     if (clampv != 0.f) gv = fminf(fmaxf(gv, -clampv), clampv);
     g[i] = gv;
-    if (update) {
+    if (!update) continue;
+    if (mode == FG_OPT_ADAM) {  // interruptable_optimizers.lua:78-90
       const float mv = m[i] * beta1 + (1.0f - beta1) * gv;
       const float vv = v[i] * beta2 + (1.0f - beta2) * gv * gv;
       m[i] = mv;
       v[i] = vv;
       p[i] = pv - step * mv / (sqrtf(vv) + eps);
+    } else if (mode == FG_OPT_ADAGRAD) {  // :33-39  paramVariance += g^2; x -= clr * g / (sqrt(paramVariance) + 1e-10)
+      const float vv = v[i] + gv * gv;
+      v[i] = vv;
+      p[i] = pv - step * gv / (sqrtf(vv) + 1e-10f);
+    } else {  // SGD :129-160 (no weight decay / nesterov / per-parameter rates in train.lua); dampening defaults to mom
+      float ge = gv;
+      if (mom != 0.f) {
+        ge = first ? gv : m[i] * mom + (1.0f - mom) * gv;
+        m[i] = ge;
+      }
+      p[i] = pv - step * ge;
     }
   }
 }
@@ -966,7 +984,15 @@ int k_adam(fg_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, f
   (void)g_out;
   adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, c->stream>>>(p, const_cast<float*>(g), m, v, n, beta1, beta2, eps,
                                                                l1_grad, l2, clampv, grad_scale, step_dev, flag_dev,
-                                                               step_host, 1);
+                                                               step_host, 1, FG_OPT_ADAM, 0.f, nullptr);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int k_optim_update(fg_ctx* c, int mode, float* p, float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                   float mom, float l1_grad, float l2, float clampv, float grad_scale, const float* step_dev,
+                   const int* flag_dev, const int* t_dev) {
+  adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, c->stream>>>(p, g, m, v, n, beta1, beta2, eps, l1_grad, l2, clampv, grad_scale,
+                                                               step_dev, flag_dev, 0.f, 1, mode, mom, t_dev);
   LAUNCH_CHECK(c);
   return FG_OK;
 }

@@ -566,9 +566,10 @@ int net_optim(fg_ctx* c, int net, const fg_hyper* h, float grad_scale, bool gate
   // G quirk: the L1 gradient term is multiplied by G_L2 (adversarial.lua:223)
   const float l1_grad = !pen ? 0.f : (isD ? l1 : l2);
   if (pen) FG_TRY(k_penalty_loss(c, p, n, l1, l2, isD ? &c->dstats->loss_D : &c->dstats->loss_G));
-  FG_TRY(k_adam(c, p, g, m, v, n, h->beta1, h->beta2, h->eps, l1_grad, pen ? l2 : 0.f, isD ? h->D_clamp : h->G_clamp,
-                grad_scale, isD ? &c->dstats->step_D : &c->dstats->step_G,
-                isD ? &c->dstats->do_train_D : &c->dstats->do_train_G, 0.f, nullptr));
+  FG_TRY(k_optim_update(c, isD ? c->opt_D : c->opt_G, p, g, m, v, n, h->beta1, h->beta2, h->eps,
+                        isD ? c->sgd_mom_D : c->sgd_mom_G, l1_grad, pen ? l2 : 0.f, isD ? h->D_clamp : h->G_clamp, grad_scale,
+                        isD ? &c->dstats->step_D : &c->dstats->step_G, isD ? &c->dstats->do_train_D : &c->dstats->do_train_G,
+                        isD ? &c->dstats->t_D : &c->dstats->t_G));
   if (isD) c->D_packed = false; else c->G_packed = false;
   return FG_OK;
 }

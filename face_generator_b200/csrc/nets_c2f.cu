@@ -467,9 +467,11 @@ int optim(fg_c2f* n, int net, const fg_hyper* h, float grad_scale) {
   const bool pen = l1 != 0.f || l2 != 0.f;
   const float l1_grad = !pen ? 0.f : (isD ? l1 : l2);  // adversarial_c2f.lua:108 scales sign(p) by G_L2
   if (pen) FG_TRY(k_penalty_loss(c, p, cnt, l1, l2, isD ? &n->dstats->loss_D : &n->dstats->loss_G));
-  FG_TRY(k_adam(c, p, g, m, v, cnt, h->beta1, h->beta2, h->eps, l1_grad, pen ? l2 : 0.f, isD ? h->D_clamp : h->G_clamp,
-                grad_scale, isD ? &n->dstats->step_D : &n->dstats->step_G,
-                isD ? &n->dstats->do_train_D : &n->dstats->do_train_G, 0.f, nullptr));
+  // optim.adam / optim.adagrad / optim.sgd (adversarial_c2f.lua:153-161, :177-185): same rules as the interruptable ones
+  FG_TRY(k_optim_update(c, isD ? c->opt_D : c->opt_G, p, g, m, v, cnt, h->beta1, h->beta2, h->eps,
+                        isD ? c->sgd_mom_D : c->sgd_mom_G, l1_grad, pen ? l2 : 0.f, isD ? h->D_clamp : h->G_clamp, grad_scale,
+                        isD ? &n->dstats->step_D : &n->dstats->step_G, isD ? &n->dstats->do_train_D : &n->dstats->do_train_G,
+                        isD ? &n->dstats->t_D : &n->dstats->t_G));
   if (isD) n->D_packed = false; else n->G_packed = false;
   return FG_OK;
 }

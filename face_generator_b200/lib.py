@@ -44,6 +44,7 @@ SYMBOLS = {
     "fg_sync": (_I, [_P]),
     "fg_set_option": (_I, [_P, C.c_char_p, _L]),
     "fg_get_option": (_L, [_P, C.c_char_p]),
+    "fg_set_option_f": (_I, [_P, C.c_char_p, C.c_double]),
     "fg_param_count": (_L, [_I, _I]),
     "fg_set_params": (_I, [_P, _I, _P]),
     "fg_get_params": (_I, [_P, _I, _P]),
@@ -277,6 +278,12 @@ class Context:
 
     def get_option(self, key):
         return int(self.lib.fg_get_option(self.h, key.encode()))
+
+    def set_optimizer(self, net, method, momentum=0.0):
+        """OPT.D_optmethod / G_optmethod: "adam" | "adagrad" | "sgd" (train.lua:38-39); momentum only for sgd."""
+        which = "D" if net == NET_D else "G"
+        self.set_option("optimizer_" + which, {"adam": 0, "adagrad": 1, "sgd": 2}[method])
+        _check(self.lib.fg_set_option_f(self.h, ("sgd_momentum_" + which).encode(), float(momentum)), "fg_set_option_f")
 
     def sync(self):
         _check(self.lib.fg_sync(self.h), "fg_sync")

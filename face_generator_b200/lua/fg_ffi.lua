@@ -23,6 +23,7 @@ int fg_set_stream(fg_ctx* ctx, void* cuda_stream);
 int fg_sync(fg_ctx* ctx);
 int fg_set_option(fg_ctx* ctx, const char* key, int64_t value);
 int64_t fg_get_option(fg_ctx* ctx, const char* key);
+int fg_set_option_f(fg_ctx* ctx, const char* key, double value);
 int64_t fg_param_count(int net, int channels);
 int fg_set_params(fg_ctx* ctx, int net, const float* src);
 int fg_get_params(fg_ctx* ctx, int net, float* dst);

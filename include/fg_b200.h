@@ -44,6 +44,15 @@ enum {
   FG_CONV_TC_COLLAPSED = 2  /* tcgen05 3xTF32, upsample folded into four 3x3 phase convolutions  */
 };
 
+/* OPT.D_optmethod / OPT.G_optmethod (train.lua:38-39; adversarial.lua:259-285):
+ * fg_set_option(ctx, "optimizer_D" | "optimizer_G", FG_OPT_*).  With FG_OPT_ADAGRAD / FG_OPT_SGD
+ * fg_hyper.lr_D / lr_G carry OPTSTATE.adagrad.*.learningRate (default 1e-3) resp.
+ * OPTSTATE.sgd.*.learningRate (--D_SGD_lr / --G_SGD_lr, default 0.02); SGD momentum (= dampening,
+ * interruptable_optimizers.lua:104-105) via fg_set_option_f(ctx, "sgd_momentum_D" | "_G", m).
+ * State reuse: Adagrad's paramVariance lives in the Adam `v` buffer, SGD's momentum buffer in `m`,
+ * state.evalCounter in `t`.                                                                        */
+enum { FG_OPT_ADAM = 0, FG_OPT_ADAGRAD = 1, FG_OPT_SGD = 2 };
+
 /* Hyper-parameters of one adversarial.lua loop body; defaults = train.lua:16-50 +
  * interruptable_optimizers.lua:53-57. */
 typedef struct fg_hyper {
@@ -77,6 +86,7 @@ int fg_set_stream(fg_ctx* ctx, void* cuda_stream);      /* cutorch's current str
 int fg_sync(fg_ctx* ctx);
 int fg_set_option(fg_ctx* ctx, const char* key, int64_t value);  /* "conv_impl", "graphs", ...    */
 int64_t fg_get_option(fg_ctx* ctx, const char* key);
+int fg_set_option_f(fg_ctx* ctx, const char* key, double value);    /* "sgd_momentum_D", "sgd_momentum_G"     */
 
 /* ---- parameters: replaces MODEL:getParameters() (train.lua:151-152) -------------------------- */
 int64_t fg_param_count(int net, int channels);
