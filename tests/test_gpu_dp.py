@@ -106,3 +106,63 @@ def test_dp_two_gpus_match_oracle_and_each_other(impl):
     assert PU.relerr(got[0][3], out[0]["gradD"]) < 2e-2
     assert PU.relerr(got[0][4], out[0]["gradG"]) < 2e-2
     assert abs(got[0][5]["loss_D"] - out[0]["lossD"]) < 1e-4 * max(1, abs(out[0]["lossD"]))
+
+
+def _worker_c2f(rank, world, port, q):
+    import torch.distributed as dist
+    import c2f_utils as CU
+    import face_generator_b200 as fg
+    from face_generator_b200.lib import NET_D, NET_G
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, C = 8, 3
+    base = CU.make_case(B, C, seed=800, init="smooth")
+    case = CU.make_case(B, C, seed=801 + rank, init="smooth")
+    # lr = 0, no penalty, no clamp: the buffers then hold the plain all-reduced mean gradient
+    hyper = fg.hyper_default(**dict(CU.HYPER, lr_D=0.0, lr_G=0.0, D_L1=0.0, D_clamp=0.0, G_clamp=0.0))
+    args = (hyper, B, case["real_diff"], case["cond_D"], case["noise_D"], case["cond_G"], case["noise_G"], case["masks_D"],
+            case["masks_G"])
+    # (a) single-GPU reference of this rank's shard
+    ctx = fg.Context(rank, max_batch=B, channels=C)
+    net = fg.C2f(ctx)
+    net.set_params(NET_G, base["PG"])
+    net.set_params(NET_D, base["PD"])
+    st1 = net.train_step(*args)
+    single = (net.get_grads(NET_D), net.get_grads(NET_G), st1)
+    # (b) the same shard inside a 2-rank data-parallel group (the c2f loop shares the ctx's communicator)
+    ids = [ctx.dp_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.dp_init(ids[0], world, rank)
+    st2 = net.train_step(*args)
+    q.put((rank, single, (net.get_grads(NET_D), net.get_grads(NET_G), st2)))
+    dist.barrier()
+    net.close()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_dp_c2f_two_gpus_average_gradients():
+    """adversarial_c2f loop under data parallelism: every rank ends with the mean of the per-shard gradients."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    import parity_utils as PU
+    world, port = 2, 29761
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_worker_c2f, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r = q.get(timeout=600)
+        got[r[0]] = r
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for k in (0, 1):  # D gradient, G gradient
+        np.testing.assert_array_equal(got[0][2][k], got[1][2][k])  # replicas identical
+        mean = 0.5 * (got[0][1][k].astype(np.float64) + got[1][1][k].astype(np.float64))
+        assert PU.relerr(got[0][2][k], mean) < 2e-5
+    conf = [a + b for a, b in zip(got[0][1][2]["conf"], got[1][1][2]["conf"])]
+    assert got[0][2][2]["conf"] == conf == got[1][2][2]["conf"]  # confusion counts ride the all-reduce
