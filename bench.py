@@ -168,6 +168,8 @@ def main():
     from face_generator_b200.lib import NET_D, NET_G, PinnedArray
     B, C, K, W = args.batch, 3, args.steps, max(args.warmup, 3)
     dist = None
+    # rank 0 must print ONE line: NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION/INFO
+    os.environ["NCCL_DEBUG"] = os.environ.get("FG_NCCL_DEBUG", "WARN")
     if world > 1:
         import torch.distributed as dist  # plumbing only: rendezvous, barrier, max-over-ranks
         dist.init_process_group("gloo")
