@@ -248,7 +248,21 @@ def main():
     for name in names:
         t, n = ctx.timing_get(name)
         fam[name] = (t / nprof, n // nprof)
-    t_all, _ = ctx.timing_get("*")
+    t_all = ctx.timing_get("G.")[0] + ctx.timing_get("D.")[0]
+    # bandwidth-bound kernels: algorithmic bytes per step (fp32, B images in the G step + B/2 in the D step's G
+    # forward) over the event-timed duration, against the measured HBM copy bandwidth
+    act = B * 131072 * 4  # one [B][32][32][128] fp32 tensor
+    hbm_bytes = {"hbm.G.bn2.stats": 1.5 * act,            # read z2
+                 "hbm.G.bn2.apply": 1.5 * 2 * act,        # read z2, write h2
+                 "hbm.G.bn2.bwd_reduce": 2 * act,         # read dh, z2
+                 "hbm.G.bn2.bwd_apply": 5 * act,          # read dh, z2; write dz2 + its TF32 hi/lo split
+                 "hbm.optim.D": 28 * ctx.count(NET_D),    # p, g, m, v read; p, g, m, v... 7 streams x 4 B
+                 "hbm.optim.G": 28 * ctx.count(NET_G)}
+    hbm = {}
+    for name, nbytes in hbm_bytes.items():
+        t, n = ctx.timing_get(name)
+        if n:
+            hbm[name] = (nbytes, t / nprof)
     ctx.timing_enable(False)
     if rank != 0:
         return
@@ -283,6 +297,9 @@ def main():
                          peaks["src"], peaks["bf16_sus"]),
                      "family_fwd_dgrad_wgrad_tflops": tf_c2,
                      "step_algorithmic_tflops": F_ITER_PER_IMG * B * K / (ms / 1e3) / 1e12},
+        "hbm_kernels": [{"kernel": k[4:], "bytes_per_step": int(nb), "ms_per_step": round(ms_k, 4),
+                         "achieved": round(nb / (ms_k / 1e3) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": round(nb / (ms_k / 1e3) / 1e9 / peaks["hbm"], 3)} for k, (nb, ms_k) in hbm.items() if ms_k > 0],
         "kernel_ms_per_step": {k: round(v[0], 4) for k, v in fam.items()},
         "conv_ms_per_step": round(t_all / nprof, 4),
     }

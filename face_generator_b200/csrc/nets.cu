@@ -369,14 +369,21 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
                           h1_split ? c->tcb.G_h1_lo : nullptr));
   FG_TRY(g_ups_fwd(c, 1, "G.C2.fwd", h1_split ? nullptr : c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, c->G_C2p, P + L.C2b,
                    c->G_z2, gC2));
+  // "hbm.*" timers: the bandwidth-bound kernels bench.py reports against the measured HBM peak
   if (training) {
-    FG_TRY(k_bn_stats(c, c->G_z2, c->bn_acc, (int64_t)B * 1024, 128));
+    {
+      ScopedTimer tm(c, "hbm.G.bn2.stats");
+      FG_TRY(k_bn_stats(c, c->G_z2, c->bn_acc, (int64_t)B * 1024, 128));
+    }
     FG_TRY(k_bn_finalize(c, c->bn_acc, c->bn_mean2, c->bn_istd2, c->bnG + 512, c->bnG + 640, (int64_t)B * 1024, 128));
   } else {
     FG_TRY(k_bn_eval_prep(c, c->bnG + 512, c->bnG + 640, c->bn_mean2, c->bn_istd2, 128));
   }
-  FG_TRY(k_bn_prelu_apply(c, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->G_h2, (int64_t)B * 1024,
-                          128));
+  {
+    ScopedTimer tm(c, "hbm.G.bn2.apply");
+    FG_TRY(k_bn_prelu_apply(c, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->G_h2, (int64_t)B * 1024,
+                            128));
+  }
   FG_TRY(conv_fwd(c, "G.C3.fwd", c->G_h2, c->G_C3p, P + L.C3b, c->G_z3, ConvGeom{B, 32, 32, 128, c->C, 3, 1}));
   FG_TRY(k_sigmoid_fwd(c, c->G_z3, c->G_y, (int64_t)B * 1024 * c->C));
   c->G_fwd_valid = true;
@@ -397,14 +404,20 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   FG_TRY(k_colsum_add(c, c->G_dz3, G + L.C3b, (int64_t)B * 1024, C, 0, 0));
   FG_TRY(conv_fwd(c, "G.C3.dgrad", c->G_dz3, c->G_C3pd, nullptr, c->G_dfull, ConvGeom{B, 32, 32, C, 128, 3, 1}));
   // BN2 + PReLU
-  FG_TRY(k_bn_prelu_bwd_reduce(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_acc,
-                               G + L.a3, B, 32, 32, 128, 0));
+  {
+    ScopedTimer tm(c, "hbm.G.bn2.bwd_reduce");
+    FG_TRY(k_bn_prelu_bwd_reduce(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_acc,
+                                 G + L.a3, B, 32, 32, 128, 0));
+  }
   FG_TRY(k_bn_bwd_finalize(c, c->bn_acc, c->bn_mg, G + L.g2, G + L.be2, (int64_t)B * 1024, 128));
   // in tcgen05 mode the BN-backward kernels also emit the TF32 hi/lo split of dz (no separate split pass)
   const ConvGeom gC2{B, 32, 32, 256, 128, 5, 2}, gC1{B, 16, 16, 128, 256, 5, 2};
   const bool tc2 = use_tc_wgrad(c, gC2), tc1 = use_tc_wgrad(c, gC1);
-  FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_mg,
-                              c->G_dz2, B, 32, 32, 128, 0, tc2 ? c->tcb.dy_hi : nullptr, tc2 ? c->tcb.dy_lo : nullptr));
+  {
+    ScopedTimer tm(c, "hbm.G.bn2.bwd_apply");
+    FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_mg,
+                                c->G_dz2, B, 32, 32, 128, 0, tc2 ? c->tcb.dy_hi : nullptr, tc2 ? c->tcb.dy_lo : nullptr));
+  }
   // C2
   bool pooled = false;
   FG_TRY(g_ups_bwd(c, 1, "G.C2.wgrad", "G.C2.dgrad", c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, tc2 ? nullptr : c->G_dz2,
@@ -566,6 +579,7 @@ int net_optim(fg_ctx* c, int net, const fg_hyper* h, float grad_scale, bool gate
   // G quirk: the L1 gradient term is multiplied by G_L2 (adversarial.lua:223)
   const float l1_grad = !pen ? 0.f : (isD ? l1 : l2);
   if (pen) FG_TRY(k_penalty_loss(c, p, n, l1, l2, isD ? &c->dstats->loss_D : &c->dstats->loss_G));
+  ScopedTimer tm(c, isD ? "hbm.optim.D" : "hbm.optim.G");
   FG_TRY(k_optim_update(c, isD ? c->opt_D : c->opt_G, p, g, m, v, n, h->beta1, h->beta2, h->eps,
                         isD ? c->sgd_mom_D : c->sgd_mom_G, l1_grad, pen ? l2 : 0.f, isD ? h->D_clamp : h->G_clamp, grad_scale,
                         isD ? &c->dstats->step_D : &c->dstats->step_G, isD ? &c->dstats->do_train_D : &c->dstats->do_train_G,
