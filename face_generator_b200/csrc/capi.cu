@@ -1,6 +1,7 @@
 // C ABI of libfg_b200.so (include/fg_b200.h).  Thin: argument checking, host/device pointer
 // classification, NCHW<->NHWC at the boundary, then nets.cu / kernels.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "fg_internal.h"
@@ -90,6 +91,7 @@ int fg_create(fg_ctx** out, int device, int max_batch, int channels) {
   c->maxB = max_batch;
   c->C = channels;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("FG_TC_MIXED")) c->tc_mixed = atoi(e) != 0;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     fg_set_error("fg_create: cudaStreamCreate failed");
     delete c;
@@ -153,6 +155,11 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
     c->G_packed = c->D_packed = false;
     return FG_OK;
   }
+  if (!strcmp(key, "tc_mixed")) {  // cross terms of the tensor-core forward/dgrad as BF16 MMAs
+    FG_REQUIRE(v == 0 || v == 1, "tc_mixed must be 0 or 1");
+    c->tc_mixed = (int)v;
+    return FG_OK;
+  }
   if (!strcmp(key, "optimizer_D") || !strcmp(key, "optimizer_G")) {  // OPT.D_optmethod / OPT.G_optmethod (train.lua:38-39)
     FG_REQUIRE(v >= FG_OPT_ADAM && v <= FG_OPT_SGD, "%s must be 0 (adam), 1 (adagrad) or 2 (sgd)", key);
     (key[10] == 'D' ? c->opt_D : c->opt_G) = (int)v;
@@ -177,6 +184,7 @@ int64_t fg_get_option(fg_ctx* c, const char* key) {
   if (!strcmp(key, "max_batch")) return c->maxB;
   if (!strcmp(key, "channels")) return c->C;
   if (!strcmp(key, "sm_count")) return c->sm_count;
+  if (!strcmp(key, "tc_mixed")) return c->tc_mixed;
   if (!strcmp(key, "optimizer_D")) return c->opt_D;
   if (!strcmp(key, "optimizer_G")) return c->opt_G;
   return -1;

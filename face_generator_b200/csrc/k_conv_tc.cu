@@ -19,6 +19,7 @@
 // tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  3 smem stages of
 // {A_hi, A_lo, B_hi, B_lo}, 128B-swizzled, mbarrier full/empty rings, tcgen05.commit releases stages.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -99,6 +100,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -141,6 +151,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D=f32, A=B=bf16 (F32F16Format: 0 F16, 1 BF16, 2 TF32), both K-major; K = 16 per instruction
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 constexpr int kStages = 3;
@@ -255,6 +270,22 @@ __global__ void combine_collapsed_wgrad_kernel(const float* __restrict__ G, floa
   }
 }
 
+// (hi, lo) fp32 [rows][C] -> BF16 pair tensor [rows][C/32][ 32 x bf16(hi) | 32 x bf16(lo) ]: the same bytes per row as
+// one fp32 tensor, so it drops into the smem slot / TMA box of the "lo" operand (mixed mode of tapconv_tc_kernel)
+__global__ void comb_kernel(const float* __restrict__ hi, const float* __restrict__ lo, __nv_bfloat16* __restrict__ comb,
+                            int64_t n4, int C) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i * 4, row = e / C;
+    const int c = (int)(e - row * C);
+    const float4 h = reinterpret_cast<const float4*>(hi)[i], l = reinterpret_cast<const float4*>(lo)[i];
+    __nv_bfloat16* dst = comb + row * 2 * C + (c >> 5) * 64 + (c & 31);
+    *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(h.x, h.y);
+    *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(h.z, h.w);
+    *reinterpret_cast<__nv_bfloat162*>(dst + 32) = __floats2bfloat162_rn(l.x, l.y);
+    *reinterpret_cast<__nv_bfloat162*>(dst + 34) = __floats2bfloat162_rn(l.z, l.w);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -277,13 +308,15 @@ int get_encode() {
 }
 
 // 4-D map over an NHWC fp32 tensor view: dims (C, W, H, B) with explicit byte strides
+// pair = true: `base` is a BF16 pair tensor (2*C bf16 per pixel, same byte strides); the box takes 2*bc elements
 int make_map4(CUtensorMap* m, const float* base, int C, int W, int H, int B, int64_t sW, int64_t sH, int64_t sB, int bc,
-              int bw, int bh, int bb, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+              int bw, int bh, int bb, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, bool pair = false) {
+  const int mul = pair ? 2 : 1;
+  cuuint64_t dims[4] = {(cuuint64_t)C * mul, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)sW, (cuuint64_t)sH, (cuuint64_t)sB};
-  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t box[4] = {(cuuint32_t)bc * mul, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+  CUresult r = g_encode(m, pair ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -311,12 +344,13 @@ int make_map5(CUtensorMap* m, const float* base, int C, int W, int H, int B, int
   }
   return FG_OK;
 }
-int make_map2(CUtensorMap* m, const float* base, int cols, int64_t rows, int bc, int br) {
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+int make_map2(CUtensorMap* m, const float* base, int cols, int64_t rows, int bc, int br, bool pair = false) {
+  const int mul = pair ? 2 : 1;
+  cuuint64_t dims[2] = {(cuuint64_t)cols * mul, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-  cuuint32_t box[2] = {(cuuint32_t)bc, (cuuint32_t)br};
+  cuuint32_t box[2] = {(cuuint32_t)bc * mul, (cuuint32_t)br};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+  CUresult r = g_encode(m, pair ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -357,6 +391,28 @@ constexpr size_t wg_smem() { return (size_t)kStages * (2 * 4 * 4096 + 2 * (BN / 
     FG_CUDA(cudaGetLastError());        \
   } while (0)
 
+// BF16 pair copy of an (hi, lo) operand into ctx scratch `slot` (0 activations, 1 weights)
+int make_comb(fg_ctx* c, int slot, const float* hi, const float* lo, int64_t rows, int C, const float** out) {
+  const size_t n = (size_t)rows * C;
+  if (c->comb_elems[slot] < n) {
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->comb[slot]) FG_CUDA(cudaFree(c->comb[slot]));
+    c->comb[slot] = nullptr;
+    c->comb_elems[slot] = 0;
+    FG_CUDA(cudaMalloc((void**)&c->comb[slot], n * sizeof(float)));
+    c->comb_elems[slot] = n;
+  }
+  int64_t g = ((int64_t)n / 4 + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  comb_kernel<<<(int)g, 256, 0, c->stream>>>(hi, lo, reinterpret_cast<__nv_bfloat16*>(c->comb[slot]), (int64_t)n / 4, C);
+  LAUNCH_CHECK(c);
+  *out = c->comb[slot];
+  return FG_OK;
+}
+inline bool mixed_ok(const fg_ctx* c, const float* a, const float* b) {
+  return c->tc_mixed && reinterpret_cast<uintptr_t>(a) % 16 == 0 && reinterpret_cast<uintptr_t>(b) % 16 == 0;
+}
+
 }  // namespace
 
 int tc_init(fg_ctx* c) {
@@ -368,7 +424,13 @@ int tc_init(fg_ctx* c) {
   FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<128>()));
   return FG_OK;
 }
-void tc_destroy(fg_ctx*) {}
+void tc_destroy(fg_ctx* c) {
+  for (int i = 0; i < 2; ++i) {
+    if (c->comb[i]) cudaFree(c->comb[i]);
+    c->comb[i] = nullptr;
+    c->comb_elems[i] = 0;
+  }
+}
 
 int tc_split(fg_ctx* c, const float* x, float* hi, float* lo, int64_t n) {
   if (n % 4) {
@@ -437,8 +499,11 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
     return FG_ERR_UNSUPPORTED;
   }
   const int64_t sW = (int64_t)g.Cin * 4, sH = sW * Wl, sB = sH * Hl;
+  const bool mixed = mixed_ok(c, x_hi, x_lo) && mixed_ok(c, w_hi, w_lo);
+  if (mixed) FG_TRY(make_comb(c, 0, x_hi, x_lo, (int64_t)g.B * Hl * Wl, g.Cin, &x_lo));
+  p.mixed = mixed ? 1 : 0;
   FG_TRY(make_map4(&p.a_hi[0], x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
-  FG_TRY(make_map4(&p.a_lo[0], x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+  FG_TRY(make_map4(&p.a_lo[0], x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, mixed));
   // N tile: 128 unless halving it keeps the same number of waves on the 148 SMs (few-tile layers such as
   // D.C4's dgrad or the Linear layers): a BN=64 tile costs ~0.6 of a BN=128 tile
   int BN = g.Cout % 128 == 0 ? 128 : 64;
@@ -482,8 +547,9 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
         p.widx[ph * 9 + t] = (int16_t)(ph * 9 + t);
       }
   }
+  if (mixed) FG_TRY(make_comb(c, 1, w_hi, w_lo, (int64_t)ntapw * g.Cout, g.Cin, &w_lo));
   FG_TRY(make_map2(&p.b_hi, w_hi, g.Cin, (int64_t)ntapw * g.Cout, 32, BN));
-  FG_TRY(make_map2(&p.b_lo, w_lo, g.Cin, (int64_t)ntapw * g.Cout, 32, BN));
+  FG_TRY(make_map2(&p.b_lo, w_lo, g.Cin, (int64_t)ntapw * g.Cout, 32, BN, mixed));
   p.kpt = g.Cin / 32;
   p.Cout = g.Cout;
   p.B = g.B; p.H = Hl; p.W = Wl;
@@ -514,12 +580,18 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
   const int Hl = g.H / 2, Wl = g.W / 2;
   if (!pick_box(Hl, Wl, 128, &p.bw, &p.bh, &p.bb)) return FG_ERR_UNSUPPORTED;
   const int Cy = g.Cout;  // contraction runs over the forward conv's output channels
+  const bool mixed = mixed_ok(c, dy_hi, dy_lo) && mixed_ok(c, wd_hi, wd_lo);
+  if (mixed) {
+    FG_TRY(make_comb(c, 0, dy_hi, dy_lo, (int64_t)g.B * g.H * g.W, Cy, &dy_lo));
+    FG_TRY(make_comb(c, 1, wd_hi, wd_lo, (int64_t)36 * g.Cin, Cy, &wd_lo));
+  }
+  p.mixed = mixed ? 1 : 0;
   for (int ph = 0; ph < 4; ++ph) {
     const int py = ph >> 1, px = ph & 1;
-    const int64_t off = ((int64_t)py * g.W + px) * Cy;
+    const int64_t off = ((int64_t)py * g.W + px) * Cy;  // the pair tensor has the same bytes per pixel
     const int64_t sW = (int64_t)2 * Cy * 4, sH = (int64_t)2 * g.W * Cy * 4, sB = (int64_t)g.H * g.W * Cy * 4;
     FG_TRY(make_map4(&p.a_hi[ph], dy_hi + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
-    FG_TRY(make_map4(&p.a_lo[ph], dy_lo + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+    FG_TRY(make_map4(&p.a_lo[ph], dy_lo + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, mixed));
   }
   const int BN = g.Cin % 128 == 0 ? 128 : 64;
   p.nphase = 1;
@@ -533,7 +605,7 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
       p.widx[ph * 9 + t] = (int16_t)(ph * 9 + t);
     }
   FG_TRY(make_map2(&p.b_hi, wd_hi, Cy, (int64_t)36 * g.Cin, 32, BN));
-  FG_TRY(make_map2(&p.b_lo, wd_lo, Cy, (int64_t)36 * g.Cin, 32, BN));
+  FG_TRY(make_map2(&p.b_lo, wd_lo, Cy, (int64_t)36 * g.Cin, 32, BN, mixed));
   p.kpt = Cy / 32;
   p.Cout = g.Cin;
   p.B = g.B; p.H = Hl; p.W = Wl;

@@ -22,6 +22,7 @@ struct alignas(64) TcFwdParams {
   int out_H, out_W, out_scale;
   int dbg;    // experiment switches (FG_TC_DBG): 1 = skip MMAs, 2 = skip TMA data movement
   int chunk;  // K-blocks accumulated in TMEM before the epilogue promotes them to fp32 registers
+  int mixed;  // 1: a_lo / b_lo are BF16 pair tensors [row][C/32][hi32|lo32]; cross terms run as kind::f16 MMAs
 };
 
 struct alignas(64) TcWgParams {

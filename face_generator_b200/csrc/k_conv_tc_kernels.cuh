@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   constexpr uint32_t kBBytes = BN * 128;
   constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
   constexpr uint32_t kIdesc = make_idesc(128, BN, 0, 0);
+  constexpr uint32_t kIdescBf = make_idesc_bf16(128, BN);
   // TMEM layout (all 512 columns): [0,256) a ring of kAcc buffers for the MAIN term hi*hi -- the MMA warp
   // accumulates `chunk` K-blocks into one buffer, the epilogue promotes it to fp32 registers and frees it;
   // [256, 256+2*BN) two buffers (tile parity) for the CROSS terms hi*lo + lo*hi, which are 2^-11 smaller, so
@@ -105,11 +106,13 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
             continue;
           }
           mbar_expect_tx(full + s, kStageBytes);
+          // mixed mode: the "lo" maps view BF16 pair tensors, 64 elements (= the same 128 bytes) per 32-channel block
+          const int c0l = p.mixed ? 2 * c0 : c0;
           tma_load_4d(st, &p.a_hi[am], full + s, c0, t.x0 + p.dx[ti], t.y0 + p.dy[ti], t.b0);
-          tma_load_4d(st + kABytes, &p.a_lo[am], full + s, c0, t.x0 + p.dx[ti], t.y0 + p.dy[ti], t.b0);
+          tma_load_4d(st + kABytes, &p.a_lo[am], full + s, c0l, t.x0 + p.dx[ti], t.y0 + p.dy[ti], t.b0);
           const int wrow = p.widx[ti] * p.Cout + t.n0;
           tma_load_2d(st + 2 * kABytes, &p.b_hi, full + s, c0, wrow);
-          tma_load_2d(st + 2 * kABytes + kBBytes, &p.b_lo, full + s, c0, wrow);
+          tma_load_2d(st + 2 * kABytes + kBBytes, &p.b_lo, full + s, c0l, wrow);
         }
       }
     }
@@ -133,13 +136,27 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
             const uint64_t a_hi = make_desc(sa, 16, 1024), a_lo = make_desc(sa + kABytes, 16, 1024);
             const uint64_t b_hi = make_desc(sa + 2 * kABytes, 16, 1024),
                            b_lo = make_desc(sa + 2 * kABytes + kBBytes, 16, 1024);
-            if (!(p.dbg & 1)) {  // (dbg bit 0: experiment without MMAs)
+            if (p.dbg & 1) {  // (dbg bit 0: experiment without MMAs)
+            } else if (!p.mixed) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 fp32 of K) in the 16B-unit start-address field
                 umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, (j | k) != 0);        // main term -> ring buffer
                 umma_tf32(tcross, a_hi + ko, b_lo + ko, kIdesc, (ch | j | k) != 0);  // cross terms -> per-tile block
                 umma_tf32(tcross, a_lo + ko, b_hi + ko, kIdesc, 1);
+              }
+            } else {
+              // main term in TF32 (exact products); the two cross terms are ~2^-12 of the result, so BF16 inputs
+              // (rel. 2^-9) keep them to ~2^-20: kind::f16 runs at twice the TF32 rate => 4 + 2 + 2 half-cost MMAs.
+              // In the pair tile a 128-byte row is [32 x bf16(hi) | 32 x bf16(lo)]: +0 B / +64 B pick the half,
+              // +32 B steps the 16-element K slice.
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(tacc, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), kIdesc, (j | k) != 0);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);
+                umma_bf16(tcross, a_lo + ko, b_lo + 4 + ko, kIdescBf, (ch | j | k) != 0);  // bf16(a_hi) . bf16(b_lo)
+                umma_bf16(tcross, a_lo + 4 + ko, b_lo + ko, kIdescBf, 1);                  // bf16(a_lo) . bf16(b_hi)
               }
             }
             umma_commit(empty + s);
