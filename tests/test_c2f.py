@@ -234,6 +234,48 @@ def test_gpu_c2f_modules_equal_fused_step():
 
 
 @pytest.mark.gpu
+def test_gpu_c2f_full_size_properties():
+    """BASELINE-size batch (256), where the oracle would take minutes: size-independent properties instead.
+    (i) the confusion counts cover the batch; (ii) Adam's first step moves every parameter by at most lr
+    (|m/(sqrt(v)+eps)| * sqrt(1-b2)/(1-b1) <= 1 at t = 1, interruptable_optimizers.lua:78-90);
+    (iii) with lr = 0 the step is idempotent on the parameters and, given the masks, reproducible;
+    (iv) MODEL_D.gradInput[1] does not depend on whether D's weight gradients are requested."""
+    import face_generator_b200 as fg
+    from face_generator_b200.lib import NET_D, NET_G
+    B, C = 256, 3
+    case = CU.make_case(B, C, seed=550)
+    ctx, net = _ctx(B, C, 2)
+    net.set_params(NET_G, case["PG"])
+    net.set_params(NET_D, case["PD"])
+    args = (B, case["real_diff"], case["cond_D"], case["noise_D"], case["cond_G"], case["noise_G"], case["masks_D"], case["masks_G"])
+    frozen = fg.hyper_default(**dict(CU.HYPER, lr_D=0.0, lr_G=0.0))
+    s1 = net.train_step(frozen, *args)
+    g1 = net.get_grads(NET_G)
+    s2 = net.train_step(frozen, *args)
+    np.testing.assert_array_equal(net.get_params(NET_D), case["PD"])
+    assert sum(s1["conf"]) == B and s1["conf"] == s2["conf"]
+    assert abs(s1["loss_D"] - s2["loss_D"]) < 1e-5 and abs(s1["loss_G"] - s2["loss_G"]) < 1e-5
+    assert PU.relerr(net.get_grads(NET_G), g1) < KINK_TOL
+    net.set_adam_state(NET_D, np.zeros(net.nD), np.zeros(net.nD), 0)
+    net.set_adam_state(NET_G, np.zeros(net.nG), np.zeros(net.nG), 0)
+    st = net.train_step(fg.hyper_default(**CU.HYPER), *args)
+    assert st["t_D"] == 1 and st["t_G"] == 1 and np.isfinite(st["loss_D"]) and np.isfinite(st["loss_G"])
+    for netid, key in ((NET_D, "PD"), (NET_G, "PG")):
+        step = np.abs(net.get_params(netid).astype(np.float64) - case[key])
+        assert step.max() <= 1e-3 * (1 + 1e-3) + 1e-7 * np.abs(case[key]).max(), key
+        assert (step > 0.5e-3).mean() > 0.5  # and most of them by (almost) exactly lr
+    diff, cond = case["real_diff"], case["cond_D"][:B // 2]
+    dd = np.random.default_rng(1).standard_normal(B // 2).astype(np.float32)
+    net.D_forward(diff, cond, masks=case["masks_D"][:B // 2])
+    a = net.D_backward(dd, want_wgrad=True)
+    net.D_forward(diff, cond, masks=case["masks_D"][:B // 2])
+    b = net.D_backward(dd, want_wgrad=False)
+    assert PU.relerr(a, b) < 1e-5
+    net.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
 def test_gpu_c2f_seeded_dropout_is_reproducible_and_trains():
     """Throughput mode: masks == NULL => keep flags drawn on the device from `seed`."""
     import face_generator_b200 as fg
