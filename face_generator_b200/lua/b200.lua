@@ -239,4 +239,89 @@ function PR:backward(input, gradOutput)
   return self.gradInput
 end
 
+
+---------------------------------------------------------------------------------------------------------------
+-- parameter-free layers (L-op level): resampling, pooling, dropout, sigmoid.  NCHW FloatTensors in and out.
+---------------------------------------------------------------------------------------------------------------
+local function dims4(t) return t:size(1), t:size(2), t:size(3), t:size(4) end
+
+local Up, upparent = torch.class('b200.SpatialUpSamplingNearest', 'nn.Module')  -- models.lua:63,68 (scale 2 only)
+function Up:__init(scale) upparent.__init(self); assert(scale == 2, 'b200.SpatialUpSamplingNearest: scale 2 only'); self.ctx = b200.context() end
+function Up:updateOutput(input)
+  local n, c, h, w = dims4(input)
+  self.output:resize(n, c, 2 * h, 2 * w)
+  F.check(C.fg_upsample2_forward(self.ctx, F.ptr(input), F.ptr(self.output), n, c, h, w), 'fg_upsample2_forward')
+  return self.output
+end
+function Up:updateGradInput(input, gradOutput)
+  local n, c, h, w = dims4(input)
+  self.gradInput:resizeAs(input)
+  F.check(C.fg_upsample2_backward(self.ctx, F.ptr(gradOutput), F.ptr(self.gradInput), n, c, h, w), 'fg_upsample2_backward')
+  return self.gradInput
+end
+
+local function pool_class(name, fwd, bwd, needs_input)
+  local P, pparent = torch.class('b200.' .. name, 'nn.Module')
+  function P:__init(kW, kH, dW, dH)
+    pparent.__init(self)
+    assert(kW == 2 and kH == 2 and (dW or 2) == 2 and (dH or 2) == 2, 'b200.' .. name .. ': 2x2 window, stride 2 only')
+    self.ctx = b200.context()
+  end
+  function P:updateOutput(input)
+    local n, c, h, w = dims4(input)
+    self.output:resize(n, c, math.floor(h / 2), math.floor(w / 2))
+    F.check(C[fwd](self.ctx, F.ptr(input), F.ptr(self.output), n, c, h, w), fwd)
+    return self.output
+  end
+  function P:updateGradInput(input, gradOutput)
+    local n, c, h, w = dims4(input)
+    self.gradInput:resizeAs(input)
+    if needs_input then
+      F.check(C[bwd](self.ctx, F.ptr(input), F.ptr(gradOutput), F.ptr(self.gradInput), n, c, h, w), bwd)
+    else
+      F.check(C[bwd](self.ctx, F.ptr(gradOutput), F.ptr(self.gradInput), n, c, h, w), bwd)
+    end
+    return self.gradInput
+  end
+end
+pool_class('SpatialAveragePooling', 'fg_avgpool2_forward', 'fg_avgpool2_backward', false)  -- models.lua:388,...
+pool_class('SpatialMaxPooling', 'fg_maxpool2_forward', 'fg_maxpool2_backward', true)       -- models_c2f.lua:251,256
+
+-- nn.Dropout(p) (v2 rescale) and nn.SpatialDropout(p) (no rescale); the keep mask is drawn on the host with
+-- torch.bernoulli like the reference modules do, so the reference's RNG stream is preserved
+local function dropout_class(name, spatial, default_p)
+  local D, dparent = torch.class('b200.' .. name, 'nn.Module')
+  function D:__init(p) dparent.__init(self); self.p = p or default_p; self.train = true; self.ctx = b200.context(); self.noise = torch.FloatTensor() end
+  function D:apply_(src, dst, fn)
+    local n, c = src:size(1), src:size(2)
+    local hw = src:nElement() / (n * c)
+    dst:resizeAs(src)
+    F.check(C[fn](self.ctx, F.ptr(src), self.train and F.ptr(self.noise) or nil, self.p, spatial and 1 or 0, F.ptr(dst), n, c, hw), fn)
+    return dst
+  end
+  function D:updateOutput(input)
+    if self.train then
+      if spatial then self.noise:resize(input:size(1), input:size(2)) else self.noise:resizeAs(input) end
+      self.noise:bernoulli(1 - self.p)
+    end
+    return self:apply_(input, self.output, 'fg_dropout_forward')
+  end
+  function D:updateGradInput(input, gradOutput) return self:apply_(gradOutput, self.gradInput, 'fg_dropout_backward') end
+end
+dropout_class('Dropout', false, 0.5)         -- models.lua:408,411; models_c2f.lua:258,264
+dropout_class('SpatialDropout', true, 0.5)   -- models.lua:387,391,396,401 (p = 0.2 there)
+
+local Sg, sgparent = torch.class('b200.Sigmoid', 'nn.Module')  -- models.lua:74,413
+function Sg:__init() sgparent.__init(self); self.ctx = b200.context() end
+function Sg:updateOutput(input)
+  self.output:resizeAs(input)
+  F.check(C.fg_sigmoid_forward(self.ctx, F.ptr(input), F.ptr(self.output), input:nElement()), 'fg_sigmoid_forward')
+  return self.output
+end
+function Sg:updateGradInput(input, gradOutput)
+  self.gradInput:resizeAs(input)
+  F.check(C.fg_sigmoid_backward(self.ctx, F.ptr(self.output), F.ptr(gradOutput), F.ptr(self.gradInput), input:nElement()), 'fg_sigmoid_backward')
+  return self.gradInput
+end
+
 return b200
