@@ -66,3 +66,17 @@ def test_lua_ffi_cdef_declares_every_symbol():
     declared = set(re.findall(r"\b(fg_[a-zA-Z0-9_]+)\s*\(", lua))
     missing = [n for n in header_symbols() if n not in declared]
     assert not missing, missing
+
+
+def test_lua_shims_only_call_declared_entry_points():
+    """Every C.fg_* / C['fg_*'] the Lua shims reference exists in include/fg_b200.h (LuaJIT cannot run here, so at
+    least the names are checked)."""
+    names = set(header_symbols())
+    lua_dir = os.path.join(ROOT, "face_generator_b200", "lua")
+    used = set()
+    for fn in os.listdir(lua_dir):
+        src = open(os.path.join(lua_dir, fn)).read()
+        if fn != "fg_ffi.lua":
+            used |= set(re.findall(r"C\.(fg_[a-zA-Z0-9_]+)", src))
+            used |= set(re.findall(r"'(fg_[a-z0-9_]+_(?:forward|backward))'", src))
+    assert used and not (used - names), sorted(used - names)
