@@ -51,6 +51,7 @@ struct fg_c2f {
   int64_t Gca[4] = {0, 0, 0, 0}, Dca[4] = {0, 0, 0, 0}, Da5 = 0, DL2W = 0, DL2b = 0;
   ConvL Gc[5], Dc[4], DL1;
   bool G_packed = false, D_packed = false;
+  int G_pack_impl = -1, D_pack_impl = -1;
   float *G_x = nullptr, *G_z[5] = {}, *G_h[4] = {};
   float *D_x = nullptr, *D_cond = nullptr, *D_z[4] = {}, *D_h[4] = {}, *D_p2 = nullptr, *D_p4 = nullptr, *D_d4 = nullptr;
   float *D_zl1 = nullptr, *D_al1 = nullptr, *D_hl1 = nullptr, *D_logit = nullptr, *D_out = nullptr, *D_masks = nullptr,
@@ -319,17 +320,21 @@ int c2f_alloc(fg_c2f* n) {
   return FG_OK;
 }
 
+// packs are rebuilt after every optimizer step / set_params, and when the ctx's "conv_impl" changed since the last
+// pack (the TF32 splits are only produced for the tensor-core implementations)
 int pack_G(fg_c2f* n) {
-  if (n->G_packed) return FG_OK;
+  if (n->G_packed && n->G_pack_impl == n->c->conv_impl) return FG_OK;
   for (int i = 0; i < 5; ++i) FG_TRY(convl_pack(n->c, n->Gc[i], n->PG));
   n->G_packed = true;
+  n->G_pack_impl = n->c->conv_impl;
   return FG_OK;
 }
 int pack_D(fg_c2f* n) {
-  if (n->D_packed) return FG_OK;
+  if (n->D_packed && n->D_pack_impl == n->c->conv_impl) return FG_OK;
   for (int i = 0; i < 4; ++i) FG_TRY(convl_pack(n->c, n->Dc[i], n->PD));
   FG_TRY(convl_pack(n->c, n->DL1, n->PD));
   n->D_packed = true;
+  n->D_pack_impl = n->c->conv_impl;
   return FG_OK;
 }
 
