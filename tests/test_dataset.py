@@ -102,3 +102,19 @@ def test_gpu_device_fed_step_equals_host_fed_step():
     assert abs(s1["loss_D"] - s2["loss_D"]) < 1e-5 and abs(s1["loss_G"] - s2["loss_G"]) < 1e-5 and s1["conf"] == s2["conf"]
     assert PU.relerr(gd1, gd2) < 2e-5 and PU.relerr(gg1, gg2) < 2e-5  # split-K atomics order only
     assert PU.relerr(p1, p2) < 1e-5
+
+
+def test_scale_restatement_vs_torch_interpolate():
+    """Where PyTorch has the same rule: integer shrink factors = 'area', enlarging = bilinear with align_corners
+    (scale (src-1)/(dst-1), image.c Main_scaleLinear_rowcol)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(3)
+    for H, W in ((64, 64), (96, 128), (32, 160)):
+        x = rng.random((2, 3, H, W))
+        ref = F.interpolate(torch.tensor(x), size=(32, 32), mode="area").numpy()
+        np.testing.assert_allclose(OD.scale(x, 32, 32), ref, rtol=1e-6, atol=1e-7)
+    for H, W in ((16, 16), (20, 9), (31, 2)):
+        x = rng.random((2, 1, H, W))
+        ref = F.interpolate(torch.tensor(x), size=(32, 32), mode="bilinear", align_corners=True).numpy()
+        np.testing.assert_allclose(OD.scale(x, 32, 32), ref, rtol=1e-5, atol=1e-6)
