@@ -19,6 +19,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# FG_ORACLE_BLAS=1 (opt-in): the CPU port's GEMMs go through scipy's OpenBLAS; its worker threads then must not fight
+# spinning OpenMP threads, so OpenMP has to idle passively (read when libgomp initialises => set before any import)
+if os.environ.get("FG_ORACLE_BLAS") == "1":
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+
+
+def port_gemm(O):
+    """-> description of the GEMM the fp32 oracle port uses in this process."""
+    if os.environ.get("FG_ORACLE_BLAS") == "1" and O.use_blas(cpu_threads()):
+        return "OpenBLAS sgemm (scipy.libs)"
+    return "blocked OpenMP loops"
 
 METRIC = "32x32 GAN train images/sec (1 D-iter + 1 G-iter per batch, batch 256/GPU)"
 # algorithmic FLOPs (SURVEY.md 8d): conv = 2*Cout*Cin*k*k*H*W per image per pass
@@ -120,6 +131,7 @@ def run_reference(args, rank, world):
     C = 3
     b = 16 if args.steps <= 24 else 8
     O.set_num_threads(cpu_threads())
+    gemm = port_gemm(O)
     rng = np.random.default_rng(1)
     PG, PD = LY.trained_like_init(LY.G_layout(C), rng), LY.trained_like_init(LY.D_layout(C), rng, 1.4)
     st = dict(PD=PD, PG=PG, mD=np.zeros_like(PD), vD=np.zeros_like(PD), mG=np.zeros_like(PG), vG=np.zeros_like(PG), tD=0,
@@ -135,8 +147,8 @@ def run_reference(args, rank, world):
         O.f32.train_iteration(b, C, hyper, real, nD, nG, masks, masks, st, want_grads=False)
     dt = time.perf_counter() - t0
     v = b * args.steps / dt
-    sample = "%d-image sample of the 256-image batch per step, %d steps, fp32 oracle port (THNN algorithm), %d threads" % (
-        b, args.steps, O.num_threads())
+    sample = "%d-image sample of the 256-image batch per step, %d steps, fp32 oracle port (THNN algorithm, %s), %d threads" % (
+        b, args.steps, gemm, O.num_threads())
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -306,6 +318,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O  # cpu_baseline leg: the checker timed as a reported baseline
         O.set_num_threads(cpu_threads())
+        gemm = port_gemm(O)
         b = 16
         rng = np.random.default_rng(1)
         PG, PD = LY.trained_like_init(LY.G_layout(C), rng), LY.trained_like_init(LY.D_layout(C), rng, 1.4)
@@ -322,7 +335,7 @@ def main():
             it += 1
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": b * it / dt, "unit": "images/s", "cores": O.num_threads(), "kind": "port",
-                               "sample": "%d iterations at batch %d (colour) of the fp32 oracle port, %.1f s" % (it, b, dt)}
+                               "sample": "%d iterations at batch %d (colour) of the fp32 oracle port (%s), %.1f s" % (it, b, gemm, dt)}
     print(json.dumps(out))
 
 

@@ -28,17 +28,29 @@
 //   Adam                  interruptable_optimizers.lua:49-94
 //   noise                 utils/nn_utils.lua:35-39
 //   SCU (c2f, factor=1)   layers/SpatialConvolutionUpsample.lua:13-30
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
 
 namespace {
+
+// Optional SGEMM for the fp32 "port" (the CPU baseline): Torch7's nn calls the system BLAS (OpenBLAS / MKL) for the
+// per-sample GEMM of SpatialConvolutionMM and for nn.Linear, so a fair reference-style baseline does too.
+// fgo_use_blas() dlopens an OpenBLAS (the one bundled with scipy in this image); without it the blocked loops below
+// are used.  The fp64 parity oracle never takes this path.
+typedef void (*sgemm_fn)(int order, int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda,
+                         const float* B, int ldb, float beta, float* C, int ldc);
+sgemm_fn g_sgemm = nullptr;
+constexpr int kRowMajor = 101, kNoTrans = 111, kTrans = 112;
 
 // ----------------------------------------------------------------------------------------------
 // dense helpers
@@ -137,6 +149,14 @@ void gemm_nt(int M, int N, int K, const T* A, const T* B, T* C, bool acc) {
 // ----------------------------------------------------------------------------------------------
 template <class T>
 void linear_fwd(int B, int in, int out, const T* x, const T* W, const T* b, T* y) {
+  if constexpr (std::is_same<T, float>::value) {
+    if (g_sgemm) {  // y = x W^T + b   (nn.Linear:updateOutput: addmm + addr)
+      g_sgemm(kRowMajor, kNoTrans, kTrans, B, out, in, 1.f, x, in, W, in, 0.f, y, out);
+      for (int n = 0; n < B; ++n)
+        for (int j = 0; j < out; ++j) y[(size_t)n * out + j] += b[j];
+      return;
+    }
+  }
 #pragma omp parallel for schedule(static)
   for (int n = 0; n < B; ++n) {
     gemm_nt(1, out, in, x + (size_t)n * in, W, y + (size_t)n * out, false);
@@ -146,6 +166,19 @@ void linear_fwd(int B, int in, int out, const T* x, const T* W, const T* b, T* y
 // dx = dy W ; dW += dy^T x ; db += sum_n dy
 template <class T>
 void linear_bwd(int B, int in, int out, const T* x, const T* W, const T* dy, T* dx, T* dW, T* db) {
+  if constexpr (std::is_same<T, float>::value) {
+    if (g_sgemm) {
+      if (dx) g_sgemm(kRowMajor, kNoTrans, kNoTrans, B, in, out, 1.f, dy, out, W, in, 0.f, dx, in);   // dx = dy W
+      if (dW) g_sgemm(kRowMajor, kTrans, kNoTrans, out, in, B, 1.f, dy, out, x, in, 1.f, dW, in);     // dW += dy^T x
+      if (db)
+        for (int j = 0; j < out; ++j) {
+          float s = 0;
+          for (int n = 0; n < B; ++n) s += dy[(size_t)n * out + j];
+          db[j] += s;
+        }
+      return;
+    }
+  }
   if (dx) {
 #pragma omp parallel for schedule(static)
     for (int n = 0; n < B; ++n) gemm_nn(1, in, out, dy + (size_t)n * out, W, dx + (size_t)n * in, false);
@@ -238,10 +271,48 @@ void im2col_rows(const T* x, int Cin, int H, int W, int k, T* col) {
 }
 // THNN SpatialConvolutionMM: loop over samples, im2col + GEMM per sample; the threads share one sample's
 // GEMM (rows of the output split across threads), so parallelism does not depend on the batch size.
+// im2col / col2im of one sample with their own parallel region (BLAS path: the GEMM is threaded by the BLAS)
+inline void im2col_par(const float* x, int Cin, int H, int W, int k, float* col) {
+#pragma omp parallel
+  im2col_rows(x, Cin, H, W, k, col);
+}
+inline void col2im_par(const float* col, int Cin, int H, int W, int k, float* dx) {
+  const int pad = (k - 1) / 2, KK = k * k, HW = H * W;
+#pragma omp parallel for schedule(static)
+  for (int c = 0; c < Cin; ++c) {
+    float* dst_c = dx + (size_t)c * HW;
+    std::fill(dst_c, dst_c + HW, 0.f);
+    for (int t = 0; t < KK; ++t) {
+      const int kh = t / k, kw = t % k;
+      const float* src = col + ((size_t)c * KK + t) * HW;
+      for (int h = 0; h < H; ++h) {
+        const int ih = h + kh - pad;
+        if (ih < 0 || ih >= H) continue;
+        for (int w = 0; w < W; ++w) {
+          const int iw = w + kw - pad;
+          if (iw >= 0 && iw < W) dst_c[(size_t)ih * W + iw] += src[(size_t)h * W + w];
+        }
+      }
+    }
+  }
+}
+
 template <class T>
 void conv_fwd(int B, int Cin, int H, int W, int Cout, int k, const T* x, const T* Wt, const T* b, T* y) {
   const int K = Cin * k * k, HW = H * W;
   std::vector<T> col((size_t)K * HW);
+  if constexpr (std::is_same<T, float>::value) {
+    if (g_sgemm) {  // THNN SpatialConvolutionMM_updateOutput_frame: output = weight * finput (+ bias)
+      for (int n = 0; n < B; ++n) {
+        im2col_par(x + (size_t)n * Cin * HW, Cin, H, W, k, col.data());
+        float* yn = y + (size_t)n * Cout * HW;
+        g_sgemm(kRowMajor, kNoTrans, kNoTrans, Cout, HW, K, 1.f, Wt, K, col.data(), HW, 0.f, yn, HW);
+        for (int o = 0; o < Cout; ++o)
+          for (int p = 0; p < HW; ++p) yn[(size_t)o * HW + p] += b[o];
+      }
+      return;
+    }
+  }
 #pragma omp parallel
   for (int n = 0; n < B; ++n) {
     im2col_rows(x + (size_t)n * Cin * HW, Cin, H, W, k, col.data());  // implicit barrier after the omp for
@@ -261,6 +332,31 @@ void conv_bwd(int B, int Cin, int H, int W, int Cout, int k, const T* x, const T
               T* dW, T* db) {
   const int K = Cin * k * k, HW = H * W, KK = k * k, pad = (k - 1) / 2;
   std::vector<T> col((size_t)K * HW);
+  if constexpr (std::is_same<T, float>::value) {
+    if (g_sgemm) {  // THNN updateGradInput_frame: fgradInput = weight^T * gradOutput; accGradParameters: gradWeight += gradOutput * finput^T
+      for (int n = 0; n < B; ++n) {
+        const float* dyn = dy + (size_t)n * Cout * HW;
+        if (dx) {
+          g_sgemm(kRowMajor, kTrans, kNoTrans, K, HW, Cout, 1.f, Wt, K, dyn, HW, 0.f, col.data(), HW);
+          col2im_par(col.data(), Cin, H, W, k, dx + (size_t)n * Cin * HW);
+        }
+        if (dW) {
+          im2col_par(x + (size_t)n * Cin * HW, Cin, H, W, k, col.data());
+          g_sgemm(kRowMajor, kNoTrans, kTrans, Cout, K, HW, 1.f, dyn, HW, col.data(), HW, 1.f, dW, K);
+        }
+      }
+      if (db) {
+#pragma omp parallel for schedule(static)
+        for (int o = 0; o < Cout; ++o) {
+          float s = 0;
+          for (int n = 0; n < B; ++n)
+            for (int p = 0; p < HW; ++p) s += dy[((size_t)n * Cout + o) * HW + p];
+          db[o] += s;
+        }
+      }
+      return;
+    }
+  }
   std::vector<T> WtT;
   if (dx) {  // W^T [K][Cout] so that column-gradient rows are independent dot products
     WtT.resize((size_t)K * Cout);
@@ -947,6 +1043,24 @@ extern "C" {
 long fgo_G_param_count(int C) { return (long)GLayout(C).total; }
 long fgo_D_param_count(int C) { return (long)DLayout(C).total; }
 int fgo_mask_per_sample() { return kMaskPerSample; }
+// Route the fp32 port's GEMMs through an OpenBLAS shared object (path = e.g. scipy.libs/libscipy_openblas-*.so);
+// threads = BLAS threads (0 = leave as is).  Returns 1 on success, 0 if the library / symbol is not there.
+int fgo_use_blas(const char* path, int threads) {
+  g_sgemm = nullptr;
+  if (!path || !*path) return 0;
+  void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return 0;
+  void* f = dlsym(h, "scipy_cblas_sgemm");
+  if (!f) f = dlsym(h, "cblas_sgemm");
+  if (!f) return 0;
+  typedef void (*setn_fn)(int);
+  void* sn = dlsym(h, "scipy_openblas_set_num_threads");
+  if (!sn) sn = dlsym(h, "openblas_set_num_threads");
+  if (sn && threads > 0) ((setn_fn)sn)(threads);
+  g_sgemm = (sgemm_fn)f;
+  return 1;
+}
+int fgo_blas_active() { return g_sgemm != nullptr; }
 long fgo_c2f_G_param_count(int C) { return (long)C2fGLayout(C).total; }
 long fgo_c2f_D_param_count(int C) { return (long)C2fDLayout(C).total; }
 int fgo_c2f_mask_per_sample() { return kC2fMaskPerSample; }

@@ -44,6 +44,29 @@ def lib():
 MASK_PER_SAMPLE = 1984
 
 
+def use_blas(threads=0):
+    """Route the fp32 port's GEMMs through the OpenBLAS bundled with scipy (what Torch7's nn would call on a CPU
+    box).  Returns the library path used, or None when no OpenBLAS is found (the blocked loops stay in use).
+    Only the *_f32 entry points are affected; the fp64 parity oracle never uses BLAS."""
+    import glob
+    cands = []
+    try:
+        import scipy
+        cands += sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs",
+                                               "libscipy_openblas*.so")))
+    except Exception:
+        pass
+    for path in cands:
+        if lib().fgo_use_blas(path.encode(), int(threads)) == 1:
+            return path
+    lib().fgo_use_blas(None, 0)
+    return None
+
+
+def blas_active():
+    return bool(lib().fgo_blas_active())
+
+
 def G_param_count(c):
     return int(lib().fgo_G_param_count(c))
 

@@ -179,3 +179,30 @@ def test_train_iteration_matches_torch():
     assert rel(res["gradG"][big], gG[big]) < 1e-7
     assert st["tD"] == 1 and st["tG"] == 1
     assert res["conf"].sum() == B
+
+
+def test_f32_port_blas_path_matches_loop_path():
+    """The optional OpenBLAS route of the fp32 port (oracle.use_blas, opt-in for the CPU baseline) computes the same
+    convolution / Linear results as the blocked loops; the fp64 oracle is unaffected."""
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((3, 16, 12, 12)).astype(np.float32)
+    w = (rng.standard_normal((8, 16, 5, 5)) * 0.05).astype(np.float32)
+    b = rng.standard_normal(8).astype(np.float32)
+    dy = rng.standard_normal((3, 8, 12, 12)).astype(np.float32)
+    y0 = O.f32.conv_fwd(x, w, b)
+    g0 = O.f32.conv_bwd(x, w, dy)
+    ref64 = O.f64.conv_fwd(x, w, b)
+    path = O.use_blas(2)
+    try:
+        if path is None:
+            pytest.skip("no OpenBLAS shared object next to scipy")
+        assert O.blas_active()
+        y1 = O.f32.conv_fwd(x, w, b)
+        g1 = O.f32.conv_bwd(x, w, dy)
+        assert rel(y1, y0) < 1e-5 and all(rel(a, c) < 1e-5 for a, c in zip(g1, g0))
+        np.testing.assert_array_equal(O.f64.conv_fwd(x, w, b), ref64)
+        xl, wl, bl = rng.standard_normal((5, 70)).astype(np.float32), rng.standard_normal((9, 70)).astype(np.float32), rng.standard_normal(9).astype(np.float32)
+        assert rel(O.f32.linear_fwd(xl, wl, bl), O.f64.linear_fwd(xl, wl, bl)) < 1e-5
+    finally:
+        O.lib().fgo_use_blas(None, 0)
+    assert not O.blas_active()
