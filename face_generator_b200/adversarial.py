@@ -60,3 +60,53 @@ def train_batch_modules(ctx: Context, hyper, real, noise_D, noise_G, masks_D, ma
     interruptableAdam(fevalG_on_D, G, hyper)
     out["grad_G"] = ctx.get_grads(G.net)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the epoch loop around the batch body (adversarial.lua:29-76, :232-334)
+# ------------------------------------------------------------------------------------------------------------------
+def epoch_batches(n_epoch, batch_size):
+    """(t, thisBatchSize) pairs of one epoch exactly as adversarial.lua:54-76 walks them: t advances by the
+    half-batch `dataBatchSize = batchSize / 2` (:35) -- each iteration consumes batchSize/2 *real* examples --
+    the batch shrinks at the tail (:56) and the loop stops at the first batch smaller than 4 (:73-76).
+    Odd tail sizes (possible when N_epoch or batchSize/2 is odd) are rounded down to even: the reference's own
+    `realDataSize = thisBatchSize / 2` is fractional there and the fused step needs an even batch."""
+    assert batch_size >= 4 and batch_size % 2 == 0
+    out, t = [], 1
+    while t <= n_epoch:
+        this = min(batch_size, n_epoch - t + 1)
+        if this < 4:
+            break
+        out.append((t, this - this % 2))
+        t += batch_size // 2
+    return out
+
+
+def train(ctx: Context, dataset, hyper, batch_size, n_epoch=-1, rng=None, seed0=0, confusion=None, progress=None):
+    """One epoch of adversarial.train(dataset, maxAccuracyD, accsInterval) (adversarial.lua:29-334) with the
+    defaults D_iterations = G_iterations = 1 (train.lua:33-34), i.e. one fused fg_train_step per batch.
+
+    dataset: array-like [N][C][32][32] float32 in [0,1] (what DATASET.loadImages returns, dataset.lua:43-75) or a
+    face_generator_b200.dataset.DeviceDataset (then batch assembly and noise happen on the device).
+    hyper.D_maxAcc / hyper.accs_interval are the maxAccuracyD / accsInterval arguments.
+    Returns (accuracy of D over the epoch = CONFUSION.totalValid (:316), confusion counts [4], batches that trained D)."""
+    from .dataset import DeviceDataset
+    rng = rng or np.random.default_rng(0)
+    on_device = isinstance(dataset, DeviceDataset)
+    N = dataset.size() if on_device else len(dataset)
+    n_epoch = N if n_epoch <= 0 else n_epoch                                   # :31-34
+    conf = np.zeros(4, np.int64) if confusion is None else confusion
+    trained = 0
+    for i, (t, B) in enumerate(epoch_batches(n_epoch, batch_size)):
+        seed = seed0 + i + 1
+        if on_device:
+            st = dataset.train_step(hyper, B, seed)
+        else:
+            real = np.ascontiguousarray(np.asarray(dataset)[rng.integers(0, N, B // 2)], np.float32)  # :244-249
+            st = ctx.train_step(hyper, B, real, create_noise_inputs(B // 2, rng), create_noise_inputs(B, rng), None, None, seed)
+        conf += np.asarray(st["conf"], np.int64)                               # :112-117
+        trained += int(st["trained_D"])
+        if progress:
+            progress(t + B, n_epoch)                                           # xlua.progress (:296)
+    total = conf.sum()
+    return (float(conf[0] + conf[3]) / total if total else 0.0), conf, trained
