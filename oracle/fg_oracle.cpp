@@ -896,6 +896,7 @@ void train_iteration(int B, int C, const Hyper& hp, const T* real, const T* nois
 }
 
 #include "fg_oracle_c2f.h"  // coarse-to-fine nets + loop (models_c2f.lua, adversarial_c2f.lua)
+#include "fg_oracle_s16.h"  // --scale 16 nets (models.lua:26-51, :279-316)
 
 }  // namespace
 
@@ -1039,6 +1040,40 @@ FG_EXPORTS(f32, float)
 FG_C2F_EXPORTS(f64, double)
 FG_C2F_EXPORTS(f32, float)
 
+#define FG_S16_EXPORTS(SFX, T)                                                                                   \
+  extern "C" {                                                                                                   \
+  void fgo_convs_fwd_##SFX(int B, int Cin, int H, int W, int Cout, int k, int stride, int pad, const T* x,       \
+                           const T* Wt, const T* b, T* y) {                                                      \
+    convs_fwd<T>(B, Cin, H, W, Cout, k, stride, pad, x, Wt, b, y);                                               \
+  }                                                                                                              \
+  void fgo_convs_bwd_##SFX(int B, int Cin, int H, int W, int Cout, int k, int stride, int pad, const T* x,       \
+                           const T* Wt, const T* dy, T* dx, T* dW, T* db) {                                      \
+    convs_bwd<T>(B, Cin, H, W, Cout, k, stride, pad, x, Wt, dy, dx, dW, db);                                     \
+  }                                                                                                              \
+  void* fgo_s16_G_new_##SFX() { return new G16Net<T>(); }                                                        \
+  void fgo_s16_G_free_##SFX(void* h) { delete (G16Net<T>*)h; }                                                   \
+  void fgo_s16_G_forward_##SFX(void* h, const T* P, const T* noise, int B, int C, T* bn_state, T* out) {         \
+    G16Net<T>* g = (G16Net<T>*)h;                                                                                \
+    g->forward(P, noise, B, C, bn_state);                                                                        \
+    std::copy(g->out.begin(), g->out.end(), out);                                                                \
+  }                                                                                                              \
+  void fgo_s16_G_backward_##SFX(void* h, const T* P, const T* dout, T* dP) { ((G16Net<T>*)h)->backward(P, dout, dP); } \
+  void* fgo_s16_D_new_##SFX() { return new D16Net<T>(); }                                                        \
+  void fgo_s16_D_free_##SFX(void* h) { delete (D16Net<T>*)h; }                                                   \
+  void fgo_s16_D_forward_##SFX(void* h, const T* P, const T* img, int B, int C, int training, const T* masks,    \
+                               T* out) {                                                                         \
+    D16Net<T>* d = (D16Net<T>*)h;                                                                                \
+    d->forward(P, img, B, C, training != 0, masks);                                                              \
+    std::copy(d->out.begin(), d->out.end(), out);                                                                \
+  }                                                                                                              \
+  void fgo_s16_D_backward_##SFX(void* h, const T* P, const T* dout, T* dP, T* dimg) {                            \
+    ((D16Net<T>*)h)->backward(P, dout, dP, dimg);                                                                \
+  }                                                                                                              \
+  }
+
+FG_S16_EXPORTS(f64, double)
+FG_S16_EXPORTS(f32, float)
+
 extern "C" {
 long fgo_G_param_count(int C) { return (long)GLayout(C).total; }
 long fgo_D_param_count(int C) { return (long)DLayout(C).total; }
@@ -1064,6 +1099,9 @@ int fgo_blas_active() { return g_sgemm != nullptr; }
 long fgo_c2f_G_param_count(int C) { return (long)C2fGLayout(C).total; }
 long fgo_c2f_D_param_count(int C) { return (long)C2fDLayout(C).total; }
 int fgo_c2f_mask_per_sample() { return kC2fMaskPerSample; }
+long fgo_s16_G_param_count(int C) { return (long)G16Layout(C).total; }
+long fgo_s16_D_param_count(int C) { return (long)D16Layout(C).total; }
+int fgo_s16_mask_per_sample() { return kD16MaskPerSample; }
 int fgo_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

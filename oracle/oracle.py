@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, "libfg_oracle.so")
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("fg_oracle.cpp", "fg_oracle_c2f.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("fg_oracle.cpp", "fg_oracle_c2f.h", "fg_oracle_s16.h")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
