@@ -84,7 +84,10 @@ int fg_create(fg_ctx** out, int device, int max_batch, int channels);
 int fg_destroy(fg_ctx* ctx);
 int fg_set_stream(fg_ctx* ctx, void* cuda_stream);      /* cutorch's current stream; NULL = own  */
 int fg_sync(fg_ctx* ctx);
-int fg_set_option(fg_ctx* ctx, const char* key, int64_t value);  /* "conv_impl", "graphs", ...    */
+/* keys: "conv_impl" (FG_CONV_*), "optimizer_D" / "optimizer_G" (FG_OPT_*), "tc_mixed" (0/1: cross
+ * terms of the 3xTF32 forward/dgrad as BF16 MMAs, experimental), "params_dirty" (re-pack weights
+ * after writing through fg_params_ptr); unknown keys return FG_ERR_INVALID                        */
+int fg_set_option(fg_ctx* ctx, const char* key, int64_t value);
 int64_t fg_get_option(fg_ctx* ctx, const char* key);
 int fg_set_option_f(fg_ctx* ctx, const char* key, double value);    /* "sgd_momentum_D", "sgd_momentum_G"     */
 
@@ -119,8 +122,9 @@ int fg_D_backward(fg_ctx* ctx, const float* d_out, int want_wgrad, float* d_imag
 /* nn.BCECriterion forward/backward (train.lua:148); x,t length n.                               */
 int fg_bce_forward(fg_ctx* ctx, const float* x, const float* t, int n, float* loss_out);
 int fg_bce_backward(fg_ctx* ctx, const float* x, const float* t, int n, float* dx);
-/* penalty + clamp + interruptableAdam on the ctx's own buffers (adversarial.lua:103-123,
- * interruptable_optimizers.lua:49-94).  grad_scale multiplies the gradient first (1/N for DP).  */
+/* penalty + clamp + interruptableAdam (or the optimizer chosen with "optimizer_D"/"optimizer_G")
+ * on the ctx's own buffers (adversarial.lua:103-123, interruptable_optimizers.lua:7-167).
+ * grad_scale multiplies the gradient first (1/N for DP).                                         */
 int fg_optim_step(fg_ctx* ctx, int net, const fg_hyper* h, float grad_scale);
 
 /* ---- L-op: raw-pointer optimizer for b200.Adam (DEVICE pointers) ----------------------------- */
