@@ -54,6 +54,7 @@ struct Obj {
 
 struct Reader {
   FILE* f = nullptr;
+  int64_t file_bytes = 0;  // nothing inside the file can be larger than the file: bounds every allocation
   std::map<int, ObjP> memo;
   std::string err;
   bool ok = true;
@@ -64,6 +65,16 @@ struct Reader {
       err = "unexpected end of file";
     }
     return ok;
+  }
+  bool fits(int64_t bytes) {
+    if (bytes < 0 || bytes > file_bytes) {
+      if (ok) {
+        ok = false;
+        err = "a length field exceeds the file size (corrupt or not a binary torch.save file)";
+      }
+      return false;
+    }
+    return true;
   }
   int32_t i32() {
     int32_t v = 0;
@@ -77,7 +88,7 @@ struct Reader {
   }
   std::string str() {
     const int32_t n = i32();
-    if (!ok || n < 0 || n > (1 << 28)) {
+    if (!ok || n < 0 || n > (1 << 28) || !fits(n)) {
       if (ok) { ok = false; err = "bad string length"; }
       return "";
     }
@@ -133,9 +144,8 @@ struct Reader {
         } else if (type == 3) {
           o->kind = K_TABLE;
           const int32_t n = i32();
-          if (n < 0 || n > (1 << 26)) {
-            ok = false;
-            err = "bad table size";
+          if (n < 0 || n > (1 << 26) || !fits((int64_t)n * 8)) {  // every pair needs at least two type words
+            if (ok) { ok = false; err = "bad table size"; }
             return o;
           }
           for (int32_t i = 0; i < n && ok; ++i) {
@@ -170,9 +180,8 @@ struct Reader {
             o->elem = elem;
             o->etype = et;
             const int64_t n = i64();
-            if (n < 0 || n > ((int64_t)1 << 36)) {
-              ok = false;
-              err = "bad storage size";
+            if (n < 0 || n > ((int64_t)1 << 36) || !fits(n * elem)) {
+              if (ok) { ok = false; err = "bad storage size"; }
               return o;
             }
             o->data.resize((size_t)n * elem);
@@ -236,16 +245,24 @@ double elem_at(const Obj* st, int64_t i) {
     default: return (double)*p;
   }
 }
+// element count, saturated so that hostile size fields cannot overflow or drive a multi-hour loop
+constexpr int64_t kMaxNumel = (int64_t)1 << 33;
 int64_t numel(const Obj* t) {
   if (t->size.empty()) return 0;
   int64_t n = 1;
-  for (int64_t s : t->size) n *= s;
+  for (int64_t s : t->size) {
+    if (s < 0) return kMaxNumel + 1;
+    if (s == 0) return 0;
+    if (n > kMaxNumel / s) return kMaxNumel + 1;
+    n *= s;
+  }
   return n;
 }
 // appends the tensor's elements in logical (row-major) order as floats; false if the storage is too small
 bool flatten(const Obj* t, std::vector<float>* out) {
   const int64_t n = numel(t);
   if (n == 0) return true;
+  if (n > kMaxNumel) return false;
   const Obj* st = t->payload.get();
   if (!st || st->kind != K_STORAGE) return false;
   const int64_t cap = (int64_t)(st->data.size() / st->elem);
@@ -310,7 +327,15 @@ int fg_t7_open(const char* path, fg_t7** out) {
     fg_set_error("fg_t7_open: cannot open %s", path);
     return FG_ERR_INVALID;
   }
-  ObjP root = r.object();
+  if (fseek(r.f, 0, SEEK_END) == 0) r.file_bytes = (int64_t)ftell(r.f);
+  rewind(r.f);
+  ObjP root;
+  try {  // nothing may throw across the C ABI (std::bad_alloc on a hostile file, ...)
+    root = r.object();
+  } catch (const std::exception& e) {
+    r.ok = false;
+    r.err = std::string("exception while parsing: ") + e.what();
+  }
   fclose(r.f);
   if (!r.ok) {
     fg_set_error("fg_t7_open(%s): %s (only the binary torch.save format is supported)", path, r.err.c_str());
@@ -347,13 +372,17 @@ int64_t fg_t7_string(fg_t7* f, const char* path, char* dst, int64_t cap) {
   }
   return (int64_t)s.size();
 }
-int64_t fg_t7_tensor(fg_t7* f, const char* path, float* dst, int64_t cap, int64_t* dims8) {
+int64_t fg_t7_tensor(fg_t7* f, const char* path, float* dst, int64_t cap, int64_t* dims8) try {
   const Obj* o = f ? lookup(f->root.get(), path) : nullptr;
   if (!o || o->kind != K_TENSOR) {
     fg_set_error("fg_t7_tensor: %s is not a tensor", path ? path : "(null)");
     return -1;
   }
   const int64_t n = numel(o);
+  if (n > kMaxNumel) {
+    fg_set_error("fg_t7_tensor: %s has an implausible size (corrupt file?)", path);
+    return -1;
+  }
   if (dims8) {
     for (int i = 0; i < 8; ++i) dims8[i] = i < (int)o->size.size() ? o->size[i] : 0;
   }
@@ -371,10 +400,13 @@ int64_t fg_t7_tensor(fg_t7* f, const char* path, float* dst, int64_t cap, int64_
     memcpy(dst, v.data(), sizeof(float) * (size_t)n);
   }
   return n;
+} catch (const std::exception& e) {  // nothing may throw across the C ABI
+  fg_set_error("fg_t7_tensor: %s", e.what());
+  return -1;
 }
 // Flat parameter vector of the nn module tree at `path` in getParameters() order (module order, weight then bias;
 // train.lua:151-152).  dst == NULL only counts.  Returns the element count or -1.
-int64_t fg_t7_net_params(fg_t7* f, const char* path, float* dst, int64_t cap) {
+int64_t fg_t7_net_params(fg_t7* f, const char* path, float* dst, int64_t cap) try {
   const Obj* o = f ? lookup(f->root.get(), path) : nullptr;
   if (!o || !table_of(o)) {
     fg_set_error("fg_t7_net_params: %s is not a module", path ? path : "(null)");
@@ -399,10 +431,13 @@ int64_t fg_t7_net_params(fg_t7* f, const char* path, float* dst, int64_t cap) {
     memcpy(dst, flat.data(), sizeof(float) * flat.size());
   }
   return (int64_t)flat.size();
+} catch (const std::exception& e) {  // nothing may throw across the C ABI
+  fg_set_error("fg_t7_net_params: %s", e.what());
+  return -1;
 }
 // BatchNorm running statistics of the module tree, per BN layer in module order: running_mean[C] then running_var[C]
 // (2015 `nn` stored running_std = 1/sqrt(var + eps) instead; it is converted back using the module's eps).
-int64_t fg_t7_net_bn_state(fg_t7* f, const char* path, float* dst, int64_t cap) {
+int64_t fg_t7_net_bn_state(fg_t7* f, const char* path, float* dst, int64_t cap) try {
   const Obj* o = f ? lookup(f->root.get(), path) : nullptr;
   if (!o || !table_of(o)) {
     fg_set_error("fg_t7_net_bn_state: %s is not a module", path ? path : "(null)");
@@ -439,9 +474,12 @@ int64_t fg_t7_net_bn_state(fg_t7* f, const char* path, float* dst, int64_t cap) 
     memcpy(dst, flat.data(), sizeof(float) * flat.size());
   }
   return (int64_t)flat.size();
+} catch (const std::exception& e) {  // nothing may throw across the C ABI
+  fg_set_error("fg_t7_net_bn_state: %s", e.what());
+  return -1;
 }
 // "nn.Sequential{nn.Copy,nn.Sequential{nn.Linear,...},nn.Copy}" -- lets a host check it loads the architecture it expects
-int64_t fg_t7_net_describe(fg_t7* f, const char* path, char* dst, int64_t cap) {
+int64_t fg_t7_net_describe(fg_t7* f, const char* path, char* dst, int64_t cap) try {
   const Obj* o = f ? lookup(f->root.get(), path) : nullptr;
   if (!o) return -1;
   std::string s;
@@ -469,6 +507,9 @@ int64_t fg_t7_net_describe(fg_t7* f, const char* path, char* dst, int64_t cap) {
     dst[n] = '\0';
   }
   return (int64_t)s.size();
+} catch (const std::exception& e) {  // nothing may throw across the C ABI
+  fg_set_error("fg_t7_net_describe: %s", e.what());
+  return -1;
 }
 
 // ---- writer: one root table {key = FloatTensor | number | string}, loadable with stock torch.load ------------
@@ -488,7 +529,7 @@ int fg_t7_writer_open(const char* path, fg_t7_writer** out) {
   *out = w;
   return FG_OK;
 }
-int fg_t7_writer_add_tensor(fg_t7_writer* w, const char* key, const float* data, const int64_t* dims, int ndim) {
+int fg_t7_writer_add_tensor(fg_t7_writer* w, const char* key, const float* data, const int64_t* dims, int ndim) try {
   if (!w || !key || !data || !dims || ndim < 1 || ndim > 8) {
     fg_set_error("fg_t7_writer_add_tensor: bad arguments");
     return FG_ERR_INVALID;
@@ -508,6 +549,9 @@ int fg_t7_writer_add_tensor(fg_t7_writer* w, const char* key, const float* data,
   e.data.assign(data, data + n);
   w->entries.push_back(std::move(e));
   return FG_OK;
+} catch (const std::exception& e) {  // nothing may throw across the C ABI
+  fg_set_error("fg_t7_writer_add_tensor: %s", e.what());
+  return FG_ERR_INVALID;
 }
 int fg_t7_writer_add_number(fg_t7_writer* w, const char* key, double v) {
   if (!w || !key) return FG_ERR_INVALID;

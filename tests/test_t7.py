@@ -236,6 +236,26 @@ def test_bad_files_fail_loudly(tmp_path):
         T7File(tmp_path / "ascii.net")
     with pytest.raises(FGError):
         T7File(tmp_path / "missing.net")
+    # length fields larger than the file are rejected before anything is allocated (nothing may throw or exhaust
+    # memory across the C ABI)
+    ps = lambda x: struct.pack("<i", len(x)) + x
+    hostile = {
+        "bigstorage": struct.pack("<ii", 4, 1) + ps(b"V 1") + ps(b"torch.FloatStorage") + struct.pack("<q", 1 << 35),
+        "bigstring": struct.pack("<ii", 2, 1 << 27),
+        "bigtable": struct.pack("<iii", 3, 1, 1 << 25),
+    }
+    for name, blob in hostile.items():
+        (tmp_path / name).write_bytes(blob)
+        with pytest.raises(FGError):
+            T7File(tmp_path / name)
+    huge = (struct.pack("<iii", 3, 1, 1) + struct.pack("<i", 2) + ps(b"a") + struct.pack("<ii", 4, 2) + ps(b"V 1") +
+            ps(b"torch.FloatTensor") + struct.pack("<i", 2) + struct.pack("<qq", 1 << 40, 1 << 40) + struct.pack("<qq", 1, 1) +
+            struct.pack("<q", 1) + struct.pack("<ii", 4, 3) + ps(b"V 1") + ps(b"torch.FloatStorage") + struct.pack("<q", 2) +
+            struct.pack("<ff", 1, 2))
+    (tmp_path / "hugetensor").write_bytes(huge)
+    with T7File(tmp_path / "hugetensor") as f:
+        with pytest.raises(FGError):
+            f.tensor("a")
     # a tensor that points outside its storage must not be read
     w = W()
     w.obj({"bad": Tensor(fstore(np.zeros(4)), [8])})
