@@ -91,6 +91,7 @@ struct fg_ctx {
   size_t comb_elems[2] = {0, 0};
   GLayout gl;
   DLayout dl;
+  std::vector<void*> allocs;  // every cudaMalloc of net_alloc(), released by net_free()
   // flat buffers (owned)
   float *PG = nullptr, *PD = nullptr, *gG = nullptr, *gD = nullptr;
   float *mG = nullptr, *vG = nullptr, *mD = nullptr, *vD = nullptr;

@@ -52,12 +52,7 @@ const int kDcin[4] = {0 /*C*/, 64, 128, 256}, kDcout[4] = {64, 128, 256, 512}, k
 const int kDmoff[4] = {0, 64, 192, 448};
 inline int dcin(const fg_ctx* c, int i) { return i == 0 ? c->C : kDcin[i]; }
 
-std::vector<void*>& allocs(fg_ctx* c);
-struct AllocList {
-  std::vector<void*> v;
-};
-std::map<fg_ctx*, AllocList> g_allocs;
-std::vector<void*>& allocs(fg_ctx* c) { return g_allocs[c].v; }
+inline std::vector<void*>& allocs(fg_ctx* c) { return c->allocs; }  // owned by the context: no process-wide state
 
 int dalloc(fg_ctx* c, float** p, size_t n) {
   void* q = nullptr;
@@ -210,7 +205,7 @@ int net_alloc(fg_ctx* c) {
 
 void net_free(fg_ctx* c) {
   for (void* p : allocs(c)) cudaFree(p);
-  g_allocs.erase(c);
+  c->allocs.clear();
   if (c->hstats) cudaFreeHost(c->hstats);
   if (c->stage_pinned) cudaFreeHost(c->stage_pinned);
   for (int i = 0; i < 8; ++i)
