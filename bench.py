@@ -19,17 +19,64 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# FG_ORACLE_BLAS=1 (opt-in): the CPU port's GEMMs go through scipy's OpenBLAS; its worker threads then must not fight
-# spinning OpenMP threads, so OpenMP has to idle passively (read when libgomp initialises => set before any import)
-if os.environ.get("FG_ORACLE_BLAS") == "1":
+# The CPU port's GEMMs go through the OpenBLAS bundled with scipy, as Torch7's `nn` calls the system BLAS on a CPU box
+# (FG_ORACLE_BLAS=0 falls back to the port's own blocked loops).  OpenBLAS worker threads must not fight spinning
+# OpenMP threads, so OpenMP idles passively (read when libgomp initialises => set before any import).
+USE_BLAS = os.environ.get("FG_ORACLE_BLAS", "1") != "0"
+if USE_BLAS:
     os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 
 
 def port_gemm(O):
     """-> description of the GEMM the fp32 oracle port uses in this process."""
-    if os.environ.get("FG_ORACLE_BLAS") == "1" and O.use_blas(cpu_threads()):
+    if USE_BLAS and O.use_blas(cpu_threads()):
         return "OpenBLAS sgemm (scipy.libs)"
     return "blocked OpenMP loops"
+
+
+def workload_config(world, B=256):
+    """the `config` object both arms print (the reference arm runs our arm's config, bench contract)"""
+    return {"workload": "train.lua color 3x32x32 batch=256 per GPU (BASELINE configs[1]), 1 D-iter + 1 G-iter, Adam",
+            "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world, "dropout": "in-kernel RNG",
+            "l2": "per-step working set (activations+grads ~1.5 GB) >> 126 MB L2, no explicit flush"}
+
+
+class CpuPort:
+    """The reference's CPU math (Torch7 `nn`: per-sample im2col + SGEMM, batch-parallel) as restated by the oracle's
+    fp32 port, on all usable host threads: one adversarial.lua iteration at batch b."""
+
+    def __init__(self):
+        from oracle import oracle as O
+        from face_generator_b200 import layouts as LY
+        self.O, self.C = O, 3
+        O.set_num_threads(cpu_threads())
+        self.gemm = port_gemm(O)
+        rng = np.random.default_rng(1)
+        PG, PD = LY.trained_like_init(LY.G_layout(3), rng), LY.trained_like_init(LY.D_layout(3), rng, 1.4)
+        self.st = dict(PD=PD, PG=PG, mD=np.zeros_like(PD), vD=np.zeros_like(PD), mG=np.zeros_like(PG), vG=np.zeros_like(PG),
+                       tD=0, tG=0, bnG=np.concatenate([np.zeros(256), np.ones(256), np.zeros(128), np.ones(128)]).astype(np.float32))
+        self.hyper = dict(lr_D=1e-3, lr_G=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, D_L1=0.0, D_L2=1e-4, G_L1=0.0, G_L2=0.0,
+                          D_clamp=1.0, G_clamp=5.0)
+        self.inputs = {}
+
+    def step(self, b):
+        if b not in self.inputs:
+            rng = np.random.default_rng(b)
+            self.inputs[b] = synth_inputs(b, self.C, 7) + ((rng.random((b, self.O.MASK_PER_SAMPLE)) < 0.7).astype(np.float32),)
+        real, nD, nG, masks = self.inputs[b]
+        t0 = time.perf_counter()
+        self.O.f32.train_iteration(b, self.C, self.hyper, real, nD, nG, masks, masks, self.st, want_grads=False)
+        return time.perf_counter() - t0
+
+    def pick_batch(self, n_steps, budget_s):
+        """largest b in {256,...,16} whose n_steps iterations fit the time budget (calibrated on one batch-16 step;
+        the iteration cost is linear in b).  256 = the whole configs[1] step."""
+        self.step(16)
+        t16 = self.step(16)
+        for b in (256, 128, 64, 32):
+            if n_steps * t16 * b / 16.0 <= budget_s:
+                return b
+        return 16
 
 METRIC = "32x32 GAN train images/sec (1 D-iter + 1 G-iter per batch, batch 256/GPU)"
 # algorithmic FLOPs (SURVEY.md 8d): conv = 2*Cout*Cin*k*k*H*W per image per pass
@@ -59,6 +106,17 @@ def ncu_traffic(profile="r1_ncu_tapconv_v12.md"):
             m = re.search(r"\| %s \| ([0-9.,]+) \| (\w+) \|" % re.escape(key), txt)
             tot += float(m.group(1).replace(",", "")) * scale[m.group(2)]
         return tot, "profiles/" + profile
+    except Exception:
+        return None, None
+
+
+def ncu_pipe_active(profile="r1_ncu_tapconv_v12.md"):
+    """sm__pipe_tensor_cycles_active (% of peak) of the G.C2 forward launch in the committed `ncu --set full` summary"""
+    import re
+    try:
+        txt = open(os.path.join(ROOT, "profiles", profile)).read().split("\n## ")[1]
+        m = re.search(r"\| sm__pipe_tensor_cycles_active\.avg\.pct_of_peak_sustained_active \| ([0-9.,]+) \|", txt)
+        return float(m.group(1).replace(",", "")), "profiles/" + profile
     except Exception:
         return None, None
 
@@ -121,42 +179,46 @@ def synth_inputs(B, C, seed):
 
 
 def run_reference(args, rank, world):
-    """The reference's own CPU path: Torch7 `nn` math (per-sample im2col + SGEMM, OpenMP batch-parallel) as
-    restated by the oracle's fp32 port, all host threads, same metric/config; each step is a bounded sample
-    (b images of the 256-image batch) so K steps end within minutes."""
+    """The reference's own CPU path on this box's host cores, same metric / config.  Each step is the full
+    256-image iteration when K+W of them fit ~3 minutes, otherwise the largest power-of-two sample of the batch that
+    does (`sample` says which)."""
     if rank != 0:
         return
-    from oracle import oracle as O
-    from face_generator_b200 import layouts as LY
-    C = 3
-    b = 16 if args.steps <= 24 else 8
-    O.set_num_threads(cpu_threads())
-    gemm = port_gemm(O)
-    rng = np.random.default_rng(1)
-    PG, PD = LY.trained_like_init(LY.G_layout(C), rng), LY.trained_like_init(LY.D_layout(C), rng, 1.4)
-    st = dict(PD=PD, PG=PG, mD=np.zeros_like(PD), vD=np.zeros_like(PD), mG=np.zeros_like(PG), vG=np.zeros_like(PG), tD=0,
-              tG=0, bnG=np.concatenate([np.zeros(256), np.ones(256), np.zeros(128), np.ones(128)]).astype(np.float32))
-    hyper = dict(lr_D=1e-3, lr_G=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, D_L1=0.0, D_L2=1e-4, G_L1=0.0, G_L2=0.0,
-                 D_clamp=1.0, G_clamp=5.0)
-    masks = (rng.random((b, O.MASK_PER_SAMPLE)) < 0.7).astype(np.float32)
-    real, nD, nG = synth_inputs(b, C, 7)
-    for _ in range(max(1, min(args.warmup, 2))):
-        O.f32.train_iteration(b, C, hyper, real, nD, nG, masks, masks, st, want_grads=False)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.f32.train_iteration(b, C, hyper, real, nD, nG, masks, masks, st, want_grads=False)
-    dt = time.perf_counter() - t0
+    port = CpuPort()
+    warm = max(1, min(args.warmup, 2))
+    b = port.pick_batch(args.steps + warm, 170.0)
+    for _ in range(warm):
+        port.step(b)
+    dt = sum(port.step(b) for _ in range(args.steps))
     v = b * args.steps / dt
-    sample = "%d-image sample of the 256-image batch per step, %d steps, fp32 oracle port (THNN algorithm, %s), %d threads" % (
-        b, args.steps, gemm, O.num_threads())
+    whole = "the whole 256-image batch" if b == 256 else "a %d-image sample of the 256-image batch" % b
+    sample = "%s per step, %d steps, fp32 oracle port (THNN algorithm, %s), %d threads" % (whole, args.steps, port.gemm,
+                                                                                         port.O.num_threads())
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "train.lua color 3x32x32 batch=256 (configs[1]); reference arm runs a bounded sample",
-                   "global_batch": 256 * args.gpus, "parallelism": "cpu"},
-        "cpu_baseline": {"value": v, "unit": "images/s", "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "config": workload_config(args.gpus),
+        "reference_detail": {"device": "cpu", "images_per_step": b, "gemm": port.gemm},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": port.O.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def secondary_configs(steps=5):
+    """the other BASELINE.json configs, measured like the headline (CUDA events on the ctx stream, warm-up, inputs in
+    HBM; e2e with host buffers): configs[0] gray batch 16, configs[3] c2f batch 32 / 256, configs[4] sample.lua 1024."""
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    res = []
+    try:
+        import bench_configs as BC
+        for job in (lambda: BC.train_small(16, 1, steps), lambda: BC.c2f(32, steps), lambda: BC.c2f(256, steps),
+                    lambda: BC.sample(16, steps), lambda: BC.sample(1024, steps)):
+            r = job()
+            r.pop("layer_ms_per_step", None)
+            res.append(r)
+    except Exception as e:
+        res.append({"error": str(e)})
+    return res
 
 
 def main():
@@ -168,6 +230,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE configs[1]: 256)")
     ap.add_argument("--conv-impl", type=int, default=-1, help="0 simt, 1 tcgen05 dense, 2 tcgen05 collapsed; -1 library default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[0]/[3]/[4] lines of the `secondary` block")
     ap.add_argument("--breakdown", action="store_true", help="per-layer kernel timings in kernel_ms_per_step")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -180,8 +243,11 @@ def main():
     from face_generator_b200.lib import NET_D, NET_G, PinnedArray
     B, C, K, W = args.batch, 3, args.steps, max(args.warmup, 3)
     dist = None
-    # rank 0 must print ONE line: NCCL writes its version banner to stdout at NCCL_DEBUG=VERSION/INFO
-    os.environ["NCCL_DEBUG"] = os.environ.get("FG_NCCL_DEBUG", "WARN")
+    # rank 0 must print ONE line on stdout; NCCL logs to stdout by default, so its log (whatever level the caller
+    # asked for; INIT lines carry "nranks N" by default) goes to stderr instead of being switched off
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         import torch.distributed as dist  # plumbing only: rendezvous, barrier, max-over-ranks
         dist.init_process_group("gloo")
@@ -276,6 +342,12 @@ def main():
         if n:
             hbm[name] = (nbytes, t / nprof)
     ctx.timing_enable(False)
+    tf32_peak = None
+    if rank == 0:
+        try:
+            tf32_peak = ctx.tf32_peak(20000)
+        except Exception as e:  # the probe must never cost the headline
+            sys.stderr.write("tf32 peak probe failed: %s\n" % e)
     if rank != 0:
         return
     peaks = load_peaks()
@@ -288,14 +360,16 @@ def main():
     tf_c2 = 3.5 * B * F_GC2 / t_c2 / 1e12 if t_c2 > 0 else 0.0
     peak = peaks["bf16_sus"] / 2.0
     traffic, traffic_src = ncu_traffic()
+    # executed tensor-core work of that launch: 3 MMAs per logical MMA (3xTF32), 9/25 of the taps (phase collapse)
+    collapsed = ctx.get_option("conv_impl") == 2
+    exec_ratio = 3.0 * (9.0 / 25.0 if collapsed else 1.0)
+    pipe_pct, pipe_src = ncu_pipe_active()
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "train.lua color 3x32x32 batch=256 per GPU (BASELINE configs[1]), 1 D-iter + 1 G-iter, Adam",
-                   "global_batch": B * world, "per_gpu_batch": B, "parallelism": "dp%d" % world,
-                   "conv_impl": ctx.get_option("conv_impl"), "dropout": "in-kernel RNG",
-                   "l2": "per-step working set (activations+grads ~1.5 GB) >> 126 MB L2, no explicit flush"},
+        "config": workload_config(world, B),
+        "config_detail": {"conv_impl": ctx.get_option("conv_impl")},
         "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(real.nbytes + nD.nbytes + nG.nbytes), "d2h_bytes_per_step": 40},
         "gpu_launches": int(launches),
@@ -307,6 +381,15 @@ def main():
                                      "input hi+lo 2x67.1 MB + output 134.2 MB + weights 9.4 MB" % (256, traffic_src),
                      "peak_source": "%s bf16 sustained %.1f TF / 2 (kind::tf32 is half rate); algorithmic fp32 FLOPs" % (
                          peaks["src"], peaks["bf16_sus"]),
+                     "executed_mma_tflops": tf_fwd * exec_ratio,
+                     "executed_note": "kind::tf32 MMAs actually issued: 3 per logical MMA (hi*hi + hi*lo + lo*hi)%s" % (
+                         " x 9/25 taps (upsample folded into four 3x3 phase convolutions)" if collapsed else ""),
+                     "measured_tf32_peak": tf32_peak,
+                     "measured_tf32_peak_note": "fg_bench_tf32_peak: back-to-back tcgen05.mma.kind::tf32 128x256x8, cta_group::1, "
+                                                "smem-resident operands, all SMs, run at bench clocks right after the timed region",
+                     "frac_executed_vs_measured_tf32": (tf_fwd * exec_ratio / tf32_peak) if tf32_peak else None,
+                     "frac_algorithmic_vs_measured_tf32": (tf_fwd / tf32_peak) if tf32_peak else None,
+                     "pipe_active_pct": pipe_pct, "pipe_active_src": pipe_src,
                      "family_fwd_dgrad_wgrad_tflops": tf_c2,
                      "step_algorithmic_tflops": F_ITER_PER_IMG * B * K / (ms / 1e3) / 1e12},
         "hbm_kernels": [{"kernel": k[4:], "bytes_per_step": int(nb), "ms_per_step": round(ms_k, 4),
@@ -315,27 +398,20 @@ def main():
         "kernel_ms_per_step": {k: round(v[0], 4) for k, v in fam.items()},
         "conv_ms_per_step": round(t_all / nprof, 4),
     }
+    if world == 1 and not args.no_secondary:
+        out["secondary"] = secondary_configs()
+    ctx.close()
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O  # cpu_baseline leg: the checker timed as a reported baseline
-        O.set_num_threads(cpu_threads())
-        gemm = port_gemm(O)
-        b = 16
-        rng = np.random.default_rng(1)
-        PG, PD = LY.trained_like_init(LY.G_layout(C), rng), LY.trained_like_init(LY.D_layout(C), rng, 1.4)
-        st = dict(PD=PD, PG=PG, mD=np.zeros_like(PD), vD=np.zeros_like(PD), mG=np.zeros_like(PG), vG=np.zeros_like(PG),
-                  tD=0, tG=0, bnG=np.concatenate([np.zeros(256), np.ones(256), np.zeros(128), np.ones(128)]).astype(np.float32))
-        hp = dict(lr_D=1e-3, lr_G=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, D_L1=0.0, D_L2=1e-4, G_L1=0.0, G_L2=0.0,
-                  D_clamp=1.0, G_clamp=5.0)
-        masks = (rng.random((b, O.MASK_PER_SAMPLE)) < 0.7).astype(np.float32)
-        r, a, g = synth_inputs(b, C, 7)
-        O.f32.train_iteration(b, C, hp, r, a, g, masks, masks, st, want_grads=False)
-        t0, it = time.perf_counter(), 0
-        while it < 3 or (time.perf_counter() - t0 < 10 and it < 12):
-            O.f32.train_iteration(b, C, hp, r, a, g, masks, masks, st, want_grads=False)
+        # cpu_baseline leg: the checker's fp32 port timed as a reported baseline on a bounded sample (10-30 s)
+        port = CpuPort()
+        b = port.pick_batch(1, 30.0)
+        t, it = 0.0, 0
+        while it < 1 or (t < 10.0 and it < 12):
+            t += port.step(b)
             it += 1
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": b * it / dt, "unit": "images/s", "cores": O.num_threads(), "kind": "port",
-                               "sample": "%d iterations at batch %d (colour) of the fp32 oracle port (%s), %.1f s" % (it, b, gemm, dt)}
+        out["cpu_baseline"] = {"value": b * it / t, "unit": "images/s", "cores": port.O.num_threads(), "kind": "port",
+                               "sample": "%d iteration(s) at batch %d of %d (colour) of the fp32 oracle port (%s), %.1f s" % (
+                                   it, b, B, port.gemm, t)}
     print(json.dumps(out))
 
 

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "fg_internal.h"
+#include "k_conv_tc.h"
 
 static thread_local char g_err[1024] = "";
 void fg_set_error(const char* fmt, ...) {
@@ -158,6 +159,10 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
   if (!strcmp(key, "tc_mixed")) {  // cross terms of the tensor-core forward/dgrad as BF16 MMAs
     FG_REQUIRE(v == 0 || v == 1, "tc_mixed must be 0 or 1");
     c->tc_mixed = (int)v;
+    return FG_OK;
+  }
+  if (!strcmp(key, "debug_keep")) {  // keep the D step's pre-activations of fg_train_step ("Dstep.*" debug tensors)
+    c->debug_keep = v != 0;
     return FG_OK;
   }
   if (!strcmp(key, "optimizer_D") || !strcmp(key, "optimizer_G")) {  // OPT.D_optmethod / OPT.G_optmethod (train.lua:38-39)
@@ -470,10 +475,18 @@ int64_t fg_debug_tensor(fg_ctx* c, const char* name, float* dst, int64_t max_ele
       {"D.z3", c->D_z[2], 16384, db}, {"D.z4", c->D_z[3], 8192, db}, {"D.p4", c->D_p[3], 2048, db},
       {"D.logit", c->D_logit, 1, db}, {"D.out", c->D_out, 1, db}, {"D.dx", c->D_dx, 1024 * c->C, db},
       {"D.masks", c->D_masks, kMaskPerSample, db}, {"G.bn_mean1", c->bn_mean1, 256, 1}, {"G.bn_istd1", c->bn_istd1, 256, 1},
-      {"G.bn_mean2", c->bn_mean2, 128, 1}, {"G.bn_istd2", c->bn_istd2, 128, 1}};
+      {"G.bn_mean2", c->bn_mean2, 128, 1}, {"G.bn_istd2", c->bn_istd2, 128, 1},
+      {"D.zl1", c->D_zl1, 512, db}, {"D.zl2", c->D_zl2, 512, db},
+      {"Dstep.z1", c->keep_D[0], 65536, c->keep_B}, {"Dstep.z2", c->keep_D[1], 32768, c->keep_B},
+      {"Dstep.z3", c->keep_D[2], 16384, c->keep_B}, {"Dstep.z4", c->keep_D[3], 8192, c->keep_B},
+      {"Dstep.zl1", c->keep_D[4], 512, c->keep_B}, {"Dstep.zl2", c->keep_D[5], 512, c->keep_B}};
   for (const Ent& e : ents)
     if (!strcmp(e.n, name)) {
       const int64_t n = e.per * e.B;
+      if (!e.p) {
+        fg_set_error("fg_debug_tensor: '%s' has not been produced (option \"debug_keep\" + fg_train_step)", name);
+        return -1;
+      }
       if (dst) {
         if (n > max_elems) return -2;
         if (to_user(c, dst, e.p, n) != FG_OK) return -3;
@@ -482,6 +495,12 @@ int64_t fg_debug_tensor(fg_ctx* c, const char* name, float* dst, int64_t max_ele
     }
   fg_set_error("fg_debug_tensor: unknown tensor '%s'", name);
   return -1;
+}
+
+int fg_bench_tf32_peak(fg_ctx* c, int iters, double* tflops) {
+  ENTER(c);
+  FG_REQUIRE(tflops && iters > 0, "fg_bench_tf32_peak: bad arguments");
+  return tc_tf32_peak(c, iters, 5, tflops);
 }
 
 int fg_event_record(fg_ctx* c, int slot) {

@@ -70,6 +70,17 @@ int net_allreduce(fg_ctx* c, float* buf, int64_t n) {
   return FG_OK;
 }
 
+// rank 0's bytes -> every rank (on the ctx stream; callers group several and synchronise once)
+int net_broadcast(fg_ctx* c, void* buf, size_t bytes) {
+  if (c->world <= 1) return FG_OK;
+  FG_NCCL(g_nccl.Broadcast(buf, buf, bytes, ncclChar, 0, (ncclComm_t)c->nccl_comm, c->stream));
+  return FG_OK;
+}
+int net_group(bool start) {
+  FG_NCCL(start ? g_nccl.GroupStart() : g_nccl.GroupEnd());
+  return FG_OK;
+}
+
 extern "C" {
 int fg_dp_unique_id(void* out128) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
@@ -107,16 +118,21 @@ int fg_dp_broadcast_params(fg_ctx* c) {
   if (!c) return FG_ERR_INVALID;
   if (c->world <= 1) return FG_OK;
   FG_CUDA(cudaSetDevice(c->device));
-  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
-  FG_NCCL(g_nccl.GroupStart());
-  FG_NCCL(g_nccl.Broadcast(c->PG, c->PG, c->gl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(g_nccl.Broadcast(c->PD, c->PD, c->dl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(g_nccl.Broadcast(c->mG, c->mG, c->gl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(g_nccl.Broadcast(c->vG, c->vG, c->gl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(g_nccl.Broadcast(c->mD, c->mD, c->dl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(g_nccl.Broadcast(c->vD, c->vD, c->dl.total, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(g_nccl.Broadcast(c->bnG, c->bnG, 768, ncclFloat, 0, comm, c->stream));
-  FG_NCCL(g_nccl.GroupEnd());
+  // everything a replica's next step depends on: parameters, optimizer moments, BN running statistics AND the
+  // device-side step counters / accuracy history (the Adam bias correction uses t: a rank that resumed from a
+  // checkpoint at t > 0 while the others start at 0 would otherwise take a different step size and diverge)
+  FG_TRY(net_group(true));
+  const size_t nG = c->gl.total * sizeof(float), nD = c->dl.total * sizeof(float);
+  FG_TRY(net_broadcast(c, c->PG, nG));
+  FG_TRY(net_broadcast(c, c->PD, nD));
+  FG_TRY(net_broadcast(c, c->mG, nG));
+  FG_TRY(net_broadcast(c, c->vG, nG));
+  FG_TRY(net_broadcast(c, c->mD, nD));
+  FG_TRY(net_broadcast(c, c->vD, nD));
+  FG_TRY(net_broadcast(c, c->bnG, 768 * sizeof(float)));
+  FG_TRY(net_broadcast(c, c->dstats, sizeof(DeviceStats)));
+  FG_TRY(net_broadcast(c, c->acc_hist, kAccHistMax * sizeof(float)));
+  FG_TRY(net_group(false));
   FG_CUDA(cudaStreamSynchronize(c->stream));
   c->G_packed = c->D_packed = false;
   return FG_OK;

@@ -137,6 +137,11 @@ struct fg_ctx {
   // data parallel
   void* nccl_comm = nullptr;
   int world = 1, rank = 0;
+  // debug (tests): "debug_keep" = 1 keeps a copy of the D step's pre-activations of fg_train_step, which the G
+  // step's D forward overwrites (the strict gradient-parity tests read PReLU branch decisions from them)
+  bool debug_keep = false;
+  int keep_B = 0;
+  float* keep_D[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // D_z[0..3], D_zl1, D_zl2
   // timing
   cudaEvent_t events[16] = {};
   bool timing = false;
@@ -270,3 +275,5 @@ int net_optim(fg_ctx* c, int net, const fg_hyper* h, float grad_scale, bool gate
 int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real_nchw_dev, const float* noiseD_dev,
                    const float* noiseG_dev, const float* masksD_dev, const float* masksG_dev, uint64_t seed);
 int net_allreduce(fg_ctx* c, float* buf, int64_t n);
+int net_broadcast(fg_ctx* c, void* buf, size_t bytes);  // rank 0 -> all (dp.cu)
+int net_group(bool start);                                // ncclGroupStart / ncclGroupEnd

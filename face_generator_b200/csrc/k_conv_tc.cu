@@ -413,7 +413,71 @@ inline bool mixed_ok(const fg_ctx* c, const float* a, const float* b) {
   return c->tc_mixed && reinterpret_cast<uintptr_t>(a) % 16 == 0 && reinterpret_cast<uintptr_t>(b) % 16 == 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// tensor-pipe probe: the issue rate of tcgen05.mma.kind::tf32 (cta_group::1, M=128, N=256, K=8) with both operands
+// resident in shared memory -- no TMA, no epilogue.  bench.py runs it at bench clocks; the number is the measured
+// TF32 peak the 3xTF32 convolutions are normalised by (MEASURED_PEAKS.json only holds a bf16 figure).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr uint32_t kA = 128 * 128, kB = 256 * 128;  // 128 x 32 fp32 and 256 x 32 fp32, SWIZZLE_128B K-major
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + kA + kB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  for (uint32_t i = threadIdx.x; i < (kA + kB) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (threadIdx.x == 0) {
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA
+  if (threadIdx.x < 32) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t kIdesc = make_idesc(128, 256, 0, 0);
+    const uint32_t sa = smem_u32(smem);
+    const uint64_t a = make_desc(sa, 16, 1024), b = make_desc(sa + kA, 16, 1024);
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t acc = tmem_base + (uint32_t)(i & 1) * 256;  // two independent accumulators
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_tf32(acc, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), kIdesc, 1);
+    }
+    umma_commit(done);
+    mbar_wait(done, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace
+
+// -> TFLOP/s of kind::tf32 MMAs (2*M*N*K per instruction) over all SMs, best of `reps` event-timed launches
+int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops) {
+  constexpr int kSmem = 128 * 128 + 256 * 128 + 64 + 1024;
+  FG_CUDA(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  cudaEvent_t e0, e1;
+  FG_CUDA(cudaEventCreate(&e0));
+  FG_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int r = 0; r < reps + 1; ++r) {  // first launch = warm-up
+    FG_CUDA(cudaEventRecord(e0, c->stream));
+    tf32_peak_kernel<<<c->sm_count, 128, kSmem, c->stream>>>(iters);
+    LAUNCH_CHECK(c);
+    FG_CUDA(cudaEventRecord(e1, c->stream));
+    FG_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    FG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flops = (double)c->sm_count * iters * 4.0 * 2.0 * 128 * 256 * 8;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return FG_OK;
+}
 
 int tc_init(fg_ctx* c) {
   (void)c;

@@ -48,3 +48,4 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
                       ConvGeom g);
 int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* out,
                   ConvGeom g);
+int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops);

@@ -718,6 +718,27 @@ int fg_c2f_parzen_dist(fg_c2f* n, const float* noise, const float* coarse, const
   return fg_nearest(c, n->in_d, 1, n->io, K, (int)img, &idx, dist_out);
 }
 
+// data parallel: rank 0's c2f parameters, optimizer moments and step counters to every rank (the nets have no
+// BatchNorm state); the communicator is the ctx's (fg_dp_init)
+int fg_c2f_dp_broadcast_params(fg_c2f* n) {
+  ENTER(n);
+  fg_ctx* c = n->c;
+  if (c->world <= 1) return FG_OK;
+  FG_TRY(net_group(true));
+  const size_t bG = n->nG * sizeof(float), bD = n->nD * sizeof(float);
+  FG_TRY(net_broadcast(c, n->PG, bG));
+  FG_TRY(net_broadcast(c, n->PD, bD));
+  FG_TRY(net_broadcast(c, n->mG, bG));
+  FG_TRY(net_broadcast(c, n->vG, bG));
+  FG_TRY(net_broadcast(c, n->mD, bD));
+  FG_TRY(net_broadcast(c, n->vD, bD));
+  FG_TRY(net_broadcast(c, n->dstats, sizeof(DeviceStats)));
+  FG_TRY(net_group(false));
+  FG_CUDA(cudaStreamSynchronize(c->stream));
+  n->G_packed = n->D_packed = false;
+  return FG_OK;
+}
+
 int fg_c2f_train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_diff, const float* cond_D,
                       const float* noise_D, const float* cond_G, const float* noise_G, const float* masks_D,
                       const float* masks_G, uint64_t seed, fg_step_stats* stats) {

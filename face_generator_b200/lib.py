@@ -132,6 +132,7 @@ SYMBOLS = {
     "fg_dp_unique_id": (_I, [_P]),
     "fg_dp_init": (_I, [_P, _P, _I, _I]),
     "fg_dp_broadcast_params": (_I, [_P]),
+    "fg_c2f_dp_broadcast_params": (_I, [_P]),
     "fg_dp_world": (_I, [_P]),
     "fg_dev_alloc": (_P, [_SZ]),
     "fg_dev_free": (_I, [_P]),
@@ -140,6 +141,7 @@ SYMBOLS = {
     "fg_memcpy": (_I, [_P, _P, _P, _SZ]),
     "fg_kernel_launches": (_L, [_P]),
     "fg_debug_tensor": (_L, [_P, C.c_char_p, _P, _L]),
+    "fg_bench_tf32_peak": (_I, [_P, _I, C.POINTER(C.c_double)]),
     "fg_event_record": (_I, [_P, _I]),
     "fg_event_elapsed_ms": (_I, [_P, _I, _I, C.POINTER(C.c_double)]),
     "fg_timing_enable": (_I, [_P, _I]),
@@ -363,6 +365,12 @@ class Context:
     def dev_free(self, p):
         self.lib.fg_dev_free(p)
 
+    def tf32_peak(self, iters=20000):
+        """measured tcgen05 kind::tf32 issue rate in TFLOP/s (roofline denominator of the 3xTF32 convolutions)"""
+        v = C.c_double(0)
+        _check(self.lib.fg_bench_tf32_peak(self.h, iters, C.byref(v)), "fg_bench_tf32_peak")
+        return v.value
+
     def debug_tensor(self, name):
         n = self.lib.fg_debug_tensor(self.h, name.encode(), None, 0)
         if n < 0:
@@ -575,6 +583,9 @@ class C2f:
         dd = np.empty((d_out.shape[0], self.C, 32, 32), np.float32) if want_ddiff else None
         _check(self.lib.fg_c2f_D_backward(self.h, _ptr(d_out), int(want_wgrad), _ptr(dd)), "fg_c2f_D_backward")
         return dd
+
+    def dp_broadcast_params(self):
+        _check(self.lib.fg_c2f_dp_broadcast_params(self.h), "fg_c2f_dp_broadcast_params")
 
     def train_step(self, hyper, B, real_diff, cond_D, noise_D, cond_G, noise_G, masks_D=None, masks_G=None, seed=0,
                    want_stats=True):

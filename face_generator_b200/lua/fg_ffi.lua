@@ -121,6 +121,7 @@ int fg_sample(fg_ctx* ctx, const float* noise, int N, int chunk, float* images_o
 int fg_dp_unique_id(void* out128);
 int fg_dp_init(fg_ctx* ctx, const void* id128, int nranks, int rank);
 int fg_dp_broadcast_params(fg_ctx* ctx);
+int fg_c2f_dp_broadcast_params(fg_c2f* n);
 int fg_dp_world(fg_ctx* ctx);
 void* fg_dev_alloc(size_t bytes);
 int fg_dev_free(void* p);
@@ -129,6 +130,7 @@ int fg_host_free_pinned(void* p);
 int fg_memcpy(fg_ctx* ctx, void* dst, const void* src, size_t bytes);
 int64_t fg_kernel_launches(fg_ctx* ctx);
 int64_t fg_debug_tensor(fg_ctx* ctx, const char* name, float* dst, int64_t max_elems);
+int fg_bench_tf32_peak(fg_ctx* ctx, int iters, double* tflops);
 int fg_event_record(fg_ctx* ctx, int slot);
 int fg_event_elapsed_ms(fg_ctx* ctx, int slot_a, int slot_b, double* ms);
 int fg_timing_enable(fg_ctx* ctx, int on);

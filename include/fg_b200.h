@@ -84,7 +84,8 @@ int fg_create(fg_ctx** out, int device, int max_batch, int channels);
 int fg_destroy(fg_ctx* ctx);
 int fg_set_stream(fg_ctx* ctx, void* cuda_stream);      /* cutorch's current stream; NULL = own  */
 int fg_sync(fg_ctx* ctx);
-/* keys: "conv_impl" (FG_CONV_*), "optimizer_D" / "optimizer_G" (FG_OPT_*), "tc_mixed" (0/1: cross
+/* keys: "conv_impl" (FG_CONV_*), "optimizer_D" / "optimizer_G" (FG_OPT_*), "debug_keep" (tests: keep the D
+ * step's pre-activations of fg_train_step as "Dstep.*" debug tensors), "tc_mixed" (0/1: cross
  * terms of the 3xTF32 forward/dgrad as BF16 MMAs, experimental), "params_dirty" (re-pack weights
  * after writing through fg_params_ptr); unknown keys return FG_ERR_INVALID                        */
 int fg_set_option(fg_ctx* ctx, const char* key, int64_t value);
@@ -305,7 +306,10 @@ int fg_t7_writer_close(fg_t7_writer* w);                  /* writes the file and
 /* ---- data parallel: one process per GPU, NCCL over NVLink (new functionality) ----- */
 int fg_dp_unique_id(void* out128);                        /* ncclGetUniqueId, 128 bytes           */
 int fg_dp_init(fg_ctx* ctx, const void* id128, int nranks, int rank);
-int fg_dp_broadcast_params(fg_ctx* ctx);                  /* rank 0's G/D params+state to all     */
+/* rank 0's G/D parameters, optimizer moments, BN running statistics, step counters (t_D, t_G) and
+ * the D-accuracy history to all ranks -- call after loading a checkpoint on rank 0               */
+int fg_dp_broadcast_params(fg_ctx* ctx);
+int fg_c2f_dp_broadcast_params(fg_c2f* n);                /* same for the coarse-to-fine nets      */
 int fg_dp_world(fg_ctx* ctx);                             /* nranks (1 when DP is off)            */
 
 /* ---- plain device-memory helpers for FFI hosts without a CUDA binding ------------------------ */
@@ -325,6 +329,9 @@ int64_t fg_debug_tensor(fg_ctx* ctx, const char* name, float* dst, int64_t max_e
 int fg_event_record(fg_ctx* ctx, int slot);
 int fg_event_elapsed_ms(fg_ctx* ctx, int slot_a, int slot_b, double* ms);
 int fg_timing_enable(fg_ctx* ctx, int on);
+/* tensor-pipe probe for the roofline: TFLOP/s of back-to-back tcgen05.mma.kind::tf32 (M=128,N=256,K=8, operands
+ * resident in shared memory) on all SMs, best of 5 event-timed launches of `iters` x 4 MMAs per SM            */
+int fg_bench_tf32_peak(fg_ctx* ctx, int iters, double* tflops);
 int fg_timing_get(fg_ctx* ctx, const char* name, double* ms_total, int64_t* launches);
 
 #ifdef __cplusplus

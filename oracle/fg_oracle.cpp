@@ -509,9 +509,57 @@ void bn_bwd(int B, int C, int HW, const T* x, const T* gamma, const BNSave<T>& s
   }
 }
 
+// ---- PReLU kink bookkeeping (used by the parity tests only; off by default) ----------------------
+// PReLU's derivative is discontinuous at 0.  A pre-activation that lies within rounding noise of 0 may be
+// rounded to the other sign by a second (fp32) implementation; both branch choices are then "correct", but
+// the two gradients differ by (1-a)*dy for that element.  To compare gradients STRICTLY the tests
+//   1. run the oracle in RECORD mode: every prelu_fwd call (numbered in call order) lists the elements with
+//      |x| < margin * max|x|  ("ambiguous" elements),
+//   2. read the branch the implementation under test took for exactly those elements,
+//   3. re-run the oracle in OVERRIDE mode: prelu_bwd takes the given branch for the listed elements and its
+//      own branch everywhere else.
+// The forward value is continuous in x, so only the backward is touched.  prelu_bwd finds its forward call
+// through the address of the pre-activation array (the nets keep those arrays alive between the two).
+struct KinkCall {
+  size_t n = 0;
+  double maxabs = 0;
+  std::vector<long> idx;           // RECORD: ambiguous elements
+  std::vector<long> ov_idx;        // OVERRIDE: elements whose branch is forced ...
+  std::vector<signed char> ov_pos;  // ... to x > 0 (1) or x <= 0 (0)
+};
+struct KinkCtx {
+  int mode = 0;  // 0 off, 1 record, 2 override
+  double margin = 0;
+  int next_call = 0;
+  std::vector<KinkCall> calls;
+  std::vector<std::pair<const void*, int>> ptr_call;  // latest forward call per pre-activation array
+} g_kink;
+
+template <class T>
+void kink_on_forward(size_t n, const T* x) {
+  const int s = g_kink.next_call++;
+  if ((int)g_kink.calls.size() <= s) g_kink.calls.resize(s + 1);
+  bool found = false;
+  for (auto& pc : g_kink.ptr_call)
+    if (pc.first == (const void*)x) { pc.second = s; found = true; }
+  if (!found) g_kink.ptr_call.emplace_back((const void*)x, s);
+  KinkCall& kc = g_kink.calls[s];
+  kc.n = n;
+  if (g_kink.mode == 1) {
+    double mx = 0;
+    for (size_t i = 0; i < n; ++i) mx = std::max(mx, (double)std::fabs(x[i]));
+    kc.maxabs = mx;
+    kc.idx.clear();
+    const double thr = g_kink.margin * mx;
+    for (size_t i = 0; i < n; ++i)
+      if ((double)std::fabs(x[i]) < thr) kc.idx.push_back((long)i);
+  }
+}
+
 // nn.PReLU() with nOutputPlane=0 => ONE shared slope         (models.lua:61,66,71,386,...)
 template <class T>
 void prelu_fwd(size_t n, const T* x, T a, T* y) {
+  if (g_kink.mode) kink_on_forward(n, x);
 #pragma omp parallel for schedule(static)
   for (size_t i = 0; i < n; ++i) y[i] = x[i] > 0 ? x[i] : a * x[i];
 }
@@ -525,6 +573,27 @@ void prelu_bwd(size_t n, const T* x, T a, const T* dy, T* dx, T* da) {
     } else {
       dx[i] = a * dy[i];
       s += dy[i] * x[i];
+    }
+  }
+  if (g_kink.mode == 2) {  // forced branches of the ambiguous elements (see above)
+    int call = -1;
+    for (const auto& pc : g_kink.ptr_call)
+      if (pc.first == (const void*)x) call = pc.second;
+    if (call >= 0 && call < (int)g_kink.calls.size()) {
+      const KinkCall& kc = g_kink.calls[call];
+      for (size_t j = 0; j < kc.ov_idx.size(); ++j) {
+        const size_t i = (size_t)kc.ov_idx[j];
+        if (i >= n) continue;
+        const bool own = x[i] > 0, want = kc.ov_pos[j] != 0;
+        if (own == want) continue;
+        if (want) {  // take the x > 0 branch: undo the slope-gradient term, pass dy through
+          s -= dy[i] * x[i];
+          dx[i] = dy[i];
+        } else {
+          s += dy[i] * x[i];
+          dx[i] = a * dy[i];
+        }
+      }
     }
   }
   *da += s;
@@ -1076,6 +1145,34 @@ FG_S16_EXPORTS(f32, float)
 
 extern "C" {
 long fgo_G_param_count(int C) { return (long)GLayout(C).total; }
+// ---- PReLU kink bookkeeping for the parity tests (see KinkCtx) ----
+// mode 1 = record ambiguous elements (|x| < margin * max|x|) per prelu_fwd call, 2 = apply overrides, 0 = off.
+// Entering a mode restarts the call numbering; overrides survive until fgo_kink_clear().
+void fgo_kink_mode(int mode, double margin) {
+  g_kink.mode = mode;
+  g_kink.margin = margin;
+  g_kink.next_call = 0;
+  g_kink.ptr_call.clear();
+}
+void fgo_kink_clear() { g_kink = KinkCtx(); }
+int fgo_kink_num_calls() { return g_kink.next_call; }
+long fgo_kink_call_info(int call, long* n, double* maxabs) {
+  if (call < 0 || call >= (int)g_kink.calls.size()) return -1;
+  if (n) *n = (long)g_kink.calls[call].n;
+  if (maxabs) *maxabs = g_kink.calls[call].maxabs;
+  return (long)g_kink.calls[call].idx.size();
+}
+void fgo_kink_call_indices(int call, long* dst) {
+  if (call < 0 || call >= (int)g_kink.calls.size()) return;
+  std::copy(g_kink.calls[call].idx.begin(), g_kink.calls[call].idx.end(), dst);
+}
+void fgo_kink_set_override(int call, long count, const long* idx, const signed char* positive) {
+  if (call < 0) return;
+  if ((int)g_kink.calls.size() <= call) g_kink.calls.resize(call + 1);
+  g_kink.calls[call].ov_idx.assign(idx, idx + count);
+  g_kink.calls[call].ov_pos.assign(positive, positive + count);
+}
+
 long fgo_D_param_count(int C) { return (long)DLayout(C).total; }
 int fgo_mask_per_sample() { return kMaskPerSample; }
 // Route the fp32 port's GEMMs through an OpenBLAS shared object (path = e.g. scipy.libs/libscipy_openblas-*.so);

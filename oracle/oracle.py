@@ -337,3 +337,58 @@ def num_threads():
 
 def set_num_threads(n):
     lib().fgo_set_num_threads(int(n))
+
+
+# ---- PReLU kink bookkeeping (fg_oracle.cpp KinkCtx; used by the strict gradient-parity tests) -------------------
+class kink:
+    """with kink.record(margin): run the oracle -> kink.calls() lists, per prelu_fwd call (in call order), the
+    pre-activation elements with |x| < margin*max|x|.  kink.set_override(call, idx, positive) + with kink.override():
+    re-run -> prelu_bwd takes the given branch for those elements.  Call numbering restarts on every `with`."""
+
+    class _Mode:
+        def __init__(self, mode, margin):
+            self.mode, self.margin = mode, margin
+
+        def __enter__(self):
+            lib().fgo_kink_mode(self.mode, C.c_double(self.margin))
+            return self
+
+        def __exit__(self, *a):
+            lib().fgo_kink_mode(0, C.c_double(0.0))
+
+    @staticmethod
+    def record(margin):
+        lib().fgo_kink_clear()
+        return kink._Mode(1, margin)
+
+    @staticmethod
+    def override():
+        return kink._Mode(2, 0.0)
+
+    @staticmethod
+    def clear():
+        lib().fgo_kink_clear()
+
+    @staticmethod
+    def calls(ncalls):
+        """[(n, maxabs, idx int64 array)] for calls 0..ncalls-1 (read after the `with kink.record()` block)."""
+        L = lib()
+        L.fgo_kink_call_info.restype = C.c_long
+        out = []
+        for s in range(ncalls):
+            n, mx = C.c_long(0), C.c_double(0)
+            cnt = L.fgo_kink_call_info(s, C.byref(n), C.byref(mx))
+            assert cnt >= 0, "prelu_fwd call %d was not recorded" % s
+            idx = np.empty(cnt, np.int64)
+            if cnt:
+                L.fgo_kink_call_indices(s, idx.ctypes.data_as(C.c_void_p))
+            out.append((int(n.value), float(mx.value), idx))
+        return out
+
+    @staticmethod
+    def set_override(call, idx, positive):
+        idx = np.ascontiguousarray(idx, np.int64)
+        pos = np.ascontiguousarray(positive, np.int8)
+        assert idx.size == pos.size
+        lib().fgo_kink_set_override(int(call), C.c_long(idx.size), idx.ctypes.data_as(C.c_void_p),
+                                    pos.ctypes.data_as(C.c_void_p))

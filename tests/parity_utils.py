@@ -49,3 +49,89 @@ def oracle_iteration(case, B, C, hyper=None, state=None):
                                 case["masks_G"], st)
     res["state"] = st
     return res
+
+
+# ---- strict gradient parity across PReLU kinks (replaces seed-shopping) -------------------------------------------
+# PReLU's derivative jumps at 0.  Among ~1e6 pre-activations a handful lie within fp32 rounding noise of 0 and two
+# correct implementations may take different branches there; the batch-summed gradients then differ at 1e-3..1e-2.
+# Instead of retrying seeds, the oracle lists the AMBIGUOUS elements (|x| < margin*max|x| per layer, decided from
+# oracle data only), the test reads the branch the CUDA path took for exactly those elements, and the oracle's
+# backward is re-run with those branches forced (oracle.kink).  Every other element keeps the oracle's own branch,
+# so a wrong x<=0 branch, a wrong slope gradient or a wrong mask shows up at the strict 1e-4 bar.  The tests also
+# assert that the ambiguous set is tiny (<= KINK_MAX_FRAC of a layer) and that the CUDA pre-activations of those
+# elements are indeed ~0 (which also proves the NCHW->NHWC index mapping).
+KINK_MARGIN = 2e-5      # single-net passes: the tcgen05 path is within ~5e-6 of the oracle (normwise)
+KINK_MAX_FRAC = 2e-3
+
+
+def nchw_to_nhwc_index(idx, Cc, H, W):
+    idx = np.asarray(idx, np.int64)
+    b, r = np.divmod(idx, Cc * H * W)
+    ch, r = np.divmod(r, H * W)
+    y, x = np.divmod(r, W)
+    return ((b * H + y) * W + x) * Cc + ch
+
+
+def bn_preact_gpu(z_nhwc, mean, istd, gamma, beta):
+    """BN output exactly as bn_prelu_apply_kernel / the BN backward kernels compute its sign:
+    u = fma(gamma, fl32(fl32(z - mean) * istd), beta)  (k_elem.cu); evaluated for selected elements only."""
+    t = ((z_nhwc.astype(np.float32) - mean.astype(np.float32)).astype(np.float32) * istd.astype(np.float32)).astype(np.float32)
+    return gamma.astype(np.float64) * t.astype(np.float64) + beta.astype(np.float64)
+
+
+def kink_overrides(calls, first_call, gpu_preacts, shapes, margin=KINK_MARGIN, label=""):
+    """calls: oracle.kink.calls(); gpu_preacts[i]: callable(idx_nhwc) -> CUDA-path pre-activation values of layer i
+    (flat NHWC indexing); shapes[i] = (C, H, W) of that layer.  Registers the overrides and returns the number of
+    ambiguous elements."""
+    from oracle import oracle as O
+    total = 0
+    for i, (get, (Cc, H, W)) in enumerate(zip(gpu_preacts, shapes)):
+        n, mx, idx = calls[first_call + i]
+        assert idx.size <= max(8, KINK_MAX_FRAC * n), "%s layer %d: %d of %d pre-activations within %.0e of 0" % (
+            label, i, idx.size, n, margin)
+        if idx.size == 0:
+            O.kink.set_override(first_call + i, idx, np.zeros(0, np.int8))
+            continue
+        v = np.asarray(get(nchw_to_nhwc_index(idx, Cc, H, W)), np.float64)
+        # the CUDA path's values of these elements must be ~0 as well (forward parity + index mapping)
+        assert np.abs(v).max() <= 10 * margin * mx + 1e-30, "%s layer %d: CUDA pre-activation %.3e at an oracle zero" % (
+            label, i, np.abs(v).max())
+        O.kink.set_override(first_call + i, idx, (v > 0).astype(np.int8))
+        total += idx.size
+    return total
+
+
+def oracle_gstep(PG, PD, noise_G, masks_G, B, C, hyper=None, bn_state=None, forward_only=False):
+    """fevalG_on_D (adversarial.lua:187-231) composed from the fp64 oracle's nets: G fwd -> D fwd (train mode) ->
+    BCE vs targets=1 -> D bwd (gradInput only) -> G bwd -> penalty (the :223 quirk: L1 gradient term scaled by G_L2)
+    -> clamp.  Used with the CUDA path's own post-Adam D parameters, so that the G step is compared on identical
+    inputs (after one Adam step a parameter whose gradient is rounding noise may have moved by +lr or -lr: the D
+    parameters of two correct implementations differ by 2*lr in a few places)."""
+    hp = hyper or HYPER
+    g, d = O.f64.G(), O.f64.D()
+    fake = g.forward(PG, noise_G, C, True, bn_state)
+    out = d.forward(PD, fake, masks_G)
+    t = np.ones(B)
+    loss = O.f64.bce_fwd(out, t)
+    if forward_only:
+        return dict(lossG=loss, fake=fake, outD=out)
+    _, dimg = d.backward(O.f64.bce_bwd(out, t), want_dP=False)
+    gG = g.backward(dimg)
+    loss += O.f64.penalty_clamp(np.asarray(PG, np.float64), gG, hp["G_L1"], hp["G_L2"], hp["G_L2"], hp["G_clamp"])
+    return dict(lossG=loss, gradG=gG, fake=fake, outD=out)
+
+
+def oracle_dstep(PD, real, fake, masks_D, B, C, hyper=None):
+    """fevalD (adversarial.lua:83-179) + interruptableAdam at t=1 composed from the fp64 oracle's ops, given the
+    fake half of the batch: D fwd -> BCE (first B/2 targets 1) -> D bwd -> penalty -> clamp -> Adam."""
+    hp = hyper or HYPER
+    d = O.f64.D()
+    out = d.forward(PD, np.concatenate([real, fake]), masks_D)
+    t = np.concatenate([np.ones(B // 2), np.zeros(B // 2)])
+    loss = O.f64.bce_fwd(out, t)
+    gD, _ = d.backward(O.f64.bce_bwd(out, t), want_dimg=False)
+    P = np.array(PD, np.float64)
+    loss += O.f64.penalty_clamp(P, gD, hp["D_L1"], hp["D_L1"], hp["D_L2"], hp["D_clamp"])
+    m, v = np.zeros_like(P), np.zeros_like(P)
+    O.f64.adam(P, gD, m, v, 1, hp["lr_D"], hp["beta1"], hp["beta2"], hp["eps"])
+    return dict(lossD=loss, gradD=gD, mD=m, vD=v, PD=P, outD=out)

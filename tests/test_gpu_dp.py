@@ -166,3 +166,58 @@ def test_dp_c2f_two_gpus_average_gradients():
         assert PU.relerr(got[0][2][k], mean) < 2e-5
     conf = [a + b for a, b in zip(got[0][1][2]["conf"], got[1][1][2]["conf"])]
     assert got[0][2][2]["conf"] == conf == got[1][2][2]["conf"]  # confusion counts ride the all-reduce
+
+
+def _worker_resume(rank, world, port, q):
+    import torch.distributed as dist
+    import parity_utils as PU
+    import face_generator_b200 as fg
+    from face_generator_b200.lib import NET_D, NET_G
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, C = 8, 3
+    base = PU.make_case(B, C, seed=900)
+    ctx = fg.Context(rank, max_batch=B, channels=C)
+    if rank == 0:  # "load_flat_checkpoint on rank 0": parameters, moments AND step counters t_D = 7, t_G = 5
+        rng = np.random.default_rng(9)
+        ctx.set_params(NET_G, base["PG"])
+        ctx.set_params(NET_D, base["PD"])
+        ctx.set_adam_state(NET_D, rng.standard_normal(ctx.nD) * 1e-3, rng.random(ctx.nD) * 1e-5, 7)
+        ctx.set_adam_state(NET_G, rng.standard_normal(ctx.nG) * 1e-3, rng.random(ctx.nG) * 1e-5, 5)
+    ids = [ctx.dp_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.dp_init(ids[0], world, rank)
+    ctx.dp_broadcast_params()
+    t0 = (ctx.get_adam_state(NET_D)[2], ctx.get_adam_state(NET_G)[2])
+    for it in range(3):
+        case = PU.make_case(B, C, seed=910 + 10 * it + rank)
+        st = ctx.train_step(fg.hyper_default(), B, case["real"], case["noise_D"], case["noise_G"], case["masks_D"], case["masks_G"])
+    q.put((rank, t0, (st["t_D"], st["t_G"]), ctx.get_params(NET_D), ctx.get_params(NET_G), ctx.get_adam_state(NET_D)[0]))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_dp_resume_broadcasts_step_counters():
+    """fg_dp_broadcast_params carries t_D / t_G (Adam's bias correction depends on them): after a resume on rank 0
+    only, replicas must stay bit-identical over the following steps."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, port = 2, 29781
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_worker_resume, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r = q.get(timeout=600)
+        got[r[0]] = r
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1] == (7, 5)
+    assert got[0][2] == got[1][2] == (10, 8)
+    for k in (3, 4, 5):
+        np.testing.assert_array_equal(got[0][k], got[1][k])

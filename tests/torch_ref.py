@@ -15,28 +15,31 @@ def _split(P, layout):
     return {k: P[o:o + int(np.prod(s))].reshape(s) for k, (o, s) in layout.items()}
 
 
-def prelu(x, a):
-    return torch.where(x > 0, x, a * x)
+def prelu(x, a, branch=None, name=None):
+    """branch (tests at the headline batch size): callable(name, x) -> bool tensor "take the x > 0 branch" (lets a
+    test force the branch of pre-activations that lie within rounding noise of 0, see parity_utils)."""
+    pos = (x > 0) if branch is None else branch(name, x.detach())
+    return torch.where(pos, x, a * x)
 
 
-def G_forward(P, noise, C=3):
+def G_forward(P, noise, C=3, branch=None):
     p = _split(P, O.G_layout(C))
     B = noise.shape[0]
     z0 = F.linear(noise, p["L1W"], p["L1b"]).view(B, 128, 8, 8)
-    h0 = prelu(z0, p["a1"])
+    h0 = prelu(z0, p["a1"], branch, "z0")
     u0 = F.interpolate(h0, scale_factor=2, mode="nearest")
     z1 = F.conv2d(u0, p["C1W"], p["C1b"], padding=2)
     y1 = F.batch_norm(z1, None, None, p["g1"], p["be1"], training=True, momentum=0.1, eps=1e-5)
-    h1 = prelu(y1, p["a2"])
+    h1 = prelu(y1, p["a2"], branch, "y1")
     u1 = F.interpolate(h1, scale_factor=2, mode="nearest")
     z2 = F.conv2d(u1, p["C2W"], p["C2b"], padding=2)
     y2 = F.batch_norm(z2, None, None, p["g2"], p["be2"], training=True, momentum=0.1, eps=1e-5)
-    h2 = prelu(y2, p["a3"])
+    h2 = prelu(y2, p["a3"], branch, "y2")
     z3 = F.conv2d(h2, p["C3W"], p["C3b"], padding=1)
-    return torch.sigmoid(z3), dict(z0=z0, h0=h0, z1=z1, h1=h1, z2=z2, h2=h2, z3=z3)
+    return torch.sigmoid(z3), dict(z0=z0, h0=h0, z1=z1, y1=y1, h1=h1, z2=z2, y2=y2, h2=h2, z3=z3)
 
 
-def D_forward(P, img, masks, C=3):
+def D_forward(P, img, masks, C=3, branch=None):
     p = _split(P, O.D_layout(C))
     B = img.shape[0]
     moff = [0, 64, 192, 448]
@@ -44,12 +47,12 @@ def D_forward(P, img, masks, C=3):
     x = img
     for i in range(4):
         z = F.conv2d(x, p["c%dW" % (i + 1)], p["c%db" % (i + 1)], padding=1)
-        a = prelu(z, p["a%d" % (i + 1)])
+        a = prelu(z, p["a%d" % (i + 1)], branch, "z%d" % (i + 1))
         m = masks[:, moff[i]:moff[i] + cout[i]].reshape(B, cout[i], 1, 1)
         x = F.avg_pool2d(a * m, 2, 2)  # SpatialDropout: no 1/(1-p) rescale in training
     x = x.reshape(B, 2048)
-    h = prelu(F.linear(x, p["L1W"], p["L1b"]), p["a5"]) * masks[:, 960:1472] * 2.0
-    h = prelu(F.linear(h, p["L2W"], p["L2b"]), p["a6"]) * masks[:, 1472:1984] * 2.0
+    h = prelu(F.linear(x, p["L1W"], p["L1b"]), p["a5"], branch, "zl1") * masks[:, 960:1472] * 2.0
+    h = prelu(F.linear(h, p["L2W"], p["L2b"]), p["a6"], branch, "zl2") * masks[:, 1472:1984] * 2.0
     return torch.sigmoid(F.linear(h, p["L3W"], p["L3b"])).reshape(B)
 
 
