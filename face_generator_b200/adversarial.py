@@ -82,16 +82,31 @@ def epoch_batches(n_epoch, batch_size):
     return out
 
 
-def train(ctx: Context, dataset, hyper, batch_size, n_epoch=-1, rng=None, seed0=0, confusion=None, progress=None):
+SEED_EPOCH_STRIDE = 1000000   # the Lua shim's offset: seeds of epoch e start at (e-1)*1e6 (adversarial_b200.lua)
+SEED_RANK_STRIDE = 1 << 40    # data parallel: every rank draws its own indices / noise / dropout masks
+
+
+def epoch_seed0(epoch, rank=0):
+    """first step seed of `epoch` (1-based, = the global EPOCH of train.lua:198-208) on `rank`"""
+    assert epoch >= 1 and rank >= 0
+    return (epoch - 1) * SEED_EPOCH_STRIDE + rank * SEED_RANK_STRIDE
+
+
+def train(ctx: Context, dataset, hyper, batch_size, n_epoch=-1, rng=None, epoch=1, rank=0, confusion=None, progress=None):
     """One epoch of adversarial.train(dataset, maxAccuracyD, accsInterval) (adversarial.lua:29-334) with the
     defaults D_iterations = G_iterations = 1 (train.lua:33-34), i.e. one fused fg_train_step per batch.
 
     dataset: array-like [N][C][32][32] float32 in [0,1] (what DATASET.loadImages returns, dataset.lua:43-75) or a
     face_generator_b200.dataset.DeviceDataset (then batch assembly and noise happen on the device).
     hyper.D_maxAcc / hyper.accs_interval are the maxAccuracyD / accsInterval arguments.
+    epoch / rank: the reference draws fresh math.random indices and uniform noise on every call
+    (adversarial.lua:245, :276), so successive epochs must not replay the same draws: the step seeds (device-side
+    indices, noise and dropout masks derive from them) are epoch_seed0(epoch, rank) + i, and the host generator used
+    for host-resident datasets is derived from (epoch, rank) unless the caller passes (and keeps) its own `rng`.
     Returns (accuracy of D over the epoch = CONFUSION.totalValid (:316), confusion counts [4], batches that trained D)."""
     from .dataset import DeviceDataset
-    rng = rng or np.random.default_rng(0)
+    seed0 = epoch_seed0(epoch, rank)
+    rng = rng if rng is not None else np.random.default_rng([int(epoch), int(rank), 0x6661636573])
     on_device = isinstance(dataset, DeviceDataset)
     N = dataset.size() if on_device else len(dataset)
     n_epoch = N if n_epoch <= 0 else n_epoch                                   # :31-34

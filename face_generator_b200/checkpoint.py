@@ -133,6 +133,15 @@ def load_reference_checkpoint(ctx, path, want_D=True):
         bn = f.net_bn_state("G")
         if bn.size == 768:
             ctx.set_bn_state(bn)
+        elif bn.size:
+            raise FGError("checkpoint G carries %d BatchNorm running statistics, expected 768 (2 layers: 256 + 128 channels)"
+                          % bn.size)
+        else:
+            # prepareNetworkForSave never strips running_mean / running_var (utils/nn_utils.lua:259-279), so a stock
+            # checkpoint always has them; without them evaluate()-mode G would silently use stale statistics
+            import warnings
+            warnings.warn("checkpoint G holds no BatchNorm running statistics: evaluate()-mode forwards will use the "
+                          "context's current ones (training-mode forwards, incl. sample.lua's, are unaffected)")
         if want_D and f.kind("D") is not None:
             pd = f.net_params("D")
             if pd.size != ctx.count(NET_D):

@@ -266,6 +266,9 @@ bool flatten(const Obj* t, std::vector<float>* out) {
   const Obj* st = t->payload.get();
   if (!st || st->kind != K_STORAGE) return false;
   const int64_t cap = (int64_t)(st->data.size() / st->elem);
+  // a tensor of a checkpoint never has more logical elements than its storage holds; an "expanded" (stride-0) view
+  // over a tiny storage would otherwise turn a 200-byte file into a multi-GiB allocation
+  if (n > cap) return false;
   const int nd = (int)t->size.size();
   std::vector<int64_t> idx(nd, 0);
   for (int64_t i = 0; i < n; ++i) {
@@ -281,16 +284,38 @@ bool flatten(const Obj* t, std::vector<float>* out) {
   return true;
 }
 // nn.Module:parameters() order: containers recurse over self.modules[1..n]; a leaf contributes weight then bias
-void walk_modules(const Obj* m, std::vector<const Obj*>* leaves, int depth = 0) {
-  if (!m || depth > 64) return;
+// The object memo lets a hostile file make a `modules` table contain its own parent (a cycle) or the same subtree
+// many times (exponential fan-out): the walk refuses cycles and stops after kMaxModules visits.
+constexpr int kMaxModules = 1 << 16;
+struct Walk {
+  std::vector<const Obj*> path;  // containers on the current recursion path
+  int visited = 0;
+  bool ok = true;
+  bool enter(const Obj* m) {
+    if (++visited > kMaxModules || path.size() > 64) return ok = false;
+    for (const Obj* p : path)
+      if (p == m) return ok = false;
+    path.push_back(m);
+    return true;
+  }
+  void leave() { path.pop_back(); }
+};
+void walk_modules(const Obj* m, std::vector<const Obj*>* leaves, Walk* w) {
+  if (!m || !w->ok) return;
   const Obj* mods = field(m, "modules");
   const Obj* mt = table_of(mods);
   if (mt) {
-    for (int i = 1;; ++i) {
+    if (!w->enter(m)) return;
+    for (int i = 1; w->ok; ++i) {
       const Obj* child = field(mods, std::to_string(i));
       if (!child) break;
-      walk_modules(child, leaves, depth + 1);
+      walk_modules(child, leaves, w);
     }
+    w->leave();
+    return;
+  }
+  if (++w->visited > kMaxModules) {
+    w->ok = false;
     return;
   }
   leaves->push_back(m);
@@ -413,7 +438,12 @@ int64_t fg_t7_net_params(fg_t7* f, const char* path, float* dst, int64_t cap) tr
     return -1;
   }
   std::vector<const Obj*> leaves;
-  walk_modules(o, &leaves);
+  Walk w;
+  walk_modules(o, &leaves, &w);
+  if (!w.ok) {
+    fg_set_error("fg_t7_net_params: %s is not a module tree (cyclic or implausibly large `modules` tables)", path);
+    return -1;
+  }
   std::vector<float> flat;
   for (const Obj* m : leaves)
     for (const char* name : {"weight", "bias"}) {
@@ -444,7 +474,12 @@ int64_t fg_t7_net_bn_state(fg_t7* f, const char* path, float* dst, int64_t cap) 
     return -1;
   }
   std::vector<const Obj*> leaves;
-  walk_modules(o, &leaves);
+  Walk w;
+  walk_modules(o, &leaves, &w);
+  if (!w.ok) {
+    fg_set_error("fg_t7_net_bn_state: %s is not a module tree (cyclic or implausibly large `modules` tables)", path);
+    return -1;
+  }
   std::vector<float> flat;
   for (const Obj* m : leaves) {
     const Obj* rm = field(m, "running_mean");
@@ -484,23 +519,32 @@ int64_t fg_t7_net_describe(fg_t7* f, const char* path, char* dst, int64_t cap) t
   if (!o) return -1;
   std::string s;
   struct Rec {
-    static void go(const Obj* m, std::string* s, int depth) {
-      if (!m || depth > 64) return;
+    static void go(const Obj* m, std::string* s, Walk* w) {
+      if (!m || !w->ok) return;
       *s += m->kind == K_OBJECT ? m->str : "?";
       const Obj* mods = field(m, "modules");
       if (table_of(mods)) {
+        if (!w->enter(m)) return;
         *s += "{";
-        for (int i = 1;; ++i) {
+        for (int i = 1; w->ok; ++i) {
           const Obj* ch = field(mods, std::to_string(i));
           if (!ch) break;
           if (i > 1) *s += ",";
-          go(ch, s, depth + 1);
+          go(ch, s, w);
         }
         *s += "}";
+        w->leave();
+      } else if (++w->visited > kMaxModules) {
+        w->ok = false;
       }
     }
   };
-  Rec::go(o, &s, 0);
+  Walk w;
+  Rec::go(o, &s, &w);
+  if (!w.ok) {
+    fg_set_error("fg_t7_net_describe: %s is not a module tree (cyclic or implausibly large `modules` tables)", path);
+    return -1;
+  }
   if (dst && cap > 0) {
     const size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
     memcpy(dst, s.data(), n);

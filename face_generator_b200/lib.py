@@ -241,9 +241,17 @@ class Context:
     def count(self, net):
         return self.nD if net == NET_D else self.nG
 
+    def _sized(self, what, a, n):
+        """the C ABI copies exactly n floats from the pointer it is given: a shorter buffer (a checkpoint written by a
+        1- vs 3-channel build, a truncated or hostile file) would be read out of bounds, so sizes are checked here
+        with a real error (asserts vanish under python -O)"""
+        a = f32(a)
+        if a.size != n:
+            raise FGError("%s: expected %d floats, got %d" % (what, n, a.size))
+        return a
+
     def set_params(self, net, p):
-        p = f32(p)
-        assert p.size == self.count(net)
+        p = self._sized("set_params", p, self.count(net))
         _check(self.lib.fg_set_params(self.h, net, _ptr(p)), "fg_set_params")
 
     def get_params(self, net):
@@ -260,7 +268,9 @@ class Context:
         _check(self.lib.fg_zero_grads(self.h, net), "fg_zero_grads")
 
     def set_adam_state(self, net, m, v, t):
-        _check(self.lib.fg_set_adam_state(self.h, net, _ptr(f32(m)), _ptr(f32(v)), int(t)), "fg_set_adam_state")
+        m = None if m is None else self._sized("set_adam_state m", m, self.count(net))
+        v = None if v is None else self._sized("set_adam_state v", v, self.count(net))
+        _check(self.lib.fg_set_adam_state(self.h, net, _ptr(m), _ptr(v), int(t)), "fg_set_adam_state")
 
     def get_adam_state(self, net):
         m, v, t = np.empty(self.count(net), np.float32), np.empty(self.count(net), np.float32), C.c_int(0)
@@ -268,7 +278,7 @@ class Context:
         return m, v, t.value
 
     def set_bn_state(self, s):
-        _check(self.lib.fg_set_bn_state(self.h, _ptr(f32(s))), "fg_set_bn_state")
+        _check(self.lib.fg_set_bn_state(self.h, _ptr(self._sized("set_bn_state", s, 768))), "fg_set_bn_state")
 
     def get_bn_state(self):
         out = np.empty(768, np.float32)
@@ -533,9 +543,14 @@ class C2f:
     def count(self, net):
         return self.nD if net == NET_D else self.nG
 
+    def _sized(self, what, a, n):
+        a = f32(a)
+        if a.size != n:
+            raise FGError("%s: expected %d floats, got %d" % (what, n, a.size))
+        return a
+
     def set_params(self, net, p):
-        p = f32(p)
-        assert p.size == self.count(net)
+        p = self._sized("c2f set_params", p, self.count(net))
         _check(self.lib.fg_c2f_set_params(self.h, net, _ptr(p)), "fg_c2f_set_params")
 
     def get_params(self, net):
@@ -552,7 +567,9 @@ class C2f:
         _check(self.lib.fg_c2f_zero_grads(self.h, net), "fg_c2f_zero_grads")
 
     def set_adam_state(self, net, m, v, t):
-        _check(self.lib.fg_c2f_set_adam_state(self.h, net, _ptr(f32(m)), _ptr(f32(v)), int(t)), "fg_c2f_set_adam_state")
+        m = None if m is None else self._sized("c2f set_adam_state m", m, self.count(net))
+        v = None if v is None else self._sized("c2f set_adam_state v", v, self.count(net))
+        _check(self.lib.fg_c2f_set_adam_state(self.h, net, _ptr(m), _ptr(v), int(t)), "fg_c2f_set_adam_state")
 
     def get_adam_state(self, net):
         m, v, t = np.empty(self.count(net), np.float32), np.empty(self.count(net), np.float32), C.c_int(0)

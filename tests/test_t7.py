@@ -263,6 +263,42 @@ def test_bad_files_fail_loudly(tmp_path):
     with T7File(tmp_path / "oob.t7") as f:
         with pytest.raises(FGError):
             f.tensor("bad")
+    # an "expanded" (stride-0) weight of 2^31 logical elements over a 1-element storage: a ~300-byte file must not
+    # turn into a multi-GiB flatten, neither through the tensor nor through the net accessors (count-only calls too)
+    w = W()
+    big = Tensor(fstore(np.zeros(1)), [1 << 16, 1 << 15], stride=[0, 0])
+    w.obj({"t": big, "G": seq(Obj("nn.Linear", {"weight": big, "bias": big, "running_mean": big, "running_var": big}))})
+    (tmp_path / "expanded.t7").write_bytes(bytes(w.buf))
+    assert len(w.buf) < 1000
+    with T7File(tmp_path / "expanded.t7") as f:
+        for call in (lambda: f.tensor("t"), lambda: f.net_params("G"), lambda: f.net_bn_state("G")):
+            with pytest.raises(FGError):
+                call()
+    # the object memo allows a `modules` table to contain its own parent: the walkers must refuse the cycle ...
+    w = W()
+    inner = seq(Obj("nn.Linear", {"weight": Tensor(fstore(np.ones(2)), [2])}))
+    inner.fields["modules"][2] = inner
+    w.obj({"G": inner})
+    (tmp_path / "cycle.t7").write_bytes(bytes(w.buf))
+    with T7File(tmp_path / "cycle.t7") as f:
+        for call in (lambda: f.net_params("G"), lambda: f.net_bn_state("G"), lambda: f.net_describe("G")):
+            with pytest.raises(FGError):
+                call()
+    # ... and a DAG that repeats one subtree 4^20 times (tiny file, exponential walk) must stop at the visit budget
+    w = W()
+    node = seq(Obj("nn.Linear", {"weight": Tensor(fstore(np.ones(2)), [2])}))
+    for _ in range(20):
+        node = seq(node, node, node, node)
+    w.obj({"G": node})
+    (tmp_path / "fanout.t7").write_bytes(bytes(w.buf))
+    assert len(w.buf) < 20000
+    import time
+    with T7File(tmp_path / "fanout.t7") as f:
+        t0 = time.time()
+        for call in (lambda: f.net_params("G"), lambda: f.net_describe("G")):
+            with pytest.raises(FGError):
+                call()
+        assert time.time() - t0 < 20
 
 
 # ------------------------------------------------------------------ independent reader for the writer test
