@@ -342,10 +342,13 @@ def main():
         if n:
             hbm[name] = (nbytes, t / nprof)
     ctx.timing_enable(False)
-    tf32_peak = None
+    tf32_peak = tf32_peak_n128 = None
     if rank == 0:
         try:
             tf32_peak = ctx.tf32_peak(20000)
+            os.environ["FG_TF32_PROBE_N"] = "128"  # the instruction shape the convolution kernels issue
+            tf32_peak_n128 = ctx.tf32_peak(40000)
+            os.environ.pop("FG_TF32_PROBE_N")
         except Exception as e:  # the probe must never cost the headline
             sys.stderr.write("tf32 peak probe failed: %s\n" % e)
     if rank != 0:
@@ -385,6 +388,7 @@ def main():
                      "executed_note": "kind::tf32 MMAs actually issued: 3 per logical MMA (hi*hi + hi*lo + lo*hi)%s" % (
                          " x 9/25 taps (upsample folded into four 3x3 phase convolutions)" if collapsed else ""),
                      "measured_tf32_peak": tf32_peak,
+                     "measured_tf32_peak_n128": tf32_peak_n128,
                      "measured_tf32_peak_note": "fg_bench_tf32_peak: back-to-back tcgen05.mma.kind::tf32 128x256x8, cta_group::1, "
                                                 "smem-resident operands, all SMs, run at bench clocks right after the timed region",
                      "frac_executed_vs_measured_tf32": (tf_fwd * exec_ratio / tf32_peak) if tf32_peak else None,

@@ -232,9 +232,29 @@ int fg_get_grads(fg_ctx* c, int net, float* dst) {
 }
 int fg_zero_grads(fg_ctx* c, int net) {
   ENTER(c);
-  float* g; int64_t n;
-  FG_TRY(net_bufs(c, net, nullptr, &g, nullptr, nullptr, &n));
-  FG_CUDA(cudaMemsetAsync(g, 0, (n + kGradTail) * sizeof(float), c->stream));
+  FG_REQUIRE(net == FG_NET_G || net == FG_NET_D, "net must be FG_NET_G or FG_NET_D");
+  return net_zero_grads(c, net);
+}
+// Borrow caller-owned DEVICE buffers as the flat parameter / gradient vectors of `net` (see include/fg_b200.h).
+int fg_bind_params(fg_ctx* c, int net, float* params_dev, float* grads_dev) {
+  ENTER(c);
+  FG_REQUIRE(net == FG_NET_G || net == FG_NET_D, "net must be FG_NET_G or FG_NET_D");
+  for (const float* p : {params_dev, grads_dev}) {
+    if (!p) continue;
+    cudaPointerAttributes a;
+    const bool dev = cudaPointerGetAttributes(&a, p) == cudaSuccess && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged);
+    if (!dev) cudaGetLastError();
+    FG_REQUIRE(dev, "fg_bind_params: buffers must be DEVICE memory (CudaTensor:data())");
+    FG_REQUIRE(reinterpret_cast<uintptr_t>(p) % 16 == 0, "fg_bind_params: buffers must be 16-byte aligned");
+  }
+  FG_CUDA(cudaStreamSynchronize(c->stream));
+  const bool d = net == FG_NET_D;
+  (d ? c->PD : c->PG) = params_dev ? params_dev : (d ? c->ownPD : c->ownPG);
+  float* own_g = d ? c->ownGD : c->ownGG;
+  const int64_t n = d ? c->dl.total : c->gl.total;
+  (d ? c->gD : c->gG) = grads_dev ? grads_dev : own_g;
+  (d ? c->tailD : c->tailG) = grads_dev ? c->tail_sep + (d ? kGradTail : 0) : own_g + n;
+  c->G_packed = c->D_packed = false;
   return FG_OK;
 }
 float* fg_params_ptr(fg_ctx* c, int net) { return !c ? nullptr : net == FG_NET_D ? c->PD : net == FG_NET_G ? c->PG : nullptr; }
@@ -361,7 +381,7 @@ int fg_optim_step(fg_ctx* c, int net, const fg_hyper* h, float grad_scale) {
   // no accuracy information at this level: force the gate open by clearing the history influence
   fg_hyper hh = *h;
   hh.D_maxAcc = 2.0f;
-  float* g = net == FG_NET_D ? c->gD + c->dl.total : c->gG + c->gl.total;
+  float* g = net == FG_NET_D ? c->tailD : c->tailG;
   FG_TRY(k_gate_and_prep(c, net, &hh, g, 1, 1.0f));
   return net_optim(c, net, h, grad_scale, false);
 }

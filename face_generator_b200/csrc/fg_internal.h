@@ -94,6 +94,10 @@ struct fg_ctx {
   std::vector<void*> allocs;  // every cudaMalloc of net_alloc(), released by net_free()
   // flat buffers (owned)
   float *PG = nullptr, *PD = nullptr, *gG = nullptr, *gD = nullptr;
+  // the library's own allocations (PG.. point here unless fg_bind_params borrowed caller-owned buffers) and the 8
+  // DP-reduced scalars behind each gradient: contiguous with the own gradient buffer, separate for a bound one
+  float *ownPG = nullptr, *ownPD = nullptr, *ownGG = nullptr, *ownGD = nullptr;
+  float *tailG = nullptr, *tailD = nullptr, *tail_sep = nullptr;
   float *mG = nullptr, *vG = nullptr, *mD = nullptr, *vD = nullptr;
   float* bnG = nullptr;  // [768] running stats
   DeviceStats* dstats = nullptr;
@@ -275,5 +279,7 @@ int net_optim(fg_ctx* c, int net, const fg_hyper* h, float grad_scale, bool gate
 int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real_nchw_dev, const float* noiseD_dev,
                    const float* noiseG_dev, const float* masksD_dev, const float* masksG_dev, uint64_t seed);
 int net_allreduce(fg_ctx* c, float* buf, int64_t n);
+int net_zero_grads(fg_ctx* c, int net);
+int net_allreduce_grads(fg_ctx* c, int net);  // flat gradient + its 8 tail scalars (one call when contiguous)
 int net_broadcast(fg_ctx* c, void* buf, size_t bytes);  // rank 0 -> all (dp.cu)
 int net_group(bool start);                                // ncclGroupStart / ncclGroupEnd

@@ -418,6 +418,7 @@ inline bool mixed_ok(const fg_ctx* c, const float* a, const float* b) {
 // resident in shared memory -- no TMA, no epilogue.  bench.py runs it at bench clocks; the number is the measured
 // TF32 peak the 3xTF32 convolutions are normalised by (MEASURED_PEAKS.json only holds a bf16 figure).
 // ------------------------------------------------------------------------------------------------
+template <int N, int NACC>
 __global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -436,11 +437,11 @@ __global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) {
-    constexpr uint32_t kIdesc = make_idesc(128, 256, 0, 0);
+    constexpr uint32_t kIdesc = make_idesc(128, N, 0, 0);
     const uint32_t sa = smem_u32(smem);
     const uint64_t a = make_desc(sa, 16, 1024), b = make_desc(sa + kA, 16, 1024);
     for (int i = 0; i < iters; ++i) {
-      const uint32_t acc = tmem_base + (uint32_t)(i & 1) * 256;  // two independent accumulators
+      const uint32_t acc = tmem_base + (uint32_t)(i % NACC) * N;  // NACC independent accumulators
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_tf32(acc, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), kIdesc, 1);
     }
@@ -454,17 +455,22 @@ __global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
 
 }  // namespace
 
-// -> TFLOP/s of kind::tf32 MMAs (2*M*N*K per instruction) over all SMs, best of `reps` event-timed launches
+// -> TFLOP/s of kind::tf32 MMAs (2*M*N*K per instruction) over all SMs, best of `reps` event-timed launches.
+// FG_TF32_PROBE_N=128 probes the N=128 instruction shape the convolution kernels issue (operand reads from shared
+// memory: 8 KB per 64-cycle MMA = the full 128 B/clk of one SM; N=256: 12 KB per 128 cycles)
 int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops) {
   constexpr int kSmem = 128 * 128 + 256 * 128 + 64 + 1024;
-  FG_CUDA(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  const char* env = getenv("FG_TF32_PROBE_N");
+  const int N = env && atoi(env) == 128 ? 128 : 256;
+  auto kern = N == 128 ? tf32_peak_kernel<128, 4> : tf32_peak_kernel<256, 2>;
+  FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   cudaEvent_t e0, e1;
   FG_CUDA(cudaEventCreate(&e0));
   FG_CUDA(cudaEventCreate(&e1));
   float best = 1e30f;
   for (int r = 0; r < reps + 1; ++r) {  // first launch = warm-up
     FG_CUDA(cudaEventRecord(e0, c->stream));
-    tf32_peak_kernel<<<c->sm_count, 128, kSmem, c->stream>>>(iters);
+    kern<<<c->sm_count, 128, kSmem, c->stream>>>(iters);
     LAUNCH_CHECK(c);
     FG_CUDA(cudaEventRecord(e1, c->stream));
     FG_CUDA(cudaEventSynchronize(e1));
@@ -474,7 +480,7 @@ int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops) {
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  const double flops = (double)c->sm_count * iters * 4.0 * 2.0 * 128 * 256 * 8;
+  const double flops = (double)c->sm_count * iters * 4.0 * 2.0 * 128 * N * 8;
   *tflops = flops / (best * 1e-3) / 1e12;
   return FG_OK;
 }

@@ -73,6 +73,9 @@ int net_alloc(fg_ctx* c) {
   FG_TRY(dalloc(c, &c->PD, nD));
   FG_TRY(dalloc(c, &c->gG, nG + kGradTail));
   FG_TRY(dalloc(c, &c->gD, nD + kGradTail));
+  c->ownPG = c->PG; c->ownPD = c->PD; c->ownGG = c->gG; c->ownGD = c->gD;
+  c->tailG = c->gG + nG; c->tailD = c->gD + nD;
+  FG_TRY(dalloc(c, &c->tail_sep, 2 * kGradTail));
   FG_TRY(dalloc(c, &c->mG, nG));
   FG_TRY(dalloc(c, &c->vG, nG));
   FG_TRY(dalloc(c, &c->mD, nD));
@@ -583,6 +586,30 @@ int net_optim(fg_ctx* c, int net, const fg_hyper* h, float grad_scale, bool gate
   return FG_OK;
 }
 
+// GRAD_PARAMETERS_x:zero() incl. the DP tail scalars
+int net_zero_grads(fg_ctx* c, int net) {
+  const bool d = net == FG_NET_D;
+  float *g = d ? c->gD : c->gG, *tail = d ? c->tailD : c->tailG;
+  const int64_t n = d ? c->dl.total : c->gl.total;
+  if (tail == g + n) {
+    FG_CUDA(cudaMemsetAsync(g, 0, sizeof(float) * (n + kGradTail), c->stream));
+  } else {  // caller-owned gradient buffer (fg_bind_params): the tail lives in the library
+    FG_CUDA(cudaMemsetAsync(g, 0, sizeof(float) * n, c->stream));
+    FG_CUDA(cudaMemsetAsync(tail, 0, sizeof(float) * kGradTail, c->stream));
+  }
+  return FG_OK;
+}
+int net_allreduce_grads(fg_ctx* c, int net) {
+  const bool d = net == FG_NET_D;
+  float *g = d ? c->gD : c->gG, *tail = d ? c->tailD : c->tailG;
+  const int64_t n = d ? c->dl.total : c->gl.total;
+  if (tail == g + n) return net_allreduce(c, g, n + kGradTail);
+  FG_TRY(net_group(true));
+  FG_TRY(net_allreduce(c, g, n));
+  FG_TRY(net_allreduce(c, tail, kGradTail));
+  return net_group(false);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // one iteration of the adversarial.lua loop body (D_iterations = G_iterations = 1)
 // ---------------------------------------------------------------------------------------------------
@@ -601,7 +628,7 @@ int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const
                             c->stream));
   else
     FG_TRY(k_masks_generate(c, c->D_masks, B, seed * 2 + 1, h->p_spatial, h->p_drop));
-  FG_CUDA(cudaMemsetAsync(c->gD, 0, sizeof(float) * (c->dl.total + kGradTail), c->stream));
+  FG_TRY(net_zero_grads(c, FG_NET_D));
   FG_TRY(net_D_forward(c, c->D_x, B, true, h));
   if (c->debug_keep) {  // tests: the G step's D forward overwrites these
     const float* src[6] = {c->D_z[0], c->D_z[1], c->D_z[2], c->D_z[3], c->D_zl1, c->D_zl2};
@@ -612,13 +639,13 @@ int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const
     }
     c->keep_B = B;
   }
-  FG_TRY(k_sigmoid_bce(c, c->D_logit, c->D_out, c->D_dlogit, &c->dstats->loss_D, c->gD + c->dl.total, B, Bh));
+  FG_TRY(k_sigmoid_bce(c, c->D_logit, c->D_out, c->D_dlogit, &c->dstats->loss_D, c->tailD, B, Bh));
   FG_TRY(net_D_backward(c, c->D_dlogit, true, false));
-  if (c->world > 1) FG_TRY(net_allreduce(c, c->gD, c->dl.total + kGradTail));
-  FG_TRY(k_gate_and_prep(c, FG_NET_D, h, c->gD + c->dl.total, B, world));
+  if (c->world > 1) FG_TRY(net_allreduce_grads(c, FG_NET_D));
+  FG_TRY(k_gate_and_prep(c, FG_NET_D, h, c->tailD, B, world));
   FG_TRY(net_optim(c, FG_NET_D, h, 1.0f / world, true));
   // ---- G step (adversarial.lua:275-288) ----
-  FG_CUDA(cudaMemsetAsync(c->gG, 0, sizeof(float) * (c->gl.total + kGradTail), c->stream));
+  FG_TRY(net_zero_grads(c, FG_NET_G));
   FG_TRY(net_G_forward(c, noiseG, B, true));
   if (masksG)
     FG_CUDA(cudaMemcpyAsync(c->D_masks, masksG, sizeof(float) * (size_t)B * kMaskPerSample, cudaMemcpyDeviceToDevice,
@@ -626,11 +653,11 @@ int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const
   else
     FG_TRY(k_masks_generate(c, c->D_masks, B, seed * 2 + 2, h->p_spatial, h->p_drop));
   FG_TRY(net_D_forward(c, c->G_y, B, true, h));
-  FG_TRY(k_sigmoid_bce(c, c->D_logit, c->D_out, c->D_dlogit, &c->dstats->loss_G, c->gG + c->gl.total, B, B));
+  FG_TRY(k_sigmoid_bce(c, c->D_logit, c->D_out, c->D_dlogit, &c->dstats->loss_G, c->tailG, B, B));
   FG_TRY(net_D_backward(c, c->D_dlogit, false, true));  // D's weight grads are discarded by the reference (:209 vs :92)
   FG_TRY(net_G_backward(c, c->D_dx, nullptr));
-  if (c->world > 1) FG_TRY(net_allreduce(c, c->gG, c->gl.total + kGradTail));
-  FG_TRY(k_gate_and_prep(c, FG_NET_G, h, c->gG + c->gl.total, B, world));
+  if (c->world > 1) FG_TRY(net_allreduce_grads(c, FG_NET_G));
+  FG_TRY(k_gate_and_prep(c, FG_NET_G, h, c->tailG, B, world));
   FG_TRY(net_optim(c, FG_NET_G, h, 1.0f / world, false));
   FG_CUDA(cudaMemcpyAsync(c->hstats, c->dstats, sizeof(DeviceStats), cudaMemcpyDeviceToHost, c->stream));
   return FG_OK;

@@ -49,6 +49,7 @@ SYMBOLS = {
     "fg_set_params": (_I, [_P, _I, _P]),
     "fg_get_params": (_I, [_P, _I, _P]),
     "fg_get_grads": (_I, [_P, _I, _P]),
+    "fg_bind_params": (_I, [_P, _I, _P, _P]),
     "fg_zero_grads": (_I, [_P, _I]),
     "fg_params_ptr": (_P, [_P, _I]),
     "fg_grads_ptr": (_P, [_P, _I]),

@@ -22,75 +22,170 @@ function b200.context(device, maxBatch, channels)
   return b200._ctx
 end
 
--- hyper-parameters from the reference's OPT / OPTSTATE tables
+-- hyper-parameters from the reference's OPT / OPTSTATE tables; also selects the optimizer the fused step runs
+-- (OPT.D_optmethod / OPT.G_optmethod, train.lua:38-39; adversarial.lua:259-266, :279-286)
+local OPTMETHOD = {adam = 0, adagrad = 1, sgd = 2}
 function b200.hyperFromOPT(OPT, OPTSTATE)
   local h = b200._hyper[0]
   h.D_L1, h.D_L2, h.G_L1, h.G_L2 = OPT.D_L1, OPT.D_L2, OPT.G_L1, OPT.G_L2
   h.D_clamp, h.G_clamp, h.D_maxAcc = OPT.D_clamp, OPT.G_clamp, OPT.D_maxAcc
-  if OPTSTATE and OPTSTATE.adam then
-    h.lr_D = OPTSTATE.adam.D.learningRate or 1e-3
-    h.lr_G = OPTSTATE.adam.G.learningRate or 1e-3
+  for _, net in ipairs({'D', 'G'}) do
+    local method = OPT[net .. '_optmethod'] or 'adam'
+    assert(OPTMETHOD[method], 'b200: unknown optimizer method ' .. tostring(method))
+    F.check(C.fg_set_option(b200._ctx, 'optimizer_' .. net, OPTMETHOD[method]), 'fg_set_option')
+    local st = OPTSTATE and OPTSTATE[method] and OPTSTATE[method][net] or {}
+    -- adam: learningRate or 1e-3 (interruptable_optimizers.lua:53); adagrad: 1e-3 (:10); sgd: OPT.*_SGD_lr (train.lua:180-191)
+    h['lr_' .. net] = st.learningRate or 1e-3
+    if method == 'sgd' then
+      F.check(C.fg_set_option_f(b200._ctx, 'sgd_momentum_' .. net, st.momentum or 0), 'fg_set_option_f')
+    end
   end
   return b200._hyper
 end
 
+-- a CudaTensor over raw device memory: torch.CudaStorage(size, address) wraps existing memory without owning it
+-- ([3P] cutorch shares torch7's generic/Storage.c constructor `Storage(size, ptr)`)
+function b200.aliasCuda(ptr, n)
+  local addr = tonumber(ffi.cast('intptr_t', ptr))
+  return torch.CudaTensor(torch.CudaStorage(n, addr))
+end
+local function devptr(t) return ffi.cast('float*', t:data()) end
+
 ---------------------------------------------------------------------------------------------------------------
--- Fused networks: a single nn.Module whose flat weight/gradWeight alias the library's device buffers, so
--- getParameters() (train.lua:151-152) is trivial and torch.save of params keeps working.
+-- Fused networks.  train.lua / adversarial.lua stay UNMODIFIED when MODELS.create_G / create_D return these
+-- (INTEGRATION.md section 2); face_generator_b200/nn.py is the executable mirror, tests/test_gpu_lnet_dropin.py
+-- runs the transcribed reference flow through it.  What the reference does to a model, and how this class answers:
+--   NN_UTILS.initializeWeights(model)  walks model.modules[m].weight/.bias (nn_utils.lua:17-29)
+--        -> self.modules = one proxy per reference layer, weight/bias = views into the flat device vector
+--   NN_UTILS.activateCuda(model)       net:clone(), :cuda(), wrapped into Sequential{Copy, net, Copy} (:328-363)
+--        -> clone() returns self (one fused net per context), type()/cuda() are no-ops, CudaTensor in / out
+--   MODEL:getParameters()              stock Module.flatten on the wrapping Sequential (train.lua:151-152): allocates
+--        ONE new flat storage, copies, re-points self.weight / self.gradWeight at it
+--        -> sync() sees weight:data() change and passes the new pointers to fg_bind_params: PARAMETERS_x /
+--           GRAD_PARAMETERS_x (zeroed, penalised, clamped by adversarial.lua:92-123, updated in place by the stock
+--           interruptable optimizers) then ARE the buffers the kernels read and write
+--   MODEL_D.modules[1].gradInput       is the leading nn.Copy's gradInput (adversarial.lua:210): stock nn
+--   torch.save({D = MODEL_D, ...})     write()/read() serialise the flat parameters + BN statistics
 ---------------------------------------------------------------------------------------------------------------
 local Fused, parent = torch.class('b200.Fused', 'nn.Module')
 
-function Fused:__init(net, channels)
+function Fused:__init(net, channels, layers)
   parent.__init(self)
-  self.net, self.channels = net, channels
-  self.ctx = b200.context()
-  self.n = tonumber(C.fg_param_count(net, channels))
-  self.train = true
-  self.output = torch.FloatTensor()
-  self.gradInput = torch.FloatTensor()
+  self.net, self.channels, self.layers = net, channels, layers
+  self:attach()
 end
-
+function Fused:attach()
+  self.ctx = b200.context()
+  self.n = tonumber(C.fg_param_count(self.net, self.channels))
+  self.train = true
+  self.output, self.gradInput = torch.CudaTensor(), torch.CudaTensor()
+  self.weight = b200.aliasCuda(C.fg_params_ptr(self.ctx, self.net), self.n)
+  self.gradWeight = b200.aliasCuda(C.fg_grads_ptr(self.ctx, self.net), self.n)
+  self._w, self._g = devptr(self.weight), devptr(self.gradWeight)
+  self:views()
+end
+-- per-layer proxies in models.lua's module order; flat offsets follow getParameters() (weight, then bias)
+function Fused:views()
+  self.modules = {}
+  local o = 1
+  local function view(shape)
+    local cnt = 1
+    for _, d in ipairs(shape) do cnt = cnt * d end
+    local w, g = self.weight:narrow(1, o, cnt):view(unpack(shape)), self.gradWeight:narrow(1, o, cnt):view(unpack(shape))
+    o = o + cnt
+    return w, g
+  end
+  for i, L in ipairs(self.layers) do
+    local m = {typename = L[1]}
+    if L[2] then m.weight, m.gradWeight = view(L[2]) end
+    if L[3] then m.bias, m.gradBias = view(L[3]) end
+    self.modules[i] = m
+  end
+  assert(o == self.n + 1)
+end
+function Fused:sync()
+  local w, g = devptr(self.weight), devptr(self.gradWeight)
+  if w ~= self._w or g ~= self._g then       -- Module.flatten moved us into the caller's flat storage
+    F.check(C.fg_bind_params(self.ctx, self.net, w, g), 'fg_bind_params')
+    self._w, self._g = w, g
+    self:views()
+  end
+  F.check(C.fg_set_stream(self.ctx, cutorch.getStream and ffi.cast('void*', cutorch.getStream()) or nil), 'fg_set_stream')
+end
 function Fused:training() self.train = true; return self end
 function Fused:evaluate() self.train = false; return self end
-
--- flat parameter / gradient vectors as host copies (reference tools read them; the device stays authoritative)
-function Fused:getParameters()
-  local p, g = torch.FloatTensor(self.n), torch.FloatTensor(self.n)
-  F.check(C.fg_get_params(self.ctx, self.net, F.ptr(p)), 'fg_get_params')
-  F.check(C.fg_get_grads(self.ctx, self.net, F.ptr(g)), 'fg_get_grads')
-  return p, g
+function Fused:type() return self end        -- :cuda() / :float(): the parameters live on the device
+function Fused:clone() return self end       -- NN_UTILS.activateCuda (nn_utils.lua:352)
+function Fused:listModules() return {self} end
+function Fused:parameters() return {self.weight}, {self.gradWeight} end
+function Fused:zeroGradParameters() self:sync(); F.check(C.fg_zero_grads(self.ctx, self.net), 'fg_zero_grads') end
+function Fused:accGradParameters() end       -- folded into backward()
+-- torch.save / torch.load (adversarial.lua:319-329): flat parameters (+ G's BatchNorm running statistics)
+function Fused:write(file)
+  local p = torch.FloatTensor(self.n)
+  self:sync()
+  F.check(C.fg_sync(self.ctx), 'fg_sync')
+  p:copy(self.weight)
+  local bn = torch.FloatTensor(768)
+  F.check(C.fg_get_bn_state(self.ctx, F.ptr(bn)), 'fg_get_bn_state')
+  file:writeObject({net = self.net, channels = self.channels, layers = self.layers, params = p, bn = bn, train = self.train})
 end
-function Fused:setParameters(p) F.check(C.fg_set_params(self.ctx, self.net, F.ptr(p:float():contiguous())), 'fg_set_params') end
-function Fused:zeroGradParameters() F.check(C.fg_zero_grads(self.ctx, self.net), 'fg_zero_grads') end
+function Fused:read(file)
+  local t = file:readObject()
+  self.net, self.channels, self.layers = t.net, t.channels, t.layers
+  b200.context(nil, nil, t.channels)
+  self:attach()
+  self.train = t.train
+  self.weight:copy(t.params)
+  if self.net == F.NET_G then F.check(C.fg_set_bn_state(self.ctx, F.ptr(t.bn)), 'fg_set_bn_state') end
+end
 
--- MODELS.create_G(dimensions, noiseDim)  (models.lua:87-93)
+-- MODELS.create_G(dimensions, noiseDim)  (models.lua:87-93 -> create_G_decoder_upsampling32 :57-81)
 local FusedG = torch.class('b200.FusedG', 'b200.Fused')
 function FusedG:__init(dimensions, noiseDim)
   assert(noiseDim == 100 and dimensions[2] == 32, 'b200.FusedG implements create_G_decoder_upsampling32 with noiseDim 100')
-  b200.Fused.__init(self, F.NET_G, dimensions[1])
+  local c = dimensions[1]
+  b200.Fused.__init(self, F.NET_G, c, {
+    {'nn.Linear', {8192, 100}, {8192}}, {'nn.View'}, {'nn.PReLU', {1}}, {'nn.SpatialUpSamplingNearest'},
+    {'cudnn.SpatialConvolution', {256, 128, 5, 5}, {256}}, {'nn.SpatialBatchNormalization', {256}, {256}}, {'nn.PReLU', {1}},
+    {'nn.SpatialUpSamplingNearest'}, {'cudnn.SpatialConvolution', {128, 256, 5, 5}, {128}},
+    {'nn.SpatialBatchNormalization', {128}, {128}}, {'nn.PReLU', {1}}, {'cudnn.SpatialConvolution', {c, 128, 3, 3}, {c}},
+    {'nn.Sigmoid'}})
 end
 function FusedG:updateOutput(input)
+  self:sync()
   local B = input:size(1)
   self.output:resize(B, self.channels, 32, 32)
   F.check(C.fg_G_forward(self.ctx, F.ptr(input:contiguous()), B, self.train and 1 or 0, F.ptr(self.output)), 'fg_G_forward')
   return self.output
 end
 function FusedG:backward(input, gradOutput)  -- updateGradInput + accGradParameters in one call
+  self:sync()
   self.gradInput:resizeAs(input)
   F.check(C.fg_G_backward(self.ctx, F.ptr(gradOutput:contiguous()), F.ptr(self.gradInput)), 'fg_G_backward')
   return self.gradInput
 end
+FusedG.updateGradInput = FusedG.backward
 
--- MODELS.create_D(dimensions)  (models.lua:98-104)
+-- MODELS.create_D(dimensions)  (models.lua:98-104 -> create_D32b :382-416)
 local FusedD = torch.class('b200.FusedD', 'b200.Fused')
 function FusedD:__init(dimensions)
   assert(dimensions[2] == 32, 'b200.FusedD implements create_D32b')
-  b200.Fused.__init(self, F.NET_D, dimensions[1])
+  local layers, cin = {}, dimensions[1]
+  for _, cout in ipairs({64, 128, 256, 512}) do
+    for _, L in ipairs({{'nn.SpatialConvolution', {cout, cin, 3, 3}, {cout}}, {'nn.PReLU', {1}}, {'nn.SpatialDropout'},
+                        {'nn.SpatialAveragePooling'}}) do layers[#layers + 1] = L end
+    cin = cout
+  end
+  for _, L in ipairs({{'nn.View'}, {'nn.Linear', {512, 2048}, {512}}, {'nn.PReLU', {1}}, {'nn.Dropout'},
+                      {'nn.Linear', {512, 512}, {512}}, {'nn.PReLU', {1}}, {'nn.Dropout'}, {'nn.Linear', {1, 512}, {1}},
+                      {'nn.Sigmoid'}}) do layers[#layers + 1] = L end
+  b200.Fused.__init(self, F.NET_D, dimensions[1], layers)
   self.seed = 0
-  self.modules = {self}  -- adversarial.lua:210 reads MODEL_D.modules[1].gradInput
-  self.wantWeightGrads = true
+  self.wantWeightGrads = true   -- set false inside fevalG_on_D to skip the D weight gradients the reference discards
 end
 function FusedD:updateOutput(input)
+  self:sync()
   local B = input:size(1)
   self.output:resize(B, 1)
   self.seed = self.seed + 1
@@ -98,13 +193,16 @@ function FusedD:updateOutput(input)
   return self.output
 end
 function FusedD:backward(input, gradOutput)
+  self:sync()
   self.gradInput:resizeAs(input)
   F.check(C.fg_D_backward(self.ctx, F.ptr(gradOutput:contiguous()), self.wantWeightGrads and 1 or 0, F.ptr(self.gradInput)), 'fg_D_backward')
   return self.gradInput
 end
+FusedD.updateGradInput = FusedD.backward
 
 ---------------------------------------------------------------------------------------------------------------
--- nn.BCECriterion replacement (train.lua:148)
+-- nn.BCECriterion replacement (train.lua:148); optional: the stock CPU criterion keeps working on the
+-- FloatTensor outputs of the wrapping Sequential
 ---------------------------------------------------------------------------------------------------------------
 local BCE, bparent = torch.class('b200.BCECriterion', 'nn.Criterion')
 function BCE:__init() bparent.__init(self); self.ctx = b200.context(); self.gradInput = torch.FloatTensor() end
@@ -121,15 +219,25 @@ function BCE:updateGradInput(input, target)
 end
 
 ---------------------------------------------------------------------------------------------------------------
--- interruptableAdam(opfunc, x, config) (interruptable_optimizers.lua:49-94): x is the b200.Fused module whose
--- parameters live on the device; penalty + clamp are fused into the step (adversarial.lua:103-123, :218-228).
+-- interruptableAdam(opfunc, x, config[, state]) (interruptable_optimizers.lua:49-94), optional drop-in for the
+-- stock one (which also works: it updates the aliased flat tensor in place with cutorch ops).  x is the FLAT
+-- PARAMETER TENSOR exactly as adversarial.lua:264 / :284 pass it; opfunc(x) returns f, dfdx or false, false.
+-- The update is one fused kernel on the raw device pointers; penalty and clamp were already applied to dfdx by the
+-- caller's opfunc (adversarial.lua:103-123), so none is applied here.
 ---------------------------------------------------------------------------------------------------------------
-function b200.interruptableAdam(opfunc, module, config)
-  local fx = opfunc(module)
-  if fx == false then return false end
-  F.check(C.fg_optim_step(module.ctx, module.net, b200._hyper, 1.0), 'fg_optim_step')
-  config.t = (config.t or 0) + 1
-  return module, {fx}
+function b200.interruptableAdam(opfunc, x, config, state)
+  local config = config or {}
+  local state = state or config
+  local lr = config.learningRate or 0.001
+  local beta1, beta2, epsilon = config.beta1 or 0.9, config.beta2 or 0.999, config.epsilon or 1e-8
+  local fx, dfdx = opfunc(x)
+  if fx == false then return false end                                -- interruptable_optimizers.lua:64-66
+  state.t = (state.t or 0) + 1
+  state.m = state.m or x.new(dfdx:size()):zero()
+  state.v = state.v or x.new(dfdx:size()):zero()
+  F.check(C.fg_adam_step(b200.context(), devptr(x), devptr(dfdx), devptr(state.m), devptr(state.v), x:nElement(), lr, beta1,
+                         beta2, epsilon, state.t, 0, 0, 0, 1), 'fg_adam_step')
+  return x, {fx}
 end
 
 ---------------------------------------------------------------------------------------------------------------

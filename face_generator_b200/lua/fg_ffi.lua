@@ -29,6 +29,7 @@ int fg_set_params(fg_ctx* ctx, int net, const float* src);
 int fg_get_params(fg_ctx* ctx, int net, float* dst);
 int fg_get_grads(fg_ctx* ctx, int net, float* dst);
 int fg_zero_grads(fg_ctx* ctx, int net);
+int fg_bind_params(fg_ctx* ctx, int net, float* params_dev, float* grads_dev);
 float* fg_params_ptr(fg_ctx* ctx, int net);
 float* fg_grads_ptr(fg_ctx* ctx, int net);
 int fg_set_adam_state(fg_ctx* ctx, int net, const float* m, const float* v, int t);

@@ -100,6 +100,15 @@ int fg_get_grads(fg_ctx* ctx, int net, float* dst);
 int fg_zero_grads(fg_ctx* ctx, int net);                 /* GRAD_PARAMETERS_x:zero()              */
 float* fg_params_ptr(fg_ctx* ctx, int net);              /* device pointers for Torch aliasing    */
 float* fg_grads_ptr(fg_ctx* ctx, int net);
+/* Borrow caller-owned DEVICE buffers (fg_param_count floats each, 16-byte aligned) as the flat
+ * parameter / gradient vectors of `net`.  train.lua:151-152 `MODEL:getParameters()` re-points every
+ * module's weight / gradWeight into ONE new flat storage; a b200.Fused module then passes
+ * weight:data() / gradWeight:data() here, so that the tensors the reference's loop mutates
+ * (GRAD_PARAMETERS:zero() / :add() / :clamp(), the optimizer's in-place update of PARAMETERS,
+ * adversarial.lua:92-123, interruptable_optimizers.lua:78-90) ARE the buffers the kernels read and
+ * write.  The buffers are used as they are (nothing is copied).  NULL restores the library's own
+ * buffer for that vector.  Packed weights are rebuilt on the next forward.                        */
+int fg_bind_params(fg_ctx* ctx, int net, float* params_dev, float* grads_dev);
 /* OPTSTATE.adam.{D,G}.{m,v,t} (interruptable_optimizers.lua:69-75); any pointer may be NULL     */
 int fg_set_adam_state(fg_ctx* ctx, int net, const float* m, const float* v, int t);
 int fg_get_adam_state(fg_ctx* ctx, int net, float* m, float* v, int* t);
