@@ -161,6 +161,14 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
     c->tc_mixed = (int)v;
     return FG_OK;
   }
+  if (!strcmp(key, "edge_impl")) {  // 1 (default): k_conv_edge.cu for the 3-channel-side convolutions; 0: k_conv_small.cu
+    c->edge_impl = v != 0;
+    return FG_OK;
+  }
+  if (!strcmp(key, "bn_epilogue")) {  // 1 (default): BatchNorm statistics from the tensor-core conv epilogue; 0: separate pass
+    c->bn_epilogue = v != 0;
+    return FG_OK;
+  }
   if (!strcmp(key, "debug_keep")) {  // keep the D step's pre-activations of fg_train_step ("Dstep.*" debug tensors)
     c->debug_keep = v != 0;
     return FG_OK;
@@ -190,6 +198,8 @@ int64_t fg_get_option(fg_ctx* c, const char* key) {
   if (!strcmp(key, "channels")) return c->C;
   if (!strcmp(key, "sm_count")) return c->sm_count;
   if (!strcmp(key, "tc_mixed")) return c->tc_mixed;
+  if (!strcmp(key, "bn_epilogue")) return c->bn_epilogue;
+  if (!strcmp(key, "edge_impl")) return c->edge_impl;
   if (!strcmp(key, "optimizer_D")) return c->opt_D;
   if (!strcmp(key, "optimizer_G")) return c->opt_G;
   return -1;

@@ -117,6 +117,9 @@ struct fg_ctx {
   bool G_train = true, G_fwd_valid = false;
   float *G_noise = nullptr, *G_z0 = nullptr, *G_h0 = nullptr, *G_z1 = nullptr, *G_h1 = nullptr, *G_z2 = nullptr,
         *G_h2 = nullptr, *G_z3 = nullptr, *G_y = nullptr;
+  float* bn_parts = nullptr;  // [m-tile][2][C] BatchNorm partials written by the tensor-core conv epilogue
+  int edge_impl = 1;          // option "edge_impl": 0 = the round-1 small-channel kernels (k_conv_small.cu) for G.C3 / D.C1
+  int bn_epilogue = 1;        // option "bn_epilogue": 0 = separate statistics pass over z (the round-1 path)
   double* bn_acc = nullptr;  // [4][256] double accumulators (sum, sumsq / sum g, sum g xhat)
   float *bn_mean1 = nullptr, *bn_istd1 = nullptr, *bn_mean2 = nullptr, *bn_istd2 = nullptr, *bn_mg = nullptr;
   float *G_dz3 = nullptr, *G_dfull = nullptr, *G_dz2 = nullptr, *G_dz1 = nullptr, *G_dz0 = nullptr;
@@ -208,6 +211,8 @@ int k_bn_bwd_reduce4(fg_ctx* c, const float* dh, const float* z, const float* me
                      const float* beta, const float* slope, double* acc, float* dslope, int64_t P, int C);
 int k_bn_finalize(fg_ctx* c, double* acc2C, float* mean, float* istd, float* run_mean, float* run_var, int64_t P,
                   int C);
+int k_bn_finalize_parts(fg_ctx* c, const float* part, int nparts, float* mean, float* istd, float* run_mean, float* run_var,
+                        int64_t P, int C);  // statistics from the conv epilogue's per-tile partials
 int k_bn_eval_prep(fg_ctx* c, const float* run_mean, const float* run_var, float* mean, float* istd, int C);
 int k_bn_prelu_apply(fg_ctx* c, const float* z, const float* mean, const float* istd, const float* gamma,
                      const float* beta, const float* slope, float* h, int64_t P, int C, float* hi = nullptr,
@@ -261,6 +266,10 @@ int k_wgrad_simt(fg_ctx* c, const float* in, const float* dY, float* dWp, ConvGe
 bool k_small_eligible(const ConvGeom& g);
 int k_conv_small(fg_ctx* c, const float* in, const float* Wp, const float* bias, float* out, ConvGeom g);
 int k_wgrad_small(fg_ctx* c, const float* in, const float* dY, float* dWp, ConvGeom g);
+
+// ---- k_conv_edge.cu: the same layers at width 32, weights in registers, TMA / smem staged (the default) ----------
+bool k_edge_eligible(const ConvGeom& g);
+int k_conv_edge(fg_ctx* c, const float* in, const float* Wp, const float* bias, float* out, ConvGeom g);
 
 // ---- k_conv_tc.cu ----------------------------------------------------------------------------------
 int tc_init(fg_ctx* c);

@@ -381,7 +381,7 @@ bool pick_box(int H, int W, int npix, int* bw, int* bh, int* bb) {
 }
 
 template <int BN>
-constexpr size_t fwd_smem() { return (size_t)kStages * (2 * kABytes + 2 * BN * 128) + 256 + 1024; }
+constexpr size_t fwd_smem() { return (size_t)kStages * (2 * kABytes + 2 * BN * 128) + 256 + 2 * 4 * BN * 4 + 1024; }
 template <int BN>
 constexpr size_t wg_smem() { return (size_t)kStages * (2 * 4 * 4096 + 2 * (BN / 32) * 4096) + 128 + 1024; }
 
@@ -485,6 +485,14 @@ int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops) {
   return FG_OK;
 }
 
+// plain (un-swizzled) 4-D TMA map over a dense NHWC fp32 tensor with the given box -- for the HBM-shaped kernels
+// that only use TMA as a deep-prefetch copy engine (k_conv_edge.cu)
+int tc_encode_nhwc_box(CUtensorMap* m, const float* base, int C, int W, int H, int B, int bc, int bw, int bh, int bb) {
+  FG_TRY(get_encode());
+  const int64_t sW = (int64_t)C * 4, sH = sW * W, sB = sH * H;
+  return make_map4(m, base, C, W, H, B, sW, sH, sB, bc, bw, bh, bb, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
 int tc_init(fg_ctx* c) {
   (void)c;
   FG_TRY(get_encode());
@@ -567,8 +575,16 @@ bool tc_conv_eligible(const ConvGeom& g) {
 // mode: 0 plain k x k conv (taps k*k, weights [t][n][c]);
 //       1 up2+5x5 dense (25 taps per output phase, weights [25][n][c]);
 //       2 up2+5x5 collapsed (9 taps per phase, weights [36][n][c])
+int tc_stat_parts(const ConvGeom& g, int mode) {
+  int bw, bh, bb;
+  const int Hl = g.H / g.ups, Wl = g.W / g.ups;
+  if (!pick_box(Hl, Wl, 128, &bw, &bh, &bb)) return 0;
+  const int per_phase = bb == 1 ? g.B * (Wl / bw) * (Hl / bh) : (g.B + bb - 1) / bb;
+  return per_phase * (mode == 0 ? 1 : 4);
+}
+
 int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
-                const float* bias, float* out, ConvGeom g, int mode) {
+                const float* bias, float* out, ConvGeom g, int mode, float* stats, int* n_parts) {
   TcFwdParams p;
   memset(&p, 0, sizeof(p));
   const int Hl = g.H / g.ups, Wl = g.W / g.ups;
@@ -636,6 +652,8 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
   p.out = out;
   p.bias = bias;
+  p.stats = stats;
+  if (n_parts) *n_parts = p.tiles_per_phase * p.nphase;
   p.out_H = g.H; p.out_W = g.W;
   p.out_scale = g.ups;
   p.ntiles = p.tiles_per_phase * p.nphase * (g.Cout / BN);

@@ -19,6 +19,7 @@ struct alignas(64) TcFwdParams {
   int tiles_x, tiles_y, tiles_per_phase, ntiles;
   float* out;
   const float* bias;
+  float* stats;  // optional [m-tile][2][Cout]: per-tile column sums of the output and of its square (BatchNorm)
   int out_H, out_W, out_scale;
   int dbg;    // experiment switches (FG_TC_DBG): 1 = skip MMAs, 2 = skip TMA data movement
   int chunk;  // K-blocks accumulated in TMEM before the epilogue promotes them to fp32 registers
@@ -42,10 +43,13 @@ int tc_split(fg_ctx* c, const float* x, float* hi, float* lo, int64_t n);
 int tc_pack_split(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK);
 int tc_pack_collapsed(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc);
 int tc_combine_collapsed_wgrad(fg_ctx* c, const float* G, float* dW, int N, int Cc);
+// stats / n_parts (optional): the kernel also writes per-tile BatchNorm partials [*n_parts][2][Cout] (see TcFwdParams)
 int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* bias,
-                float* out, ConvGeom g, int mode);
+                float* out, ConvGeom g, int mode, float* stats = nullptr, int* n_parts = nullptr);
+int tc_stat_parts(const ConvGeom& g, int mode);  // number of per-tile partials tc_conv_fwd writes for this geometry
 int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const float* wd_hi, const float* wd_lo, float* out,
                       ConvGeom g);
 int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* out,
                   ConvGeom g);
 int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops);
+int tc_encode_nhwc_box(CUtensorMap* m, const float* base, int C, int W, int H, int B, int bc, int bw, int bh, int bb);

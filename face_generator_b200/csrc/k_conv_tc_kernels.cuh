@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   uint64_t* tmem_empty = tmem_full + kAcc;    // [kAcc]
   uint64_t* cross_empty = tmem_empty + kAcc;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cross_empty + 2);
+  float* stat_sm = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [2][4 warps][BN] (p.stats only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.ntaps * p.kpt;
@@ -212,22 +213,57 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
         if (lane == 0) mbar_arrive(cross_empty + (tl & 1));
       }
       const int b = t.b0 + bi;
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < BN; ++i) acc[i] += p.bias[t.n0 + i];
+      }
+      if (p.stats) {
+        // BatchNorm statistics from the convolution epilogue (nn.SpatialBatchNormalization, models.lua:65,70): per
+        // tile the column sums of z and z^2 over its (valid) 128 pixels.  Within a warp a transpose-reduce (31
+        // shuffles per 32 columns) leaves lane l with the total of column l; the 4 warps meet in shared memory and
+        // one thread per column writes the tile's partial.  Every sum has a fixed order => replicas stay identical.
+        const bool valid = b < p.B;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          float x[32], y[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float v = valid ? acc[j * 32 + i] : 0.f;
+            x[i] = v;
+            y[i] = v * v;
+          }
+#pragma unroll
+          for (int sft = 16; sft >= 1; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int k = 0; k < sft; ++k) {
+              const float sx = up ? x[k] : x[k + sft], kx = up ? x[k + sft] : x[k];
+              const float sy = up ? y[k] : y[k + sft], ky = up ? y[k + sft] : y[k];
+              x[k] = kx + __shfl_xor_sync(0xffffffffu, sx, sft);
+              y[k] = ky + __shfl_xor_sync(0xffffffffu, sy, sft);
+            }
+          }
+          stat_sm[(0 * 4 + q) * BN + j * 32 + lane] = x[0];
+          stat_sm[(1 * 4 + q) * BN + j * 32 + lane] = y[0];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = (int)threadIdx.x - 64;  // 0..127 over the 4 epilogue warps
+        if (et < BN) {
+          const float s0 = (stat_sm[0 * BN + et] + stat_sm[1 * BN + et]) + (stat_sm[2 * BN + et] + stat_sm[3 * BN + et]);
+          const float s1 = (stat_sm[4 * BN + et] + stat_sm[5 * BN + et]) + (stat_sm[6 * BN + et] + stat_sm[7 * BN + et]);
+          const int mt = tile / (p.Cout / BN);
+          p.stats[((int64_t)mt * 2 + 0) * p.Cout + t.n0 + et] = s0;
+          p.stats[((int64_t)mt * 2 + 1) * p.Cout + t.n0 + et] = s1;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       if (b < p.B) {
         const int Y = p.out_scale * (t.y0 + yi) + (t.ph >> 1) * (p.out_scale - 1);
         const int X = p.out_scale * (t.x0 + xi) + (t.ph & 1) * (p.out_scale - 1);
         float* orow = p.out + (((int64_t)b * p.out_H + Y) * p.out_W + X) * p.Cout + t.n0;
 #pragma unroll
-        for (int i = 0; i < BN; i += 4) {
-          float4 o = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-          if (p.bias) {
-            const float* bp = p.bias + t.n0 + i;
-            o.x += bp[0];
-            o.y += bp[1];
-            o.z += bp[2];
-            o.w += bp[3];
-          }
-          *reinterpret_cast<float4*>(orow + i) = o;
-        }
+        for (int i = 0; i < BN; i += 4)
+          *reinterpret_cast<float4*>(orow + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
       }
     }
   }

@@ -287,6 +287,45 @@ int k_bn_finalize(fg_ctx* c, double* acc, float* mean, float* istd, float* run_m
   LAUNCH_CHECK(c);
   return FG_OK;
 }
+// BatchNorm statistics from the per-tile partials the tensor-core convolution wrote in its epilogue
+// (part[tile][2][C]: sum z, sum z^2 over the tile's pixels).  One block per 32 channels: 8 groups of threads walk
+// disjoint tile subsets in a fixed order with double accumulators and are combined in a fixed order, so the result
+// does not depend on scheduling (data-parallel replicas stay bit-identical).
+__global__ void __launch_bounds__(256) bn_finalize_parts_kernel(const float* __restrict__ part, int nparts, float* __restrict__ mean,
+                                                                float* __restrict__ istd, float* __restrict__ run_mean,
+                                                                float* __restrict__ run_var, int64_t P, int C) {
+  __shared__ double sm[2][8][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + lane;
+  double s = 0, q = 0;
+  if (ch < C)
+    for (int i = g; i < nparts; i += 8) {
+      s += (double)part[((int64_t)i * 2 + 0) * C + ch];
+      q += (double)part[((int64_t)i * 2 + 1) * C + ch];
+    }
+  sm[0][g][lane] = s;
+  sm[1][g][lane] = q;
+  __syncthreads();
+  if (g != 0 || ch >= C) return;
+  for (int k = 1; k < 8; ++k) {
+    s += sm[0][k][lane];
+    q += sm[1][k][lane];
+  }
+  const double n = (double)P;
+  const double m = s / n;
+  double var = q / n - m * m;
+  if (var < 0) var = 0;
+  mean[ch] = (float)m;
+  istd[ch] = (float)(1.0 / sqrt(var + 1e-5));
+  if (run_mean) run_mean[ch] = 0.9f * run_mean[ch] + 0.1f * (float)m;
+  if (run_var) run_var[ch] = 0.9f * run_var[ch] + 0.1f * (float)(P > 1 ? var * n / (n - 1.0) : var);
+}
+int k_bn_finalize_parts(fg_ctx* c, const float* part, int nparts, float* mean, float* istd, float* run_mean, float* run_var,
+                        int64_t P, int C) {
+  bn_finalize_parts_kernel<<<(C + 31) / 32, 256, 0, c->stream>>>(part, nparts, mean, istd, run_mean, run_var, P, C);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
 __global__ void bn_eval_prep_kernel(const float* __restrict__ rm, const float* __restrict__ rv, float* __restrict__ mean,
                                     float* __restrict__ istd, int C) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;

@@ -95,7 +95,8 @@ int fg_conv2d_forward(fg_ctx* c, const float* x, const float* w, const float* b,
     FG_TRY(tc_conv_fwd(c, xs, xs + nx, ws, ws + nw, bd, yn, g, 0));
   } else {
     FG_TRY(k_pack_weights(c, wd, wp, nullptr, Cout, Cin, k * k, 0, 0, 0, 0));
-    FG_TRY(k_conv_simt(c, xn, wp, bd, yn, g));
+    if (c->edge_impl && k_edge_eligible(g)) FG_TRY(k_conv_edge(c, xn, wp, bd, yn, g));  // 3-channel image edge
+    else FG_TRY(k_conv_simt(c, xn, wp, bd, yn, g));
   }
   FG_TRY(out_dev(c, y, ny, 6, &yd, false));
   FG_TRY(k_nhwc_to_nchw(c, yn, yd, N, Cout, H * W));
@@ -125,7 +126,8 @@ int fg_conv2d_backward_data(fg_ctx* c, const float* dy, const float* w, float* d
     FG_TRY(tc_conv_fwd(c, ys, ys + ny, ws + 2 * nw, ws + 3 * nw, nullptr, dxn, gd, 0));
   } else {
     FG_TRY(k_pack_weights(c, wd, nullptr, wpd, Cout, Cin, k * k, 0, 0, 0, 0));
-    FG_TRY(k_conv_simt(c, dyn, wpd, nullptr, dxn, gd));
+    if (c->edge_impl && k_edge_eligible(gd)) FG_TRY(k_conv_edge(c, dyn, wpd, nullptr, dxn, gd));
+    else FG_TRY(k_conv_simt(c, dyn, wpd, nullptr, dxn, gd));
   }
   FG_TRY(out_dev(c, dx, nx, 6, &dxd, false));
   FG_TRY(k_nhwc_to_nchw(c, dxn, dxd, N, Cin, H * W));

@@ -126,6 +126,7 @@ int net_alloc(fg_ctx* c) {
   FG_TRY(dalloc(c, &c->G_y, B * 1024 * C));
   FG_TRY(dalloc(c, &tmp, 4 * 256 * 2));  // doubles
   c->bn_acc = (double*)tmp;
+  FG_TRY(dalloc(c, &c->bn_parts, B * 2048));  // G.C2: 8 tiles/image x 2 x 128 ch; G.C1: 2 tiles/image x 2 x 256 ch
   FG_TRY(dalloc(c, &c->bn_mean1, 256));
   FG_TRY(dalloc(c, &c->bn_istd1, 256));
   FG_TRY(dalloc(c, &c->bn_mean2, 128));
@@ -262,7 +263,8 @@ int net_pack_D(fg_ctx* c) {
 static int conv_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp, const float* bias, float* out,
                     ConvGeom g) {
   ScopedTimer t(c, tag);
-  // 3-channel-side 3x3 convolutions get bandwidth-shaped kernels (k_conv_small.cu)
+  // 3-channel-side 3x3 convolutions get bandwidth-shaped kernels (k_conv_edge.cu; k_conv_small.cu for other widths)
+  if (c->edge_impl && k_edge_eligible(g)) return k_conv_edge(c, in, Wp, bias, out, g);
   return k_small_eligible(g) ? k_conv_small(c, in, Wp, bias, out, g) : k_conv_simt(c, in, Wp, bias, out, g);
 }
 static int conv_wgrad(fg_ctx* c, const char* tag, const float* in, const float* dY, ConvGeom g, float* dW, int nA, int nS,
@@ -307,14 +309,19 @@ static int lin_wgrad_tc(fg_ctx* c, const char* tag, const float* x_hi, const flo
 
 // G's two nn.SpatialUpSamplingNearest(2) -> 5x5 convolutions (li = 0: C1, li = 1: C2), forward.
 // tcgen05 path: split the low-res input into TF32 hi/lo once (kept for wgrad), then the phase conv.
+// *stat_parts (optional, in: want BatchNorm partials; out: how many tiles wrote one into c->bn_parts, 0 = none)
 static int g_ups_fwd(fg_ctx* c, int li, const char* tag, const float* h, float* h_hi, float* h_lo, const float* Wp,
-                     const float* bias, float* z, ConvGeom g) {
+                     const float* bias, float* z, ConvGeom g, int* stat_parts = nullptr) {
+  const bool want = stat_parts && *stat_parts;
+  if (stat_parts) *stat_parts = 0;
   if (!use_tc(c, g)) return conv_fwd(c, tag, h, Wp, bias, z, g);
   fg_ctx::TcBufs& t = c->tcb;
   if (h) FG_TRY(tc_split(c, h, h_hi, h_lo, (int64_t)g.B * (g.H / 2) * (g.W / 2) * g.Cin));  // nullptr: producer wrote hi/lo
   ScopedTimer tm(c, tag);
-  if (c->conv_impl == FG_CONV_TC_DENSE) return tc_conv_fwd(c, h_hi, h_lo, t.G_Wx_hi[li], t.G_Wx_lo[li], bias, z, g, 1);
-  return tc_conv_fwd(c, h_hi, h_lo, t.G_Wf_hi[li], t.G_Wf_lo[li], bias, z, g, 2);
+  float* st = want && c->bn_epilogue ? c->bn_parts : nullptr;
+  if (c->conv_impl == FG_CONV_TC_DENSE)
+    return tc_conv_fwd(c, h_hi, h_lo, t.G_Wx_hi[li], t.G_Wx_lo[li], bias, z, g, 1, st, st ? stat_parts : nullptr);
+  return tc_conv_fwd(c, h_hi, h_lo, t.G_Wf_hi[li], t.G_Wf_lo[li], bias, z, g, 2, st, st ? stat_parts : nullptr);
 }
 // backward of the same layer: dW += wgrad, dh = dgrad.  *pooled tells whether `dh` already is the gradient of
 // the LOW-RES input (tcgen05 path: the 2x2 sum of the upsample backward is folded into the dgrad GEMM) or the
@@ -352,11 +359,18 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
   c->G_train = training;
   FG_TRY(conv_fwd(c, "G.L1.fwd", c->G_noise, c->G_L1p, c->G_L1p + 8192 * 100, c->G_z0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}));
   FG_TRY(k_prelu_fwd(c, c->G_z0, P + L.a1, c->G_h0, (int64_t)B * 8192));
+  // training: the BatchNorm statistics come out of the convolution's epilogue (per-tile partials) when it ran on
+  // the tensor cores; otherwise a separate pass over z computes them
+  int parts = training ? 1 : 0;
   FG_TRY(g_ups_fwd(c, 0, "G.C1.fwd", c->G_h0, c->tcb.G_h0_hi, c->tcb.G_h0_lo, c->G_C1p, P + L.C1b, c->G_z1,
-                   ConvGeom{B, 16, 16, 128, 256, 5, 2}));
+                   ConvGeom{B, 16, 16, 128, 256, 5, 2}, &parts));
   if (training) {
-    FG_TRY(k_bn_stats(c, c->G_z1, c->bn_acc, (int64_t)B * 256, 256));
-    FG_TRY(k_bn_finalize(c, c->bn_acc, c->bn_mean1, c->bn_istd1, c->bnG, c->bnG + 256, (int64_t)B * 256, 256));
+    if (parts) {
+      FG_TRY(k_bn_finalize_parts(c, c->bn_parts, parts, c->bn_mean1, c->bn_istd1, c->bnG, c->bnG + 256, (int64_t)B * 256, 256));
+    } else {
+      FG_TRY(k_bn_stats(c, c->G_z1, c->bn_acc, (int64_t)B * 256, 256));
+      FG_TRY(k_bn_finalize(c, c->bn_acc, c->bn_mean1, c->bn_istd1, c->bnG, c->bnG + 256, (int64_t)B * 256, 256));
+    }
   } else {
     FG_TRY(k_bn_eval_prep(c, c->bnG, c->bnG + 256, c->bn_mean1, c->bn_istd1, 256));
   }
@@ -365,15 +379,21 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
   FG_TRY(k_bn_prelu_apply(c, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2,
                           c->G_h1, (int64_t)B * 256, 256, h1_split ? c->tcb.G_h1_hi : nullptr,
                           h1_split ? c->tcb.G_h1_lo : nullptr));
+  parts = training ? 1 : 0;
   FG_TRY(g_ups_fwd(c, 1, "G.C2.fwd", h1_split ? nullptr : c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, c->G_C2p, P + L.C2b,
-                   c->G_z2, gC2));
+                   c->G_z2, gC2, &parts));
   // "hbm.*" timers: the bandwidth-bound kernels bench.py reports against the measured HBM peak
   if (training) {
-    {
-      ScopedTimer tm(c, "hbm.G.bn2.stats");
-      FG_TRY(k_bn_stats(c, c->G_z2, c->bn_acc, (int64_t)B * 1024, 128));
+    if (parts) {
+      ScopedTimer tm(c, "G.bn2.finalize");
+      FG_TRY(k_bn_finalize_parts(c, c->bn_parts, parts, c->bn_mean2, c->bn_istd2, c->bnG + 512, c->bnG + 640, (int64_t)B * 1024, 128));
+    } else {
+      {
+        ScopedTimer tm(c, "hbm.G.bn2.stats");
+        FG_TRY(k_bn_stats(c, c->G_z2, c->bn_acc, (int64_t)B * 1024, 128));
+      }
+      FG_TRY(k_bn_finalize(c, c->bn_acc, c->bn_mean2, c->bn_istd2, c->bnG + 512, c->bnG + 640, (int64_t)B * 1024, 128));
     }
-    FG_TRY(k_bn_finalize(c, c->bn_acc, c->bn_mean2, c->bn_istd2, c->bnG + 512, c->bnG + 640, (int64_t)B * 1024, 128));
   } else {
     FG_TRY(k_bn_eval_prep(c, c->bnG + 512, c->bnG + 640, c->bn_mean2, c->bn_istd2, 128));
   }

@@ -163,6 +163,7 @@ int convl_fwd(fg_c2f* n, ConvL& L, const float* in, const float* P, float* out, 
     return tc_conv_fwd(c, L.x_hi, L.x_lo, L.Wf_hi, L.Wf_lo, P + L.b_off, out, g, 0);
   }
   ScopedTimer t(c, L.tf);
+  if (c->edge_impl && k_edge_eligible(g)) return k_conv_edge(c, in, L.Wp, P + L.b_off, out, g);
   return k_small_eligible(g) ? k_conv_small(c, in, L.Wp, P + L.b_off, out, g) : k_conv_simt(c, in, L.Wp, P + L.b_off, out, g);
 }
 // G (may be null): dW += wgrad, db += colsum(dy).  din (may be null) = dgrad.
@@ -203,6 +204,7 @@ int convl_bwd(fg_c2f* n, ConvL& L, const float* in, const float* dy, float* G, f
   if (din) {
     ScopedTimer t(c, L.td);
     if (d_tc) return tc_conv_fwd(c, n->dy_hi, n->dy_lo, L.Wd_hi, L.Wd_lo, nullptr, din, gd, 0);
+    if (c->edge_impl && k_edge_eligible(gd)) return k_conv_edge(c, dy, L.Wpd, nullptr, din, gd);
     return k_small_eligible(gd) ? k_conv_small(c, dy, L.Wpd, nullptr, din, gd) : k_conv_simt(c, dy, L.Wpd, nullptr, din, gd);
   }
   return FG_OK;

@@ -201,3 +201,31 @@ def test_full_train_step_at_headline_batch_vs_oracle(fg, init):
     post-clamp gradients, Adam moments at 1e-4 ("trained": real PReLU slopes with the kink override)."""
     import test_gpu_parity as TP
     TP._train_step_matches_oracle(fg, 3, 256, init, 2, 4000, max_batch=256)
+
+
+@pytest.mark.parametrize("N,Cin,Cout", [(256, 128, 3), (130, 128, 3), (5, 128, 1), (256, 3, 64), (130, 3, 128), (6, 1, 64),
+                                        (256, 64, 3), (7, 64, 1), (256, 3, 128), (3, 4, 64)])
+def test_edge_conv_launches(fg, N, Cin, Cout):
+    """the 3-channel-side 3x3 convolutions (G.C3: models.lua:73, D.C1: models.lua:385) in isolation through the L-op
+    ABI: forward of shape Cin -> Cout and its dgrad (a Cout -> Cin convolution) = the "reduce" and "expand" kernels
+    of k_conv_edge.cu, incl. the headline batch (TMA double buffering over ~7 strips per SM) and odd batches."""
+    from face_generator_b200.lib import _ptr
+    F = torch.nn.functional
+    rng = np.random.default_rng(N + Cin + Cout)
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    x, w, b = f(rng.standard_normal((N, Cin, 32, 32))), f(rng.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(Cin * 9)), f(rng.standard_normal(Cout))
+    dy = f(rng.standard_normal((N, Cout, 32, 32)))
+    ctx = fg.Context(0, max_batch=8, channels=3)
+    lib, h = ctx.lib, ctx.h
+    y, dx = np.empty((N, Cout, 32, 32), np.float32), np.empty_like(x)
+    assert lib.fg_conv2d_forward(h, _ptr(x), _ptr(w), _ptr(b), _ptr(y), N, Cin, 32, 32, Cout, 3) == 0, lib.fg_last_error()
+    assert lib.fg_conv2d_backward_data(h, _ptr(dy), _ptr(w), _ptr(dx), N, Cin, 32, 32, Cout, 3) == 0, lib.fg_last_error()
+    # the round-1 kernels as a second opinion on the same inputs
+    ctx.set_option("edge_impl", 0)
+    y0 = np.empty_like(y)
+    assert lib.fg_conv2d_forward(h, _ptr(x), _ptr(w), _ptr(b), _ptr(y0), N, Cin, 32, 32, Cout, 3) == 0, lib.fg_last_error()
+    ctx.close()
+    xt, wt, dyt = dev(x), dev(w), dev(dy)
+    assert rel(y, F.conv2d(xt, wt, dev(b), padding=1)) < KTOL
+    assert rel(dx, torch.nn.grad.conv2d_input(xt.shape, wt, dyt, padding=1)) < KTOL
+    assert rel(y0, y) < KTOL
