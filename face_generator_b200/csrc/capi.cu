@@ -509,7 +509,8 @@ int64_t fg_debug_tensor(fg_ctx* c, const char* name, float* dst, int64_t max_ele
       {"D.zl1", c->D_zl1, 512, db}, {"D.zl2", c->D_zl2, 512, db},
       {"Dstep.z1", c->keep_D[0], 65536, c->keep_B}, {"Dstep.z2", c->keep_D[1], 32768, c->keep_B},
       {"Dstep.z3", c->keep_D[2], 16384, c->keep_B}, {"Dstep.z4", c->keep_D[3], 8192, c->keep_B},
-      {"Dstep.zl1", c->keep_D[4], 512, c->keep_B}, {"Dstep.zl2", c->keep_D[5], 512, c->keep_B}};
+      {"Dstep.zl1", c->keep_D[4], 512, c->keep_B}, {"Dstep.zl2", c->keep_D[5], 512, c->keep_B},
+      {"Dstep.logit", c->keep_D[6], 1, c->keep_B}, {"Dstep.out", c->keep_D[7], 1, c->keep_B}};
   for (const Ent& e : ents)
     if (!strcmp(e.n, name)) {
       const int64_t n = e.per * e.B;

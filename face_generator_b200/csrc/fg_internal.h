@@ -148,7 +148,7 @@ struct fg_ctx {
   // step's D forward overwrites (the strict gradient-parity tests read PReLU branch decisions from them)
   bool debug_keep = false;
   int keep_B = 0;
-  float* keep_D[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // D_z[0..3], D_zl1, D_zl2
+  float* keep_D[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // D_z[0..3], D_zl1, D_zl2, D_logit, D_out
   // timing
   cudaEvent_t events[16] = {};
   bool timing = false;

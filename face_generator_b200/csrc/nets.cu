@@ -650,16 +650,16 @@ int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const
     FG_TRY(k_masks_generate(c, c->D_masks, B, seed * 2 + 1, h->p_spatial, h->p_drop));
   FG_TRY(net_zero_grads(c, FG_NET_D));
   FG_TRY(net_D_forward(c, c->D_x, B, true, h));
+  FG_TRY(k_sigmoid_bce(c, c->D_logit, c->D_out, c->D_dlogit, &c->dstats->loss_D, c->tailD, B, Bh));
   if (c->debug_keep) {  // tests: the G step's D forward overwrites these
-    const float* src[6] = {c->D_z[0], c->D_z[1], c->D_z[2], c->D_z[3], c->D_zl1, c->D_zl2};
-    const size_t per[6] = {65536, 32768, 16384, 8192, 512, 512};
-    for (int i = 0; i < 6; ++i) {
+    const float* src[8] = {c->D_z[0], c->D_z[1], c->D_z[2], c->D_z[3], c->D_zl1, c->D_zl2, c->D_logit, c->D_out};
+    const size_t per[8] = {65536, 32768, 16384, 8192, 512, 512, 1, 1};
+    for (int i = 0; i < 8; ++i) {
       if (!c->keep_D[i]) FG_TRY(dalloc(c, &c->keep_D[i], (size_t)c->maxB * per[i]));
       FG_CUDA(cudaMemcpyAsync(c->keep_D[i], src[i], sizeof(float) * B * per[i], cudaMemcpyDeviceToDevice, c->stream));
     }
     c->keep_B = B;
   }
-  FG_TRY(k_sigmoid_bce(c, c->D_logit, c->D_out, c->D_dlogit, &c->dstats->loss_D, c->tailD, B, Bh));
   FG_TRY(net_D_backward(c, c->D_dlogit, true, false));
   if (c->world > 1) FG_TRY(net_allreduce_grads(c, FG_NET_D));
   FG_TRY(k_gate_and_prep(c, FG_NET_D, h, c->tailD, B, world));

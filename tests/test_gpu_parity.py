@@ -196,8 +196,20 @@ def _train_step_matches_oracle(fg, C, B, init, impl, seed, max_batch=None):
     with O.kink.record(PU.KINK_MARGIN if kinks else 0.0):
         ref = PU.oracle_iteration(case, B, C)
     calls = O.kink.calls(18)
-    assert abs(st["loss_D"] - ref["lossD"]) < TOL * max(1.0, abs(ref["lossD"]))
-    assert abs(st["loss_G"] - ref["lossG"]) < TOL * max(1.0, abs(ref["lossG"]))
+    # Losses.  nn.BCECriterion (train.lua:148) sees D's sigmoid outputs as FLOAT32 (the reference's nn.Copy hands it
+    # a FloatTensor): near saturation log(1 - x + eps) amplifies the fp32 rounding of x by 1/(1-x), so the loss of two
+    # correct fp32 pipelines agrees only to ~1e-4..1e-3 at batch 256, while the fp64 oracle never rounds x.  The
+    # well-conditioned statement is therefore split in two: (i) the logits match the oracle at 1e-4; (ii) the loss
+    # equals the oracle's criterion (+ penalty) evaluated ON the CUDA path's own float32 outputs at 1e-5.
+    tD = np.concatenate([np.ones(B // 2), np.zeros(B // 2)])
+    logit = lambda x: np.log(x) - np.log1p(-x)
+    out_D, out_G = ctx.debug_tensor("Dstep.out").astype(np.float64), ctx.debug_tensor("D.out").astype(np.float64)
+    assert PU.relerr(ctx.debug_tensor("Dstep.logit"), logit(ref["outD"])) < TOL
+    pen_D = ref["lossD"] - O.f64.bce_fwd(ref["outD"], tD)  # the L1/L2 term of fevalD (adversarial.lua:103-106)
+    assert abs(st["loss_D"] - (O.f64.bce_fwd(out_D, tD) + pen_D)) < 1e-5 * max(1.0, abs(ref["lossD"]))
+    assert abs(st["loss_D"] - ref["lossD"]) < 2e-3 * max(1.0, abs(ref["lossD"]))
+    assert abs(st["loss_G"] - O.f64.bce_fwd(out_G, np.ones(B))) < 1e-5 * max(1.0, abs(ref["lossG"]))  # G_L1 = G_L2 = 0
+    assert abs(st["loss_G"] - ref["lossG"]) < 2e-3 * max(1.0, abs(ref["lossG"]))
     assert st["conf"] == [int(v) for v in ref["conf"]]
     assert st["t_D"] == 1 and st["t_G"] == 1 and st["trained_D"] == 1
     gD, gG = ctx.get_grads(NET_D), ctx.get_grads(NET_G)
@@ -227,8 +239,9 @@ def _train_step_matches_oracle(fg, C, B, init, impl, seed, max_batch=None):
     with O.kink.override():
         rg = PU.oracle_gstep(case["PG"], PDn, case["noise_G"], case["masks_G"], B, C)
     O.kink.clear()
+    ctx_logit_G = ctx.debug_tensor("D.logit")
     ctx.close()
-    assert abs(st["loss_G"] - rg["lossG"]) < 2e-5 * max(1.0, abs(rg["lossG"]))
+    assert PU.relerr(ctx_logit_G, logit(rg["outD"])) < TOL  # the G step's D logits on identical D parameters
     if init in ("trained", "smooth"):
         check_grads(O.G_layout(C), gG, rg["gradG"], skip=("C1b", "C2b"))
     else:
