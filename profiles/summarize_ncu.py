@@ -16,7 +16,11 @@ KEYS = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elap
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__maximum_warps_per_active_cycle_pct",
         "smsp__inst_executed.sum", "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__sass_inst_executed_op_shared_ld.sum",
-        "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "sm__mio_inst_issued.sum"]
+        "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "sm__mio_inst_issued.sum",
+        "smsp__average_warps_issue_stalled", "smsp__issue_active.avg.pct", "smsp__inst_executed_pipe_fma",
+        "sm__pipe_fma_cycles_active.avg.pct", "sm__inst_executed_pipe_lsu", "smsp__inst_executed_pipe_fmaheavy",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared",
+        "smsp__inst_executed_op_shared", "sm__warps_active.avg.per_cycle_active", "smsp__inst_issued.avg.per_cycle_active"]
 
 
 def main(path):

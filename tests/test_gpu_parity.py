@@ -202,9 +202,18 @@ def _train_step_matches_oracle(fg, C, B, init, impl, seed, max_batch=None):
     # well-conditioned statement is therefore split in two: (i) the logits match the oracle at 1e-4; (ii) the loss
     # equals the oracle's criterion (+ penalty) evaluated ON the CUDA path's own float32 outputs at 1e-5.
     tD = np.concatenate([np.ones(B // 2), np.zeros(B // 2)])
-    logit = lambda x: np.log(x) - np.log1p(-x)
+    def logits_match(got, x_ref):
+        """logit(x_ref) is finite in fp64 up to ~36; beyond ~25 the sigmoid output carries no digits of the logit
+        any more: compare where it does, require agreement in saturation elsewhere"""
+        with np.errstate(divide="ignore"):
+            ref = np.log(x_ref) - np.log1p(-x_ref)
+        ok = np.isfinite(ref) & (np.abs(ref) < 25)
+        got = np.asarray(got, np.float64)
+        assert np.all(np.abs(got[~ok]) > 20) and np.all(np.sign(got[~ok]) == np.sign(x_ref[~ok] - 0.5))
+        return not ok.any() or np.abs(got[ok] - ref[ok]).max() < TOL * max(1.0, np.abs(ref[ok]).max())
+
     out_D, out_G = ctx.debug_tensor("Dstep.out").astype(np.float64), ctx.debug_tensor("D.out").astype(np.float64)
-    assert PU.relerr(ctx.debug_tensor("Dstep.logit"), logit(ref["outD"])) < TOL
+    assert logits_match(ctx.debug_tensor("Dstep.logit"), ref["outD"])
     pen_D = ref["lossD"] - O.f64.bce_fwd(ref["outD"], tD)  # the L1/L2 term of fevalD (adversarial.lua:103-106)
     assert abs(st["loss_D"] - (O.f64.bce_fwd(out_D, tD) + pen_D)) < 1e-5 * max(1.0, abs(ref["lossD"]))
     assert abs(st["loss_D"] - ref["lossD"]) < 2e-3 * max(1.0, abs(ref["lossD"]))
@@ -241,7 +250,7 @@ def _train_step_matches_oracle(fg, C, B, init, impl, seed, max_batch=None):
     O.kink.clear()
     ctx_logit_G = ctx.debug_tensor("D.logit")
     ctx.close()
-    assert PU.relerr(ctx_logit_G, logit(rg["outD"])) < TOL  # the G step's D logits on identical D parameters
+    assert logits_match(ctx_logit_G, rg["outD"])  # the G step's D logits on identical D parameters
     if init in ("trained", "smooth"):
         check_grads(O.G_layout(C), gG, rg["gradG"], skip=("C1b", "C2b"))
     else:
