@@ -621,6 +621,15 @@ void avgpool2_bwd(int BC, int H, int W, const T* dy, T* dx) {
         dx[((size_t)nc * H + h) * W + w] = dy[((size_t)nc * Ho + h / 2) * Wo + w / 2] * T(0.25);
 }
 
+// D's sigmoid output as the reference's criterion and backward pass see it: a FLOAT32 value.  The reference
+// computes D on the GPU in fp32 and hands `outputs` to nn.BCECriterion through nn.Copy as a FloatTensor
+// (train.lua:148; utils/nn_utils.lua:359), so a saturated output is EXACTLY 0 or 1: BCE's log(1 - x + eps) then sees
+// eps alone and the composed gradient BCE' * y(1 - y) is exactly 0.  The fp64 oracle models
+// that storage precision here (and only here); everything else stays double.
+template <class T>
+inline T d_output(T y) {
+  return (T)(float)y;
+}
 template <class T>
 inline T sigmoid(T x) {
   return T(1) / (T(1) + std::exp(-x));
@@ -810,7 +819,7 @@ struct DNet {
                                            : al2[(size_t)b * 512 + j];
     logit.resize(B); out.resize(B);
     linear_fwd(B, 512, 1, hl2.data(), P + L.L3W, P + L.L3b, logit.data());
-    for (int b = 0; b < B; ++b) out[b] = sigmoid(logit[b]);
+    for (int b = 0; b < B; ++b) out[b] = d_output(sigmoid(logit[b]));
   }
   // dout: [B] gradient wrt sigmoid output. grads accumulate into dP (may be null => skip
   // weight grads). dimg optional [B][C][32][32].

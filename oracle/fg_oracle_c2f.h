@@ -172,7 +172,7 @@ struct C2fDNet {
                                            : al1[(size_t)b * 512 + j];
     logit.resize(B); out.resize(B);
     linear_fwd(B, 512, 1, hl1.data(), P + L.L2W, P + L.L2b, logit.data());
-    for (int b = 0; b < B; ++b) out[b] = sigmoid(logit[b]);
+    for (int b = 0; b < B; ++b) out[b] = d_output(sigmoid(logit[b]));  // fp32 at the criterion boundary (fg_oracle.cpp)
   }
   // dout [B] = dLoss/d(sigmoid output); dP may be null (weight grads skipped); ddiff = MODEL_D.gradInput[1]
   void backward(const T* P, const T* dout, T* dP, T* ddiff) {

@@ -256,7 +256,7 @@ struct D16Net {
     }
     logit.resize(B); out.resize(B);
     linear_fwd(B, 1152, 1, joint.data(), P + L.JW, P + L.Jb, logit.data());
-    for (int b = 0; b < B; ++b) out[b] = sigmoid(logit[b]);
+    for (int b = 0; b < B; ++b) out[b] = d_output(sigmoid(logit[b]));  // fp32 at the criterion boundary (fg_oracle.cpp)
   }
   void backward(const T* P, const T* dout, T* dP, T* dimg) {
     D16Layout L(C);

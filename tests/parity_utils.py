@@ -29,6 +29,12 @@ def make_case(B, C, seed, init="trained"):
         sl = 1.0 if init == "smooth" else 0.25
         PG = LY.trained_like_init(LY.G_layout(C), rng, slope=sl)
         PD = LY.trained_like_init(LY.D_layout(C), rng, 1.4, slope=sl)
+        if init == "smooth":
+            # with slopes 1 nothing damps D's activations: shrink its last layer so that the logits stay O(1).  With
+            # |logit| > 17 the fp32 sigmoid saturates, the reference's composed gradient is exactly 0 (SURVEY.md appendix
+            # 12) and a "strict gradient" case would compare nothing but zeros / near-saturation rounding noise
+            o, shape = LY.D_layout(C)[0]["L3W"]
+            PD[o:o + int(np.prod(shape))] *= 0.1
     else:  # the reference's own init: N(0, 0.005^2) weights (incl. BN gamma, PReLU slope), N(0, 0.001^2) biases
         PG, PD = LY.reference_init(LY.G_layout(C), rng), LY.reference_init(LY.D_layout(C), rng)
     f = lambda a: np.ascontiguousarray(a, np.float32)

@@ -6,6 +6,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from torch_ref import d_sigmoid
+
 from oracle import oracle_s16 as OS
 from torch_ref import _split, prelu
 from torch_ref_c2f import trained_like
@@ -55,7 +57,7 @@ def torch_D16(P, img, masks, C):
     fine = prelu(F.linear(h.reshape(B, 4096), p["F1W"], p["F1b"]), p["af"])
     e = prelu(F.linear(img.reshape(B, -1), p["E1W"], p["E1b"]), p["ae1"]) * masks[:, 1024:] * 2.0
     e = prelu(F.linear(e, p["E2W"], p["E2b"]), p["ae2"])
-    return torch.sigmoid(F.linear(torch.cat([fine, e], dim=1), p["JW"], p["Jb"])).reshape(B)
+    return d_sigmoid(F.linear(torch.cat([fine, e], dim=1), p["JW"], p["Jb"])).reshape(B)
 
 
 def test_param_counts():

@@ -15,6 +15,27 @@ def _split(P, layout):
     return {k: P[o:o + int(np.prod(s))].reshape(s) for k, (o, s) in layout.items()}
 
 
+class SigmoidF32Out(torch.autograd.Function):
+    """D's output sigmoid as the reference's criterion / backward see it: the value is a float32 (the reference
+    computes D in fp32 and hands a FloatTensor to nn.BCECriterion, train.lua:148), and the
+    backward uses that stored float32 output: dz = g * y * (1 - y).  Mirrors d_output() in oracle/fg_oracle.cpp."""
+
+    @staticmethod
+    def forward(ctx, z):
+        y = torch.sigmoid(z).to(torch.float32).to(z.dtype)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return g * y * (1 - y)
+
+
+def d_sigmoid(z):
+    return SigmoidF32Out.apply(z)
+
+
 def prelu(x, a, branch=None, name=None):
     """branch (tests at the headline batch size): callable(name, x) -> bool tensor "take the x > 0 branch" (lets a
     test force the branch of pre-activations that lie within rounding noise of 0, see parity_utils)."""
@@ -53,7 +74,7 @@ def D_forward(P, img, masks, C=3, branch=None):
     x = x.reshape(B, 2048)
     h = prelu(F.linear(x, p["L1W"], p["L1b"]), p["a5"], branch, "zl1") * masks[:, 960:1472] * 2.0
     h = prelu(F.linear(h, p["L2W"], p["L2b"]), p["a6"], branch, "zl2") * masks[:, 1472:1984] * 2.0
-    return torch.sigmoid(F.linear(h, p["L3W"], p["L3b"])).reshape(B)
+    return d_sigmoid(F.linear(h, p["L3W"], p["L3b"])).reshape(B)
 
 
 def bce(x, t):

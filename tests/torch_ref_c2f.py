@@ -4,6 +4,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from torch_ref import d_sigmoid
+
 from oracle import oracle_c2f as OC
 from torch_ref import _split, prelu
 
@@ -29,7 +31,7 @@ def D_forward(P, diff, cond, masks, C=3):
             x = F.max_pool2d(x, 2, 2)
     x = x.reshape(B, 16384) * masks[:, :16384] * 2.0  # nn.Dropout p=0.5 (v2), then View in (c,h,w) order
     h = prelu(F.linear(x, p["L1W"], p["L1b"]), p["a5"]) * masks[:, 16384:] * 2.0
-    return torch.sigmoid(F.linear(h, p["L2W"], p["L2b"])).reshape(B)
+    return d_sigmoid(F.linear(h, p["L2W"], p["L2b"])).reshape(B)
 
 
 def trained_like(layout, count, rng, gain=1.4):
