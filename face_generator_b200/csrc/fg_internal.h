@@ -117,6 +117,7 @@ struct fg_ctx {
   bool G_train = true, G_fwd_valid = false;
   float *G_noise = nullptr, *G_z0 = nullptr, *G_h0 = nullptr, *G_z1 = nullptr, *G_h1 = nullptr, *G_z2 = nullptr,
         *G_h2 = nullptr, *G_z3 = nullptr, *G_y = nullptr;
+  double* bn_slice_acc = nullptr;  // workspace of k_bn_finalize_parts: 32 slices x 2 x 256 doubles + tickets
   float* bn_parts = nullptr;  // [m-tile][2][C] BatchNorm partials written by the tensor-core conv epilogue
   int edge_impl = 1;          // option "edge_impl": 0 = the round-1 small-channel kernels (k_conv_small.cu) for G.C3 / D.C1
   int bn_epilogue = 1;        // option "bn_epilogue": 0 = separate statistics pass over z (the round-1 path)

@@ -50,6 +50,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// explicit shared-space loads: the tile pointer is derived from an integer-aligned base, which hides the address space
+// from the compiler (it would emit generic LD, which goes through address translation and the long scoreboard)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -106,7 +118,7 @@ __global__ void __launch_bounds__(256, 1) conv_reduce_kernel(const __grid_consta
     const int buf = it & 1;
     if (threadIdx.x == 0 && unit + (int)gridDim.x < nunits) issue(unit + gridDim.x, buf ^ 1);
     mbar_wait(full + buf, (it >> 1) & 1);
-    const float* tile = reinterpret_cast<const float*>(smem + buf * kTile);
+    const uint32_t tile = smem_u32(smem + buf * kTile) + (uint32_t)lane * VEC * 4;  // this lane's channels of tile pixel 0
     const int b = unit / strips, y = (unit - b * strips) * kRedRows + row;
 #pragma unroll 1
     for (int g = 0; g < 16 / PX; ++g) {
@@ -116,34 +128,33 @@ __global__ void __launch_bounds__(256, 1) conv_reduce_kernel(const __grid_consta
       for (int i = 0; i < PX; ++i)
 #pragma unroll
         for (int n = 0; n < NS; ++n) acc[i][n] = 0.f;
-      // column-major walk: tile column x0 + j (= image column x0 + j - 1) feeds pixels j-2 .. j
+      // column-major walk: tile column x0 + j (= image column x0 + j - 1) feeds pixels j-2 .. j.  The FMA order puts
+      // the (up to 9) independent accumulators of a column innermost, so consecutive FMAs never depend on each other.
 #pragma unroll
       for (int j = 0; j < PX + 2; ++j) {
         float v[3][VEC];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
-          const float* ip = tile + ((row + dy) * (kW + 2) + x0 + j) * C + lane * VEC;
+          const uint32_t ad = tile + (uint32_t)(((row + dy) * (kW + 2) + x0 + j) * C) * 4;
           if (VEC == 4) {
-            const float4 q = *reinterpret_cast<const float4*>(ip);
+            const float4 q = lds128(ad);
             v[dy][0] = q.x; v[dy][1 % VEC] = q.y; v[dy][2 % VEC] = q.z; v[dy][3 % VEC] = q.w;
-          } else if (VEC == 2) {
-            const float2 q = *reinterpret_cast<const float2*>(ip);
-            v[dy][0] = q.x; v[dy][1 % VEC] = q.y;
           } else {
-            v[dy][0] = ip[0];
+            const float2 q = lds64(ad);
+            v[dy][0] = q.x; v[dy][1 % VEC] = q.y;
           }
         }
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int i = j - dx;  // output pixel whose tap column dx is this column
-          if (i < 0 || i >= PX) continue;
+        for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy)
+          for (int k = 0; k < VEC; ++k)
 #pragma unroll
-            for (int n = 0; n < NS; ++n)
+            for (int dx = 0; dx < 3; ++dx) {
+              const int i = j - dx;  // output pixel whose tap column dx is this column
+              if (i < 0 || i >= PX) continue;
 #pragma unroll
-              for (int k = 0; k < VEC; ++k) acc[i][n] = fmaf(v[dy][k], w[dy * 3 + dx][n][k], acc[i][n]);
-        }
+              for (int n = 0; n < NS; ++n) acc[i][n] = fmaf(v[dy][k], w[dy * 3 + dx][n][k], acc[i][n]);
+            }
       }
       // 16-value butterfly transpose-reduce inside each half-warp, then the two halves are added
       float r[16];
@@ -174,13 +185,13 @@ template <int CS, int N>
 __global__ void __launch_bounds__(256, 1) conv_expand_kernel(const float* __restrict__ in, const float* __restrict__ Wp,
                                                              const float* __restrict__ bias, float* __restrict__ out, int H,
                                                              int nunits) {
-  constexpr int RW = (kW + 2) * CS;               // floats per tile row incl. the two halo pixels
+  constexpr int RW = (kW + 2) * 4;                // floats per tile row: one float4 per pixel incl. the two halo pixels
   constexpr int ROWF = kW * CS;                   // floats per image row
   constexpr int NPF = ((kExpRows + 2) * ROWF + 255) / 256;  // prefetch registers per thread
-  __shared__ float tile[2][(kExpRows + 2) * RW];
+  __shared__ __align__(16) float tile[2][(kExpRows + 2) * RW];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strips = H / kExpRows;
-  for (int i = threadIdx.x; i < 2 * (kExpRows + 2) * RW; i += 256) (&tile[0][0])[i] = 0.f;  // halo columns stay zero
+  for (int i = threadIdx.x; i < 2 * (kExpRows + 2) * RW; i += 256) (&tile[0][0])[i] = 0.f;  // halo / pad lanes stay zero
   // this thread's 4 output channels and their 9 * CS * 4 weights
   const int n4 = (N == 128 ? lane : (lane & 15)) * 4;
   float w[9][CS][4];
@@ -207,7 +218,7 @@ __global__ void __launch_bounds__(256, 1) conv_expand_kernel(const float* __rest
     for (int i = 0; i < NPF; ++i) {
       const int idx = threadIdx.x + 256 * i;
       const int r = idx / ROWF, off = idx - r * ROWF;
-      if (r < kExpRows + 2) tile[buf][r * RW + CS + off] = pf[i];
+      if (r < kExpRows + 2) tile[buf][r * RW + (off / CS + 1) * 4 + off % CS] = pf[i];
     }
   };
   __syncthreads();
@@ -216,33 +227,42 @@ __global__ void __launch_bounds__(256, 1) conv_expand_kernel(const float* __rest
     stash(0);
   }
   __syncthreads();
+  // a thread produces 2 neighbouring pixels per iteration (8 independent accumulator chains, the 4 tile columns they
+  // need are loaded once); N = 64: the two half-warps take neighbouring pixel pairs
+  constexpr int STEP = N == 128 ? 2 : 4;
+  const int xoff = N == 128 ? 0 : 2 * (lane >> 4);
   int it = 0;
   for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x, ++it) {
     const int buf = it & 1;
     const bool more = unit + (int)gridDim.x < nunits;
     if (more) prefetch(unit + gridDim.x);  // in flight while this strip is computed
     const int b = unit / strips, y = (unit - b * strips) * kExpRows + warp;
-    const float* t0 = &tile[buf][warp * RW];
+    const float4* t0 = reinterpret_cast<const float4*>(&tile[buf][warp * RW]);
     float* orow = out + ((size_t)(b * H + y) * kW) * N + n4;
-    constexpr int STEP = N == 128 ? 1 : 2;  // N = 64: the two half-warps take neighbouring pixels
-    const int xoff = N == 128 ? 0 : (lane >> 4);
-#pragma unroll 2
+#pragma unroll 1
     for (int xb = 0; xb < kW; xb += STEP) {
       const int x = xb + xoff;
-      float4 acc = b4;
+      float4 a0 = b4, a1 = b4;
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
+      for (int dy = 0; dy < 3; ++dy) {
+        float4 col[4];  // tile columns x .. x+3 = image columns x-1 .. x+2 (broadcast within the (half-)warp)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) col[j] = t0[dy * (kW + 2) + x + j];
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
           for (int c = 0; c < CS; ++c) {
-            const float v = t0[dy * RW + (x + dx) * CS + c];  // broadcast within the (half-)warp
-            acc.x = fmaf(v, w[dy * 3 + dx][c][0], acc.x);
-            acc.y = fmaf(v, w[dy * 3 + dx][c][1], acc.y);
-            acc.z = fmaf(v, w[dy * 3 + dx][c][2], acc.z);
-            acc.w = fmaf(v, w[dy * 3 + dx][c][3], acc.w);
+            const float v0 = c == 0 ? col[dx].x : (c == 1 ? col[dx].y : (c == 2 ? col[dx].z : col[dx].w));
+            const float v1 = c == 0 ? col[dx + 1].x : (c == 1 ? col[dx + 1].y : (c == 2 ? col[dx + 1].z : col[dx + 1].w));
+            const float* wp = w[dy * 3 + dx][c];
+            a0.x = fmaf(v0, wp[0], a0.x); a1.x = fmaf(v1, wp[0], a1.x);
+            a0.y = fmaf(v0, wp[1], a0.y); a1.y = fmaf(v1, wp[1], a1.y);
+            a0.z = fmaf(v0, wp[2], a0.z); a1.z = fmaf(v1, wp[2], a1.z);
+            a0.w = fmaf(v0, wp[3], a0.w); a1.w = fmaf(v1, wp[3], a1.w);
           }
-      *reinterpret_cast<float4*>(orow + (size_t)x * N) = acc;
+      }
+      *reinterpret_cast<float4*>(orow + (size_t)x * N) = a0;
+      *reinterpret_cast<float4*>(orow + (size_t)(x + 1) * N) = a1;
     }
     if (more) stash(buf ^ 1);  // buf ^ 1 was last read in iteration it - 1 (barrier below)
     __syncthreads();

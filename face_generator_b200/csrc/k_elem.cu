@@ -288,28 +288,51 @@ int k_bn_finalize(fg_ctx* c, double* acc, float* mean, float* istd, float* run_m
   return FG_OK;
 }
 // BatchNorm statistics from the per-tile partials the tensor-core convolution wrote in its epilogue
-// (part[tile][2][C]: sum z, sum z^2 over the tile's pixels).  One block per 32 channels: 8 groups of threads walk
-// disjoint tile subsets in a fixed order with double accumulators and are combined in a fixed order, so the result
-// does not depend on scheduling (data-parallel replicas stay bit-identical).
-__global__ void __launch_bounds__(256) bn_finalize_parts_kernel(const float* __restrict__ part, int nparts, float* __restrict__ mean,
+// (part[tile][2][C]: sum z, sum z^2 over the tile's pixels).  Grid (C/32, S slices): a block of 32 channels x 8
+// thread groups sums its slice of the tiles with double accumulators in a fixed order and writes a per-slice partial;
+// the block that finishes LAST (atomic ticket per channel group) adds the S slice partials in slice order and
+// finalises.  Every sum has a fixed order whatever the scheduling => data-parallel replicas stay bit-identical.
+constexpr int kBnSlices = 32;
+__global__ void __launch_bounds__(256) bn_finalize_parts_kernel(const float* __restrict__ part, int nparts, double* __restrict__ slice_acc,
+                                                                unsigned int* __restrict__ ticket, float* __restrict__ mean,
                                                                 float* __restrict__ istd, float* __restrict__ run_mean,
                                                                 float* __restrict__ run_var, int64_t P, int C) {
   __shared__ double sm[2][8][32];
+  __shared__ bool last;
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + lane;
+  const int per = (nparts + kBnSlices - 1) / kBnSlices;
+  const int i0 = blockIdx.y * per, i1 = min(nparts, i0 + per);
   double s = 0, q = 0;
   if (ch < C)
-    for (int i = g; i < nparts; i += 8) {
+    for (int i = i0 + g; i < i1; i += 8) {
       s += (double)part[((int64_t)i * 2 + 0) * C + ch];
       q += (double)part[((int64_t)i * 2 + 1) * C + ch];
     }
   sm[0][g][lane] = s;
   sm[1][g][lane] = q;
   __syncthreads();
+  if (g == 0 && ch < C) {
+    for (int k = 1; k < 8; ++k) {
+      s += sm[0][k][lane];
+      q += sm[1][k][lane];
+    }
+    slice_acc[((int64_t)blockIdx.y * 2 + 0) * C + ch] = s;
+    slice_acc[((int64_t)blockIdx.y * 2 + 1) * C + ch] = q;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket + blockIdx.x, 1u) == (unsigned)kBnSlices - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x == 0) ticket[blockIdx.x] = 0;  // ready for the next launch
   if (g != 0 || ch >= C) return;
-  for (int k = 1; k < 8; ++k) {
-    s += sm[0][k][lane];
-    q += sm[1][k][lane];
+  s = 0;
+  q = 0;
+  for (int k = 0; k < kBnSlices; ++k) {
+    s += slice_acc[((int64_t)k * 2 + 0) * C + ch];
+    q += slice_acc[((int64_t)k * 2 + 1) * C + ch];
   }
   const double n = (double)P;
   const double m = s / n;
@@ -320,9 +343,13 @@ __global__ void __launch_bounds__(256) bn_finalize_parts_kernel(const float* __r
   if (run_mean) run_mean[ch] = 0.9f * run_mean[ch] + 0.1f * (float)m;
   if (run_var) run_var[ch] = 0.9f * run_var[ch] + 0.1f * (float)(P > 1 ? var * n / (n - 1.0) : var);
 }
+// slice_ws: kBnSlices * 2 * C doubles + (C/32) tickets (zeroed once at allocation)
 int k_bn_finalize_parts(fg_ctx* c, const float* part, int nparts, float* mean, float* istd, float* run_mean, float* run_var,
                         int64_t P, int C) {
-  bn_finalize_parts_kernel<<<(C + 31) / 32, 256, 0, c->stream>>>(part, nparts, mean, istd, run_mean, run_var, P, C);
+  double* acc = c->bn_slice_acc;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(acc + (size_t)kBnSlices * 2 * 256);
+  bn_finalize_parts_kernel<<<dim3((C + 31) / 32, kBnSlices), 256, 0, c->stream>>>(part, nparts, acc, ticket, mean, istd, run_mean,
+                                                                                run_var, P, C);
   LAUNCH_CHECK(c);
   return FG_OK;
 }

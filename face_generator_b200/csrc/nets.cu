@@ -126,6 +126,8 @@ int net_alloc(fg_ctx* c) {
   FG_TRY(dalloc(c, &c->G_y, B * 1024 * C));
   FG_TRY(dalloc(c, &tmp, 4 * 256 * 2));  // doubles
   c->bn_acc = (double*)tmp;
+  FG_TRY(dalloc(c, &tmp, 32 * 2 * 256 * 2 + 64));  // doubles + tickets (zero-initialised)
+  c->bn_slice_acc = (double*)tmp;
   FG_TRY(dalloc(c, &c->bn_parts, B * 2048));  // G.C2: 8 tiles/image x 2 x 128 ch; G.C1: 2 tiles/image x 2 x 256 ch
   FG_TRY(dalloc(c, &c->bn_mean1, 256));
   FG_TRY(dalloc(c, &c->bn_istd1, 256));
@@ -221,8 +223,13 @@ int net_pack_G(fg_ctx* c) {
   const GLayout& L = c->gl;
   FG_TRY(k_pack_weights(c, c->PG + L.L1W, c->G_L1p, c->G_L1pd, 8192, 100, 1, 128, 64, 0, 0));
   FG_TRY(k_pack_weights(c, c->PG + L.L1b, c->G_L1p + 8192 * 100, nullptr, 8192, 1, 1, 128, 64, 0, 0));
-  FG_TRY(k_pack_weights(c, c->PG + L.C1W, c->G_C1p, c->G_C1pd, 256, 128, 25, 0, 0, 0, 0));
-  FG_TRY(k_pack_weights(c, c->PG + L.C2W, c->G_C2p, c->G_C2pd, 128, 256, 25, 0, 0, 0, 0));
+  // the tap-major fp32 packs of the two 5x5 layers only feed the SIMT kernels (fallback / cross-check path)
+  const bool tc_g = c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(ConvGeom{c->maxB, 16, 16, 128, 256, 5, 2}) &&
+                    tc_conv_eligible(ConvGeom{c->maxB, 32, 32, 256, 128, 5, 2});
+  if (!tc_g) {
+    FG_TRY(k_pack_weights(c, c->PG + L.C1W, c->G_C1p, c->G_C1pd, 256, 128, 25, 0, 0, 0, 0));
+    FG_TRY(k_pack_weights(c, c->PG + L.C2W, c->G_C2p, c->G_C2pd, 128, 256, 25, 0, 0, 0, 0));
+  }
   FG_TRY(k_pack_weights(c, c->PG + L.C3W, c->G_C3p, c->G_C3pd, c->C, 128, 9, 0, 0, 0, 0));
   if (c->conv_impl != FG_CONV_SIMT) {
     fg_ctx::TcBufs& t = c->tcb;
@@ -239,8 +246,11 @@ int net_pack_G(fg_ctx* c) {
 int net_pack_D(fg_ctx* c) {
   if (c->D_packed) return FG_OK;
   const DLayout& L = c->dl;
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i) {  // c2..c4 run on the tensor cores from their own TF32 packs (below) unless conv_impl = SIMT
+    const ConvGeom gf{c->maxB, kDhw[i], kDhw[i], dcin(c, i), kDcout[i], 3, 1}, gd{c->maxB, kDhw[i], kDhw[i], kDcout[i], dcin(c, i), 3, 1};
+    if (i > 0 && c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(gf) && tc_conv_eligible(gd)) continue;
     FG_TRY(k_pack_weights(c, c->PD + L.cW[i], c->D_cp[i], c->D_cpd[i], kDcout[i], dcin(c, i), 9, 0, 0, 0, 0));
+  }
   // View(2048) flattens [512][2][2] in (c,h,w) order; ours is NHWC (h,w,c): permute the columns
   FG_TRY(k_pack_weights(c, c->PD + L.L1W, c->D_L1p, c->D_L1pd, 512, 2048, 1, 0, 0, 512, 4));
   FG_TRY(k_pack_weights(c, c->PD + L.L2W, nullptr, c->D_L2pd, 512, 512, 1, 0, 0, 0, 0));
