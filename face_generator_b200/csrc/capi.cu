@@ -161,6 +161,10 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
     c->tc_mixed = (int)v;
     return FG_OK;
   }
+  if (!strcmp(key, "tc_halo")) {  // 1 (default): haloed-tile operand feed where the geometry allows it; 0: one TMA box per tap
+    c->tc_halo = v != 0;
+    return FG_OK;
+  }
   if (!strcmp(key, "edge_impl")) {  // 1 (default): k_conv_edge.cu for the 3-channel-side convolutions; 0: k_conv_small.cu
     c->edge_impl = v != 0;
     return FG_OK;
@@ -200,6 +204,7 @@ int64_t fg_get_option(fg_ctx* c, const char* key) {
   if (!strcmp(key, "tc_mixed")) return c->tc_mixed;
   if (!strcmp(key, "bn_epilogue")) return c->bn_epilogue;
   if (!strcmp(key, "edge_impl")) return c->edge_impl;
+  if (!strcmp(key, "tc_halo")) return c->tc_halo;
   if (!strcmp(key, "optimizer_D")) return c->opt_D;
   if (!strcmp(key, "optimizer_G")) return c->opt_G;
   return -1;
@@ -528,6 +533,13 @@ int64_t fg_debug_tensor(fg_ctx* c, const char* name, float* dst, int64_t max_ele
   return -1;
 }
 
+// tests: tensor-core operand taken as a shifted window of a haloed, 128B-swizzled tile (see tc_umma_window_probe)
+int fg_debug_umma_window(fg_ctx* c, const float* x_dev, const float* ident_dev, int dy, int dx, int use_base_offset,
+                         float* out_dev) {
+  ENTER(c);
+  FG_REQUIRE(x_dev && ident_dev && out_dev && dy >= 0 && dy <= 2 && dx >= 0 && dx <= 7, "fg_debug_umma_window: bad arguments");
+  return tc_umma_window_probe(c, x_dev, ident_dev, dy, dx, use_base_offset, out_dev);
+}
 int fg_bench_tf32_peak(fg_ctx* c, int iters, double* tflops) {
   ENTER(c);
   FG_REQUIRE(tflops && iters > 0, "fg_bench_tf32_peak: bad arguments");

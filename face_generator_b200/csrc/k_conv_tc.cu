@@ -382,6 +382,11 @@ bool pick_box(int H, int W, int npix, int* bw, int* bh, int* bb) {
 
 template <int BN>
 constexpr size_t fwd_smem() { return (size_t)kStages * (2 * kABytes + 2 * BN * 128) + 256 + 2 * 4 * BN * 4 + 1024; }
+// haloed-tile variant: 2 stages x {hi, lo} activation tiles in front of a ring of weight stages
+inline uint32_t halo_box_bytes(int pad) { return 128u * (8 + 2 * pad) * (16 + 2 * pad); }
+inline uint32_t halo_tile_bytes(int pad) { return (halo_box_bytes(pad) + 1023u) & ~1023u; }
+template <int BN>
+size_t fwd_smem_halo(int pad) { return 4 * (size_t)halo_tile_bytes(pad) + (size_t)kStages * 2 * BN * 128 + 256 + 2 * 4 * BN * 4 + 1024; }
 template <int BN>
 constexpr size_t wg_smem() { return (size_t)kStages * (2 * 4 * 4096 + 2 * (BN / 32) * 4096) + 128 + 1024; }
 
@@ -453,7 +458,73 @@ __global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
   if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// descriptor probe (tests): an A operand that is a SHIFTED WINDOW of a larger 128B-swizzled tile.  The tile is a
+// "haloed" pixel block [18 rows][16 pixels][32 ch] (288 rows of 128 B) landed by TMA; the operand of tap (dy, dx) is
+// the 128 rows { (yi + dy) * 16 + xi + dx : yi < 16, xi < 8 }: 8-row core groups 2048 B apart (SBO), start address
+// base + (dy * 16 + dx) * 128 -- not 1024-aligned, so the descriptor's base-offset field must carry (addr >> 7) & 7.
+// With B = identity the accumulator is the gathered operand itself.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) umma_window_probe_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                   const __grid_constant__ CUtensorMap bmap, int dy, int dx,
+                                                                   int use_base_offset, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr uint32_t kX = 288 * 128, kBb = 32 * 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kX + kBb);
+  uint64_t* done = full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) tmem_alloc<32>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(full, kX + kBb);
+    tma_load_2d(smem, &xmap, full, 0, 0);
+    tma_load_2d(smem + 144 * 128, &xmap, full, 0, 144);
+    tma_load_2d(smem + kX, &bmap, full, 0, 0);
+    mbar_wait(full, 0);
+    tc_fence_after();
+    const int pitch = (use_base_offset >> 8) ? (use_base_offset >> 8) : 16;  // pixels per halo row (bits 8..)
+    const uint32_t sa = smem_u32(smem) + (uint32_t)(dy * pitch + dx) * 128;
+    uint64_t a = make_desc(sa, 16, (uint32_t)pitch * 128);
+    if (use_base_offset & 1) a |= (uint64_t)((sa >> 7) & 7) << 49;
+    const uint64_t b = make_desc(smem_u32(smem + kX), 16, 1024);
+    constexpr uint32_t kIdesc = make_idesc(128, 32, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), kIdesc, k != 0);
+    umma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  uint32_t v[32];
+  tmem_ld_32x32(tmem_base + ((uint32_t)((threadIdx.x >> 5) * 32) << 16), v);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) out[threadIdx.x * 32 + i] = __uint_as_float(v[i]);
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc<32>(tmem_base);
+}
+
 }  // namespace
+
+// x: device [288][32] fp32 (tf32-exact values), ident: device [32][32] identity; out: device [128][32]
+int tc_umma_window_probe(fg_ctx* c, const float* x, const float* ident, int dy, int dx, int use_base_offset, float* out) {
+  FG_TRY(get_encode());
+  CUtensorMap xm, bm;
+  FG_TRY(make_map2(&xm, x, 32, 288, 32, 144));
+  FG_TRY(make_map2(&bm, ident, 32, 32, 32, 32));
+  constexpr int kSmem = 288 * 128 + 32 * 128 + 64 + 1024;
+  umma_window_probe_kernel<<<1, 128, kSmem, c->stream>>>(xm, bm, dy, dx, use_base_offset, out);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
 
 // -> TFLOP/s of kind::tf32 MMAs (2*M*N*K per instruction) over all SMs, best of `reps` event-timed launches.
 // FG_TF32_PROBE_N=128 probes the N=128 instruction shape the convolution kernels issue (operand reads from shared
@@ -496,8 +567,10 @@ int tc_encode_nhwc_box(CUtensorMap* m, const float* base, int C, int W, int H, i
 int tc_init(fg_ctx* c) {
   (void)c;
   FG_TRY(get_encode());
-  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
-  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>()));
+  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
+  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>()));
+  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_halo<64>(2)));
+  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_halo<128>(2)));
   FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<64>()));
   FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<128>()));
   return FG_OK;
@@ -562,6 +635,33 @@ static int tc_chunk(bool forward_type = false) {
   return v[forward_type ? 1 : 0];
 }
 
+// haloed-tile feed (tapconv_tc_kernel<BN, true>): 8 x 16 pixel tiles of one image, all taps within +-pad <= 2
+static bool halo_ok(const fg_ctx* c, int Hl, int Wl, int pad, bool mixed) {
+  return c->tc_halo && !mixed && pad >= 0 && pad <= 2 && Wl % 8 == 0 && Hl % 16 == 0;
+}
+static void halo_setup(TcFwdParams* p, int B, int Hl, int Wl, int pad, int tpg) {
+  p->halo = pad;
+  p->tpg = tpg;
+  p->a_box_bytes = halo_box_bytes(pad);
+  p->a_tile_bytes = halo_tile_bytes(pad);
+  p->bw = 8; p->bh = 16; p->bb = 1;
+  p->tiles_x = Wl / 8;
+  p->tiles_y = Hl / 16;
+  p->tiles_per_phase = B * p->tiles_x * p->tiles_y;
+}
+static int launch_tapconv(fg_ctx* c, const TcFwdParams& p, int BN, bool halo) {
+  dim3 grid(std::min(p.ntiles, c->sm_count));
+  if (halo) {
+    if (BN == 128) tapconv_tc_kernel<128, true><<<grid, 192, fwd_smem_halo<128>(p.halo), c->stream>>>(p);
+    else tapconv_tc_kernel<64, true><<<grid, 192, fwd_smem_halo<64>(p.halo), c->stream>>>(p);
+  } else {
+    if (BN == 128) tapconv_tc_kernel<128, false><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
+    else tapconv_tc_kernel<64, false><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
+  }
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+
 bool tc_conv_eligible(const ConvGeom& g) {
   int bw, bh, bb;
   const int Hl = g.H / g.ups, Wl = g.W / g.ups;
@@ -596,13 +696,17 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   const bool mixed = mixed_ok(c, x_hi, x_lo) && mixed_ok(c, w_hi, w_lo);
   if (mixed) FG_TRY(make_comb(c, 0, x_hi, x_lo, (int64_t)g.B * Hl * Wl, g.Cin, &x_lo));
   p.mixed = mixed ? 1 : 0;
-  FG_TRY(make_map4(&p.a_hi[0], x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
-  FG_TRY(make_map4(&p.a_lo[0], x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, mixed));
+  const int pad = mode == 0 ? (g.k - 1) / 2 : 1;  // the up2+5x5 modes only reach low-res offsets -1..1
+  const bool halo = halo_ok(c, Hl, Wl, pad, mixed);
+  if (halo) halo_setup(&p, g.B, Hl, Wl, pad, mode == 0 ? g.k * g.k : (mode == 1 ? 25 : 9));
+  const int abw = halo ? 8 + 2 * pad : p.bw, abh = halo ? 16 + 2 * pad : p.bh;
+  FG_TRY(make_map4(&p.a_hi[0], x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, abw, abh, p.bb));
+  FG_TRY(make_map4(&p.a_lo[0], x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, abw, abh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, mixed));
   // N tile: 128 unless halving it keeps the same number of waves on the 148 SMs (few-tile layers such as
   // D.C4's dgrad or the Linear layers): a BN=64 tile costs ~0.6 of a BN=128 tile
   int BN = g.Cout % 128 == 0 ? 128 : 64;
   if (BN == 128) {
-    const int mt = (mode == 0 ? 1 : 4) * (p.bb == 1 ? g.B * (Wl / p.bw) * (Hl / p.bh) : (g.B + p.bb - 1) / p.bb);
+    const int mt = (mode == 0 ? 1 : 4) * (p.bb == 1 ? g.B * (Wl / p.bw) * (Hl / p.bh) : (g.B + p.bb - 1) / p.bb);  // (same count for halo tiles)
     const int t128 = mt * (g.Cout / 128), t64 = mt * (g.Cout / 64);
     const int w128 = (t128 + c->sm_count - 1) / c->sm_count, w64 = (t64 + c->sm_count - 1) / c->sm_count;
     if (w64 * 6 < w128 * 10) BN = 64;
@@ -647,9 +751,11 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   p.kpt = g.Cin / 32;
   p.Cout = g.Cout;
   p.B = g.B; p.H = Hl; p.W = Wl;
-  p.tiles_x = Wl / p.bw;
-  p.tiles_y = Hl / p.bh;
-  p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
+  if (!halo) {
+    p.tiles_x = Wl / p.bw;
+    p.tiles_y = Hl / p.bh;
+    p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
+  }
   p.out = out;
   p.bias = bias;
   p.stats = stats;
@@ -659,11 +765,7 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   p.ntiles = p.tiles_per_phase * p.nphase * (g.Cout / BN);
   p.dbg = getenv("FG_TC_DBG") ? atoi(getenv("FG_TC_DBG")) : 0;
   p.chunk = tc_chunk(g.H * g.W > 1);  // Linear layers (1x1 images, K up to 16384) keep the short chunk
-  dim3 grid(std::min(p.ntiles, c->sm_count));
-  if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
-  else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
-  LAUNCH_CHECK(c);
-  return FG_OK;
+  return launch_tapconv(c, p, BN, halo);
 }
 
 // dgrad of an up2+5x5 conv straight to the LOW-RES input gradient (the 2x2 sum of the upsample backward is
@@ -682,12 +784,15 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
     FG_TRY(make_comb(c, 1, wd_hi, wd_lo, (int64_t)36 * g.Cin, Cy, &wd_lo));
   }
   p.mixed = mixed ? 1 : 0;
+  const bool halo = halo_ok(c, Hl, Wl, 1, mixed);
+  if (halo) halo_setup(&p, g.B, Hl, Wl, 1, 9);  // 4 groups (the output phases of dY) x 9 taps
+  const int abw = halo ? 10 : p.bw, abh = halo ? 18 : p.bh;
   for (int ph = 0; ph < 4; ++ph) {
     const int py = ph >> 1, px = ph & 1;
     const int64_t off = ((int64_t)py * g.W + px) * Cy;  // the pair tensor has the same bytes per pixel
     const int64_t sW = (int64_t)2 * Cy * 4, sH = (int64_t)2 * g.W * Cy * 4, sB = (int64_t)g.H * g.W * Cy * 4;
-    FG_TRY(make_map4(&p.a_hi[ph], dy_hi + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
-    FG_TRY(make_map4(&p.a_lo[ph], dy_lo + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, mixed));
+    FG_TRY(make_map4(&p.a_hi[ph], dy_hi + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, abw, abh, p.bb));
+    FG_TRY(make_map4(&p.a_lo[ph], dy_lo + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, abw, abh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, mixed));
   }
   const int BN = g.Cin % 128 == 0 ? 128 : 64;
   p.nphase = 1;
@@ -705,9 +810,11 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
   p.kpt = Cy / 32;
   p.Cout = g.Cin;
   p.B = g.B; p.H = Hl; p.W = Wl;
-  p.tiles_x = Wl / p.bw;
-  p.tiles_y = Hl / p.bh;
-  p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
+  if (!halo) {
+    p.tiles_x = Wl / p.bw;
+    p.tiles_y = Hl / p.bh;
+    p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
+  }
   p.out = out;
   p.bias = nullptr;
   p.out_H = Hl; p.out_W = Wl;
@@ -715,11 +822,7 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
   p.ntiles = p.tiles_per_phase * (g.Cin / BN);
   p.dbg = getenv("FG_TC_DBG") ? atoi(getenv("FG_TC_DBG")) : 0;
   p.chunk = tc_chunk(true);
-  dim3 grid(std::min(p.ntiles, c->sm_count));
-  if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
-  else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
-  LAUNCH_CHECK(c);
-  return FG_OK;
+  return launch_tapconv(c, p, BN, halo);
 }
 
 // wgrad.  x_hi/lo: [B][H/ups][W/ups][Cin]; dy_hi/lo: [B][H][W][Cout]; out (overwritten):

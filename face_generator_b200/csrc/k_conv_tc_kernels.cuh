@@ -39,10 +39,20 @@ __device__ __forceinline__ FwdTile fwd_decode(const TcFwdParams& p, int tile) {
 // ------------------------------------------------------------------------------------------------
 // tapconv: forward / dgrad.  Persistent: CTA i handles tiles i, i+gridDim.x, ...
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+// HALO = true ("haloed tile" operand feed, 16x16 / 32x32 images, k <= 5): the M tile is 8 pixels wide x 16 rows of ONE
+// image and, per 32-channel chunk, ONE TMA box of (8 + 2 pad) x (16 + 2 pad) pixels lands in shared memory (hi and lo);
+// the A operand of tap (dy, dx) is the shifted 128-row window { (yi + dy + pad) * pitch + xi + dx + pad } of that box --
+// the 128B-swizzle XOR is derived from the absolute shared-memory address, so a window that starts at any 128-byte
+// row is a valid K-major operand with SBO = pitch * 128 and base-offset 0 (tests/test_gpu_umma_window.py).  The k*k
+// taps thus share one activation load: 46 KB per 9 taps instead of 9 x 32 KB; only the weights still stream per tap
+// (-42 % bytes landed per MMA at BN = 128 -- the forward kernel sat on its operand-feed floor).
+// K-block order: (tap group sharing an activation view, channel chunk, tap).
+template <int BN, bool HALO>
 __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constant__ TcFwdParams p) {
   constexpr uint32_t kBBytes = BN * 128;
-  constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+  constexpr uint32_t kStageBytes = HALO ? 2 * kBBytes : 2 * kABytes + 2 * kBBytes;  // HALO: a stage holds the weights only
+  const uint32_t kAH = HALO ? p.a_tile_bytes : 0;                                  // one haloed activation tile (1 KB multiple)
+  const uint32_t kAReg = 4 * kAH;                                                  // 2 stages x {hi, lo} in front of the ring
   constexpr uint32_t kIdesc = make_idesc(128, BN, 0, 0);
   constexpr uint32_t kIdescBf = make_idesc_bf16(128, BN);
   // TMEM layout (all 512 columns): [0,256) a ring of kAcc buffers for the MAIN term hi*hi -- the MMA warp
@@ -54,13 +64,16 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   constexpr uint32_t kAcc = 256 / BN;
   constexpr uint32_t kCrossCol = 256;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_a + kAReg;  // the stage ring
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty = full + kStages;
   uint64_t* tmem_full = empty + kStages;      // [kAcc]
   uint64_t* tmem_empty = tmem_full + kAcc;    // [kAcc]
   uint64_t* cross_empty = tmem_empty + kAcc;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cross_empty + 2);
+  uint64_t* a_full = cross_empty + 2;         // [2] (HALO)
+  uint64_t* a_empty = a_full + 2;             // [2] (HALO)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
   float* stat_sm = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [2][4 warps][BN] (p.stats only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,6 +93,10 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
     }
     mbar_init(cross_empty + 0, 4);
     mbar_init(cross_empty + 1, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a_full + i, 1);
+      mbar_init(a_empty + i, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -87,15 +104,40 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int tpg = p.tpg;  // HALO: taps per group (= taps sharing one activation view)
 
   if (warp == 0) {
     if (lane == 0) {
       prefetch_tmap(&p.b_hi);
       prefetch_tmap(&p.b_lo);
-      uint32_t kbg = 0;
+      uint32_t kbg = 0, acg = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const FwdTile t = fwd_decode<BN>(p, tile);
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          if (HALO) {
+            const int per_grp = p.kpt * tpg;
+            const int grp = kb / per_grp, rem = kb - grp * per_grp;
+            const int kc = rem / tpg, tig = rem - kc * tpg;
+            const int ti = t.ph * p.ntaps + grp * tpg + tig;
+            if (tig == 0) {  // a new (activation view, channel chunk): one haloed box each for hi and lo
+              const uint32_t sa = acg & 1, ita = acg >> 1;
+              if (ita > 0) mbar_wait(a_empty + sa, (ita - 1) & 1);
+              const int am = p.amap[ti];
+              uint8_t* at = smem_a + sa * 2 * kAH;
+              mbar_expect_tx(a_full + sa, 2 * p.a_box_bytes);
+              tma_load_4d(at, &p.a_hi[am], a_full + sa, kc * 32, t.x0 - p.halo, t.y0 - p.halo, t.b0);
+              tma_load_4d(at + kAH, &p.a_lo[am], a_full + sa, kc * 32, t.x0 - p.halo, t.y0 - p.halo, t.b0);
+              ++acg;
+            }
+            const uint32_t s = kbg % kStages, it = kbg / kStages;
+            if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+            uint8_t* st = smem + s * kStageBytes;
+            mbar_expect_tx(full + s, kStageBytes);
+            const int wrow = p.widx[ti] * p.Cout + t.n0;
+            tma_load_2d(st, &p.b_hi, full + s, kc * 32, wrow);
+            tma_load_2d(st + kBBytes, &p.b_lo, full + s, kc * 32, wrow);
+            continue;
+          }
           const uint32_t s = kbg % kStages, it = kbg / kStages;
           if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
           const int tap = kb / p.kpt, c0 = (kb - tap * p.kpt) * 32;
@@ -119,8 +161,9 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t kbg = 0, cg = 0, tl = 0;
+      uint32_t kbg = 0, cg = 0, tl = 0, acm = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+        const FwdTile t = fwd_decode<BN>(p, tile);
         const uint32_t tcross = tmem_base + kCrossCol + (tl & 1) * BN;
         if (tl >= 2) mbar_wait(cross_empty + (tl & 1), ((tl >> 1) - 1) & 1);  // epilogue has read tile tl-2's cross block
         for (int ch = 0; ch < nchunks; ++ch, ++cg) {
@@ -131,12 +174,34 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
           const int nk = min(kChunk, nkb - ch * kChunk);
           for (int j = 0; j < nk; ++j, ++kbg) {
             const uint32_t s = kbg % kStages, it = kbg / kStages;
+            const uint32_t sa = smem_u32(smem + s * kStageBytes);
+            uint64_t a_hi, a_lo, b_hi, b_lo;
+            bool last_of_view = false;
+            uint32_t sav = 0;
+            if (HALO) {
+              const int kb = ch * kChunk + j;
+              const int per_grp = p.kpt * tpg;
+              const int grp = kb / per_grp, rem = kb - grp * per_grp;
+              const int tig = rem % tpg;
+              const int ti = t.ph * p.ntaps + grp * tpg + tig;
+              sav = acm & 1;
+              if (tig == 0) mbar_wait(a_full + sav, (acm >> 1) & 1);
+              last_of_view = tig == tpg - 1;
+              const uint32_t pitch = 8 + 2 * p.halo;
+              const uint32_t off = (uint32_t)((p.dy[ti] + p.halo) * (int)pitch + p.dx[ti] + p.halo) * 128;
+              const uint32_t ab = smem_u32(smem_a + sav * 2 * kAH) + off;
+              a_hi = make_desc(ab, 16, pitch * 128);  // shifted window: 8-row groups one image row apart
+              a_lo = make_desc(ab + kAH, 16, pitch * 128);
+              b_hi = make_desc(sa, 16, 1024);
+              b_lo = make_desc(sa + kBBytes, 16, 1024);
+            } else {
+              a_hi = make_desc(sa, 16, 1024);
+              a_lo = make_desc(sa + kABytes, 16, 1024);
+              b_hi = make_desc(sa + 2 * kABytes, 16, 1024);
+              b_lo = make_desc(sa + 2 * kABytes + kBBytes, 16, 1024);
+            }
             mbar_wait(full + s, it & 1);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + s * kStageBytes);
-            const uint64_t a_hi = make_desc(sa, 16, 1024), a_lo = make_desc(sa + kABytes, 16, 1024);
-            const uint64_t b_hi = make_desc(sa + 2 * kABytes, 16, 1024),
-                           b_lo = make_desc(sa + 2 * kABytes + kBBytes, 16, 1024);
             if (p.dbg & 1) {  // (dbg bit 0: experiment without MMAs)
             } else if (!p.mixed) {
 #pragma unroll
@@ -161,6 +226,10 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
               }
             }
             umma_commit(empty + s);
+            if (HALO && last_of_view) {  // every tap of this activation view has been issued: its tile may be refilled
+              umma_commit(a_empty + sav);
+              ++acm;
+            }
           }
           umma_commit(tmem_full + buf);
         }

@@ -142,6 +142,7 @@ SYMBOLS = {
     "fg_memcpy": (_I, [_P, _P, _P, _SZ]),
     "fg_kernel_launches": (_L, [_P]),
     "fg_debug_tensor": (_L, [_P, C.c_char_p, _P, _L]),
+    "fg_debug_umma_window": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "fg_bench_tf32_peak": (_I, [_P, _I, C.POINTER(C.c_double)]),
     "fg_event_record": (_I, [_P, _I]),
     "fg_event_elapsed_ms": (_I, [_P, _I, _I, C.POINTER(C.c_double)]),

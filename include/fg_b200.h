@@ -341,6 +341,10 @@ int fg_timing_enable(fg_ctx* ctx, int on);
 /* tensor-pipe probe for the roofline: TFLOP/s of back-to-back tcgen05.mma.kind::tf32 (M=128,N=256,K=8, operands
  * resident in shared memory) on all SMs, best of 5 event-timed launches of `iters` x 4 MMAs per SM            */
 int fg_bench_tf32_peak(fg_ctx* ctx, int iters, double* tflops);
+/* hardware probe used by tests/test_gpu_umma_window.py: D = A * I where A is the 128-row window
+ * {(yi+dy)*16 + xi+dx} of a [288][32] fp32 tile (DEVICE pointers; x values must be TF32-exact)   */
+int fg_debug_umma_window(fg_ctx* ctx, const float* x_dev, const float* ident_dev, int dy, int dx, int use_base_offset,
+                         float* out_dev);
 int fg_timing_get(fg_ctx* ctx, const char* name, double* ms_total, int64_t* launches);
 
 #ifdef __cplusplus
