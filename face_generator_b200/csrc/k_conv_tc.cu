@@ -54,6 +54,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// pure spin (mbarrier.test_wait never suspends the thread): for the single-thread producer / MMA-issue roles, where the
+// wake-up latency of a suspended try_wait sits on the critical path of the stage ring
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -156,6 +171,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // D=f32, A=B=bf16 (F32F16Format: 0 F16, 1 BF16, 2 TF32), both K-major; K = 16 per instruction
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// one lane of a fully active warp (the compiler knows the predicate selects exactly one lane, so code under it can
+// keep its operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 constexpr int kStages = 3;
@@ -424,15 +451,17 @@ inline bool mixed_ok(const fg_ctx* c, const float* a, const float* b) {
 // TF32 peak the 3xTF32 convolutions are normalised by (MEASURED_PEAKS.json only holds a bf16 figure).
 // ------------------------------------------------------------------------------------------------
 template <int N, int NACC>
-__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, int commit_every, int vary) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr uint32_t kA = 128 * 128, kB = 256 * 128;  // 128 x 32 fp32 and 256 x 32 fp32, SWIZZLE_128B K-major
   uint64_t* done = reinterpret_cast<uint64_t*>(smem + kA + kB);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* dummy = done + 1;  // target of the intermediate commits (nobody waits on it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
   for (uint32_t i = threadIdx.x; i < (kA + kB) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
   if (threadIdx.x == 0) {
     mbar_init(done, 1);
+    mbar_init(dummy, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA
@@ -447,8 +476,10 @@ __global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
     const uint64_t a = make_desc(sa, 16, 1024), b = make_desc(sa + kA, 16, 1024);
     for (int i = 0; i < iters; ++i) {
       const uint32_t acc = tmem_base + (uint32_t)(i % NACC) * N;  // NACC independent accumulators
+      const uint64_t vo = vary ? (uint64_t)((i % 3) * 64) : 0;    // vary: walk the operand start by 1 KB steps
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_tf32(acc, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), kIdesc, 1);
+      for (int k = 0; k < 4; ++k) umma_tf32(acc, a + vo + (uint64_t)(k * 2), b + vo + (uint64_t)(k * 2), kIdesc, 1);
+      if (commit_every > 0 && (i + 1) % commit_every == 0) umma_commit(dummy);  // experiment: a commit every 4*commit_every MMAs
     }
     umma_commit(done);
     mbar_wait(done, 0);
@@ -533,6 +564,8 @@ int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops) {
   constexpr int kSmem = 128 * 128 + 256 * 128 + 64 + 1024;
   const char* env = getenv("FG_TF32_PROBE_N");
   const int N = env && atoi(env) == 128 ? 128 : 256;
+  const int commit_every = getenv("FG_TF32_PROBE_COMMIT") ? atoi(getenv("FG_TF32_PROBE_COMMIT")) : 0;
+  const int vary = getenv("FG_TF32_PROBE_VARY") ? atoi(getenv("FG_TF32_PROBE_VARY")) : 0;
   auto kern = N == 128 ? tf32_peak_kernel<128, 4> : tf32_peak_kernel<256, 2>;
   FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   cudaEvent_t e0, e1;
@@ -541,7 +574,7 @@ int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops) {
   float best = 1e30f;
   for (int r = 0; r < reps + 1; ++r) {  // first launch = warm-up
     FG_CUDA(cudaEventRecord(e0, c->stream));
-    kern<<<c->sm_count, 128, kSmem, c->stream>>>(iters);
+    kern<<<c->sm_count, 128, kSmem, c->stream>>>(iters, commit_every, vary);
     LAUNCH_CHECK(c);
     FG_CUDA(cudaEventRecord(e1, c->stream));
     FG_CUDA(cudaEventSynchronize(e1));

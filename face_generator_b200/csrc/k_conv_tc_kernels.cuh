@@ -47,6 +47,7 @@ __device__ __forceinline__ FwdTile fwd_decode(const TcFwdParams& p, int tile) {
 // taps thus share one activation load: 46 KB per 9 taps instead of 9 x 32 KB; only the weights still stream per tap
 // (-42 % bytes landed per MMA at BN = 128 -- the forward kernel sat on its operand-feed floor).
 // K-block order: (tap group sharing an activation view, channel chunk, tap).
+#define MBW(bar, par) do { if (p.dbg & 32) mbar_wait((bar), (par)); else mbar_wait_spin((bar), (par)); } while (0)
 template <int BN, bool HALO>
 __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constant__ TcFwdParams p) {
   constexpr uint32_t kBBytes = BN * 128;
@@ -81,6 +82,12 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   const int kChunk = p.chunk;
   const int nchunks = (nkb + kChunk - 1) / kChunk;
   const int ntiles = p.ntiles;
+  long long dbg_c0 = 0;
+  unsigned long long dbg_t0 = 0;
+  if ((p.dbg & 128) && threadIdx.x == 0) {  // experiment: effective SM clock during this launch
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -103,7 +110,10 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // all 512 columns are allocated (one CTA per SM), so the allocation can only start at column 0 / lane 0: using the
+  // literal keeps every TMEM address in uniform registers
+  if (*tmem_slot != 0) __trap();
+  constexpr uint32_t tmem_base = 0;
   const int tpg = p.tpg;  // HALO: taps per group (= taps sharing one activation view)
 
   if (warp == 0) {
@@ -121,17 +131,25 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
             const int ti = t.ph * p.ntaps + grp * tpg + tig;
             if (tig == 0) {  // a new (activation view, channel chunk): one haloed box each for hi and lo
               const uint32_t sa = acg & 1, ita = acg >> 1;
-              if (ita > 0) mbar_wait(a_empty + sa, (ita - 1) & 1);
+              if (ita > 0) MBW(a_empty + sa, (ita - 1) & 1);
               const int am = p.amap[ti];
               uint8_t* at = smem_a + sa * 2 * kAH;
-              mbar_expect_tx(a_full + sa, 2 * p.a_box_bytes);
-              tma_load_4d(at, &p.a_hi[am], a_full + sa, kc * 32, t.x0 - p.halo, t.y0 - p.halo, t.b0);
-              tma_load_4d(at + kAH, &p.a_lo[am], a_full + sa, kc * 32, t.x0 - p.halo, t.y0 - p.halo, t.b0);
+              if (p.dbg & 2) {
+                mbar_arrive(a_full + sa);
+              } else {
+                mbar_expect_tx(a_full + sa, 2 * p.a_box_bytes);
+                tma_load_4d(at, &p.a_hi[am], a_full + sa, kc * 32, t.x0 - p.halo, t.y0 - p.halo, t.b0);
+                tma_load_4d(at + kAH, &p.a_lo[am], a_full + sa, kc * 32, t.x0 - p.halo, t.y0 - p.halo, t.b0);
+              }
               ++acg;
             }
             const uint32_t s = kbg % kStages, it = kbg / kStages;
-            if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+            if (it > 0) MBW(empty + s, (it - 1) & 1);
             uint8_t* st = smem + s * kStageBytes;
+            if (p.dbg & 2) {  // experiment: no data movement, only the barrier protocol
+              mbar_arrive(full + s);
+              continue;
+            }
             mbar_expect_tx(full + s, kStageBytes);
             const int wrow = p.widx[ti] * p.Cout + t.n0;
             tma_load_2d(st, &p.b_hi, full + s, kc * 32, wrow);
@@ -139,7 +157,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
             continue;
           }
           const uint32_t s = kbg % kStages, it = kbg / kStages;
-          if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+          if (it > 0) MBW(empty + s, (it - 1) & 1);
           const int tap = kb / p.kpt, c0 = (kb - tap * p.kpt) * 32;
           const int ti = t.ph * p.ntaps + tap;
           const int am = p.amap[ti];
@@ -160,21 +178,25 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issue.  The WHOLE warp runs the (warp-uniform) control flow and the barrier waits; one elected lane issues the
+    // tcgen05 instructions.  Under `if (lane == 0)` the compiler could not prove the operands uniform and wrapped every
+    // UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: ~14 instructions and ~107 clocks of issue per 64-clock MMA
+    // (measured with the data movement switched off) -- the tensor pipe idled 40 % of the time waiting for its one thread.
+    {
       uint32_t kbg = 0, cg = 0, tl = 0, acm = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
         const FwdTile t = fwd_decode<BN>(p, tile);
         const uint32_t tcross = tmem_base + kCrossCol + (tl & 1) * BN;
-        if (tl >= 2) mbar_wait(cross_empty + (tl & 1), ((tl >> 1) - 1) & 1);  // epilogue has read tile tl-2's cross block
+        if (tl >= 2) MBW(cross_empty + (tl & 1), ((tl >> 1) - 1) & 1);  // epilogue has read tile tl-2's cross block
         for (int ch = 0; ch < nchunks; ++ch, ++cg) {
           const uint32_t buf = cg % kAcc, use = cg / kAcc;
-          if (use > 0) mbar_wait(tmem_empty + buf, (use - 1) & 1);
+          if (use > 0) MBW(tmem_empty + buf, (use - 1) & 1);
           tc_fence_after();
           const uint32_t tacc = tmem_base + buf * BN;
           const int nk = min(kChunk, nkb - ch * kChunk);
           for (int j = 0; j < nk; ++j, ++kbg) {
             const uint32_t s = kbg % kStages, it = kbg / kStages;
-            const uint32_t sa = smem_u32(smem + s * kStageBytes);
+            const uint32_t sa = smem_u32(smem + ((p.dbg & 16) ? 0 : s) * kStageBytes);  // dbg 16: constant operand addresses
             uint64_t a_hi, a_lo, b_hi, b_lo;
             bool last_of_view = false;
             uint32_t sav = 0;
@@ -185,10 +207,11 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
               const int tig = rem % tpg;
               const int ti = t.ph * p.ntaps + grp * tpg + tig;
               sav = acm & 1;
-              if (tig == 0) mbar_wait(a_full + sav, (acm >> 1) & 1);
+              if (tig == 0) MBW(a_full + sav, (acm >> 1) & 1);
               last_of_view = tig == tpg - 1;
               const uint32_t pitch = 8 + 2 * p.halo;
-              const uint32_t off = (uint32_t)((p.dy[ti] + p.halo) * (int)pitch + p.dx[ti] + p.halo) * 128;
+              uint32_t off = (uint32_t)((p.dy[ti] + p.halo) * (int)pitch + p.dx[ti] + p.halo) * 128;
+              if (p.dbg & 4) off = 0;  // experiment (wrong results): every window 1024-aligned
               const uint32_t ab = smem_u32(smem_a + sav * 2 * kAH) + off;
               a_hi = make_desc(ab, 16, pitch * 128);  // shifted window: 8-row groups one image row apart
               a_lo = make_desc(ab + kAH, 16, pitch * 128);
@@ -200,10 +223,11 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
               b_hi = make_desc(sa + 2 * kABytes, 16, 1024);
               b_lo = make_desc(sa + 2 * kABytes + kBBytes, 16, 1024);
             }
-            mbar_wait(full + s, it & 1);
+            MBW(full + s, it & 1);
             tc_fence_after();
-            if (p.dbg & 1) {  // (dbg bit 0: experiment without MMAs)
-            } else if (!p.mixed) {
+            if (!elect_one()) {
+            } else if (p.dbg & 1) {  // (dbg bit 0: experiment without MMAs)
+            } else if (!p.mixed && (p.dbg & 64)) {  // (round-1 order: the accumulator alternates with every instruction)
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 fp32 of K) in the 16B-unit start-address field
@@ -211,6 +235,14 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
                 umma_tf32(tcross, a_hi + ko, b_lo + ko, kIdesc, (ch | j | k) != 0);  // cross terms -> per-tile block
                 umma_tf32(tcross, a_lo + ko, b_hi + ko, kIdesc, 1);
               }
+            } else if (!p.mixed) {
+              // the 4 K slices of one product back to back: the accumulator changes twice per K block instead of 8 times
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(tacc, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), kIdesc, (j | k) != 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(tcross, a_hi + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), kIdesc, (ch | j | k) != 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(tcross, a_lo + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), kIdesc, 1);
             } else {
               // main term in TF32 (exact products); the two cross terms are ~2^-12 of the result, so BF16 inputs
               // (rel. 2^-9) keep them to ~2^-20: kind::f16 runs at twice the TF32 rate => 4 + 2 + 2 half-cost MMAs.
@@ -225,13 +257,15 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
                 umma_bf16(tcross, a_lo + 4 + ko, b_lo + ko, kIdescBf, 1);                  // bf16(a_lo) . bf16(b_hi)
               }
             }
-            umma_commit(empty + s);
+            if (elect_one()) umma_commit(empty + s);
             if (HALO && last_of_view) {  // every tap of this activation view has been issued: its tile may be refilled
-              umma_commit(a_empty + sav);
+              if (elect_one()) umma_commit(a_empty + sav);
               ++acm;
             }
+            __syncwarp();
           }
-          umma_commit(tmem_full + buf);
+          if (elect_one()) umma_commit(tmem_full + buf);
+          __syncwarp();
         }
       }
     }
@@ -250,15 +284,17 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
         const uint32_t buf = cg % kAcc, use = cg / kAcc;
         mbar_wait(tmem_full + buf, use & 1);
         tc_fence_after();
+        if (!(p.dbg & 8)) {  // dbg 8: experiment without the promotion's TMEM reads
 #pragma unroll
-        for (int j = 0; j < BN / 32; j += 2) {
-          uint32_t va[32], vb[32];
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32);
-          tmem_ld_32x32_x2(ta, ta + 32, va, vb);
+          for (int j = 0; j < BN / 32; j += 2) {
+            uint32_t va[32], vb[32];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(j * 32);
+            tmem_ld_32x32_x2(ta, ta + 32, va, vb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            acc[j * 32 + i] += __uint_as_float(va[i]);
-            acc[j * 32 + 32 + i] += __uint_as_float(vb[i]);
+            for (int i = 0; i < 32; ++i) {
+              acc[j * 32 + i] += __uint_as_float(va[i]);
+              acc[j * 32 + 32 + i] += __uint_as_float(vb[i]);
+            }
           }
         }
         tc_fence_before();
@@ -339,8 +375,15 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if ((p.dbg & 128) && threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    printf("tapconv<%d,%d> block 0: %lld cycles in %llu ns = %.3f GHz, %d tiles x %d kblocks\n", BN, (int)HALO, clock64() - dbg_c0,
+           t1 - dbg_t0, (double)(clock64() - dbg_c0) / (double)(t1 - dbg_t0), (ntiles + (int)gridDim.x - 1) / (int)gridDim.x, nkb);
+  }
 }
 
+#undef MBW
 // ------------------------------------------------------------------------------------------------
 // wgrad: D[n (M=128 of Cout)][c (BN of Cin)] += sum over a pixel range of dY[p][n] * X[p+off][c]
 // grid: x = tile-tap, y = mtile * ntiles_n + ntile, z = K split.  Output accumulated with atomics.
@@ -386,7 +429,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  if (*tmem_slot != 0) __trap();  // the whole TMEM is allocated: base 0 (keeps TMEM addresses uniform, see tapconv)
+  constexpr uint32_t tmem_base = 0;
 
   if (nkb > 0) {
     if (warp == 0) {
@@ -419,7 +463,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {  // whole warp, one elected lane issues (see tapconv_tc_kernel)
         int i = 0;
         for (int ch = 0; ch < nchunks; ++ch) {
           const uint32_t buf = ch & 1, use = ch >> 1;
@@ -438,16 +482,20 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
             // SBO = distance between 4-pixel groups (512 B).
             const uint64_t a_hi = make_desc(sa, kBox, 512, 1), a_lo = make_desc(sa + kAB, kBox, 512, 1);
             const uint64_t b_hi = make_desc(sa + 2 * kAB, kBox, 512, 1), b_lo = make_desc(sa + 2 * kAB + kBB, kBox, 512, 1);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ko = (uint64_t)(k * 64);  // +1024 bytes = next 8 pixels
-              umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, (j | k) != 0);        // main term -> ring buffer
-              umma_tf32(tcross, a_hi + ko, b_lo + ko, kIdesc, (ch | j | k) != 0);  // cross terms stay in TMEM
-              umma_tf32(tcross, a_lo + ko, b_hi + ko, kIdesc, 1);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ko = (uint64_t)(k * 64);  // +1024 bytes = next 8 pixels
+                umma_tf32(tacc, a_hi + ko, b_hi + ko, kIdesc, (j | k) != 0);        // main term -> ring buffer
+                umma_tf32(tcross, a_hi + ko, b_lo + ko, kIdesc, (ch | j | k) != 0);  // cross terms stay in TMEM
+                umma_tf32(tcross, a_lo + ko, b_hi + ko, kIdesc, 1);
+              }
+              umma_commit(empty + s);
             }
-            umma_commit(empty + s);
+            __syncwarp();
           }
-          umma_commit(tmem_full + buf);
+          if (elect_one()) umma_commit(tmem_full + buf);
+          __syncwarp();
         }
       }
     } else {
