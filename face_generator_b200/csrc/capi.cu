@@ -161,7 +161,7 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
     c->tc_mixed = (int)v;
     return FG_OK;
   }
-  if (!strcmp(key, "tc_halo")) {  // 1 (default): haloed-tile operand feed where the geometry allows it; 0: one TMA box per tap
+  if (!strcmp(key, "tc_halo")) {  // 1: haloed-tile operand feed where the geometry allows it (experiment); 0 (default): one TMA box per tap
     c->tc_halo = v != 0;
     return FG_OK;
   }

@@ -451,14 +451,16 @@ inline bool mixed_ok(const fg_ctx* c, const float* a, const float* b) {
 // TF32 peak the 3xTF32 convolutions are normalised by (MEASURED_PEAKS.json only holds a bf16 figure).
 // ------------------------------------------------------------------------------------------------
 template <int N, int NACC>
-__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, int commit_every, int vary) {
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, int mode) {
+  // mode bits (experiments): 1 = a tcgen05.commit after every 4 MMAs; 2 = operands cycle through a 3 x 64 KB footprint
+  // like the stage ring of the convolution kernels; 4 = the accumulator changes with every instruction
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr uint32_t kA = 128 * 128, kB = 256 * 128;  // 128 x 32 fp32 and 256 x 32 fp32, SWIZZLE_128B K-major
-  uint64_t* done = reinterpret_cast<uint64_t*>(smem + kA + kB);
+  constexpr uint32_t kFoot = 3 * 65536;
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + kFoot);
   uint64_t* dummy = done + 1;  // target of the intermediate commits (nobody waits on it)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
-  for (uint32_t i = threadIdx.x; i < (kA + kB) / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  for (uint32_t i = threadIdx.x; i < kFoot / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
   if (threadIdx.x == 0) {
     mbar_init(done, 1);
     mbar_init(dummy, 1);
@@ -469,19 +471,24 @@ __global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, int commit
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) {
+  if (*tmem_slot != 0) __trap();
+  constexpr uint32_t tmem_base = 0;
+  if (threadIdx.x < 32) {
     constexpr uint32_t kIdesc = make_idesc(128, N, 0, 0);
     const uint32_t sa = smem_u32(smem);
-    const uint64_t a = make_desc(sa, 16, 1024), b = make_desc(sa + kA, 16, 1024);
     for (int i = 0; i < iters; ++i) {
+      const uint32_t st = (mode & 2) ? (uint32_t)(i % 3) * 65536 : 0;
+      const uint64_t a = make_desc(sa + st, 16, 1024), b = make_desc(sa + st + 16384, 16, 1024);
       const uint32_t acc = tmem_base + (uint32_t)(i % NACC) * N;  // NACC independent accumulators
-      const uint64_t vo = vary ? (uint64_t)((i % 3) * 64) : 0;    // vary: walk the operand start by 1 KB steps
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_tf32(acc, a + vo + (uint64_t)(k * 2), b + vo + (uint64_t)(k * 2), kIdesc, 1);
-      if (commit_every > 0 && (i + 1) % commit_every == 0) umma_commit(dummy);  // experiment: a commit every 4*commit_every MMAs
+        for (int k = 0; k < 4; ++k)
+          umma_tf32((mode & 4) ? tmem_base + (uint32_t)((i + k) % NACC) * N : acc, a + (uint64_t)(k * 2), b + (uint64_t)(k * 2), kIdesc, 1);
+        if (mode & 1) umma_commit(dummy);
+      }
+      __syncwarp();
     }
-    umma_commit(done);
+    if (elect_one()) umma_commit(done);
     mbar_wait(done, 0);
   }
   tc_fence_before();
@@ -561,11 +568,10 @@ int tc_umma_window_probe(fg_ctx* c, const float* x, const float* ident, int dy, 
 // FG_TF32_PROBE_N=128 probes the N=128 instruction shape the convolution kernels issue (operand reads from shared
 // memory: 8 KB per 64-cycle MMA = the full 128 B/clk of one SM; N=256: 12 KB per 128 cycles)
 int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops) {
-  constexpr int kSmem = 128 * 128 + 256 * 128 + 64 + 1024;
+  constexpr int kSmem = 3 * 65536 + 64 + 1024;
   const char* env = getenv("FG_TF32_PROBE_N");
   const int N = env && atoi(env) == 128 ? 128 : 256;
-  const int commit_every = getenv("FG_TF32_PROBE_COMMIT") ? atoi(getenv("FG_TF32_PROBE_COMMIT")) : 0;
-  const int vary = getenv("FG_TF32_PROBE_VARY") ? atoi(getenv("FG_TF32_PROBE_VARY")) : 0;
+  const int mode = getenv("FG_TF32_PROBE_MODE") ? atoi(getenv("FG_TF32_PROBE_MODE")) : 0;
   auto kern = N == 128 ? tf32_peak_kernel<128, 4> : tf32_peak_kernel<256, 2>;
   FG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   cudaEvent_t e0, e1;
@@ -574,7 +580,7 @@ int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops) {
   float best = 1e30f;
   for (int r = 0; r < reps + 1; ++r) {  // first launch = warm-up
     FG_CUDA(cudaEventRecord(e0, c->stream));
-    kern<<<c->sm_count, 128, kSmem, c->stream>>>(iters, commit_every, vary);
+    kern<<<c->sm_count, 128, kSmem, c->stream>>>(iters, mode);
     LAUNCH_CHECK(c);
     FG_CUDA(cudaEventRecord(e1, c->stream));
     FG_CUDA(cudaEventSynchronize(e1));
@@ -651,21 +657,22 @@ int tc_combine_collapsed_wgrad(fg_ctx* c, const float* G, float* dW, int N, int 
 }
 
 // K-blocks (32 channels of one tap) accumulated in TMEM before the epilogue promotes them into fp32 registers.
-// The truncation drift of a TMEM accumulator grows with the length of the run: 4 keeps the
-// pixel-long reductions of wgrad (and of the Linear layers) at ~1e-6.  Forward/dgrad can be set separately
-// (FG_TC_CHUNK_FWD): 8 was measured at +1 % step throughput (38 659 vs 38 282 img/s) with twice the drift, which is
-// not worth the margin, so both default to 4.
+// The truncation drift of a TMEM accumulator grows with the length of the run, the hand-over
+// of an accumulator buffer costs the MMA warp a completion round trip (~1 us: commit -> epilogue -> release), so the
+// chunk is a trade: convolution forward / dgrad 12 (measured at batch 256: chunk 4 / 8 / 12 / 16 -> 41.2 / 42.6 / 42.9 /
+// 43.0 k img/s, every isolated launch still <= 1e-5 of fp64 at all four), wgrad and the Linear layers (K = pixels
+// resp. up to 16384 features) 8 resp. 4.  FG_TC_CHUNK / FG_TC_CHUNK_FWD override for experiments.
 static int tc_chunk(bool forward_type = false) {
   static int v[2] = {-1, -1};
   if (v[0] < 0) {
     const char* e = getenv("FG_TC_CHUNK");
-    v[0] = e ? atoi(e) : 4;
-    if (v[0] < 1) v[0] = 1;
+    v[0] = e ? atoi(e) : 0;
     const char* f = getenv("FG_TC_CHUNK_FWD");
     v[1] = f ? atoi(f) : v[0];
-    if (v[1] < 1) v[1] = 1;
   }
-  return v[forward_type ? 1 : 0];
+  const int d = forward_type ? 12 : 4;
+  const int x = v[forward_type ? 1 : 0];
+  return x >= 1 ? x : d;
 }
 
 // haloed-tile feed (tapconv_tc_kernel<BN, true>): 8 x 16 pixel tiles of one image, all taps within +-pad <= 2
@@ -912,7 +919,7 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
   p.kb_per_split = (p.kblocks + splits - 1) / splits;
   splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
   p.out = out;
-  p.chunk = tc_chunk();
+  p.chunk = tc_chunk() == 4 && !getenv("FG_TC_CHUNK") ? ((int64_t)g.H * g.W > 1 ? 8 : 4) : tc_chunk();  // wgrad of convolutions 8, of Linear layers 4
   FG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)ntt * g.Cout * g.Cin, c->stream));
   dim3 grid(ntt, (g.Cout / 128) * (g.Cin / BN), splits);
   if (BN == 128) wgrad_tc_kernel<128><<<grid, 192, wg_smem<128>(), c->stream>>>(p);

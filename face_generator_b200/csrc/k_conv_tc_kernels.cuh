@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
             continue;
           }
           const uint32_t s = kbg % kStages, it = kbg / kStages;
-          if (it > 0) MBW(empty + s, (it - 1) & 1);
+          if (it > 0 && !(p.dbg & 512)) MBW(empty + s, (it - 1) & 1);  // dbg 512 (with 2): stages always "full"
           const int tap = kb / p.kpt, c0 = (kb - tap * p.kpt) * 32;
           const int ti = t.ph * p.ntaps + tap;
           const int am = p.amap[ti];
@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
               b_lo = make_desc(sa + 2 * kABytes + kBBytes, 16, 1024);
             }
             MBW(full + s, it & 1);
-            tc_fence_after();
+            // (no tcgen05 fence here: the stage was filled by TMA through the mbarrier's complete_tx, which the wait
+            // acquires; a fence::after_thread_sync per K block is only needed where TMEM changes hands, see above)
+            if (p.dbg & 256) tc_fence_after();
             if (!elect_one()) {
             } else if (p.dbg & 1) {  // (dbg bit 0: experiment without MMAs)
             } else if (!p.mixed && (p.dbg & 64)) {  // (round-1 order: the accumulator alternates with every instruction)
