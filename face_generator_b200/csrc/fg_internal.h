@@ -158,6 +158,9 @@ struct fg_ctx {
   // tcgen05 path: TF32 hi/lo splits of activations / gradients / packed weights (k_conv_tc.cu)
   struct TcBufs {
     float *G_h0_hi = nullptr, *G_h0_lo = nullptr, *G_h1_hi = nullptr, *G_h1_lo = nullptr;  // conv inputs (fwd -> wgrad)
+    // G.L1 (nn.Linear 100 -> 8192, models.lua:59) as a 1x1 convolution with K padded 100 -> 128: zero-padded noise
+    // [B][128] and its split, packed weights [8192'][128] (rows permuted for the View) and their split
+    float *G_xpad = nullptr, *G_x_hi = nullptr, *G_x_lo = nullptr, *G_L1pad = nullptr, *G_L1w_hi = nullptr, *G_L1w_lo = nullptr;
     float *dy_hi = nullptr, *dy_lo = nullptr;                                             // current dY (dgrad + wgrad)
     float *G_Wf_hi[2] = {nullptr, nullptr}, *G_Wf_lo[2] = {nullptr, nullptr};  // C1,C2 collapsed fwd [36][n][c]
     float *G_Wd_hi[2] = {nullptr, nullptr}, *G_Wd_lo[2] = {nullptr, nullptr};  // collapsed dgrad [36][c][n]
@@ -225,14 +228,17 @@ int k_bn_prelu_bwd_reduce(fg_ctx* c, const float* dh, const float* z, const floa
 int k_bn_bwd_finalize(fg_ctx* c, double* acc2C, float* mg2C, float* dgamma, float* dbeta, int64_t P, int C);
 int k_bn_prelu_bwd_apply(fg_ctx* c, const float* dh, const float* z, const float* mean, const float* istd,
                          const float* gamma, const float* beta, const float* slope, const float* mg2C, float* dz,
-                         int B, int H, int W, int C, int pool, float* hi = nullptr, float* lo = nullptr);
+                         int B, int H, int W, int C, int pool, float* hi = nullptr, float* lo = nullptr,
+                         float* dbias = nullptr);  // dbias: += column sums of dz (bias gradient of the conv in front)
 int k_sigmoid_fwd(fg_ctx* c, const float* z, float* y, int64_t n);
 int k_sigmoid_bwd(fg_ctx* c, const float* dy, const float* y, float* dz, int64_t n);
 int k_masks_generate(fg_ctx* c, float* masks, int B, uint64_t seed, float p_spatial, float p_drop);
+// hi / lo (optional): also emit the TF32 split of the result (16-byte aligned buffers of the output's size)
 int k_d_act_pool_fwd(fg_ctx* c, const float* z, const float* slope, const float* masks, int moff, float eval_scale,
-                     float* p, int B, int H, int W, int C);
+                     float* p, int B, int H, int W, int C, float* hi = nullptr, float* lo = nullptr);
 int k_d_act_pool_bwd(fg_ctx* c, const float* dp, const float* z, const float* slope, const float* masks, int moff,
-                     float eval_scale, float* dz, float* dslope, int B, int H, int W, int C);
+                     float eval_scale, float* dz, float* dslope, int B, int H, int W, int C, float* hi = nullptr,
+                     float* lo = nullptr, float* dbias = nullptr);  // dbias: += column sums of dz (conv bias gradient)
 int k_lin_act_drop_fwd(fg_ctx* c, const float* z, const float* slope, const float* masks, int moff, float scale,
                        float* h, int B, int N);
 int k_lin_act_drop_bwd(fg_ctx* c, const float* dh, const float* z, const float* slope, const float* masks, int moff,

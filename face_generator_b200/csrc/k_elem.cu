@@ -558,7 +558,13 @@ __global__ void bn_prelu_bwd_apply4_kernel(const float* __restrict__ dh, const f
                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                            const float* __restrict__ slope, const float* __restrict__ mg,
                                            float* __restrict__ dz, float* __restrict__ hi, float* __restrict__ lo,
-                                           int64_t n4, int C) {
+                                           float* __restrict__ dbias, int64_t n4, int C) {
+  // dbias (optional): += column sums of dz = the gradient of the convolution bias in front of the BatchNorm.  The grid
+  // stride is a multiple of C/4, so a thread always sees the same 4 channels: thread-local sums -> shared -> global
+  __shared__ float bsum[1024];
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (dbias)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) bsum[i] = 0.f;
   const bool act = slope != nullptr;
   const float a = act ? *slope : 1.f;
   const float4* dh4 = reinterpret_cast<const float4*>(dh);
@@ -584,6 +590,7 @@ __global__ void bn_prelu_bwd_apply4_kernel(const float* __restrict__ dh, const f
       o[j] = ga * is * (g - mg[ch + j] - xh * mg[C + ch + j]);
     }
     dz4[i] = make_float4(o[0], o[1], o[2], o[3]);
+    bs[0] += o[0]; bs[1] += o[1]; bs[2] += o[2]; bs[3] += o[3];
     if (hi) {  // TF32 hi/lo split of dz for the tensor-core dgrad / wgrad, written by the producer
       float h[4];
 #pragma unroll
@@ -592,14 +599,22 @@ __global__ void bn_prelu_bwd_apply4_kernel(const float* __restrict__ dh, const f
       lo4[i] = make_float4(o[0] - h[0], o[1] - h[1], o[2] - h[2], o[3] - h[3]);
     }
   }
+  if (dbias) {
+    __syncthreads();
+    const int ch = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) % C4) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(bsum + ch + j, bs[j]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, bsum[i]);
+  }
 }
 int k_bn_prelu_bwd_apply(fg_ctx* c, const float* dh, const float* z, const float* mean, const float* istd,
                          const float* gamma, const float* beta, const float* slope, const float* mg, float* dz, int B,
-                         int H, int W, int C, int pool, float* hi, float* lo) {
+                         int H, int W, int C, int pool, float* hi, float* lo, float* dbias) {
   const int64_t n = (int64_t)B * H * W * C;
-  if (!pool && C % 4 == 0) {
+  if (!pool && C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0) {
     bn_prelu_bwd_apply4_kernel<<<grid_for(n / 4, 256), 256, 0, c->stream>>>(dh, z, mean, istd, gamma, beta, slope, mg, dz,
-                                                                           hi, lo, n / 4, C);
+                                                                           hi, lo, dbias, n / 4, C);
     LAUNCH_CHECK(c);
     return FG_OK;
   }
@@ -610,6 +625,7 @@ int k_bn_prelu_bwd_apply(fg_ctx* c, const float* dh, const float* z, const float
   bn_prelu_bwd_apply_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(dh, z, mean, istd, gamma, beta, slope, mg, dz, B, H,
                                                                     W, C, pool);
   LAUNCH_CHECK(c);
+  if (dbias) return k_colsum_add(c, dz, dbias, (int64_t)B * H * W, C, 0, 0);  // not fused on this path
   return FG_OK;
 }
 
@@ -678,9 +694,20 @@ __device__ __forceinline__ float4 prelu4(float4 v, float a) {
   v.w = v.w > 0.f ? v.w : a * v.w;
   return v;
 }
+// TF32 hi/lo split of a float4 (hi = mantissa rounded to 10 bits, lo = exact remainder): emitted by the producers of
+// the tensor-core operands so that no separate split pass reads the tensor again
+__device__ __forceinline__ void split4(const float4& o, float4* hi, float4* lo, uint32_t i) {
+  float4 h;
+  h.x = __uint_as_float((__float_as_uint(o.x) + 0x1000u) & 0xFFFFE000u);
+  h.y = __uint_as_float((__float_as_uint(o.y) + 0x1000u) & 0xFFFFE000u);
+  h.z = __uint_as_float((__float_as_uint(o.z) + 0x1000u) & 0xFFFFE000u);
+  h.w = __uint_as_float((__float_as_uint(o.w) + 0x1000u) & 0xFFFFE000u);
+  hi[i] = h;
+  lo[i] = make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);
+}
 __global__ void d_act_pool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ slope,
                                       const float* __restrict__ masks, int moff, float eval_scale, float* __restrict__ p,
-                                      int B, int H, int W, int C) {
+                                      float4* __restrict__ hi, float4* __restrict__ lo, int B, int H, int W, int C) {
   const float a = *slope;
   const uint32_t Ho = H / 2, Wo = W / 2, C4 = C / 4;
   const uint32_t n = (uint32_t)B * Ho * Wo * C4;
@@ -703,24 +730,33 @@ __global__ void d_act_pool_fwd_kernel(const float* __restrict__ z, const float* 
     o.z = (v0.z * m.z + v1.z * m.z + v2.z * m.z + v3.z * m.z) * 0.25f;
     o.w = (v0.w * m.w + v1.w * m.w + v2.w * m.w + v3.w * m.w) * 0.25f;
     p4[i] = o;
+    if (hi) split4(o, hi, lo, i);
   }
 }
 int k_d_act_pool_fwd(fg_ctx* c, const float* z, const float* slope, const float* masks, int moff, float eval_scale,
-                     float* p, int B, int H, int W, int C) {
+                     float* p, int B, int H, int W, int C, float* hi, float* lo) {
   const int64_t n = (int64_t)B * (H / 2) * (W / 2) * C / 4;
   if (C % 4 || (moff % 4) || (int64_t)B * H * W * C >= ((int64_t)1 << 31)) {
     fg_set_error("d_act_pool_fwd: unsupported shape (C %% 4, size)");
     return FG_ERR_UNSUPPORTED;
   }
-  d_act_pool_fwd_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(z, slope, masks, moff, eval_scale, p, B, H, W, C);
+  d_act_pool_fwd_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(z, slope, masks, moff, eval_scale, p, reinterpret_cast<float4*>(hi),
+                                                                 reinterpret_cast<float4*>(lo), B, H, W, C);
   LAUNCH_CHECK(c);
   return FG_OK;
 }
 __global__ void d_act_pool_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ z,
                                       const float* __restrict__ slope, const float* __restrict__ masks, int moff,
-                                      float eval_scale, float* __restrict__ dz, float* __restrict__ dslope, int B, int H,
-                                      int W, int C) {
-  // one thread = one pooled pixel x 4 channels: reads dp once, handles its 2x2 window of z / dz
+                                      float eval_scale, float* __restrict__ dz, float* __restrict__ dslope,
+                                      float4* __restrict__ hi, float4* __restrict__ lo, float* __restrict__ dbias, int B,
+                                      int H, int W, int C) {
+  // one thread = one pooled pixel x 4 channels: reads dp once, handles its 2x2 window of z / dz.
+  // dbias (optional): += column sums of dz (the conv bias gradient); a thread always sees the same 4 channels because the
+  // grid stride is a multiple of C/4
+  __shared__ float bsum[512];
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (dbias)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) bsum[i] = 0.f;
   const float a = *slope;
   const uint32_t Ho = H / 2, Wo = W / 2, C4 = C / 4;
   const uint32_t n = (uint32_t)B * Ho * Wo * C4;
@@ -755,22 +791,38 @@ __global__ void d_act_pool_bwd_kernel(const float* __restrict__ dp, const float*
       if (!(v.z > 0.f)) s = fmaf(g.z, v.z, s);
       if (!(v.w > 0.f)) s = fmaf(g.w, v.w, s);
       dz4[idx] = o;
+      bs[0] += o.x; bs[1] += o.y; bs[2] += o.z; bs[3] += o.w;
+      if (hi) split4(o, hi, lo, idx);
     }
     sd += (double)s;
   }
   sd = block_sum(sd);
   if (threadIdx.x == 0 && dslope) atomicAdd(dslope, (float)sd);
+  if (dbias) {
+    __syncthreads();
+    const uint32_t ch = ((blockIdx.x * blockDim.x + threadIdx.x) % C4) * 4;
+    atomicAdd(bsum + ch, bs[0]);
+    atomicAdd(bsum + ch + 1, bs[1]);
+    atomicAdd(bsum + ch + 2, bs[2]);
+    atomicAdd(bsum + ch + 3, bs[3]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, bsum[i]);
+  }
 }
 int k_d_act_pool_bwd(fg_ctx* c, const float* dp, const float* z, const float* slope, const float* masks, int moff,
-                     float eval_scale, float* dz, float* dslope, int B, int H, int W, int C) {
+                     float eval_scale, float* dz, float* dslope, int B, int H, int W, int C, float* hi, float* lo,
+                     float* dbias) {
   const int64_t n = (int64_t)B * (H / 2) * (W / 2) * C / 4;
   if (C % 4 || (moff % 4) || (int64_t)B * H * W * C >= ((int64_t)1 << 31)) {
     fg_set_error("d_act_pool_bwd: unsupported shape (C %% 4, size)");
     return FG_ERR_UNSUPPORTED;
   }
+  const bool fuse = dbias && C <= 512 && 256 % (C / 4) == 0;
   d_act_pool_bwd_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, c->stream>>>(dp, z, slope, masks, moff, eval_scale, dz, dslope,
-                                                                         B, H, W, C);
+                                                                         reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo),
+                                                                         fuse ? dbias : nullptr, B, H, W, C);
   LAUNCH_CHECK(c);
+  if (dbias && !fuse) return k_colsum_add(c, dz, dbias, (int64_t)B * H * W, C, 0, 0);
   return FG_OK;
 }
 // D linear blocks: PReLU -> nn.Dropout(p) (v2: kept / (1-p) in training; identity in eval)

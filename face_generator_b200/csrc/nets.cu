@@ -167,6 +167,12 @@ int net_alloc(fg_ctx* c) {
     fg_ctx::TcBufs& t = c->tcb;
     FG_TRY(dalloc(c, &t.G_h0_hi, B * 8192));
     FG_TRY(dalloc(c, &t.G_h0_lo, B * 8192));
+    FG_TRY(dalloc(c, &t.G_xpad, B * 128));  // dalloc zero-fills: the 28 pad columns stay zero
+    FG_TRY(dalloc(c, &t.G_x_hi, B * 128));
+    FG_TRY(dalloc(c, &t.G_x_lo, B * 128));
+    FG_TRY(dalloc(c, &t.G_L1pad, 8192 * 128));
+    FG_TRY(dalloc(c, &t.G_L1w_hi, 8192 * 128));
+    FG_TRY(dalloc(c, &t.G_L1w_lo, 8192 * 128));
     FG_TRY(dalloc(c, &t.G_h1_hi, B * 65536));
     FG_TRY(dalloc(c, &t.G_h1_lo, B * 65536));
     FG_TRY(dalloc(c, &t.dy_hi, B * 131072));
@@ -233,6 +239,10 @@ int net_pack_G(fg_ctx* c) {
   FG_TRY(k_pack_weights(c, c->PG + L.C3W, c->G_C3p, c->G_C3pd, c->C, 128, 9, 0, 0, 0, 0));
   if (c->conv_impl != FG_CONV_SIMT) {
     fg_ctx::TcBufs& t = c->tcb;
+    // G.L1 on the tensor cores: [8192'][100] -> [8192'][128] (pad columns stay zero), then the TF32 split
+    FG_CUDA(cudaMemcpy2DAsync(t.G_L1pad, 128 * sizeof(float), c->G_L1p, 100 * sizeof(float), 100 * sizeof(float), 8192,
+                              cudaMemcpyDeviceToDevice, c->stream));
+    FG_TRY(tc_split(c, t.G_L1pad, t.G_L1w_hi, t.G_L1w_lo, 8192 * 128));
     FG_TRY(tc_pack_collapsed(c, c->PG + L.C1W, t.G_Wf_hi[0], t.G_Wf_lo[0], t.G_Wd_hi[0], t.G_Wd_lo[0], 256, 128));
     FG_TRY(tc_pack_collapsed(c, c->PG + L.C2W, t.G_Wf_hi[1], t.G_Wf_lo[1], t.G_Wd_hi[1], t.G_Wd_lo[1], 128, 256));
     if (c->conv_impl == FG_CONV_TC_DENSE) {
@@ -301,7 +311,7 @@ static int lin_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp,
   fg_ctx::TcBufs& t = c->tcb;
   float* hi = keep_hi ? keep_hi : t.dy_hi;  // forward keeps the split of its input for the tensor-core wgrad
   float* lo = keep_lo ? keep_lo : t.dy_lo;
-  FG_TRY(tc_split(c, in, hi, lo, (int64_t)g.B * g.Cin));
+  if (in) FG_TRY(tc_split(c, in, hi, lo, (int64_t)g.B * g.Cin));  // nullptr: the producer already wrote keep_hi / keep_lo
   ScopedTimer tm(c, tag);
   return tc_conv_fwd(c, hi, lo, t.D_Lw_hi[wi], t.D_Lw_lo[wi], bias, out, g, 0);
 }
@@ -367,7 +377,17 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
     FG_CUDA(cudaMemcpyAsync(c->G_noise, noise, sizeof(float) * B * kNoiseDim, cudaMemcpyDeviceToDevice, c->stream));
   c->G_B = B;
   c->G_train = training;
-  FG_TRY(conv_fwd(c, "G.L1.fwd", c->G_noise, c->G_L1p, c->G_L1p + 8192 * 100, c->G_z0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}));
+  const ConvGeom gL1{B, 1, 1, 128, 8192, 1, 1};  // K padded 100 -> 128 for the tensor-core path
+  if (use_tc(c, gL1)) {
+    fg_ctx::TcBufs& t = c->tcb;
+    FG_CUDA(cudaMemcpy2DAsync(t.G_xpad, 128 * sizeof(float), c->G_noise, kNoiseDim * sizeof(float), kNoiseDim * sizeof(float), B,
+                              cudaMemcpyDeviceToDevice, c->stream));
+    FG_TRY(tc_split(c, t.G_xpad, t.G_x_hi, t.G_x_lo, (int64_t)B * 128));  // kept for the weight gradient
+    ScopedTimer tm(c, "G.L1.fwd");
+    FG_TRY(tc_conv_fwd(c, t.G_x_hi, t.G_x_lo, t.G_L1w_hi, t.G_L1w_lo, c->G_L1p + 8192 * 100, c->G_z0, gL1, 0));
+  } else {
+    FG_TRY(conv_fwd(c, "G.L1.fwd", c->G_noise, c->G_L1p, c->G_L1p + 8192 * 100, c->G_z0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}));
+  }
   FG_TRY(k_prelu_fwd(c, c->G_z0, P + L.a1, c->G_h0, (int64_t)B * 8192));
   // training: the BatchNorm statistics come out of the convolution's epilogue (per-tile partials) when it ran on
   // the tensor cores; otherwise a separate pass over z computes them
@@ -444,13 +464,13 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   {
     ScopedTimer tm(c, "hbm.G.bn2.bwd_apply");
     FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_mg,
-                                c->G_dz2, B, 32, 32, 128, 0, tc2 ? c->tcb.dy_hi : nullptr, tc2 ? c->tcb.dy_lo : nullptr));
+                                c->G_dz2, B, 32, 32, 128, 0, tc2 ? c->tcb.dy_hi : nullptr, tc2 ? c->tcb.dy_lo : nullptr,
+                                G + L.C2b));  // + the bias gradient of C2 (column sums of dz2) in the same pass
   }
   // C2
   bool pooled = false;
   FG_TRY(g_ups_bwd(c, 1, "G.C2.wgrad", "G.C2.dgrad", c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, tc2 ? nullptr : c->G_dz2,
                    c->G_C2pd, gC2, G + L.C2W, c->G_dfull, &pooled));
-  FG_TRY(k_colsum_add(c, c->G_dz2, G + L.C2b, (int64_t)B * 1024, 128, 0, 0));
   // BN1 + PReLU (the 2x2 sum = backward of the nearest upsample is folded into the loads)
   FG_TRY(k_bn_prelu_bwd_reduce(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_acc,
                                G + L.a2, B, 16, 16, 256, pooled ? 0 : 1));
@@ -458,15 +478,28 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   const bool split1 = tc1 && pooled;
   FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_mg,
                               c->G_dz1, B, 16, 16, 256, pooled ? 0 : 1, split1 ? c->tcb.dy_hi : nullptr,
-                              split1 ? c->tcb.dy_lo : nullptr));
+                              split1 ? c->tcb.dy_lo : nullptr, G + L.C1b));
   // C1
   FG_TRY(g_ups_bwd(c, 0, "G.C1.wgrad", "G.C1.dgrad", c->G_h0, c->tcb.G_h0_hi, c->tcb.G_h0_lo, split1 ? nullptr : c->G_dz1,
                    c->G_C1pd,
                    ConvGeom{B, 16, 16, 128, 256, 5, 2}, G + L.C1W, c->G_dfull, &pooled));
-  FG_TRY(k_colsum_add(c, c->G_dz1, G + L.C1b, (int64_t)B * 256, 256, 0, 0));
   FG_TRY(k_prelu_bwd(c, c->G_dfull, c->G_z0, P + L.a1, c->G_dz0, G + L.a1, B, 8, 8, 128, pooled ? 0 : 1));
   // L1
-  FG_TRY(conv_wgrad(c, "G.L1.wgrad", c->G_noise, c->G_dz0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}, G + L.L1W, 128, 64, 0, 0));
+  const ConvGeom gL1{B, 1, 1, 128, 8192, 1, 1};
+  if (use_tc_wgrad(c, gL1)) {  // dW[8192'][128 (100 used)] = dz0^T x on the tensor cores (K = batch), pad columns dropped
+    fg_ctx::TcBufs& t = c->tcb;
+    FG_TRY(tc_split(c, c->G_dz0, t.dy_hi, t.dy_lo, (int64_t)B * 8192));
+    {
+      ScopedTimer tm(c, "G.L1.wgrad");
+      FG_TRY(tc_conv_wgrad(c, t.G_x_hi, t.G_x_lo, t.dy_hi, t.dy_lo, t.G_L1pad, gL1));
+    }
+    FG_CUDA(cudaMemcpy2DAsync(c->wgrad_ws, 100 * sizeof(float), t.G_L1pad, 128 * sizeof(float), 100 * sizeof(float), 8192,
+                              cudaMemcpyDeviceToDevice, c->stream));
+    FG_TRY(k_unpack_wgrad(c, c->wgrad_ws, G + L.L1W, 8192, 100, 1, 128, 64, 0, 0));
+    c->G_packed = false;  // G_L1pad was used as scratch: the next forward re-packs (it does anyway after the optimizer step)
+  } else {
+    FG_TRY(conv_wgrad(c, "G.L1.wgrad", c->G_noise, c->G_dz0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}, G + L.L1W, 128, 64, 0, 0));
+  }
   FG_TRY(k_colsum_add(c, c->G_dz0, G + L.L1b, B, 8192, 128, 64));
   if (dnoise)
     FG_TRY(conv_fwd(c, "G.L1.dgrad", c->G_dz0, c->G_L1pd, nullptr, dnoise, ConvGeom{B, 1, 1, 8192, 100, 1, 1}));
@@ -488,25 +521,36 @@ int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hype
   const float* masks = training ? c->D_masks : nullptr;
   const float* cur = c->D_x;
   static const char* tags[4] = {"D.C1.fwd", "D.C2.fwd", "D.C3.fwd", "D.C4.fwd"};
+  const ConvGeom gL1d{B, 1, 1, 2048, 512, 1, 1};
+  bool have_split = false;  // tcb.D_p_hi/lo[i-1] (resp. D_lin_hi/lo[0]) already written by the previous pooling kernel
   for (int i = 0; i < 4; ++i) {
     const int H = kDhw[i];
     const ConvGeom g{B, H, H, dcin(c, i), kDcout[i], 3, 1};
+    fg_ctx::TcBufs& t = c->tcb;
     if (i > 0 && use_tc(c, g)) {
-      fg_ctx::TcBufs& t = c->tcb;
-      FG_TRY(tc_split(c, cur, t.D_p_hi[i - 1], t.D_p_lo[i - 1], (int64_t)B * H * H * g.Cin));
+      if (!have_split) FG_TRY(tc_split(c, cur, t.D_p_hi[i - 1], t.D_p_lo[i - 1], (int64_t)B * H * H * g.Cin));
       ScopedTimer tm(c, tags[i]);
       FG_TRY(tc_conv_fwd(c, t.D_p_hi[i - 1], t.D_p_lo[i - 1], t.D_Wf_hi[i], t.D_Wf_lo[i], P + L.cb[i], c->D_z[i], g, 0));
     } else {
       FG_TRY(conv_fwd(c, tags[i], cur, c->D_cp[i], P + L.cb[i], c->D_z[i], g));
     }
+    // the pooled activation is the next tensor-core operand: its TF32 split comes out of the same kernel
+    float *nhi = nullptr, *nlo = nullptr;
+    if (i < 3) {
+      const ConvGeom gn{B, kDhw[i + 1], kDhw[i + 1], kDcout[i], kDcout[i + 1], 3, 1};
+      if (use_tc(c, gn)) { nhi = t.D_p_hi[i]; nlo = t.D_p_lo[i]; }
+    } else if (use_tc(c, gL1d)) {
+      nhi = t.D_lin_hi[0]; nlo = t.D_lin_lo[0];
+    }
+    have_split = nhi != nullptr;
     FG_TRY(k_d_act_pool_fwd(c, c->D_z[i], P + L.ca[i], masks, kDmoff[i], 1.0f - h->p_spatial, c->D_p[i], B, H, H,
-                            kDcout[i]));
+                            kDcout[i], nhi, nlo));
     cur = c->D_p[i];
   }
   const float scale = 1.0f / (1.0f - h->p_drop);
   c->D_drop_scale = scale;
   c->D_spatial_eval = 1.0f - h->p_spatial;
-  FG_TRY(lin_fwd(c, "D.L1.fwd", c->D_p[3], c->D_L1p, 0, P + L.L1b, c->D_zl1, ConvGeom{B, 1, 1, 2048, 512, 1, 1},
+  FG_TRY(lin_fwd(c, "D.L1.fwd", have_split ? nullptr : c->D_p[3], c->D_L1p, 0, P + L.L1b, c->D_zl1, gL1d,
                  c->tcb.D_lin_hi[0], c->tcb.D_lin_lo[0]));
   FG_TRY(k_lin_act_drop_fwd(c, c->D_zl1, P + L.a5, masks, 960, scale, c->D_hl1, B, 512));
   FG_TRY(lin_fwd(c, "D.L2.fwd", c->D_hl1, P + L.L2W, 2, P + L.L2b, c->D_zl2, ConvGeom{B, 1, 1, 512, 512, 1, 1},
@@ -563,13 +607,14 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
   static const char* dt[4] = {"D.C1.dgrad", "D.C2.dgrad", "D.C3.dgrad", "D.C4.dgrad"};
   for (int i = 3; i >= 0; --i) {
     const int H = kDhw[i], cin = dcin(c, i), cout = kDcout[i];
-    FG_TRY(k_d_act_pool_bwd(c, c->D_dp, c->D_z[i], P + L.ca[i], masks, kDmoff[i], eval_scale, c->D_dz,
-                            want_wgrad ? G + L.ca[i] : nullptr, B, H, H, cout));
     const float* in = i == 0 ? c->D_x : c->D_p[i - 1];
     const ConvGeom gf{B, H, H, cin, cout, 3, 1}, gd{B, H, H, cout, cin, 3, 1};
     const bool tc = i > 0 && use_tc(c, gf) && use_tc(c, gd);
     fg_ctx::TcBufs& t = c->tcb;
-    if (tc) FG_TRY(tc_split(c, c->D_dz, t.dy_hi, t.dy_lo, (int64_t)B * H * H * cout));
+    // dz and, for the tensor-core layers, its TF32 split in one pass
+    FG_TRY(k_d_act_pool_bwd(c, c->D_dp, c->D_z[i], P + L.ca[i], masks, kDmoff[i], eval_scale, c->D_dz,
+                            want_wgrad ? G + L.ca[i] : nullptr, B, H, H, cout, tc ? t.dy_hi : nullptr, tc ? t.dy_lo : nullptr,
+                            want_wgrad ? G + L.cb[i] : nullptr));  // + the conv bias gradient (column sums of dz)
     if (want_wgrad) {
       if (tc && use_tc_wgrad(c, gf)) {
         {
@@ -580,7 +625,6 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
       } else {
         FG_TRY(conv_wgrad(c, wt[i], in, c->D_dz, gf, G + L.cW[i], 0, 0, 0, 0));
       }
-      FG_TRY(k_colsum_add(c, c->D_dz, G + L.cb[i], (int64_t)B * H * H, cout, 0, 0));
     }
     if (i > 0 || want_dx) {
       if (tc) {
