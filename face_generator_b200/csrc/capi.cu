@@ -92,7 +92,6 @@ int fg_create(fg_ctx** out, int device, int max_batch, int channels) {
   c->maxB = max_batch;
   c->C = channels;
   c->sm_count = prop.multiProcessorCount;
-  if (const char* e = getenv("FG_TC_MIXED")) c->tc_mixed = atoi(e) != 0;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     fg_set_error("fg_create: cudaStreamCreate failed");
     delete c;
@@ -156,15 +155,6 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
     c->G_packed = c->D_packed = false;
     return FG_OK;
   }
-  if (!strcmp(key, "tc_mixed")) {  // cross terms of the tensor-core forward/dgrad as BF16 MMAs
-    FG_REQUIRE(v == 0 || v == 1, "tc_mixed must be 0 or 1");
-    c->tc_mixed = (int)v;
-    return FG_OK;
-  }
-  if (!strcmp(key, "tc_halo")) {  // 1: haloed-tile operand feed where the geometry allows it (experiment); 0 (default): one TMA box per tap
-    c->tc_halo = v != 0;
-    return FG_OK;
-  }
   if (!strcmp(key, "edge_impl")) {  // 1 (default): k_conv_edge.cu for the 3-channel-side convolutions; 0: k_conv_small.cu
     c->edge_impl = v != 0;
     return FG_OK;
@@ -201,10 +191,8 @@ int64_t fg_get_option(fg_ctx* c, const char* key) {
   if (!strcmp(key, "max_batch")) return c->maxB;
   if (!strcmp(key, "channels")) return c->C;
   if (!strcmp(key, "sm_count")) return c->sm_count;
-  if (!strcmp(key, "tc_mixed")) return c->tc_mixed;
   if (!strcmp(key, "bn_epilogue")) return c->bn_epilogue;
   if (!strcmp(key, "edge_impl")) return c->edge_impl;
-  if (!strcmp(key, "tc_halo")) return c->tc_halo;
   if (!strcmp(key, "optimizer_D")) return c->opt_D;
   if (!strcmp(key, "optimizer_G")) return c->opt_G;
   return -1;

@@ -84,12 +84,6 @@ struct fg_ctx {
   // OPT.D_optmethod / OPT.G_optmethod (train.lua:38-39): FG_OPT_ADAM | FG_OPT_ADAGRAD | FG_OPT_SGD, and SGD momentum
   int opt_D = 0, opt_G = 0;
   float sgd_mom_D = 0.f, sgd_mom_G = 0.f;
-  // tensor-core forward/dgrad: cross terms as BF16 MMAs (option "tc_mixed"); scratch for the BF16 pair tensors of
-  // the activation / weight operand, grown on demand (k_conv_tc.cu)
-  int tc_halo = 0;  // option "tc_halo": haloed-tile operand feed of the tcgen05 forward / dgrad kernel (measured slower: off)
-  int tc_mixed = 0;
-  float* comb[2] = {nullptr, nullptr};
-  size_t comb_elems[2] = {0, 0};
   GLayout gl;
   DLayout dl;
   std::vector<void*> allocs;  // every cudaMalloc of net_alloc(), released by net_free()

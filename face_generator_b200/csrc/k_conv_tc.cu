@@ -19,7 +19,6 @@
 // tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  3 smem stages of
 // {A_hi, A_lo, B_hi, B_lo}, 128B-swizzled, mbarrier full/empty rings, tcgen05.commit releases stages.
 #include <cuda.h>
-#include <cuda_bf16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -115,15 +114,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -166,11 +156,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// D=f32, A=B=bf16 (F32F16Format: 0 F16, 1 BF16, 2 TF32), both K-major; K = 16 per instruction
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // one lane of a fully active warp (the compiler knows the predicate selects exactly one lane, so code under it can
@@ -297,22 +282,6 @@ __global__ void combine_collapsed_wgrad_kernel(const float* __restrict__ G, floa
   }
 }
 
-// (hi, lo) fp32 [rows][C] -> BF16 pair tensor [rows][C/32][ 32 x bf16(hi) | 32 x bf16(lo) ]: the same bytes per row as
-// one fp32 tensor, so it drops into the smem slot / TMA box of the "lo" operand (mixed mode of tapconv_tc_kernel)
-__global__ void comb_kernel(const float* __restrict__ hi, const float* __restrict__ lo, __nv_bfloat16* __restrict__ comb,
-                            int64_t n4, int C) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = i * 4, row = e / C;
-    const int c = (int)(e - row * C);
-    const float4 h = reinterpret_cast<const float4*>(hi)[i], l = reinterpret_cast<const float4*>(lo)[i];
-    __nv_bfloat16* dst = comb + row * 2 * C + (c >> 5) * 64 + (c & 31);
-    *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(h.x, h.y);
-    *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(h.z, h.w);
-    *reinterpret_cast<__nv_bfloat162*>(dst + 32) = __floats2bfloat162_rn(l.x, l.y);
-    *reinterpret_cast<__nv_bfloat162*>(dst + 34) = __floats2bfloat162_rn(l.z, l.w);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -409,11 +378,6 @@ bool pick_box(int H, int W, int npix, int* bw, int* bh, int* bb) {
 
 template <int BN>
 constexpr size_t fwd_smem() { return (size_t)kStages * (2 * kABytes + 2 * BN * 128) + 256 + 2 * 4 * BN * 4 + 1024; }
-// haloed-tile variant: 2 stages x {hi, lo} activation tiles in front of a ring of weight stages
-inline uint32_t halo_box_bytes(int pad) { return 128u * (8 + 2 * pad) * (16 + 2 * pad); }
-inline uint32_t halo_tile_bytes(int pad) { return (halo_box_bytes(pad) + 1023u) & ~1023u; }
-template <int BN>
-size_t fwd_smem_halo(int pad) { return 4 * (size_t)halo_tile_bytes(pad) + (size_t)kStages * 2 * BN * 128 + 256 + 2 * 4 * BN * 4 + 1024; }
 template <int BN>
 constexpr size_t wg_smem() { return (size_t)kStages * (2 * 4 * 4096 + 2 * (BN / 32) * 4096) + 128 + 1024; }
 
@@ -423,27 +387,6 @@ constexpr size_t wg_smem() { return (size_t)kStages * (2 * 4 * 4096 + 2 * (BN / 
     FG_CUDA(cudaGetLastError());        \
   } while (0)
 
-// BF16 pair copy of an (hi, lo) operand into ctx scratch `slot` (0 activations, 1 weights)
-int make_comb(fg_ctx* c, int slot, const float* hi, const float* lo, int64_t rows, int C, const float** out) {
-  const size_t n = (size_t)rows * C;
-  if (c->comb_elems[slot] < n) {
-    FG_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->comb[slot]) FG_CUDA(cudaFree(c->comb[slot]));
-    c->comb[slot] = nullptr;
-    c->comb_elems[slot] = 0;
-    FG_CUDA(cudaMalloc((void**)&c->comb[slot], n * sizeof(float)));
-    c->comb_elems[slot] = n;
-  }
-  int64_t g = ((int64_t)n / 4 + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
-  comb_kernel<<<(int)g, 256, 0, c->stream>>>(hi, lo, reinterpret_cast<__nv_bfloat16*>(c->comb[slot]), (int64_t)n / 4, C);
-  LAUNCH_CHECK(c);
-  *out = c->comb[slot];
-  return FG_OK;
-}
-inline bool mixed_ok(const fg_ctx* c, const float* a, const float* b) {
-  return c->tc_mixed && reinterpret_cast<uintptr_t>(a) % 16 == 0 && reinterpret_cast<uintptr_t>(b) % 16 == 0;
-}
 
 // ------------------------------------------------------------------------------------------------
 // tensor-pipe probe: the issue rate of tcgen05.mma.kind::tf32 (cta_group::1, M=128, N=256, K=8) with both operands
@@ -606,21 +549,13 @@ int tc_encode_nhwc_box(CUtensorMap* m, const float* base, int C, int W, int H, i
 int tc_init(fg_ctx* c) {
   (void)c;
   FG_TRY(get_encode());
-  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
-  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>()));
-  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_halo<64>(2)));
-  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem_halo<128>(2)));
+  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
+  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>()));
   FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<64>()));
   FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<128>()));
   return FG_OK;
 }
-void tc_destroy(fg_ctx* c) {
-  for (int i = 0; i < 2; ++i) {
-    if (c->comb[i]) cudaFree(c->comb[i]);
-    c->comb[i] = nullptr;
-    c->comb_elems[i] = 0;
-  }
-}
+void tc_destroy(fg_ctx* c) { (void)c; }
 
 int tc_split(fg_ctx* c, const float* x, float* hi, float* lo, int64_t n) {
   if (n % 4) {
@@ -675,29 +610,10 @@ static int tc_chunk(bool forward_type = false) {
   return x >= 1 ? x : d;
 }
 
-// haloed-tile feed (tapconv_tc_kernel<BN, true>): 8 x 16 pixel tiles of one image, all taps within +-pad <= 2
-static bool halo_ok(const fg_ctx* c, int Hl, int Wl, int pad, bool mixed) {
-  return c->tc_halo && !mixed && pad >= 0 && pad <= 2 && Wl % 8 == 0 && Hl % 16 == 0;
-}
-static void halo_setup(TcFwdParams* p, int B, int Hl, int Wl, int pad, int tpg) {
-  p->halo = pad;
-  p->tpg = tpg;
-  p->a_box_bytes = halo_box_bytes(pad);
-  p->a_tile_bytes = halo_tile_bytes(pad);
-  p->bw = 8; p->bh = 16; p->bb = 1;
-  p->tiles_x = Wl / 8;
-  p->tiles_y = Hl / 16;
-  p->tiles_per_phase = B * p->tiles_x * p->tiles_y;
-}
-static int launch_tapconv(fg_ctx* c, const TcFwdParams& p, int BN, bool halo) {
+static int launch_tapconv(fg_ctx* c, const TcFwdParams& p, int BN) {
   dim3 grid(std::min(p.ntiles, c->sm_count));
-  if (halo) {
-    if (BN == 128) tapconv_tc_kernel<128, true><<<grid, 192, fwd_smem_halo<128>(p.halo), c->stream>>>(p);
-    else tapconv_tc_kernel<64, true><<<grid, 192, fwd_smem_halo<64>(p.halo), c->stream>>>(p);
-  } else {
-    if (BN == 128) tapconv_tc_kernel<128, false><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
-    else tapconv_tc_kernel<64, false><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
-  }
+  if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
+  else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
   LAUNCH_CHECK(c);
   return FG_OK;
 }
@@ -733,20 +649,13 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
     return FG_ERR_UNSUPPORTED;
   }
   const int64_t sW = (int64_t)g.Cin * 4, sH = sW * Wl, sB = sH * Hl;
-  const bool mixed = mixed_ok(c, x_hi, x_lo) && mixed_ok(c, w_hi, w_lo);
-  if (mixed) FG_TRY(make_comb(c, 0, x_hi, x_lo, (int64_t)g.B * Hl * Wl, g.Cin, &x_lo));
-  p.mixed = mixed ? 1 : 0;
-  const int pad = mode == 0 ? (g.k - 1) / 2 : 1;  // the up2+5x5 modes only reach low-res offsets -1..1
-  const bool halo = halo_ok(c, Hl, Wl, pad, mixed);
-  if (halo) halo_setup(&p, g.B, Hl, Wl, pad, mode == 0 ? g.k * g.k : (mode == 1 ? 25 : 9));
-  const int abw = halo ? 8 + 2 * pad : p.bw, abh = halo ? 16 + 2 * pad : p.bh;
-  FG_TRY(make_map4(&p.a_hi[0], x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, abw, abh, p.bb));
-  FG_TRY(make_map4(&p.a_lo[0], x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, abw, abh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, mixed));
+  FG_TRY(make_map4(&p.a_hi[0], x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+  FG_TRY(make_map4(&p.a_lo[0], x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
   // N tile: 128 unless halving it keeps the same number of waves on the 148 SMs (few-tile layers such as
   // D.C4's dgrad or the Linear layers): a BN=64 tile costs ~0.6 of a BN=128 tile
   int BN = g.Cout % 128 == 0 ? 128 : 64;
   if (BN == 128) {
-    const int mt = (mode == 0 ? 1 : 4) * (p.bb == 1 ? g.B * (Wl / p.bw) * (Hl / p.bh) : (g.B + p.bb - 1) / p.bb);  // (same count for halo tiles)
+    const int mt = (mode == 0 ? 1 : 4) * (p.bb == 1 ? g.B * (Wl / p.bw) * (Hl / p.bh) : (g.B + p.bb - 1) / p.bb);
     const int t128 = mt * (g.Cout / 128), t64 = mt * (g.Cout / 64);
     const int w128 = (t128 + c->sm_count - 1) / c->sm_count, w64 = (t64 + c->sm_count - 1) / c->sm_count;
     if (w64 * 6 < w128 * 10) BN = 64;
@@ -785,17 +694,14 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
         p.widx[ph * 9 + t] = (int16_t)(ph * 9 + t);
       }
   }
-  if (mixed) FG_TRY(make_comb(c, 1, w_hi, w_lo, (int64_t)ntapw * g.Cout, g.Cin, &w_lo));
   FG_TRY(make_map2(&p.b_hi, w_hi, g.Cin, (int64_t)ntapw * g.Cout, 32, BN));
-  FG_TRY(make_map2(&p.b_lo, w_lo, g.Cin, (int64_t)ntapw * g.Cout, 32, BN, mixed));
+  FG_TRY(make_map2(&p.b_lo, w_lo, g.Cin, (int64_t)ntapw * g.Cout, 32, BN));
   p.kpt = g.Cin / 32;
   p.Cout = g.Cout;
   p.B = g.B; p.H = Hl; p.W = Wl;
-  if (!halo) {
-    p.tiles_x = Wl / p.bw;
-    p.tiles_y = Hl / p.bh;
-    p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
-  }
+  p.tiles_x = Wl / p.bw;
+  p.tiles_y = Hl / p.bh;
+  p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
   p.out = out;
   p.bias = bias;
   p.stats = stats;
@@ -805,7 +711,7 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   p.ntiles = p.tiles_per_phase * p.nphase * (g.Cout / BN);
   p.dbg = getenv("FG_TC_DBG") ? atoi(getenv("FG_TC_DBG")) : 0;
   p.chunk = tc_chunk(g.H * g.W > 1);  // Linear layers (1x1 images, K up to 16384) keep the short chunk
-  return launch_tapconv(c, p, BN, halo);
+  return launch_tapconv(c, p, BN);
 }
 
 // dgrad of an up2+5x5 conv straight to the LOW-RES input gradient (the 2x2 sum of the upsample backward is
@@ -818,21 +724,12 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
   const int Hl = g.H / 2, Wl = g.W / 2;
   if (!pick_box(Hl, Wl, 128, &p.bw, &p.bh, &p.bb)) return FG_ERR_UNSUPPORTED;
   const int Cy = g.Cout;  // contraction runs over the forward conv's output channels
-  const bool mixed = mixed_ok(c, dy_hi, dy_lo) && mixed_ok(c, wd_hi, wd_lo);
-  if (mixed) {
-    FG_TRY(make_comb(c, 0, dy_hi, dy_lo, (int64_t)g.B * g.H * g.W, Cy, &dy_lo));
-    FG_TRY(make_comb(c, 1, wd_hi, wd_lo, (int64_t)36 * g.Cin, Cy, &wd_lo));
-  }
-  p.mixed = mixed ? 1 : 0;
-  const bool halo = halo_ok(c, Hl, Wl, 1, mixed);
-  if (halo) halo_setup(&p, g.B, Hl, Wl, 1, 9);  // 4 groups (the output phases of dY) x 9 taps
-  const int abw = halo ? 10 : p.bw, abh = halo ? 18 : p.bh;
   for (int ph = 0; ph < 4; ++ph) {
     const int py = ph >> 1, px = ph & 1;
     const int64_t off = ((int64_t)py * g.W + px) * Cy;  // the pair tensor has the same bytes per pixel
     const int64_t sW = (int64_t)2 * Cy * 4, sH = (int64_t)2 * g.W * Cy * 4, sB = (int64_t)g.H * g.W * Cy * 4;
-    FG_TRY(make_map4(&p.a_hi[ph], dy_hi + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, abw, abh, p.bb));
-    FG_TRY(make_map4(&p.a_lo[ph], dy_lo + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, abw, abh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, mixed));
+    FG_TRY(make_map4(&p.a_hi[ph], dy_hi + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+    FG_TRY(make_map4(&p.a_lo[ph], dy_lo + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
   }
   const int BN = g.Cin % 128 == 0 ? 128 : 64;
   p.nphase = 1;
@@ -846,15 +743,13 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
       p.widx[ph * 9 + t] = (int16_t)(ph * 9 + t);
     }
   FG_TRY(make_map2(&p.b_hi, wd_hi, Cy, (int64_t)36 * g.Cin, 32, BN));
-  FG_TRY(make_map2(&p.b_lo, wd_lo, Cy, (int64_t)36 * g.Cin, 32, BN, mixed));
+  FG_TRY(make_map2(&p.b_lo, wd_lo, Cy, (int64_t)36 * g.Cin, 32, BN));
   p.kpt = Cy / 32;
   p.Cout = g.Cin;
   p.B = g.B; p.H = Hl; p.W = Wl;
-  if (!halo) {
-    p.tiles_x = Wl / p.bw;
-    p.tiles_y = Hl / p.bh;
-    p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
-  }
+  p.tiles_x = Wl / p.bw;
+  p.tiles_y = Hl / p.bh;
+  p.tiles_per_phase = p.bb == 1 ? g.B * p.tiles_x * p.tiles_y : (g.B + p.bb - 1) / p.bb;
   p.out = out;
   p.bias = nullptr;
   p.out_H = Hl; p.out_W = Wl;
@@ -862,7 +757,7 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
   p.ntiles = p.tiles_per_phase * (g.Cin / BN);
   p.dbg = getenv("FG_TC_DBG") ? atoi(getenv("FG_TC_DBG")) : 0;
   p.chunk = tc_chunk(true);
-  return launch_tapconv(c, p, BN, halo);
+  return launch_tapconv(c, p, BN);
 }
 
 // wgrad.  x_hi/lo: [B][H/ups][W/ups][Cin]; dy_hi/lo: [B][H][W][Cout]; out (overwritten):

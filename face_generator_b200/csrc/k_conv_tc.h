@@ -21,14 +21,8 @@ struct alignas(64) TcFwdParams {
   const float* bias;
   float* stats;  // optional [m-tile][2][Cout]: per-tile column sums of the output and of its square (BatchNorm)
   int out_H, out_W, out_scale;
-  // "haloed tile" operand feed (tapconv_tc_kernel<BN, true>): halo = (k-1)/2 pixels around an 8 x 16 pixel tile, tpg = taps
-  // per group of taps that share one activation view, a_box_bytes = bytes of one haloed TMA box, a_tile_bytes = its
-  // 1 KB-rounded slot in shared memory
-  int halo, tpg;
-  uint32_t a_box_bytes, a_tile_bytes;
   int dbg;    // experiment switches (FG_TC_DBG): 1 = skip MMAs, 2 = skip TMA data movement
   int chunk;  // K-blocks accumulated in TMEM before the epilogue promotes them to fp32 registers
-  int mixed;  // 1: a_lo / b_lo are BF16 pair tensors [row][C/32][hi32|lo32]; cross terms run as kind::f16 MMAs
 };
 
 struct alignas(64) TcWgParams {

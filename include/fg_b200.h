@@ -85,8 +85,9 @@ int fg_destroy(fg_ctx* ctx);
 int fg_set_stream(fg_ctx* ctx, void* cuda_stream);      /* cutorch's current stream; NULL = own  */
 int fg_sync(fg_ctx* ctx);
 /* keys: "conv_impl" (FG_CONV_*), "optimizer_D" / "optimizer_G" (FG_OPT_*), "debug_keep" (tests: keep the D
- * step's pre-activations of fg_train_step as "Dstep.*" debug tensors), "tc_mixed" (0/1: cross
- * terms of the 3xTF32 forward/dgrad as BF16 MMAs, experimental), "params_dirty" (re-pack weights
+ * step's pre-activations of fg_train_step as "Dstep.*" debug tensors), "edge_impl" / "bn_epilogue"
+ * (0 selects the round-1 kernels for the 3-channel convolutions / a separate BatchNorm statistics
+ * pass: cross-checks), "params_dirty" (re-pack weights
  * after writing through fg_params_ptr); unknown keys return FG_ERR_INVALID                        */
 int fg_set_option(fg_ctx* ctx, const char* key, int64_t value);
 int64_t fg_get_option(fg_ctx* ctx, const char* key);

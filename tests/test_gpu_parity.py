@@ -421,33 +421,6 @@ def test_sample_chunked(fg):
     ctx.close()
 
 
-@pytest.mark.parametrize("N,Cin,H,Cout,k", [(8, 64, 16, 128, 3), (2, 32, 32, 64, 5), (3, 256, 8, 128, 3)])
-def test_tc_mixed_cross_terms(fg, N, Cin, H, Cout, k):
-    """Option "tc_mixed": main term in TF32, the two cross terms of 3xTF32 as BF16 MMAs.  The cross
-    terms are ~2^-12 of the result, BF16 inputs keep them to ~2^-20: the forward / dgrad results must stay within
-    2e-5 of the oracle (1e-4 is the parity bar) and must differ from the pure 3xTF32 result only at that level."""
-    from face_generator_b200.lib import _ptr
-    rng = np.random.default_rng(300 + N + Cin)
-    f = lambda a: np.ascontiguousarray(a, np.float32)
-    x, w, b = f(rng.standard_normal((N, Cin, H, H))), f(rng.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k)), f(rng.standard_normal(Cout))
-    dy = f(rng.standard_normal((N, Cout, H, H)))
-    ref = O.f64.conv_fwd(x, w, b)
-    rdx = O.f64.conv_bwd(x, w, dy)[0]
-    outs = {}
-    for mixed in (0, 1):
-        ctx = fg.Context(0, max_batch=8, channels=3)
-        ctx.set_option("conv_impl", 2)
-        ctx.set_option("tc_mixed", mixed)
-        assert ctx.get_option("tc_mixed") == mixed
-        y, dx = np.empty((N, Cout, H, H), np.float32), np.empty_like(x)
-        assert ctx.lib.fg_conv2d_forward(ctx.h, _ptr(x), _ptr(w), _ptr(b), _ptr(y), N, Cin, H, H, Cout, k) == 0
-        assert ctx.lib.fg_conv2d_backward_data(ctx.h, _ptr(dy), _ptr(w), _ptr(dx), N, Cin, H, H, Cout, k) == 0
-        assert PU.relerr(y, ref) < 2e-5 and PU.relerr(dx, rdx) < 2e-5, (mixed, PU.relerr(y, ref), PU.relerr(dx, rdx))
-        outs[mixed] = (y, dx)
-        ctx.close()
-    assert PU.relerr(outs[1][0], outs[0][0]) < 2e-5
-
-
 def test_accuracy_gate_closes_and_reopens(fg):
     """adversarial.lua:156-178 + interruptable_optimizers.lua:64-66: when the mean of D's last `accsInterval` batch
     accuracies is >= maxAccuracyD, fevalD returns false and interruptableAdam returns without touching x, m, v or
