@@ -94,7 +94,7 @@ def load_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
 
 
-def ncu_traffic(profile="r1_ncu_tapconv_v12.md"):
+def ncu_traffic(profile="r2_ncu_gc2fwd_v2.md"):
     """dram__bytes_read.sum + dram__bytes_write.sum of the G.C2 forward launch at batch 256 (the first kernel of the
     committed `ncu --set full` summary; a number taken under the profiler, quoted only as traffic, never as time)."""
     import re
@@ -110,7 +110,7 @@ def ncu_traffic(profile="r1_ncu_tapconv_v12.md"):
         return None, None
 
 
-def ncu_pipe_active(profile="r1_ncu_tapconv_v12.md"):
+def ncu_pipe_active(profile="r2_ncu_gc2fwd_v2.md"):
     """sm__pipe_tensor_cycles_active (% of peak) of the G.C2 forward launch in the committed `ncu --set full` summary"""
     import re
     try:
@@ -334,6 +334,11 @@ def main():
                  "hbm.G.bn2.apply": 1.5 * 2 * act,        # read z2, write h2
                  "hbm.G.bn2.bwd_reduce": 2 * act,         # read dh, z2
                  "hbm.G.bn2.bwd_apply": 5 * act,          # read dh, z2; write dz2 + its TF32 hi/lo split
+                 # the 3-channel-side 3x3 convolutions (k_conv_edge.cu): input + output of the images they process per step
+                 "G.C3.fwd": 1.5 * B * 1024 * (128 + C) * 4,   # B/2 (D step) + B (G step) images
+                 "G.C3.dgrad": B * 1024 * (C + 128) * 4,       # G step
+                 "D.C1.fwd": 2 * B * 1024 * (C + 64) * 4,      # B (D step) + B (G step)
+                 "D.C1.dgrad": B * 1024 * (64 + C) * 4,        # G step (gradient into G's image)
                  "hbm.optim.D": 28 * ctx.count(NET_D),    # p, g, m, v read; p, g, m, v... 7 streams x 4 B
                  "hbm.optim.G": 28 * ctx.count(NET_G)}
     hbm = {}
@@ -396,7 +401,7 @@ def main():
                      "pipe_active_pct": pipe_pct, "pipe_active_src": pipe_src,
                      "family_fwd_dgrad_wgrad_tflops": tf_c2,
                      "step_algorithmic_tflops": F_ITER_PER_IMG * B * K / (ms / 1e3) / 1e12},
-        "hbm_kernels": [{"kernel": k[4:], "bytes_per_step": int(nb), "ms_per_step": round(ms_k, 4),
+        "hbm_kernels": [{"kernel": k[4:] if k.startswith("hbm.") else k, "bytes_per_step": int(nb), "ms_per_step": round(ms_k, 4),
                          "achieved": round(nb / (ms_k / 1e3) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
                          "frac": round(nb / (ms_k / 1e3) / 1e9 / peaks["hbm"], 3)} for k, (nb, ms_k) in hbm.items() if ms_k > 0],
         "kernel_ms_per_step": {k: round(v[0], 4) for k, v in fam.items()},

@@ -9,7 +9,6 @@ B, C = 256, 3
 rng = np.random.default_rng(1)
 ctx = fg.Context(0, max_batch=B, channels=C)
 ctx.set_option("conv_impl", int(os.environ.get("IMPL", "2")))
-ctx.set_option("tc_halo", int(os.environ.get("HALO", "1")))
 ctx.set_params(NET_G, LY.trained_like_init(LY.G_layout(C), rng))
 noise = rng.uniform(-1, 1, (B, 100)).astype(np.float32)
 dimg = rng.standard_normal((B, C, 32, 32)).astype(np.float32)
@@ -23,4 +22,4 @@ out = {}
 for k in ("G.C1.fwd", "G.C2.fwd", "G.C2.dgrad", "G.C1.dgrad", "G.C2.wgrad", "G.C1.wgrad"):
     ms, n = ctx.timing_get(k)
     out[k] = round(ms / max(n, 1), 4)
-print("HALO", os.environ.get("HALO", "1"), "DBG", os.environ.get("FG_TC_DBG", "0"), out)
+print("DBG", os.environ.get("FG_TC_DBG", "0"), out)
