@@ -6,5 +6,5 @@ This Python package is only the host-side mirror of the reference's Lua plugin s
 tests and bench.py; the reference-side binding is the LuaJIT FFI shim under face_generator_b200/lua/.
 There is NO CPU fallback: importing works anywhere, but every compute call needs a B200.
 """
-from .lib import FGError, load_library, Context, C2f, hyper_default, MASK_PER_SAMPLE, NOISE_DIM  # noqa: F401
+from .lib import FGError, load_library, Context, C2f, S16, hyper_default, MASK_PER_SAMPLE, NOISE_DIM  # noqa: F401
 from . import nn, adversarial, adversarial_c2f  # noqa: F401

@@ -170,6 +170,35 @@ int fg_conv2d_backward_filter(fg_ctx* c, const float* x, const float* dy, float*
   return FG_OK;
 }
 
+// cudnn.SpatialConvolutionUpsample (layers/cudnnSpatialConvolutionUpsample.lua): parent.__init(nInputPlane,
+// nOutputPlane*factor*factor, ...) at :14-15, and every pass only re-views the contiguous output / gradOutput between
+// [N][nOut*f*f][h][w] and [N][nOut][h*f][w*f] (:18-30, :32-58) -- the bytes do not move, so the layer IS the
+// convolution with nOut*f*f planes on the caller's buffer.
+static int scu_planes(int nOutputPlane, int factor, int* planes) {
+  FG_REQUIRE(nOutputPlane > 0 && factor >= 1 && (int64_t)nOutputPlane * factor * factor < (1 << 20),
+             "SpatialConvolutionUpsample: bad nOutputPlane %d / factor %d", nOutputPlane, factor);
+  *planes = nOutputPlane * factor * factor;
+  return FG_OK;
+}
+int fg_scu_forward(fg_ctx* c, const float* x, const float* w, const float* b, float* y, int N, int Cin, int H, int W,
+                   int nOutputPlane, int k, int factor) {
+  int planes;
+  FG_TRY(scu_planes(nOutputPlane, factor, &planes));
+  return fg_conv2d_forward(c, x, w, b, y, N, Cin, H, W, planes, k);
+}
+int fg_scu_backward_data(fg_ctx* c, const float* dy, const float* w, float* dx, int N, int Cin, int H, int W,
+                         int nOutputPlane, int k, int factor) {
+  int planes;
+  FG_TRY(scu_planes(nOutputPlane, factor, &planes));
+  return fg_conv2d_backward_data(c, dy, w, dx, N, Cin, H, W, planes, k);
+}
+int fg_scu_backward_filter(fg_ctx* c, const float* x, const float* dy, float* dw, float* db, int N, int Cin, int H, int W,
+                           int nOutputPlane, int k, int factor) {
+  int planes;
+  FG_TRY(scu_planes(nOutputPlane, factor, &planes));
+  return fg_conv2d_backward_filter(c, x, dy, dw, db, N, Cin, H, W, planes, k);
+}
+
 int fg_linear_forward(fg_ctx* c, const float* x, const float* w, const float* b, float* y, int N, int in, int out) {
   ENTER(c);
   FG_REQUIRE(x && w && y && N > 0 && in > 0 && out > 0, "fg_linear_forward: bad arguments");

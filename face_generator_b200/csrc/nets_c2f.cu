@@ -13,31 +13,13 @@
 #include <algorithm>
 #include <cstring>
 
+#include "convl.h"
 #include "fg_internal.h"
 #include "k_conv_tc.h"
 #include "k_misc.h"
 
 namespace {
 constexpr int kC2fMask = 16384 + 512;  // nn.Dropout keep flags per sample: [256][8][8] then [512]
-
-struct ConvL {  // one convolution / Linear layer (NHWC, stride 1, same padding)
-  int Cin = 0, Cout = 0, k = 1, H = 1;
-  int64_t w_off = 0, b_off = 0;
-  int cA = 0, cS = 0;  // Linear after View([C][H][W]): column j=c*S+s of the reference <-> our NHWC column s*A+c
-  float *Wp = nullptr, *Wpd = nullptr;                                            // fp32 packs [t][n][c], [t'][c][n]
-  float *Wf_hi = nullptr, *Wf_lo = nullptr, *Wd_hi = nullptr, *Wd_lo = nullptr;   // TF32 splits of the packs
-  float *x_hi = nullptr, *x_lo = nullptr;                                         // split of the input (fwd -> wgrad)
-  // Layers whose output side is too narrow for a tensor-core tile still run there with zero-padded channels:
-  //   pad_out (Cout <= 4, e.g. the 256->C 7x7 output layer): forward with the weights padded to pad_out rows;
-  //           wgrad with the roles swapped (big channel count on the 128-row M side, padded dY on the N side)
-  //   pad_dy  (Cout == 64): wgrad with dY padded to the 128 rows the M side needs
-  int pad_out = 0, pad_dy = 0;
-  float *Wq_hi = nullptr, *Wq_lo = nullptr;  // [t][pad_out][Cin] TF32 hi/lo
-  bool need_dgrad = true;
-  const char *tf = "", *td = "", *tw = "";
-  ConvGeom geom(int B) const { return ConvGeom{B, H, H, Cin, Cout, k, 1}; }
-  ConvGeom geom_d(int B) const { return ConvGeom{B, H, H, Cout, Cin, k, 1}; }
-};
 }  // namespace
 
 struct fg_c2f {
@@ -64,150 +46,17 @@ struct fg_c2f {
   bool G_valid = false, D_valid = false, D_train = true;
   float D_scale = 2.f;
   std::vector<void*> allocs;
+  ConvLEnv env;  // shared scratch of the ConvL layers (filled by c2f_alloc)
 };
 
 namespace {
-bool is_dev(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
-int to_dev(fg_ctx* c, const float* p, size_t n, float* staging, const float** out) {
-  if (is_dev(p)) {
-    *out = p;
-    return FG_OK;
-  }
-  FG_CUDA(cudaMemcpyAsync(staging, p, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  *out = staging;
-  return FG_OK;
-}
-int to_user(fg_ctx* c, float* dst, const float* src_dev, size_t n) {
-  const bool dev = is_dev(dst);
-  FG_CUDA(cudaMemcpyAsync(dst, src_dev, n * sizeof(float), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                          c->stream));
-  if (!dev) FG_CUDA(cudaStreamSynchronize(c->stream));
-  return FG_OK;
-}
-int dalloc(fg_c2f* n, float** p, size_t elems) {
-  void* q = nullptr;
-  FG_CUDA(cudaMalloc(&q, std::max<size_t>(elems, 1) * sizeof(float)));
-  FG_CUDA(cudaMemsetAsync(q, 0, std::max<size_t>(elems, 1) * sizeof(float), n->c->stream));
-  n->allocs.push_back(q);
-  *p = (float*)q;
-  return FG_OK;
-}
-
-inline bool tc_f(const fg_ctx* c, const ConvL& L, int B) { return c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(L.geom(B)); }
-inline bool tc_d(const fg_ctx* c, const ConvL& L, int B) { return c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(L.geom_d(B)); }
-inline bool tc_w(const fg_ctx* c, const ConvL& L, int B) { return tc_f(c, L, B) && L.Cout % 128 == 0 && L.Cin % 64 == 0; }
-
-int convl_alloc(fg_c2f* n, ConvL& L) {
-  const size_t nw = (size_t)L.k * L.k * L.Cout * L.Cin;
-  FG_TRY(dalloc(n, &L.Wp, nw));
-  FG_TRY(dalloc(n, &L.Wpd, nw));
-  if (tc_conv_eligible(L.geom(n->maxB))) {
-    FG_TRY(dalloc(n, &L.Wf_hi, nw));
-    FG_TRY(dalloc(n, &L.Wf_lo, nw));
-    const size_t nx = (size_t)n->maxB * L.H * L.H * L.Cin;
-    FG_TRY(dalloc(n, &L.x_hi, nx));
-    FG_TRY(dalloc(n, &L.x_lo, nx));
-  }
-  if (L.need_dgrad && tc_conv_eligible(L.geom_d(n->maxB))) {
-    FG_TRY(dalloc(n, &L.Wd_hi, nw));
-    FG_TRY(dalloc(n, &L.Wd_lo, nw));
-  }
-  // padded tensor-core variants (see ConvL)
-  const int B = n->maxB;
-  if (L.pad_out && !(tc_conv_eligible(ConvGeom{B, L.H, L.H, L.Cin, L.pad_out, L.k, 1}) &&
-                     tc_conv_eligible(ConvGeom{B, L.H, L.H, L.pad_out, L.Cin, L.k, 1}) && L.Cin % 128 == 0))
-    L.pad_out = 0;
-  if (L.pad_dy && !(L.x_hi && tc_conv_eligible(ConvGeom{B, L.H, L.H, L.Cin, L.pad_dy, L.k, 1}) && L.Cin % 64 == 0))
-    L.pad_dy = 0;
-  if (L.pad_out) {
-    const size_t nq = (size_t)L.k * L.k * L.pad_out * L.Cin;
-    FG_TRY(dalloc(n, &L.Wq_hi, nq));  // zero-initialised: the padding rows stay zero
-    FG_TRY(dalloc(n, &L.Wq_lo, nq));
-    const size_t nx = (size_t)B * L.H * L.H * L.Cin;
-    FG_TRY(dalloc(n, &L.x_hi, nx));
-    FG_TRY(dalloc(n, &L.x_lo, nx));
-  }
-  return FG_OK;
-}
-int convl_pack(fg_ctx* c, ConvL& L, const float* P) {
-  const int KK = L.k * L.k;
-  FG_TRY(k_pack_weights(c, P + L.w_off, L.Wp, L.need_dgrad ? L.Wpd : nullptr, L.Cout, L.Cin, KK, 0, 0, L.cA, L.cS));
-  if (c->conv_impl == FG_CONV_SIMT) return FG_OK;
-  const int64_t nw = (int64_t)KK * L.Cout * L.Cin;
-  if (L.Wf_hi) FG_TRY(tc_split(c, L.Wp, L.Wf_hi, L.Wf_lo, nw));
-  if (L.Wd_hi) FG_TRY(tc_split(c, L.Wpd, L.Wd_hi, L.Wd_lo, nw));
-  if (L.pad_out) FG_TRY(k_pack_pad_split(c, P + L.w_off, L.Wq_hi, L.Wq_lo, L.Cout, L.pad_out, L.Cin, KK));
-  return FG_OK;
-}
-int convl_fwd(fg_c2f* n, ConvL& L, const float* in, const float* P, float* out, int B) {
-  fg_ctx* c = n->c;
-  const ConvGeom g = L.geom(B);
-  if (L.pad_out && c->conv_impl != FG_CONV_SIMT) {
-    FG_TRY(tc_split(c, in, L.x_hi, L.x_lo, (int64_t)B * L.H * L.H * L.Cin));
-    {
-      ScopedTimer t(c, L.tf);
-      FG_TRY(tc_conv_fwd(c, L.x_hi, L.x_lo, L.Wq_hi, L.Wq_lo, nullptr, n->ga, ConvGeom{B, L.H, L.H, L.Cin, L.pad_out, L.k, 1}, 0));
-    }
-    return k_compact_bias(c, n->ga, P + L.b_off, out, (int64_t)B * L.H * L.H, L.Cout, L.pad_out);
-  }
-  if (tc_f(c, L, B)) {
-    FG_TRY(tc_split(c, in, L.x_hi, L.x_lo, (int64_t)B * L.H * L.H * L.Cin));
-    ScopedTimer t(c, L.tf);
-    return tc_conv_fwd(c, L.x_hi, L.x_lo, L.Wf_hi, L.Wf_lo, P + L.b_off, out, g, 0);
-  }
-  ScopedTimer t(c, L.tf);
-  if (c->edge_impl && k_edge_eligible(g)) return k_conv_edge(c, in, L.Wp, P + L.b_off, out, g);
-  return k_small_eligible(g) ? k_conv_small(c, in, L.Wp, P + L.b_off, out, g) : k_conv_simt(c, in, L.Wp, P + L.b_off, out, g);
-}
-// G (may be null): dW += wgrad, db += colsum(dy).  din (may be null) = dgrad.
-int convl_bwd(fg_c2f* n, ConvL& L, const float* in, const float* dy, float* G, float* din, int B) {
-  fg_ctx* c = n->c;
-  const ConvGeom g = L.geom(B), gd = L.geom_d(B);
-  const bool w_tc = G && tc_w(c, L, B), d_tc = din && tc_d(c, L, B);
-  if (w_tc || d_tc) FG_TRY(tc_split(c, dy, n->dy_hi, n->dy_lo, (int64_t)B * L.H * L.H * L.Cout));
-  const bool tc_on = c->conv_impl != FG_CONV_SIMT;
-  const int64_t P = (int64_t)B * L.H * L.H;
-  if (G && tc_on && L.pad_out) {
-    // swapped roles: Gt[t'][c][n] = sum_p X[p][c] * dYpad[p + off(t')][n]  ==  dW[KK-1-t'][n][c]
-    FG_TRY(k_pad_split(c, dy, n->pad_hi, n->pad_lo, P, L.Cout, L.pad_out));
-    {
-      ScopedTimer t(c, L.tw);
-      FG_TRY(tc_conv_wgrad(c, n->pad_hi, n->pad_lo, L.x_hi, L.x_lo, n->ws, ConvGeom{B, L.H, L.H, L.pad_out, L.Cin, L.k, 1}));
-    }
-    FG_TRY(k_unpack_wgrad_swapped(c, n->ws, G + L.w_off, L.Cout, L.pad_out, L.Cin, L.k * L.k));
-    FG_TRY(k_colsum_add(c, dy, G + L.b_off, P, L.Cout, 0, 0));
-  } else if (G && tc_on && L.pad_dy && !w_tc) {
-    FG_TRY(k_pad_split(c, dy, n->pad_hi, n->pad_lo, P, L.Cout, L.pad_dy));
-    {
-      ScopedTimer t(c, L.tw);
-      FG_TRY(tc_conv_wgrad(c, L.x_hi, L.x_lo, n->pad_hi, n->pad_lo, n->ws, ConvGeom{B, L.H, L.H, L.Cin, L.pad_dy, L.k, 1}));
-    }
-    FG_TRY(k_unpack_wgrad_pad(c, n->ws, G + L.w_off, L.Cout, L.pad_dy, L.Cin, L.k * L.k));
-    FG_TRY(k_colsum_add(c, dy, G + L.b_off, P, L.Cout, 0, 0));
-  } else if (G) {
-    {
-      ScopedTimer t(c, L.tw);
-      if (w_tc) FG_TRY(tc_conv_wgrad(c, L.x_hi, L.x_lo, n->dy_hi, n->dy_lo, n->ws, g));
-      else if (k_small_eligible(g)) FG_TRY(k_wgrad_small(c, in, dy, n->ws, g));
-      else FG_TRY(k_wgrad_simt(c, in, dy, n->ws, g));
-    }
-    FG_TRY(k_unpack_wgrad(c, n->ws, G + L.w_off, L.Cout, L.Cin, L.k * L.k, 0, 0, L.cA, L.cS));
-    FG_TRY(k_colsum_add(c, dy, G + L.b_off, P, L.Cout, 0, 0));
-  }
-  if (din) {
-    ScopedTimer t(c, L.td);
-    if (d_tc) return tc_conv_fwd(c, n->dy_hi, n->dy_lo, L.Wd_hi, L.Wd_lo, nullptr, din, gd, 0);
-    if (c->edge_impl && k_edge_eligible(gd)) return k_conv_edge(c, dy, L.Wpd, nullptr, din, gd);
-    return k_small_eligible(gd) ? k_conv_small(c, dy, L.Wpd, nullptr, din, gd) : k_conv_simt(c, dy, L.Wpd, nullptr, din, gd);
-  }
-  return FG_OK;
+int dalloc(fg_c2f* n, float** p, size_t elems) { return convl_dalloc(n->env, p, elems); }
+inline int to_dev(fg_ctx* c, const float* p, size_t n, float* staging, const float** out) { return fg_to_dev(c, p, n, staging, out); }
+inline int to_user(fg_ctx* c, float* dst, const float* src_dev, size_t n) { return fg_to_user(c, dst, src_dev, n); }
+inline int convl_alloc(fg_c2f* n, ConvL& L) { return ::convl_alloc(n->env, L); }
+inline int convl_fwd(fg_c2f* n, ConvL& L, const float* in, const float* P, float* out, int B) { return ::convl_fwd(n->env, L, in, P, out, B); }
+inline int convl_bwd(fg_c2f* n, ConvL& L, const float* in, const float* dy, float* G, float* din, int B) {
+  return ::convl_bwd(n->env, L, in, dy, G, din, B);
 }
 
 void make_layouts(fg_c2f* n) {
@@ -262,6 +111,9 @@ void make_layouts(fg_c2f* n) {
 int c2f_alloc(fg_c2f* n) {
   const size_t B = n->maxB, C = n->C;
   make_layouts(n);
+  n->env.c = n->c;
+  n->env.maxB = n->maxB;
+  n->env.allocs = &n->allocs;
   FG_TRY(dalloc(n, &n->PG, n->nG));
   FG_TRY(dalloc(n, &n->PD, n->nD));
   FG_TRY(dalloc(n, &n->gG, n->nG + kGradTail));
@@ -310,6 +162,8 @@ int c2f_alloc(fg_c2f* n) {
   FG_TRY(dalloc(n, &n->pad_hi, big / 2));  // up to 128 padded channels at 32x32
   FG_TRY(dalloc(n, &n->pad_lo, big / 2));
   FG_TRY(dalloc(n, &n->ws, std::max<size_t>((size_t)512 * 16384, (size_t)25 * 256 * 128)));
+  n->env.ga = n->ga; n->env.dy_hi = n->dy_hi; n->env.dy_lo = n->dy_lo;
+  n->env.pad_hi = n->pad_hi; n->env.pad_lo = n->pad_lo; n->env.ws = n->ws;
   FG_TRY(dalloc(n, &n->in_a, B * 1024 * C));
   FG_TRY(dalloc(n, &n->in_b, B * 1024 * C));
   FG_TRY(dalloc(n, &n->in_c, B * 1024));

@@ -68,6 +68,9 @@ SYMBOLS = {
     "fg_conv2d_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I]),
     "fg_conv2d_backward_data": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I]),
     "fg_conv2d_backward_filter": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I]),
+    "fg_scu_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I]),
+    "fg_scu_backward_data": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I]),
+    "fg_scu_backward_filter": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I]),
     "fg_linear_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I]),
     "fg_linear_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
     "fg_bn_forward_train": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I]),
@@ -134,6 +137,26 @@ SYMBOLS = {
     "fg_dp_init": (_I, [_P, _P, _I, _I]),
     "fg_dp_broadcast_params": (_I, [_P]),
     "fg_c2f_dp_broadcast_params": (_I, [_P]),
+    "fg_s16_dp_broadcast_params": (_I, [_P]),
+    "fg_s16_create": (_I, [_P, C.POINTER(_P)]),
+    "fg_s16_destroy": (_I, [_P]),
+    "fg_s16_param_count": (_L, [_I, _I]),
+    "fg_s16_mask_per_sample": (_I, []),
+    "fg_s16_set_params": (_I, [_P, _I, _P]),
+    "fg_s16_get_params": (_I, [_P, _I, _P]),
+    "fg_s16_get_grads": (_I, [_P, _I, _P]),
+    "fg_s16_zero_grads": (_I, [_P, _I]),
+    "fg_s16_params_ptr": (_P, [_P, _I]),
+    "fg_s16_grads_ptr": (_P, [_P, _I]),
+    "fg_s16_set_adam_state": (_I, [_P, _I, _P, _P, _I]),
+    "fg_s16_get_adam_state": (_I, [_P, _I, _P, _P, C.POINTER(_I)]),
+    "fg_s16_set_bn_state": (_I, [_P, _P]),
+    "fg_s16_get_bn_state": (_I, [_P, _P]),
+    "fg_s16_G_forward": (_I, [_P, _P, _I, _I, _P]),
+    "fg_s16_G_backward": (_I, [_P, _P, _P]),
+    "fg_s16_D_forward": (_I, [_P, _P, _I, _I, _P, _U64, _P]),
+    "fg_s16_D_backward": (_I, [_P, _P, _I, _P]),
+    "fg_s16_train_step": (_I, [_P, C.POINTER(Hyper), _I, _P, _P, _P, _P, _P, _U64, C.POINTER(StepStats)]),
     "fg_dp_world": (_I, [_P]),
     "fg_dev_alloc": (_P, [_SZ]),
     "fg_dev_free": (_I, [_P]),
@@ -616,3 +639,115 @@ class C2f:
         if st is None:
             return None
         return dict(loss_D=st.loss_D, loss_G=st.loss_G, conf=list(st.conf), t_D=st.t_D, t_G=st.t_G, acc_D=st.acc_D)
+
+
+S16_MASK_PER_SAMPLE = 1024 + 128
+
+
+class S16:
+    """The --scale 16 nets (models.lua:27-51 G16, :279-316 D16_d) + the adversarial.lua loop on a Context."""
+
+    def __init__(self, ctx):
+        self.ctx, self.lib, self.C = ctx, ctx.lib, ctx.C
+        h = C.c_void_p()
+        _check(self.lib.fg_s16_create(ctx.h, C.byref(h)), "fg_s16_create")
+        self.h = h
+        self.nG = int(self.lib.fg_s16_param_count(NET_G, self.C))
+        self.nD = int(self.lib.fg_s16_param_count(NET_D, self.C))
+
+    def close(self):
+        if self.h:
+            self.lib.fg_s16_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.close()
+        except Exception:
+            pass
+
+    def count(self, net):
+        return self.nD if net == NET_D else self.nG
+
+    def _sized(self, what, a, n):
+        a = f32(a)
+        if a.size != n:
+            raise FGError("%s: expected %d floats, got %d" % (what, n, a.size))
+        return a
+
+    def set_params(self, net, p):
+        p = self._sized("s16 set_params", p, self.count(net))
+        _check(self.lib.fg_s16_set_params(self.h, net, _ptr(p)), "fg_s16_set_params")
+
+    def get_params(self, net):
+        out = np.empty(self.count(net), np.float32)
+        _check(self.lib.fg_s16_get_params(self.h, net, _ptr(out)), "fg_s16_get_params")
+        return out
+
+    def get_grads(self, net):
+        out = np.empty(self.count(net), np.float32)
+        _check(self.lib.fg_s16_get_grads(self.h, net, _ptr(out)), "fg_s16_get_grads")
+        return out
+
+    def zero_grads(self, net):
+        _check(self.lib.fg_s16_zero_grads(self.h, net), "fg_s16_zero_grads")
+
+    def set_adam_state(self, net, m, v, t):
+        m = None if m is None else self._sized("s16 set_adam_state m", m, self.count(net))
+        v = None if v is None else self._sized("s16 set_adam_state v", v, self.count(net))
+        _check(self.lib.fg_s16_set_adam_state(self.h, net, _ptr(m), _ptr(v), int(t)), "fg_s16_set_adam_state")
+
+    def get_adam_state(self, net):
+        m, v, t = np.empty(self.count(net), np.float32), np.empty(self.count(net), np.float32), C.c_int(0)
+        _check(self.lib.fg_s16_get_adam_state(self.h, net, _ptr(m), _ptr(v), C.byref(t)), "fg_s16_get_adam_state")
+        return m, v, t.value
+
+    def set_bn_state(self, s):
+        s = self._sized("s16 set_bn_state", s, 768)
+        _check(self.lib.fg_s16_set_bn_state(self.h, _ptr(s)), "fg_s16_set_bn_state")
+
+    def get_bn_state(self):
+        out = np.empty(768, np.float32)
+        _check(self.lib.fg_s16_get_bn_state(self.h, _ptr(out)), "fg_s16_get_bn_state")
+        return out
+
+    def G_forward(self, noise, training=True, want_img=True):
+        noise = f32(noise)
+        B = noise.shape[0]
+        out = np.empty((B, self.C, 16, 16), np.float32) if want_img else None
+        _check(self.lib.fg_s16_G_forward(self.h, _ptr(noise), B, int(training), _ptr(out)), "fg_s16_G_forward")
+        return out
+
+    def G_backward(self, d_img, want_dnoise=False):
+        d_img = f32(d_img)
+        dn = np.empty((d_img.shape[0], NOISE_DIM), np.float32) if want_dnoise else None
+        _check(self.lib.fg_s16_G_backward(self.h, _ptr(d_img), _ptr(dn)), "fg_s16_G_backward")
+        return dn
+
+    def D_forward(self, img, masks=None, training=True, seed=0):
+        img = f32(img)
+        B = img.shape[0]
+        masks = f32(masks) if masks is not None else None
+        out = np.empty(B, np.float32)
+        _check(self.lib.fg_s16_D_forward(self.h, _ptr(img), B, int(training), _ptr(masks), seed, _ptr(out)), "fg_s16_D_forward")
+        return out
+
+    def D_backward(self, d_out, want_wgrad=True, want_dimg=True):
+        d_out = f32(d_out)
+        dd = np.empty((d_out.shape[0], self.C, 16, 16), np.float32) if want_dimg else None
+        _check(self.lib.fg_s16_D_backward(self.h, _ptr(d_out), int(want_wgrad), _ptr(dd)), "fg_s16_D_backward")
+        return dd
+
+    def dp_broadcast_params(self):
+        _check(self.lib.fg_s16_dp_broadcast_params(self.h), "fg_s16_dp_broadcast_params")
+
+    def train_step(self, hyper, B, real, noise_D, noise_G, masks_D=None, masks_G=None, seed=0, want_stats=True):
+        """Pointers may be numpy float32 arrays (host) or raw addresses (device / pinned)."""
+        st = StepStats() if want_stats else None
+        _check(self.lib.fg_s16_train_step(self.h, C.byref(hyper), B, _ptr(real), _ptr(noise_D), _ptr(noise_G), _ptr(masks_D),
+                                          _ptr(masks_G), seed, C.byref(st) if st is not None else None), "fg_s16_train_step")
+        if st is None:
+            return None
+        return dict(loss_D=st.loss_D, loss_G=st.loss_G, conf=list(st.conf), trained_D=st.trained_D, t_D=st.t_D, t_G=st.t_G,
+                    acc_D=st.acc_D)

@@ -48,6 +48,9 @@ int fg_adam_step(fg_ctx* ctx, float* p, const float* g, float* m, float* v, int6
 int fg_conv2d_forward(fg_ctx* ctx, const float* x, const float* w, const float* b, float* y, int N, int Cin, int H, int W, int Cout, int k);
 int fg_conv2d_backward_data(fg_ctx* ctx, const float* dy, const float* w, float* dx, int N, int Cin, int H, int W, int Cout, int k);
 int fg_conv2d_backward_filter(fg_ctx* ctx, const float* x, const float* dy, float* dw, float* db, int N, int Cin, int H, int W, int Cout, int k);
+int fg_scu_forward(fg_ctx* ctx, const float* x, const float* w, const float* b, float* y, int N, int Cin, int H, int W, int nOutputPlane, int k, int factor);
+int fg_scu_backward_data(fg_ctx* ctx, const float* dy, const float* w, float* dx, int N, int Cin, int H, int W, int nOutputPlane, int k, int factor);
+int fg_scu_backward_filter(fg_ctx* ctx, const float* x, const float* dy, float* dw, float* db, int N, int Cin, int H, int W, int nOutputPlane, int k, int factor);
 int fg_linear_forward(fg_ctx* ctx, const float* x, const float* w, const float* b, float* y, int N, int inp, int out);
 int fg_linear_backward(fg_ctx* ctx, const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int N, int inp, int out);
 int fg_bn_forward_train(fg_ctx* ctx, const float* x, const float* gamma, const float* beta, float* y, float* save_mean,
@@ -122,7 +125,29 @@ int fg_sample(fg_ctx* ctx, const float* noise, int N, int chunk, float* images_o
 int fg_dp_unique_id(void* out128);
 int fg_dp_init(fg_ctx* ctx, const void* id128, int nranks, int rank);
 int fg_dp_broadcast_params(fg_ctx* ctx);
+typedef struct fg_s16 fg_s16;
+int fg_s16_create(fg_ctx* ctx, fg_s16** out);
+int fg_s16_destroy(fg_s16* n);
+int64_t fg_s16_param_count(int net, int channels);
+int fg_s16_mask_per_sample(void);
+int fg_s16_set_params(fg_s16* n, int net, const float* src);
+int fg_s16_get_params(fg_s16* n, int net, float* dst);
+int fg_s16_get_grads(fg_s16* n, int net, float* dst);
+int fg_s16_zero_grads(fg_s16* n, int net);
+float* fg_s16_params_ptr(fg_s16* n, int net);
+float* fg_s16_grads_ptr(fg_s16* n, int net);
+int fg_s16_set_adam_state(fg_s16* n, int net, const float* m, const float* v, int t);
+int fg_s16_get_adam_state(fg_s16* n, int net, float* m, float* v, int* t);
+int fg_s16_set_bn_state(fg_s16* n, const float* src768);
+int fg_s16_get_bn_state(fg_s16* n, float* dst768);
+int fg_s16_G_forward(fg_s16* n, const float* noise, int B, int training, float* img_out);
+int fg_s16_G_backward(fg_s16* n, const float* d_img, float* d_noise);
+int fg_s16_D_forward(fg_s16* n, const float* img, int B, int training, const float* masks, uint64_t seed, float* out);
+int fg_s16_D_backward(fg_s16* n, const float* d_out, int want_wgrad, float* d_img);
+int fg_s16_train_step(fg_s16* n, const fg_hyper* h, int B, const float* real, const float* noise_D, const float* noise_G,
+                      const float* masks_D, const float* masks_G, uint64_t seed, fg_step_stats* stats);
 int fg_c2f_dp_broadcast_params(fg_c2f* n);
+int fg_s16_dp_broadcast_params(fg_s16* n);
 int fg_dp_world(fg_ctx* ctx);
 void* fg_dev_alloc(size_t bytes);
 int fg_dev_free(void* p);

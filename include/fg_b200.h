@@ -152,6 +152,16 @@ int fg_conv2d_backward_data(fg_ctx* ctx, const float* dy, const float* w, float*
 /* accumulates (dw += , db +=) like accGradParameters; db may be NULL                             */
 int fg_conv2d_backward_filter(fg_ctx* ctx, const float* x, const float* dy, float* dw, float* db, int N, int Cin,
                               int H, int W, int Cout, int k);
+/* layers/cudnnSpatialConvolutionUpsample.lua with any factor (:4-16 constructor, :18-30 updateOutput, :32-58 backward):
+ * a "same" convolution to nOutputPlane*factor*factor planes whose output [N][nOutputPlane*f*f][H][W] is RE-VIEWED (not
+ * permuted) as [N][nOutputPlane][H*f][W*f] -- the same contiguous bytes, so y / dy here are that buffer under either
+ * shape.  w is [nOutputPlane*f*f][Cin][k][k], b [nOutputPlane*f*f].  factor = 1 is fg_conv2d_*.                      */
+int fg_scu_forward(fg_ctx* ctx, const float* x, const float* w, const float* b, float* y, int N, int Cin, int H, int W,
+                   int nOutputPlane, int k, int factor);
+int fg_scu_backward_data(fg_ctx* ctx, const float* dy, const float* w, float* dx, int N, int Cin, int H, int W,
+                         int nOutputPlane, int k, int factor);
+int fg_scu_backward_filter(fg_ctx* ctx, const float* x, const float* dy, float* dw, float* db, int N, int Cin, int H,
+                           int W, int nOutputPlane, int k, int factor);
 /* nn.Linear (models.lua:59,406-412)                                                              */
 int fg_linear_forward(fg_ctx* ctx, const float* x, const float* w, const float* b, float* y, int N, int in, int out);
 int fg_linear_backward(fg_ctx* ctx, const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
@@ -239,6 +249,40 @@ int fg_c2f_train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_dif
                       const float* noise_D, const float* cond_G, const float* noise_G, const float* masks_D,
                       const float* masks_G, uint64_t seed, fg_step_stats* stats);
 
+/* ---- the --scale 16 nets (train.lua --scale 16; models.lua:87-104 pick them for 16x16 images) ---- */
+/* G = models.lua:27-51 create_G_decoder_upsampling16 (the 32x32 generator with every spatial size halved),
+ * D = models.lua:279-316 create_D16_d (conv branch with two stride-2 convolutions + dense branch, ConcatTable ->
+ * JoinTable -> Linear(1152,1) -> Sigmoid), loop = adversarial.lua:83-288 incl. the accuracy gate and the
+ * interruptable optimizers.  Same object model as fg_c2f (borrows the ctx; destroy it before the ctx).  Flat
+ * parameter vectors in getParameters() order: G [L1W L1b a1 C1W C1b g1 be1 a2 C2W C2b g2 be2 a3 C3W C3b],
+ * D [c1W c1b a1 .. c4W c4b a4 F1W F1b af E1W E1b ae1 E2W E2b ae2 JW Jb].                                  */
+typedef struct fg_s16 fg_s16;
+int fg_s16_create(fg_ctx* ctx, fg_s16** out);
+int fg_s16_destroy(fg_s16* n);
+int64_t fg_s16_param_count(int net, int channels);
+int fg_s16_mask_per_sample(void);                         /* 1152 = 1024 SpatialDropout planes + 128 Dropout */
+int fg_s16_set_params(fg_s16* n, int net, const float* src);
+int fg_s16_get_params(fg_s16* n, int net, float* dst);
+int fg_s16_get_grads(fg_s16* n, int net, float* dst);
+int fg_s16_zero_grads(fg_s16* n, int net);
+float* fg_s16_params_ptr(fg_s16* n, int net);
+float* fg_s16_grads_ptr(fg_s16* n, int net);
+int fg_s16_set_adam_state(fg_s16* n, int net, const float* m, const float* v, int t);
+int fg_s16_get_adam_state(fg_s16* n, int net, float* m, float* v, int* t);
+int fg_s16_set_bn_state(fg_s16* n, const float* src768);  /* [mean1 256][var1 256][mean2 128][var2 128]   */
+int fg_s16_get_bn_state(fg_s16* n, float* dst768);
+/* noise [B][100] -> images [B][C][16][16] (may be NULL); training=0 => evaluate() (running statistics).
+ * backward accumulates into G's grad buffer; d_noise [B][100] may be NULL.                                */
+int fg_s16_G_forward(fg_s16* n, const float* noise, int B, int training, float* img_out);
+int fg_s16_G_backward(fg_s16* n, const float* d_img, float* d_noise);
+/* images [B][C][16][16] -> [B] sigmoid outputs; masks [B][1152] keep flags or NULL (drawn from seed).     */
+int fg_s16_D_forward(fg_s16* n, const float* img, int B, int training, const float* masks, uint64_t seed, float* out);
+int fg_s16_D_backward(fg_s16* n, const float* d_out, int want_wgrad, float* d_img);
+/* fg_train_step on the 16x16 nets: real [B/2][C][16][16], noise_D [B/2][100], noise_G [B][100],
+ * masks_* [B][1152] or NULL.                                                                              */
+int fg_s16_train_step(fg_s16* n, const fg_hyper* h, int B, const float* real, const float* noise_D, const float* noise_G,
+                      const float* masks_D, const float* masks_G, uint64_t seed, fg_step_stats* stats);
+
 /* ---- device-resident dataset and on-GPU batch assembly ---------------------------------------- */
 /* Replaces dataset.lua:80-117 (image.load(path, nbChannels, "float") + image.scale(img, 32, 32)) and
  * the per-sample batch loop of adversarial.lua:244-249 for the train step's input side: the DECODED
@@ -320,6 +364,7 @@ int fg_dp_init(fg_ctx* ctx, const void* id128, int nranks, int rank);
  * the D-accuracy history to all ranks -- call after loading a checkpoint on rank 0               */
 int fg_dp_broadcast_params(fg_ctx* ctx);
 int fg_c2f_dp_broadcast_params(fg_c2f* n);                /* same for the coarse-to-fine nets      */
+int fg_s16_dp_broadcast_params(fg_s16* n);                /* same for the --scale 16 nets          */
 int fg_dp_world(fg_ctx* ctx);                             /* nranks (1 when DP is off)            */
 
 /* ---- plain device-memory helpers for FFI hosts without a CUDA binding ------------------------ */
