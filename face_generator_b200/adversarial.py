@@ -92,10 +92,11 @@ def epoch_seed0(epoch, rank=0):
     return (epoch - 1) * SEED_EPOCH_STRIDE + rank * SEED_RANK_STRIDE
 
 
-def train(ctx: Context, dataset, hyper, batch_size, n_epoch=-1, rng=None, epoch=1, rank=0, confusion=None, progress=None):
+def train(ctx, dataset, hyper, batch_size, n_epoch=-1, rng=None, epoch=1, rank=0, confusion=None, progress=None):
     """One epoch of adversarial.train(dataset, maxAccuracyD, accsInterval) (adversarial.lua:29-334) with the
     defaults D_iterations = G_iterations = 1 (train.lua:33-34), i.e. one fused fg_train_step per batch.
 
+    ctx: a Context (the 32x32 nets) or an S16 built on one (train.lua --scale 16: the 16x16 nets, images [N][C][16][16]).
     dataset: array-like [N][C][32][32] float32 in [0,1] (what DATASET.loadImages returns, dataset.lua:43-75) or a
     face_generator_b200.dataset.DeviceDataset (then batch assembly and noise happen on the device).
     hyper.D_maxAcc / hyper.accs_interval are the maxAccuracyD / accsInterval arguments.

@@ -163,6 +163,11 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
     c->bn_epilogue = v != 0;
     return FG_OK;
   }
+  if (!strcmp(key, "mma_f16")) {  // 1: K-major tensor-core kernels (forward, dgrad) use the 3xFP16 split + kind::f16 MMAs
+    c->mma_f16 = v != 0;
+    c->G_packed = c->D_packed = false;
+    return FG_OK;
+  }
   if (!strcmp(key, "debug_keep")) {  // keep the D step's pre-activations of fg_train_step ("Dstep.*" debug tensors)
     c->debug_keep = v != 0;
     return FG_OK;
@@ -193,6 +198,7 @@ int64_t fg_get_option(fg_ctx* c, const char* key) {
   if (!strcmp(key, "sm_count")) return c->sm_count;
   if (!strcmp(key, "bn_epilogue")) return c->bn_epilogue;
   if (!strcmp(key, "edge_impl")) return c->edge_impl;
+  if (!strcmp(key, "mma_f16")) return c->mma_f16;
   if (!strcmp(key, "optimizer_D")) return c->opt_D;
   if (!strcmp(key, "optimizer_G")) return c->opt_G;
   return -1;

@@ -116,6 +116,8 @@ struct fg_ctx {
   float* bn_parts = nullptr;  // [m-tile][2][C] BatchNorm partials written by the tensor-core conv epilogue
   int edge_impl = 1;          // option "edge_impl": 0 = the round-1 small-channel kernels (k_conv_small.cu) for G.C3 / D.C1
   int bn_epilogue = 1;        // option "bn_epilogue": 0 = separate statistics pass over z (the round-1 path)
+  int mma_f16 = 0;            // option "mma_f16": forward / dgrad tensor-core kernels on the 3xFP16 split (kind::f16)
+  float* amax_slot = nullptr; // [16] device scalars: (amax, 1/scale) pairs of the gradient tensors in the FP16 split
   double* bn_acc = nullptr;  // [4][256] double accumulators (sum, sumsq / sum g, sum g xhat)
   float *bn_mean1 = nullptr, *bn_istd1 = nullptr, *bn_mean2 = nullptr, *bn_istd2 = nullptr, *bn_mg = nullptr;
   float *G_dz3 = nullptr, *G_dfull = nullptr, *G_dz2 = nullptr, *G_dz1 = nullptr, *G_dz0 = nullptr;

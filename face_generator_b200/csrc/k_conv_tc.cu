@@ -19,6 +19,7 @@
 // tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  3 smem stages of
 // {A_hi, A_lo, B_hi, B_lo}, 128B-swizzled, mbarrier full/empty rings, tcgen05.commit releases stages.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -114,6 +115,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with FP16 operands (kind::f16: 16 K elements per 32-byte slice, twice the TF32 rate), fp32 accumulation
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (F16) umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -152,10 +168,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32 (format 2) or fp16 (format 0)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, bool f16 = false) {
+  return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // one lane of a fully active warp (the compiler knows the predicate selects exactly one lane, so code under it can
@@ -204,6 +220,57 @@ __global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi
   }
 }
 
+// 3xFP16 split: x ~= hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 significant bits like the TF32
+// split, operands of kind::f16 MMAs (2x the TF32 rate, 4 bytes per element for hi+lo instead of 8).  fp16 subnormals
+// keep the ABSOLUTE error at 2^-36, so a tensor whose max is in [2^-13, 65504] is represented to 2^-23 of that max;
+// activations and weights are used as they are, gradients are first scaled by a power of two (tc_amax).
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  const float xc = fminf(fmaxf(x, -65504.f), 65504.f);
+  hi = __float2half_rn(xc);
+  lo = __float2half_rn(fminf(fmaxf((x - __half2float(hi)) * 2048.f, -65504.f), 65504.f));
+}
+__global__ void amax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__ slot) {
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = x4[i];
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));  // non-negative floats order like their bits
+}
+// power of two that brings amax into [2^14, 2^15) (1 for an all-zero tensor); exponent clamped so that s and 1/s are normal
+__device__ __forceinline__ float scale_for_amax(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int ex;
+  frexpf(amax, &ex);  // amax = m * 2^ex, m in [0.5, 1)
+  const int e = max(-100, min(100, 15 - ex));
+  return ldexpf(1.f, e);
+}
+template <bool ALIGNED>
+__global__ void split_h_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4,
+                               float* __restrict__ amax_slot) {
+  float s = 1.f;
+  if (amax_slot) {
+    s = scale_for_amax(amax_slot[0]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) amax_slot[1] = 1.f / s;  // exact: s is a power of two
+  }
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  uint2* h2 = reinterpret_cast<uint2*>(hi);
+  uint2* l2 = reinterpret_cast<uint2*>(lo);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = ALIGNED ? x4[i] : make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    __half h[4], l[4];
+    split_f16(v.x * s, h[0], l[0]);
+    split_f16(v.y * s, h[1], l[1]);
+    split_f16(v.z * s, h[2], l[2]);
+    split_f16(v.w * s, h[3], l[3]);
+    h2[i] = *reinterpret_cast<uint2*>(h);
+    l2[i] = *reinterpret_cast<uint2*>(l);
+  }
+}
+
 // up2 -> 5x5 collapses to 3x3 per output phase: 5x5 rows/cols {0,1}{2,3}{4} (even phase) or {0}{1,2}{3,4} (odd)
 __device__ __forceinline__ void group_range(int parity, int t, int& lo, int& hi) {
   if (parity == 0) {
@@ -215,8 +282,16 @@ __device__ __forceinline__ void group_range(int parity, int t, int& lo, int& hi)
   }
 }
 // W[N][Cc][5][5] -> fwd[ph][ty][tx][n][c] (hi/lo) and dgrad[ph][ty][tx][c][n] (hi/lo)
-__global__ void pack_collapsed_kernel(const float* __restrict__ W, float* __restrict__ f_hi, float* __restrict__ f_lo,
-                                      float* __restrict__ d_hi, float* __restrict__ d_lo, int N, int Cc) {
+template <class T> struct SplitTo;
+template <> struct SplitTo<float> {
+  static __device__ __forceinline__ void run(float x, float& hi, float& lo) { split_tf32(x, hi, lo); }
+};
+template <> struct SplitTo<__half> {
+  static __device__ __forceinline__ void run(float x, __half& hi, __half& lo) { split_f16(x, hi, lo); }
+};
+template <class T>
+__global__ void pack_collapsed_kernel(const float* __restrict__ W, T* __restrict__ f_hi, T* __restrict__ f_lo,
+                                      T* __restrict__ d_hi, T* __restrict__ d_lo, int N, int Cc) {
   const int64_t total = (int64_t)36 * N * Cc;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i % Cc);
@@ -231,8 +306,8 @@ __global__ void pack_collapsed_kernel(const float* __restrict__ W, float* __rest
     float s = 0.f;
     for (int kh = h0; kh <= h1; ++kh)
       for (int kw = w0; kw <= w1; ++kw) s += w[kh * 5 + kw];
-    float hi, lo;
-    split_tf32(s, hi, lo);
+    T hi, lo;
+    SplitTo<T>::run(s, hi, lo);
     f_hi[i] = hi;
     f_lo[i] = lo;
     const int64_t j = ((int64_t)tp * Cc + ch) * N + n;
@@ -241,16 +316,17 @@ __global__ void pack_collapsed_kernel(const float* __restrict__ W, float* __rest
   }
 }
 // generic: W[N][Cc][KK] -> fwd[t][n][c] hi/lo, dgrad[KK-1-t][c][n] hi/lo
-__global__ void pack_split_kernel(const float* __restrict__ W, float* __restrict__ f_hi, float* __restrict__ f_lo,
-                                  float* __restrict__ d_hi, float* __restrict__ d_lo, int N, int Cc, int KK) {
+template <class T>
+__global__ void pack_split_kernel(const float* __restrict__ W, T* __restrict__ f_hi, T* __restrict__ f_lo,
+                                  T* __restrict__ d_hi, T* __restrict__ d_lo, int N, int Cc, int KK) {
   const int64_t total = (int64_t)N * Cc * KK;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int t = (int)(i % KK);
     const int64_t r = i / KK;
     const int ch = (int)(r % Cc);
     const int n = (int)(r / Cc);
-    float hi, lo;
-    split_tf32(W[i], hi, lo);
+    T hi, lo;
+    SplitTo<T>::run(W[i], hi, lo);
     const int64_t jf = ((int64_t)t * N + n) * Cc + ch;
     f_hi[jf] = hi;
     f_lo[jf] = lo;
@@ -306,13 +382,13 @@ int get_encode() {
 // 4-D map over an NHWC fp32 tensor view: dims (C, W, H, B) with explicit byte strides
 // pair = true: `base` is a BF16 pair tensor (2*C bf16 per pixel, same byte strides); the box takes 2*bc elements
 int make_map4(CUtensorMap* m, const float* base, int C, int W, int H, int B, int64_t sW, int64_t sH, int64_t sB, int bc,
-              int bw, int bh, int bb, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, bool pair = false) {
+              int bw, int bh, int bb, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, bool pair = false, bool f16 = false) {
   const int mul = pair ? 2 : 1;
   cuuint64_t dims[4] = {(cuuint64_t)C * mul, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)sW, (cuuint64_t)sH, (cuuint64_t)sB};
   cuuint32_t box[4] = {(cuuint32_t)bc * mul, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = g_encode(m, pair ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+  CUresult r = g_encode(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : (pair ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 4, (void*)base, dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -340,13 +416,13 @@ int make_map5(CUtensorMap* m, const float* base, int C, int W, int H, int B, int
   }
   return FG_OK;
 }
-int make_map2(CUtensorMap* m, const float* base, int cols, int64_t rows, int bc, int br, bool pair = false) {
+int make_map2(CUtensorMap* m, const float* base, int cols, int64_t rows, int bc, int br, bool pair = false, bool f16 = false) {
   const int mul = pair ? 2 : 1;
   cuuint64_t dims[2] = {(cuuint64_t)cols * mul, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * (f16 ? 2 : 4)};
   cuuint32_t box[2] = {(cuuint32_t)bc * mul, (cuuint32_t)br};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = g_encode(m, pair ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+  CUresult r = g_encode(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : (pair ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2, (void*)base, dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -551,6 +627,8 @@ int tc_init(fg_ctx* c) {
   FG_TRY(get_encode());
   FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
   FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>()));
+  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<64>()));
+  FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>()));
   FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<64>()));
   FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<128>()));
   return FG_OK;
@@ -569,17 +647,56 @@ int tc_split(fg_ctx* c, const float* x, float* hi, float* lo, int64_t n) {
   LAUNCH_CHECK(c);
   return FG_OK;
 }
+int tc_amax(fg_ctx* c, const float* x, int64_t n, float* amax_slot) {
+  if (n % 4 || reinterpret_cast<uintptr_t>(x) % 16) {
+    fg_set_error("tc_amax: needs a 16-byte aligned tensor with a multiple of 4 elements");
+    return FG_ERR_INVALID;
+  }
+  FG_CUDA(cudaMemsetAsync(amax_slot, 0, 2 * sizeof(float), c->stream));
+  int64_t g = (n / 4 + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  amax_kernel<<<(int)g, 256, 0, c->stream>>>(x, n / 4, reinterpret_cast<unsigned*>(amax_slot));
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int tc_split_h(fg_ctx* c, const float* x, float* hh, float* hl, int64_t n, float* amax_slot) {
+  if (n % 4) {
+    fg_set_error("tc_split_h: element count must be a multiple of 4");
+    return FG_ERR_INVALID;
+  }
+  int64_t g = (n / 4 + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  __half *h = reinterpret_cast<__half*>(hh), *l = reinterpret_cast<__half*>(hl);
+  if (reinterpret_cast<uintptr_t>(x) % 16 == 0) split_h_kernel<true><<<(int)g, 256, 0, c->stream>>>(x, h, l, n / 4, amax_slot);
+  else split_h_kernel<false><<<(int)g, 256, 0, c->stream>>>(x, h, l, n / 4, amax_slot);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int tc_pack_split_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK) {
+  int64_t g = ((int64_t)N * Cc * KK + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  pack_split_kernel<__half><<<(int)g, 256, 0, c->stream>>>(W, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi, (__half*)d_lo, N, Cc, KK);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int tc_pack_collapsed_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc) {
+  int64_t g = ((int64_t)36 * N * Cc + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  pack_collapsed_kernel<__half><<<(int)g, 256, 0, c->stream>>>(W, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi, (__half*)d_lo, N, Cc);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
 int tc_pack_split(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK) {
   int64_t g = ((int64_t)N * Cc * KK + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  pack_split_kernel<<<(int)g, 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc, KK);
+  pack_split_kernel<float><<<(int)g, 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc, KK);
   LAUNCH_CHECK(c);
   return FG_OK;
 }
 int tc_pack_collapsed(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc) {
   int64_t g = ((int64_t)36 * N * Cc + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  pack_collapsed_kernel<<<(int)g, 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc);
+  pack_collapsed_kernel<float><<<(int)g, 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc);
   LAUNCH_CHECK(c);
   return FG_OK;
 }
@@ -610,9 +727,12 @@ static int tc_chunk(bool forward_type = false) {
   return x >= 1 ? x : d;
 }
 
-static int launch_tapconv(fg_ctx* c, const TcFwdParams& p, int BN) {
+static int launch_tapconv(fg_ctx* c, const TcFwdParams& p, int BN, int f16 = 0) {
   dim3 grid(std::min(p.ntiles, c->sm_count));
-  if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
+  if (f16) {
+    if (BN == 128) tapconv_tc_kernel<128, true><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
+    else tapconv_tc_kernel<64, true><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
+  } else if (BN == 128) tapconv_tc_kernel<128><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
   else tapconv_tc_kernel<64><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);
   LAUNCH_CHECK(c);
   return FG_OK;
@@ -640,7 +760,7 @@ int tc_stat_parts(const ConvGeom& g, int mode) {
 }
 
 int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
-                const float* bias, float* out, ConvGeom g, int mode, float* stats, int* n_parts) {
+                const float* bias, float* out, ConvGeom g, int mode, float* stats, int* n_parts, int f16, const float* oscale) {
   TcFwdParams p;
   memset(&p, 0, sizeof(p));
   const int Hl = g.H / g.ups, Wl = g.W / g.ups;
@@ -648,9 +768,15 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
     fg_set_error("tc_conv_fwd: no 128-pixel box for %dx%d", Hl, Wl);
     return FG_ERR_UNSUPPORTED;
   }
-  const int64_t sW = (int64_t)g.Cin * 4, sH = sW * Wl, sB = sH * Hl;
-  FG_TRY(make_map4(&p.a_hi[0], x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
-  FG_TRY(make_map4(&p.a_lo[0], x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+  const int es = f16 ? 2 : 4, ke = f16 ? 64 : 32;  // element bytes, K elements of one 128-byte block
+  if (g.Cin % ke) {
+    fg_set_error("tc_conv_fwd: %d input channels are not a multiple of %d", g.Cin, ke);
+    return FG_ERR_UNSUPPORTED;
+  }
+  const bool h = f16 != 0;
+  const int64_t sW = (int64_t)g.Cin * es, sH = sW * Wl, sB = sH * Hl;
+  FG_TRY(make_map4(&p.a_hi[0], x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, ke, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, false, h));
+  FG_TRY(make_map4(&p.a_lo[0], x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, ke, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, false, h));
   // N tile: 128 unless halving it keeps the same number of waves on the 148 SMs (few-tile layers such as
   // D.C4's dgrad or the Linear layers): a BN=64 tile costs ~0.6 of a BN=128 tile
   int BN = g.Cout % 128 == 0 ? 128 : 64;
@@ -694,9 +820,10 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
         p.widx[ph * 9 + t] = (int16_t)(ph * 9 + t);
       }
   }
-  FG_TRY(make_map2(&p.b_hi, w_hi, g.Cin, (int64_t)ntapw * g.Cout, 32, BN));
-  FG_TRY(make_map2(&p.b_lo, w_lo, g.Cin, (int64_t)ntapw * g.Cout, 32, BN));
-  p.kpt = g.Cin / 32;
+  FG_TRY(make_map2(&p.b_hi, w_hi, g.Cin, (int64_t)ntapw * g.Cout, ke, BN, false, h));
+  FG_TRY(make_map2(&p.b_lo, w_lo, g.Cin, (int64_t)ntapw * g.Cout, ke, BN, false, h));
+  p.kpt = g.Cin / ke;
+  p.oscale = oscale;
   p.Cout = g.Cout;
   p.B = g.B; p.H = Hl; p.W = Wl;
   p.tiles_x = Wl / p.bw;
@@ -711,25 +838,31 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   p.ntiles = p.tiles_per_phase * p.nphase * (g.Cout / BN);
   p.dbg = getenv("FG_TC_DBG") ? atoi(getenv("FG_TC_DBG")) : 0;
   p.chunk = tc_chunk(g.H * g.W > 1);  // Linear layers (1x1 images, K up to 16384) keep the short chunk
-  return launch_tapconv(c, p, BN);
+  if (f16) p.chunk = std::max(1, p.chunk / 2);  // a 128-byte K block holds twice the K elements
+  return launch_tapconv(c, p, BN, f16);
 }
 
 // dgrad of an up2+5x5 conv straight to the LOW-RES input gradient (the 2x2 sum of the upsample backward is
 // implicit: all 4 output phases accumulate into the same accumulator).  dy_hi/lo: [B][H][W][Cout] full-res;
 // wd_hi/lo: collapsed dgrad pack [36][Cin][Cout]; out: [B][H/2][W/2][Cin].
 int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const float* wd_hi, const float* wd_lo,
-                      float* out, ConvGeom g) {
+                      float* out, ConvGeom g, int f16, const float* oscale) {
   TcFwdParams p;
   memset(&p, 0, sizeof(p));
   const int Hl = g.H / 2, Wl = g.W / 2;
   if (!pick_box(Hl, Wl, 128, &p.bw, &p.bh, &p.bb)) return FG_ERR_UNSUPPORTED;
   const int Cy = g.Cout;  // contraction runs over the forward conv's output channels
+  const int es = f16 ? 2 : 4, ke = f16 ? 64 : 32;
+  const bool h = f16 != 0;
+  if (Cy % ke) return FG_ERR_UNSUPPORTED;
   for (int ph = 0; ph < 4; ++ph) {
     const int py = ph >> 1, px = ph & 1;
-    const int64_t off = ((int64_t)py * g.W + px) * Cy;  // the pair tensor has the same bytes per pixel
-    const int64_t sW = (int64_t)2 * Cy * 4, sH = (int64_t)2 * g.W * Cy * 4, sB = (int64_t)g.H * g.W * Cy * 4;
-    FG_TRY(make_map4(&p.a_hi[ph], dy_hi + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
-    FG_TRY(make_map4(&p.a_lo[ph], dy_lo + off, Cy, Wl, Hl, g.B, sW, sH, sB, 32, p.bw, p.bh, p.bb));
+    const int64_t off_bytes = ((int64_t)py * g.W + px) * Cy * es;
+    const float* b_hi = reinterpret_cast<const float*>(reinterpret_cast<const char*>(dy_hi) + off_bytes);
+    const float* b_lo = reinterpret_cast<const float*>(reinterpret_cast<const char*>(dy_lo) + off_bytes);
+    const int64_t sW = (int64_t)2 * Cy * es, sH = (int64_t)2 * g.W * Cy * es, sB = (int64_t)g.H * g.W * Cy * es;
+    FG_TRY(make_map4(&p.a_hi[ph], b_hi, Cy, Wl, Hl, g.B, sW, sH, sB, ke, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, false, h));
+    FG_TRY(make_map4(&p.a_lo[ph], b_lo, Cy, Wl, Hl, g.B, sW, sH, sB, ke, p.bw, p.bh, p.bb, CU_TENSOR_MAP_SWIZZLE_128B, false, h));
   }
   const int BN = g.Cin % 128 == 0 ? 128 : 64;
   p.nphase = 1;
@@ -742,9 +875,10 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
       p.amap[ph * 9 + t] = (int8_t)ph;
       p.widx[ph * 9 + t] = (int16_t)(ph * 9 + t);
     }
-  FG_TRY(make_map2(&p.b_hi, wd_hi, Cy, (int64_t)36 * g.Cin, 32, BN));
-  FG_TRY(make_map2(&p.b_lo, wd_lo, Cy, (int64_t)36 * g.Cin, 32, BN));
-  p.kpt = Cy / 32;
+  FG_TRY(make_map2(&p.b_hi, wd_hi, Cy, (int64_t)36 * g.Cin, ke, BN, false, h));
+  FG_TRY(make_map2(&p.b_lo, wd_lo, Cy, (int64_t)36 * g.Cin, ke, BN, false, h));
+  p.kpt = Cy / ke;
+  p.oscale = oscale;
   p.Cout = g.Cin;
   p.B = g.B; p.H = Hl; p.W = Wl;
   p.tiles_x = Wl / p.bw;
@@ -756,8 +890,8 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
   p.out_scale = 1;
   p.ntiles = p.tiles_per_phase * (g.Cin / BN);
   p.dbg = getenv("FG_TC_DBG") ? atoi(getenv("FG_TC_DBG")) : 0;
-  p.chunk = tc_chunk(true);
-  return launch_tapconv(c, p, BN);
+  p.chunk = f16 ? std::max(1, tc_chunk(true) / 2) : tc_chunk(true);
+  return launch_tapconv(c, p, BN, f16);
 }
 
 // wgrad.  x_hi/lo: [B][H/ups][W/ups][Cin]; dy_hi/lo: [B][H][W][Cout]; out (overwritten):

@@ -21,6 +21,7 @@ struct alignas(64) TcFwdParams {
   const float* bias;
   float* stats;  // optional [m-tile][2][Cout]: per-tile column sums of the output and of its square (BatchNorm)
   int out_H, out_W, out_scale;
+  const float* oscale;  // optional device scalar the accumulators are multiplied by (inverse of the A operand's scale)
   int dbg;    // experiment switches (FG_TC_DBG): 1 = skip MMAs, 2 = skip TMA data movement
   int chunk;  // K-blocks accumulated in TMEM before the epilogue promotes them to fp32 registers
 };
@@ -43,11 +44,21 @@ int tc_pack_split(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_
 int tc_pack_collapsed(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc);
 int tc_combine_collapsed_wgrad(fg_ctx* c, const float* G, float* dW, int N, int Cc);
 // stats / n_parts (optional): the kernel also writes per-tile BatchNorm partials [*n_parts][2][Cout] (see TcFwdParams)
+// f16 != 0: the four operand pointers are __half arrays holding the FP16 split (tc_split_h / tc_pack_*_h: hi = fp16(x),
+// lo = fp16((x - hi) * 2^11)) and the kernel issues kind::f16 MMAs (twice the tensor rate, half the operand bytes);
+// oscale: optional device scalar multiplied into the result (inverse of the power-of-two scale tc_split_h applied)
 int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* bias,
-                float* out, ConvGeom g, int mode, float* stats = nullptr, int* n_parts = nullptr);
+                float* out, ConvGeom g, int mode, float* stats = nullptr, int* n_parts = nullptr, int f16 = 0,
+                const float* oscale = nullptr);
 int tc_stat_parts(const ConvGeom& g, int mode);  // number of per-tile partials tc_conv_fwd writes for this geometry
 int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const float* wd_hi, const float* wd_lo, float* out,
-                      ConvGeom g);
+                      ConvGeom g, int f16 = 0, const float* oscale = nullptr);
+// FP16 split of x (n % 4 == 0) into two __half arrays.  amax_slot (optional, device, 2 floats): x is first scaled by the
+// power of two that brings max|x| (slot[0], filled by tc_amax) into [2^14, 2^15); slot[1] receives the inverse scale.
+int tc_amax(fg_ctx* c, const float* x, int64_t n, float* amax_slot);
+int tc_split_h(fg_ctx* c, const float* x, float* hh, float* hl, int64_t n, float* amax_slot = nullptr);
+int tc_pack_split_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK);
+int tc_pack_collapsed_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc);
 int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* out,
                   ConvGeom g);
 int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops);

@@ -46,7 +46,8 @@ __device__ __forceinline__ FwdTile fwd_decode(const TcFwdParams& p, int tile) {
 }
 
 // acc[0..BN) += main half + cross half of one TMEM accumulator buffer (lane quadrant q of this warp)
-template <int BN>
+// F16 (3xFP16 split operands, see k_conv_tc.cu): the lo halves are stored scaled by 2^11, so the cross half carries 2^11
+template <int BN, bool F16 = false>
 __device__ __forceinline__ void promote(float (&acc)[BN], uint32_t tbuf, int q) {
 #pragma unroll
   for (int j = 0; j < BN / 32; ++j) {
@@ -54,19 +55,22 @@ __device__ __forceinline__ void promote(float (&acc)[BN], uint32_t tbuf, int q) 
     const uint32_t ta = tbuf + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32);
     tmem_ld_32x32_x2(ta, ta + BN, va, vb);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[j * 32 + i] += __uint_as_float(va[i]) + __uint_as_float(vb[i]);
+    for (int i = 0; i < 32; ++i)
+      acc[j * 32 + i] += F16 ? fmaf(__uint_as_float(vb[i]), 0x1p-11f, __uint_as_float(va[i]))
+                             : __uint_as_float(va[i]) + __uint_as_float(vb[i]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // tapconv: forward / dgrad.  Persistent: CTA i handles tiles i, i+gridDim.x, ...
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool F16 = false>
 __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constant__ TcFwdParams p) {
   constexpr uint32_t kBBytes = BN * 128;
   constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;  // {a_hi, a_lo, b_hi, b_lo}; b_lo directly behind b_hi
-  constexpr uint32_t kIdesc2 = make_idesc(128, 2 * BN, 0, 0);  // a_hi x [b_hi | b_lo]
-  constexpr uint32_t kIdesc1 = make_idesc(128, BN, 0, 0);      // a_lo x b_hi
+  constexpr uint32_t kIdesc2 = make_idesc(128, 2 * BN, 0, 0, F16);  // a_hi x [b_hi | b_lo]
+  constexpr uint32_t kIdesc1 = make_idesc(128, BN, 0, 0, F16);      // a_lo x b_hi
+  constexpr int kKE = F16 ? 64 : 32;                                // K elements of one 128-byte K block
   constexpr uint32_t kRing = 512 / (2 * BN);                   // accumulator buffers of 2*BN columns: [main | cross]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const uint32_t s = kbg % kStages, it = kbg / kStages;
           if (it > 0) mbar_wait_spin(empty + s, (it - 1) & 1);
-          const int tap = kb / p.kpt, c0 = (kb - tap * p.kpt) * 32;
+          const int tap = kb / p.kpt, c0 = (kb - tap * p.kpt) * kKE;
           const int ti = t.ph * p.ntaps + tap;
           const int am = p.amap[ti];
           uint8_t* st = smem + s * kStageBytes;
@@ -158,9 +162,9 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
             if (!(p.dbg & 1)) {  // (dbg bit 0: experiment without MMAs)
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 fp32 of K) in the 16B-unit start-address field
-                umma_tf32(tacc, a_hi + ko, b_cat + ko, kIdesc2, (j | k) != 0);  // [main | cross] (+)= a_hi x [b_hi | b_lo]
-                umma_tf32(tacc + BN, a_lo + ko, b_cat + ko, kIdesc1, 1);        // cross += a_lo x b_hi
+                const uint64_t ko = (uint64_t)(k * 2);  // +32 bytes (8 tf32 / 16 fp16 of K) in the 16B-unit start-address field
+                umma<F16>(tacc, a_hi + ko, b_cat + ko, kIdesc2, (j | k) != 0);  // [main | cross] (+)= a_hi x [b_hi | b_lo]
+                umma<F16>(tacc + BN, a_lo + ko, b_cat + ko, kIdesc1, 1);        // cross += a_lo x b_hi
               }
             }
             umma_commit(empty + s);
@@ -186,10 +190,15 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
         const uint32_t buf = cg % kRing, use = cg / kRing;
         mbar_wait(tmem_full + buf, use & 1);
         tc_fence_after();
-        promote<BN>(acc, tmem_base + buf * 2 * BN, q);
+        promote<BN, F16>(acc, tmem_base + buf * 2 * BN, q);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + buf);
+      }
+      if (p.oscale) {  // the A operand was stored scaled by a power of two (gradients in the FP16 split): undo it
+        const float os = *p.oscale;
+#pragma unroll
+        for (int i = 0; i < BN; ++i) acc[i] *= os;
       }
       const int b = t.b0 + bi;
       if (p.bias) {

@@ -86,7 +86,14 @@ int fg_conv2d_forward(fg_ctx* c, const float* x, const float* w, const float* b,
   FG_TRY(scratch(c, 5, ny, &yn));
   FG_TRY(k_nchw_to_nhwc(c, xd, xn, N, Cin, H * W));
   const ConvGeom g{N, H, W, Cin, Cout, k, 1};
-  if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(g)) {
+  if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(g) && c->mma_f16 && Cin % 64 == 0 && nx % 4 == 0) {
+    float *xs, *ws;  // FP16 split: nx (nw) halves each for hi and lo = nx (nw) floats of scratch
+    FG_TRY(scratch(c, 4, nx, &xs));
+    FG_TRY(scratch(c, 7, nw, &ws));
+    FG_TRY(tc_split_h(c, xn, xs, xs + nx / 2, (int64_t)nx));
+    FG_TRY(tc_pack_split_h(c, wd, ws, ws + nw / 2, nullptr, nullptr, Cout, Cin, k * k));
+    FG_TRY(tc_conv_fwd(c, xs, xs + nx / 2, ws, ws + nw / 2, bd, yn, g, 0, nullptr, nullptr, 1));
+  } else if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(g)) {
     float *xs, *ws;
     FG_TRY(scratch(c, 4, 2 * nx, &xs));
     FG_TRY(scratch(c, 7, 2 * nw, &ws));
@@ -117,7 +124,15 @@ int fg_conv2d_backward_data(fg_ctx* c, const float* dy, const float* w, float* d
   FG_TRY(scratch(c, 5, nx, &dxn));
   FG_TRY(k_nchw_to_nhwc(c, dyd, dyn, N, Cout, H * W));
   const ConvGeom gd{N, H, W, Cout, Cin, k, 1};
-  if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(gd)) {
+  if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(gd) && c->mma_f16 && Cout % 64 == 0 && ny % 4 == 0 && nw % 2 == 0) {
+    float *ys, *ws;  // the gradient is scaled by a power of two into fp16's range first (tc_amax), the kernel undoes it
+    FG_TRY(scratch(c, 2, ny, &ys));
+    FG_TRY(scratch(c, 7, 2 * nw, &ws));
+    FG_TRY(tc_amax(c, dyn, (int64_t)ny, c->amax_slot));
+    FG_TRY(tc_split_h(c, dyn, ys, ys + ny / 2, (int64_t)ny, c->amax_slot));
+    FG_TRY(tc_pack_split_h(c, wd, ws, ws + nw / 2, ws + nw, ws + nw + nw / 2, Cout, Cin, k * k));
+    FG_TRY(tc_conv_fwd(c, ys, ys + ny / 2, ws + nw, ws + nw + nw / 2, nullptr, dxn, gd, 0, nullptr, nullptr, 1, c->amax_slot + 1));
+  } else if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(gd)) {
     float *ys, *ws;
     FG_TRY(scratch(c, 2, 2 * ny, &ys));
     FG_TRY(scratch(c, 7, 4 * nw, &ws));

@@ -94,6 +94,7 @@ int net_alloc(fg_ctx* c) {
   FG_TRY(dalloc(c, &c->acc_hist, kAccHistMax));
   FG_CUDA(cudaMallocHost((void**)&c->hstats, sizeof(DeviceStats)));
   memset(c->hstats, 0, sizeof(DeviceStats));
+  FG_TRY(dalloc(c, &c->amax_slot, 16));
   // packs
   FG_TRY(dalloc(c, &c->G_L1p, 8192 * 100 + 8192));  // + permuted bias behind the weights
   FG_TRY(dalloc(c, &c->G_L1pd, 8192 * 100));

@@ -45,14 +45,22 @@ function adversarial.train(dataset, maxAccuracyD, accsInterval)
   if N_epoch <= 0 then N_epoch = dataset:size() end
   local dataBatchSize = OPT.batchSize / 2
   local ctx = b200.context(OPT.gpu, OPT.batchSize, IMG_DIMENSIONS[1])
+  -- train.lua --scale 16: models.create_G / create_D built the 16x16 nets (models.lua:87-104); same loop, fg_s16_* entry points
+  local s16 = IMG_DIMENSIONS[2] == 16 and b200.s16(ctx) or nil
   local hyper = b200.hyperFromOPT(OPT, OPTSTATE)
   hyper[0].D_maxAcc, hyper[0].accs_interval = maxAccuracyD, accsInterval
   -- the stock models' parameters (MODELS.create_* + NN_UTILS.initializeWeights, train.lua:134-138) are uploaded once;
   -- from then on the device copy is authoritative and written back at every checkpoint (below)
   if not adversarial.uploaded then
-    F.check(C.fg_set_params(ctx, F.NET_D, F.ptr(PARAMETERS_D)), 'fg_set_params')
-    F.check(C.fg_set_params(ctx, F.NET_G, F.ptr(PARAMETERS_G)), 'fg_set_params')
+    if s16 then
+      F.check(C.fg_s16_set_params(s16, F.NET_D, F.ptr(PARAMETERS_D)), 'fg_s16_set_params')
+      F.check(C.fg_s16_set_params(s16, F.NET_G, F.ptr(PARAMETERS_G)), 'fg_s16_set_params')
+    else
+      F.check(C.fg_set_params(ctx, F.NET_D, F.ptr(PARAMETERS_D)), 'fg_set_params')
+      F.check(C.fg_set_params(ctx, F.NET_G, F.ptr(PARAMETERS_G)), 'fg_set_params')
+    end
     dp_init(ctx)                                          -- after the upload: rank 0's parameters win
+    if s16 then F.check(C.fg_s16_dp_broadcast_params(s16), 'fg_s16_dp_broadcast_params') end
     adversarial.uploaded = true
   end
   local stats = ffi.new('fg_step_stats[1]')
@@ -70,7 +78,11 @@ function adversarial.train(dataset, maxAccuracyD, accsInterval)
     local noiseD = NN_UTILS.createNoiseInputs(half)
     local noiseG = NN_UTILS.createNoiseInputs(thisBatchSize)
     seed = seed + 1
-    F.check(C.fg_train_step(ctx, hyper, thisBatchSize, F.ptr(real), F.ptr(noiseD), F.ptr(noiseG), nil, nil, seed, stats), 'fg_train_step')
+    if s16 then
+      F.check(C.fg_s16_train_step(s16, hyper, thisBatchSize, F.ptr(real), F.ptr(noiseD), F.ptr(noiseG), nil, nil, seed, stats), 'fg_s16_train_step')
+    else
+      F.check(C.fg_train_step(ctx, hyper, thisBatchSize, F.ptr(real), F.ptr(noiseD), F.ptr(noiseG), nil, nil, seed, stats), 'fg_train_step')
+    end
     local s = stats[0]
     -- feed optim.ConfusionMatrix exactly like adversarial.lua:112-117 (rows = predicted class, cols = target)
     CONFUSION.mat[2][2] = CONFUSION.mat[2][2] + s.conf[0]
@@ -92,8 +104,13 @@ function adversarial.train(dataset, maxAccuracyD, accsInterval)
   -- the live device parameters are copied back into the flat tensors train.lua:151-152 obtained from
   -- MODEL_x:getParameters() at the end of every epoch (20 MB), so MODEL_D / MODEL_G -- which train.lua's plotting
   -- (NN_UTILS.visualizeProgress, train.lua:204) and the save sequence below use -- hold the trained weights
-  F.check(C.fg_get_params(ctx, F.NET_D, F.ptr(PARAMETERS_D)), 'fg_get_params')
-  F.check(C.fg_get_params(ctx, F.NET_G, F.ptr(PARAMETERS_G)), 'fg_get_params')
+  if s16 then
+    F.check(C.fg_s16_get_params(s16, F.NET_D, F.ptr(PARAMETERS_D)), 'fg_s16_get_params')
+    F.check(C.fg_s16_get_params(s16, F.NET_G, F.ptr(PARAMETERS_G)), 'fg_s16_get_params')
+  else
+    F.check(C.fg_get_params(ctx, F.NET_D, F.ptr(PARAMETERS_D)), 'fg_get_params')
+    F.check(C.fg_get_params(ctx, F.NET_G, F.ptr(PARAMETERS_G)), 'fg_get_params')
+  end
   -- checkpoint every OPT.saveFreq epochs: the reference's own sequence (adversarial.lua:319-329)
   if EPOCH % OPT.saveFreq == 0 then
     local filename = paths.concat(OPT.save, 'adversarial.net')

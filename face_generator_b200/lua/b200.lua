@@ -22,6 +22,16 @@ function b200.context(device, maxBatch, channels)
   return b200._ctx
 end
 
+-- the --scale 16 nets (models.lua:87-104 pick create_G_decoder_upsampling16 / create_D16_d for 16x16 images)
+function b200.s16(ctx)
+  if not b200._s16 then
+    local out = ffi.new('fg_s16*[1]')
+    F.check(C.fg_s16_create(ctx, out), 'fg_s16_create')
+    b200._s16 = ffi.gc(out[0], C.fg_s16_destroy)
+  end
+  return b200._s16
+end
+
 -- hyper-parameters from the reference's OPT / OPTSTATE tables; also selects the optimizer the fused step runs
 -- (OPT.D_optmethod / OPT.G_optmethod, train.lua:38-39; adversarial.lua:259-266, :279-286)
 local OPTMETHOD = {adam = 0, adagrad = 1, sgd = 2}
@@ -275,11 +285,32 @@ function Conv:accGradParameters(input, gradOutput, scale)
   F.check(C.fg_conv2d_backward_filter(self.ctx, F.ptr(input:contiguous()), F.ptr(gradOutput:contiguous()), F.ptr(self.gradWeight), F.ptr(self.gradBias), N, self.nIn, H, W, self.nOut, self.k), 'fg_conv2d_backward_filter')
 end
 
--- layers/cudnnSpatialConvolutionUpsample.lua with factor = 1 (the only instantiation, models_c2f.lua:123-131)
+-- layers/cudnnSpatialConvolutionUpsample.lua: a convolution to nOut*factor^2 planes (:14-15) whose contiguous output is
+-- viewed as [N][nOut][h*factor][w*factor] (:18-30) and whose gradOutput is viewed back (:32-58).  The reference only
+-- instantiates factor = 1 (models_c2f.lua:123-131); fg_scu_* takes any factor (default 2 like the reference's :5).
 local SCU = torch.class('b200.SpatialConvolutionUpsample', 'b200.SpatialConvolution')
 function SCU:__init(nIn, nOut, kW, kH, factor)
-  assert((factor or 1) == 1, 'b200.SpatialConvolutionUpsample: only factor = 1 is used by the reference')
-  b200.SpatialConvolution.__init(self, nIn, nOut, kW, kH, 1, 1, (kW - 1) / 2, (kH - 1) / 2)
+  factor = factor or 2
+  assert(kW % 2 == 1 and kH % 2 == 1 and kW == kH, 'b200.SpatialConvolutionUpsample: odd square kernels')
+  self.factor, self.nOutU = factor, nOut
+  b200.SpatialConvolution.__init(self, nIn, nOut * factor * factor, kW, kH, 1, 1, (kW - 1) / 2, (kH - 1) / 2)
+end
+function SCU:updateOutput(input)
+  local N, H, W = input:size(1), input:size(3), input:size(4)
+  self.output:resize(N, self.nOutU, H * self.factor, W * self.factor)   -- the view of :24; same bytes as [N][nOut*f*f][H][W]
+  F.check(C.fg_scu_forward(self.ctx, F.ptr(input:contiguous()), F.ptr(self.weight), F.ptr(self.bias), F.ptr(self.output), N, self.nIn, H, W, self.nOutU, self.k, self.factor), 'fg_scu_forward')
+  return self.output
+end
+function SCU:updateGradInput(input, gradOutput)
+  local N, H, W = input:size(1), input:size(3), input:size(4)
+  self.gradInput:resizeAs(input)
+  F.check(C.fg_scu_backward_data(self.ctx, F.ptr(gradOutput:contiguous()), F.ptr(self.weight), F.ptr(self.gradInput), N, self.nIn, H, W, self.nOutU, self.k, self.factor), 'fg_scu_backward_data')
+  return self.gradInput
+end
+function SCU:accGradParameters(input, gradOutput, scale)
+  assert((scale or 1) == 1, 'b200.SpatialConvolutionUpsample: scale must be 1')
+  local N, H, W = input:size(1), input:size(3), input:size(4)
+  F.check(C.fg_scu_backward_filter(self.ctx, F.ptr(input:contiguous()), F.ptr(gradOutput:contiguous()), F.ptr(self.gradWeight), F.ptr(self.gradBias), N, self.nIn, H, W, self.nOutU, self.k, self.factor), 'fg_scu_backward_filter')
 end
 
 local Lin, lparent = torch.class('b200.Linear', 'nn.Module')

@@ -212,6 +212,24 @@ def test_gpu_s16_batch_256_runs_on_the_tensor_cores():
     assert PU.relerr(outs[1][0], outs[0][0]) < TOL and PU.relerr(outs[1][1], outs[0][1]) < TOL
 
 
+@pytest.mark.gpu
+def test_gpu_s16_epoch_loop():
+    """adversarial.train (the adversarial.lua:29-334 epoch loop) drives the 16x16 nets through the same call"""
+    from face_generator_b200 import adversarial
+    from face_generator_b200.lib import NET_D, NET_G, hyper_default
+    B, C = 8, 3
+    case = SU.make_case(B, C, seed=1300, init="trained")
+    ctx, net = _ctx(B, C, 2)
+    net.set_params(NET_G, case["PG"])
+    net.set_params(NET_D, case["PD"])
+    data = np.random.default_rng(3).random((40, C, 16, 16)).astype(np.float32)
+    acc, conf, trained = adversarial.train(net, data, hyper_default(), B, n_epoch=16, epoch=1)
+    batches = adversarial.epoch_batches(16, B)  # the tail batch shrinks (adversarial.lua:56)
+    nb = len(batches)
+    assert conf.sum() == sum(b for _, b in batches) and trained == nb and 0.0 <= acc <= 1.0
+    assert net.get_adam_state(NET_G)[2] == nb
+
+
 # ------------------------------------------------------------------------------------------ SCU factor != 1
 @pytest.mark.gpu
 @pytest.mark.parametrize("impl", [0, 2])
