@@ -116,7 +116,7 @@ struct fg_ctx {
   float* bn_parts = nullptr;  // [m-tile][2][C] BatchNorm partials written by the tensor-core conv epilogue
   int edge_impl = 1;          // option "edge_impl": 0 = the round-1 small-channel kernels (k_conv_small.cu) for G.C3 / D.C1
   int bn_epilogue = 1;        // option "bn_epilogue": 0 = separate statistics pass over z (the round-1 path)
-  int mma_f16 = 0;            // option "mma_f16": forward / dgrad tensor-core kernels on the 3xFP16 split (kind::f16)
+  int mma_f16 = 1;            // option "mma_f16": 1 (default) = tensor-core operands in the 3xFP16 split (kind::f16 MMAs); 0 = 3xTF32
   float* amax_slot = nullptr; // [16] device scalars: (amax, 1/scale) pairs of the gradient tensors in the FP16 split
   double* bn_acc = nullptr;  // [4][256] double accumulators (sum, sumsq / sum g, sum g xhat)
   float *bn_mean1 = nullptr, *bn_istd1 = nullptr, *bn_mean2 = nullptr, *bn_istd2 = nullptr, *bn_mg = nullptr;
@@ -167,6 +167,16 @@ struct fg_ctx {
     // D's Linear layers: [0] L1 fwd [512][2048'], [1] L1 dgrad [2048'][512], [2] L2 fwd, [3] L2 dgrad
     float *D_Lw_hi[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Lw_lo[4] = {nullptr, nullptr, nullptr, nullptr};
     float *D_lin_hi[2] = {nullptr, nullptr}, *D_lin_lo[2] = {nullptr, nullptr};  // splits of p4 / hl1 kept for wgrad
+    // 3xFP16 split twins (option mma_f16) of the K-major operands: n halves = n/2 floats per buffer
+    float *G_h0_hh = nullptr, *G_h0_hl = nullptr, *G_h1_hh = nullptr, *G_h1_hl = nullptr, *dy_hh = nullptr, *dy_hl = nullptr;
+    float *G_Wf_hh[2] = {nullptr, nullptr}, *G_Wf_hl[2] = {nullptr, nullptr}, *G_Wd_hh[2] = {nullptr, nullptr},
+          *G_Wd_hl[2] = {nullptr, nullptr};
+    float *D_p_hh[3] = {nullptr, nullptr, nullptr}, *D_p_hl[3] = {nullptr, nullptr, nullptr};
+    float *D_Wf_hh[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Wf_hl[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *D_Wd_hh[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Wd_hl[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *G_x_hh = nullptr, *G_x_hl = nullptr, *G_L1w_hh = nullptr, *G_L1w_hl = nullptr;
+    float *D_lin_hh[2] = {nullptr, nullptr}, *D_lin_hl[2] = {nullptr, nullptr};
+    float *D_Lw_hh[4] = {nullptr, nullptr, nullptr, nullptr}, *D_Lw_hl[4] = {nullptr, nullptr, nullptr, nullptr};
   } tcb;
 };
 

@@ -400,14 +400,16 @@ int make_map4(CUtensorMap* m, const float* base, int C, int W, int H, int B, int
 }
 // 5-D map for the MN-major wgrad operands: dims (32 ch-in-group, W, H, B, C/32 groups); the box takes `ngroups`
 // channel groups of one 32-pixel box so the tile lands as [group][pixel][32 ch] (SWIZZLE_128B_ATOM_32B)
+// f16: groups of 64 fp16 channels (128 bytes), plain SWIZZLE_128B
 int make_map5(CUtensorMap* m, const float* base, int C, int W, int H, int B, int64_t sW, int64_t sH, int64_t sB, int bw,
-              int bh, int bb, int ngroups) {
-  cuuint64_t dims[5] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(C / 32)};
+              int bh, int bb, int ngroups, bool f16 = false) {
+  const int gch = f16 ? 64 : 32;
+  cuuint64_t dims[5] = {(cuuint64_t)gch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)(C / gch)};
   cuuint64_t strides[4] = {(cuuint64_t)sW, (cuuint64_t)sH, (cuuint64_t)sB, 128};
-  cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb, (cuuint32_t)ngroups};
+  cuuint32_t box[5] = {(cuuint32_t)gch, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb, (cuuint32_t)ngroups};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+  CUresult r = g_encode(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fg_set_error("cuTensorMapEncodeTiled(5d) failed: %d (C=%d W=%d H=%d B=%d box %d,%d,%d x%d)", (int)r, C, W, H, B, bw, bh,
@@ -631,6 +633,8 @@ int tc_init(fg_ctx* c) {
   FG_CUDA(cudaFuncSetAttribute(tapconv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<128>()));
   FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<64>()));
   FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<128>()));
+  FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<64>()));
+  FG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem<128>()));
   return FG_OK;
 }
 void tc_destroy(fg_ctx* c) { (void)c; }
@@ -760,7 +764,8 @@ int tc_stat_parts(const ConvGeom& g, int mode) {
 }
 
 int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
-                const float* bias, float* out, ConvGeom g, int mode, float* stats, int* n_parts, int f16, const float* oscale) {
+                const float* bias, float* out, ConvGeom g, int mode, float* stats, int* n_parts, int f16, const float* oscale,
+                const float* oscale2) {
   TcFwdParams p;
   memset(&p, 0, sizeof(p));
   const int Hl = g.H / g.ups, Wl = g.W / g.ups;
@@ -823,7 +828,8 @@ int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_
   FG_TRY(make_map2(&p.b_hi, w_hi, g.Cin, (int64_t)ntapw * g.Cout, ke, BN, false, h));
   FG_TRY(make_map2(&p.b_lo, w_lo, g.Cin, (int64_t)ntapw * g.Cout, ke, BN, false, h));
   p.kpt = g.Cin / ke;
-  p.oscale = oscale;
+  p.oscale = oscale ? oscale : oscale2;
+  p.oscale2 = oscale ? oscale2 : nullptr;
   p.Cout = g.Cout;
   p.B = g.B; p.H = Hl; p.W = Wl;
   p.tiles_x = Wl / p.bw;
@@ -897,22 +903,27 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
 // wgrad.  x_hi/lo: [B][H/ups][W/ups][Cin]; dy_hi/lo: [B][H][W][Cout]; out (overwritten):
 //   ups==1: [k*k][Cout][Cin]          ups==2: collapsed [36][Cout][Cin]
 int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* out,
-                  ConvGeom g) {
+                  ConvGeom g, int f16, const float* oscale, const float* oscale2) {
   TcWgParams p;
   memset(&p, 0, sizeof(p));
   const int Hl = g.H / g.ups, Wl = g.W / g.ups;
-  if (!pick_box(Hl, Wl, 32, &p.bw, &p.bh, &p.bb)) return FG_ERR_UNSUPPORTED;
+  const bool h = f16 != 0;
+  const int es = h ? 2 : 4, gch = h ? 64 : 32;  // element bytes; channels per 128-byte group
+  if (!pick_box(Hl, Wl, h ? 64 : 32, &p.bw, &p.bh, &p.bb)) return FG_ERR_UNSUPPORTED;
+  if (g.Cin % 64 || g.Cout % 128) return FG_ERR_UNSUPPORTED;
+  const int BN = g.Cin % 128 == 0 ? 128 : 64;
   {
-    const int64_t sW = (int64_t)g.Cin * 4, sH = sW * Wl, sB = sH * Hl;
-    const int ngx = (g.Cin % 128 == 0 ? 128 : 64) / 32;
-    FG_TRY(make_map5(&p.x_hi, x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, ngx));
-    FG_TRY(make_map5(&p.x_lo, x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, ngx));
+    const int64_t sW = (int64_t)g.Cin * es, sH = sW * Wl, sB = sH * Hl;
+    const int ngx = BN / gch;
+    FG_TRY(make_map5(&p.x_hi, x_hi, g.Cin, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, ngx, h));
+    FG_TRY(make_map5(&p.x_lo, x_lo, g.Cin, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, ngx, h));
   }
+  const int ngy = 128 / gch;
   int ntt;
   if (g.ups == 1) {
-    const int64_t sW = (int64_t)g.Cout * 4, sH = sW * g.W, sB = sH * g.H;
-    FG_TRY(make_map5(&p.dy_hi[0], dy_hi, g.Cout, g.W, g.H, g.B, sW, sH, sB, p.bw, p.bh, p.bb, 4));
-    FG_TRY(make_map5(&p.dy_lo[0], dy_lo, g.Cout, g.W, g.H, g.B, sW, sH, sB, p.bw, p.bh, p.bb, 4));
+    const int64_t sW = (int64_t)g.Cout * es, sH = sW * g.W, sB = sH * g.H;
+    FG_TRY(make_map5(&p.dy_hi[0], dy_hi, g.Cout, g.W, g.H, g.B, sW, sH, sB, p.bw, p.bh, p.bb, ngy, h));
+    FG_TRY(make_map5(&p.dy_lo[0], dy_lo, g.Cout, g.W, g.H, g.B, sW, sH, sB, p.bw, p.bh, p.bb, ngy, h));
     const int pad = (g.k - 1) / 2;
     ntt = g.k * g.k;
     for (int t = 0; t < ntt; ++t) {
@@ -923,10 +934,12 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
   } else {
     for (int ph = 0; ph < 4; ++ph) {
       const int py = ph >> 1, px = ph & 1;
-      const int64_t off = ((int64_t)py * g.W + px) * g.Cout;
-      const int64_t sW = (int64_t)2 * g.Cout * 4, sH = (int64_t)2 * g.W * g.Cout * 4, sB = (int64_t)g.H * g.W * g.Cout * 4;
-      FG_TRY(make_map5(&p.dy_hi[ph], dy_hi + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, 4));
-      FG_TRY(make_map5(&p.dy_lo[ph], dy_lo + off, g.Cout, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, 4));
+      const int64_t off_bytes = ((int64_t)py * g.W + px) * g.Cout * es;
+      const float* b_hi = reinterpret_cast<const float*>(reinterpret_cast<const char*>(dy_hi) + off_bytes);
+      const float* b_lo = reinterpret_cast<const float*>(reinterpret_cast<const char*>(dy_lo) + off_bytes);
+      const int64_t sW = (int64_t)2 * g.Cout * es, sH = (int64_t)2 * g.W * g.Cout * es, sB = (int64_t)g.H * g.W * g.Cout * es;
+      FG_TRY(make_map5(&p.dy_hi[ph], b_hi, g.Cout, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, ngy, h));
+      FG_TRY(make_map5(&p.dy_lo[ph], b_lo, g.Cout, Wl, Hl, g.B, sW, sH, sB, p.bw, p.bh, p.bb, ngy, h));
     }
     ntt = 36;
     for (int ph = 0; ph < 4; ++ph)
@@ -936,7 +949,6 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
         p.phase[ph * 9 + t] = (int8_t)ph;
       }
   }
-  const int BN = g.Cin % 128 == 0 ? 128 : 64;
   p.Cout = g.Cout;
   p.Cin = g.Cin;
   p.tiles_x = Wl / p.bw;
@@ -948,10 +960,16 @@ int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* 
   p.kb_per_split = (p.kblocks + splits - 1) / splits;
   splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
   p.out = out;
+  p.oscale = oscale ? oscale : oscale2;
+  p.oscale2 = oscale ? oscale2 : nullptr;
   p.chunk = tc_chunk() == 4 && !getenv("FG_TC_CHUNK") ? ((int64_t)g.H * g.W > 1 ? 8 : 4) : tc_chunk();  // wgrad of convolutions 8, of Linear layers 4
+  if (h) p.chunk = std::max(1, p.chunk / 2);  // an fp16 K block holds 64 pixels
   FG_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)ntt * g.Cout * g.Cin, c->stream));
   dim3 grid(ntt, (g.Cout / 128) * (g.Cin / BN), splits);
-  if (BN == 128) wgrad_tc_kernel<128><<<grid, 192, wg_smem<128>(), c->stream>>>(p);
+  if (h) {
+    if (BN == 128) wgrad_tc_kernel<128, true><<<grid, 192, wg_smem<128>(), c->stream>>>(p);
+    else wgrad_tc_kernel<64, true><<<grid, 192, wg_smem<64>(), c->stream>>>(p);
+  } else if (BN == 128) wgrad_tc_kernel<128><<<grid, 192, wg_smem<128>(), c->stream>>>(p);
   else wgrad_tc_kernel<64><<<grid, 192, wg_smem<64>(), c->stream>>>(p);
   LAUNCH_CHECK(c);
   return FG_OK;

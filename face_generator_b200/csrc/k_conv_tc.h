@@ -21,7 +21,7 @@ struct alignas(64) TcFwdParams {
   const float* bias;
   float* stats;  // optional [m-tile][2][Cout]: per-tile column sums of the output and of its square (BatchNorm)
   int out_H, out_W, out_scale;
-  const float* oscale;  // optional device scalar the accumulators are multiplied by (inverse of the A operand's scale)
+  const float *oscale, *oscale2;  // optional device scalars the accumulators are multiplied by (inverse operand scales)
   int dbg;    // experiment switches (FG_TC_DBG): 1 = skip MMAs, 2 = skip TMA data movement
   int chunk;  // K-blocks accumulated in TMEM before the epilogue promotes them to fp32 registers
 };
@@ -35,6 +35,7 @@ struct alignas(64) TcWgParams {
   int tiles_x, tiles_y;
   int kblocks, kb_per_split;
   float* out;
+  const float *oscale, *oscale2;  // optional device scalars multiplied into the result (inverse scales of dY and X)
   int chunk;
 };
 
@@ -49,7 +50,7 @@ int tc_combine_collapsed_wgrad(fg_ctx* c, const float* G, float* dW, int N, int 
 // oscale: optional device scalar multiplied into the result (inverse of the power-of-two scale tc_split_h applied)
 int tc_conv_fwd(fg_ctx* c, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, const float* bias,
                 float* out, ConvGeom g, int mode, float* stats = nullptr, int* n_parts = nullptr, int f16 = 0,
-                const float* oscale = nullptr);
+                const float* oscale = nullptr, const float* oscale2 = nullptr);
 int tc_stat_parts(const ConvGeom& g, int mode);  // number of per-tile partials tc_conv_fwd writes for this geometry
 int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const float* wd_hi, const float* wd_lo, float* out,
                       ConvGeom g, int f16 = 0, const float* oscale = nullptr);
@@ -60,7 +61,7 @@ int tc_split_h(fg_ctx* c, const float* x, float* hh, float* hl, int64_t n, float
 int tc_pack_split_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK);
 int tc_pack_collapsed_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc);
 int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* out,
-                  ConvGeom g);
+                  ConvGeom g, int f16 = 0, const float* oscale = nullptr, const float* oscale2 = nullptr);
 int tc_tf32_peak(fg_ctx* c, int iters, int reps, double* tflops);
 int tc_encode_nhwc_box(CUtensorMap* m, const float* base, int C, int W, int H, int B, int bc, int bw, int bh, int bb);
 int tc_umma_window_probe(fg_ctx* c, const float* x, const float* ident, int dy, int dx, int use_base_offset, float* out);

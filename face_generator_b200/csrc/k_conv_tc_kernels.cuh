@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + buf);
       }
-      if (p.oscale) {  // the A operand was stored scaled by a power of two (gradients in the FP16 split): undo it
-        const float os = *p.oscale;
+      if (p.oscale) {  // operands stored scaled by powers of two (FP16 split): undo it
+        const float os = *p.oscale * (p.oscale2 ? *p.oscale2 : 1.f);
 #pragma unroll
         for (int i = 0; i < BN; ++i) acc[i] *= os;
       }
@@ -271,14 +271,16 @@ __global__ void __launch_bounds__(192, 1) tapconv_tc_kernel(const __grid_constan
 // grid: x = tile-tap, y = mtile * ntiles_n + ntile, z = K split.  Output accumulated with atomics.
 // Same two-instruction scheme: dY_hi x [X_hi | X_lo] (N = 2*BN) and dY_lo x X_hi (N = BN).
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+// F16 (3xFP16 split): a K block is 64 pixels, a channel group 64 channels (128 bytes of fp16), standard SWIZZLE_128B.
+template <int BN, bool F16 = false>
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ TcWgParams p) {
-  constexpr uint32_t kBox = 32 * 128;  // one (32 ch x 32 px) box = 4 KB
-  constexpr uint32_t kAB = 4 * kBox;   // M = 128 channels of dY
-  constexpr uint32_t kBB = (BN / 32) * kBox;
+  constexpr int kG = F16 ? 64 : 32;                  // channels per 128-byte group
+  constexpr uint32_t kBox = (F16 ? 64 : 32) * 128;   // one (group x K-block pixels) box: 32 px (tf32) / 64 px (fp16)
+  constexpr uint32_t kAB = (128 / kG) * kBox;        // M = 128 channels of dY
+  constexpr uint32_t kBB = (BN / kG) * kBox;
   constexpr uint32_t kStageBytes = 2 * kAB + 2 * kBB;  // {dy_hi, dy_lo, x_hi, x_lo}; x_lo directly behind x_hi
-  constexpr uint32_t kIdesc2 = make_idesc(128, 2 * BN, 1, 1);
-  constexpr uint32_t kIdesc1 = make_idesc(128, BN, 1, 1);
+  constexpr uint32_t kIdesc2 = make_idesc(128, 2 * BN, 1, 1, F16);
+  constexpr uint32_t kIdesc1 = make_idesc(128, BN, 1, 1, F16);
   constexpr uint32_t kRing = 512 / (2 * BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -340,10 +342,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           mbar_expect_tx(full + s, kStageBytes);
           // 5-D maps (32 ch, w, h, b, channel-group): ONE bulk copy lands [group][pixel][32 ch] = all the 4 KB
           // boxes of an operand (16 single-box copies per stage made the kernel TMA-issue bound)
-          tma_load_5d(st, &p.dy_hi[ph], full + s, 0, x0, y0, b0, m0 / 32);
-          tma_load_5d(st + kAB, &p.dy_lo[ph], full + s, 0, x0, y0, b0, m0 / 32);
-          tma_load_5d(st + 2 * kAB, &p.x_hi, full + s, 0, x0 + dxo, y0 + dyo, b0, c0 / 32);
-          tma_load_5d(st + 2 * kAB + kBB, &p.x_lo, full + s, 0, x0 + dxo, y0 + dyo, b0, c0 / 32);
+          tma_load_5d(st, &p.dy_hi[ph], full + s, 0, x0, y0, b0, m0 / kG);
+          tma_load_5d(st + kAB, &p.dy_lo[ph], full + s, 0, x0, y0, b0, m0 / kG);
+          tma_load_5d(st + 2 * kAB, &p.x_hi, full + s, 0, x0 + dxo, y0 + dyo, b0, c0 / kG);
+          tma_load_5d(st + 2 * kAB + kBB, &p.x_lo, full + s, 0, x0 + dxo, y0 + dyo, b0, c0 / kG);
         }
       }
     } else if (warp == 1) {
@@ -362,15 +364,20 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           // MN-major tf32 (4 pixel rows x 128 B per swizzle atom, 32 B chunks XOR row%4; TMA side
           // SWIZZLE_128B_ATOM_32B).  LBO = distance between 32-channel groups (one 4 KB box),
           // SBO = distance between 4-pixel groups (512 B).  x_hi's BN/32 groups are followed by x_lo's: 2*BN columns.
-          const uint64_t a_hi = make_desc(sa, kBox, 512, 1), a_lo = make_desc(sa + kAB, kBox, 512, 1);
-          const uint64_t b_cat = make_desc(sa + 2 * kAB, kBox, 512, 1);
+          // fp16: the canonical MN-major SWIZZLE_128B layout (layout 2): atoms of 64 channels x 8 pixels (1 KB), LBO =
+          // distance between 64-channel groups (one 8 KB box), SBO = distance between 8-pixel groups (1 KB); one MMA
+          // takes K = 16 pixels = 2 KB.
+          constexpr uint32_t kSbo = F16 ? 1024 : 512;
+          constexpr uint64_t kLay = F16 ? 2 : 1;
+          const uint64_t a_hi = make_desc(sa, kBox, kSbo, kLay), a_lo = make_desc(sa + kAB, kBox, kSbo, kLay);
+          const uint64_t b_cat = make_desc(sa + 2 * kAB, kBox, kSbo, kLay);
           mbar_wait_spin(full + s, it & 1);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t ko = (uint64_t)(k * 64);  // +1024 bytes = next 8 pixels
-              umma_tf32(tacc, a_hi + ko, b_cat + ko, kIdesc2, (j | k) != 0);  // [main | cross] (+)= dY_hi x [X_hi | X_lo]
-              umma_tf32(tacc + BN, a_lo + ko, b_cat + ko, kIdesc1, 1);        // cross += dY_lo x X_hi
+              const uint64_t ko = (uint64_t)(k * (F16 ? 128 : 64));  // +1024 bytes = next 8 pixels (tf32) / +2048 = next 16 (fp16)
+              umma<F16>(tacc, a_hi + ko, b_cat + ko, kIdesc2, (j | k) != 0);  // [main | cross] (+)= dY_hi x [X_hi | X_lo]
+              umma<F16>(tacc + BN, a_lo + ko, b_cat + ko, kIdesc1, 1);        // cross += dY_lo x X_hi
             }
             umma_commit(empty + s);
           }
@@ -389,10 +396,15 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         const uint32_t buf = ch % kRing, use = ch / kRing;
         mbar_wait(tmem_full + buf, use & 1);
         tc_fence_after();
-        promote<BN>(acc, tmem_base + buf * 2 * BN, q);
+        promote<BN, F16>(acc, tmem_base + buf * 2 * BN, q);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty + buf);
+      }
+      if (p.oscale) {  // dY (and X) were stored scaled by powers of two
+        const float os = *p.oscale * (p.oscale2 ? *p.oscale2 : 1.f);
+#pragma unroll
+        for (int i = 0; i < BN; ++i) acc[i] *= os;
       }
       float* orow = p.out + ((int64_t)tt * p.Cout + n) * p.Cin + c0;
 #pragma unroll

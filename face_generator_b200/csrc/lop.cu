@@ -164,7 +164,16 @@ int fg_conv2d_backward_filter(fg_ctx* c, const float* x, const float* dy, float*
   FG_TRY(k_nchw_to_nhwc(c, xd, xn, N, Cin, H * W));
   FG_TRY(k_nchw_to_nhwc(c, dyd, dyn, N, Cout, H * W));
   const ConvGeom gw{N, H, W, Cin, Cout, k, 1};
-  if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(gw) && Cout % 128 == 0 && Cin % 64 == 0) {
+  if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(gw) && Cout % 128 == 0 && Cin % 64 == 0 && c->mma_f16 && nx % 8 == 0 &&
+      ny % 8 == 0) {
+    float *xs, *ys;  // FP16 split; dY scaled into range by a power of two that the kernel undoes
+    FG_TRY(scratch(c, 2, nx, &xs));
+    FG_TRY(scratch(c, 7, ny, &ys));
+    FG_TRY(tc_split_h(c, xn, xs, xs + nx / 2, (int64_t)nx));
+    FG_TRY(tc_amax(c, dyn, (int64_t)ny, c->amax_slot));
+    FG_TRY(tc_split_h(c, dyn, ys, ys + ny / 2, (int64_t)ny, c->amax_slot));
+    FG_TRY(tc_conv_wgrad(c, xs, xs + nx / 2, ys, ys + ny / 2, ws, gw, 1, c->amax_slot + 1));
+  } else if (c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(gw) && Cout % 128 == 0 && Cin % 64 == 0) {
     float *xs, *ys;
     FG_TRY(scratch(c, 2, 2 * nx, &xs));
     FG_TRY(scratch(c, 7, 2 * ny, &ys));

@@ -94,7 +94,7 @@ int net_alloc(fg_ctx* c) {
   FG_TRY(dalloc(c, &c->acc_hist, kAccHistMax));
   FG_CUDA(cudaMallocHost((void**)&c->hstats, sizeof(DeviceStats)));
   memset(c->hstats, 0, sizeof(DeviceStats));
-  FG_TRY(dalloc(c, &c->amax_slot, 16));
+  FG_TRY(dalloc(c, &c->amax_slot, 32));
   // packs
   FG_TRY(dalloc(c, &c->G_L1p, 8192 * 100 + 8192));  // + permuted bias behind the weights
   FG_TRY(dalloc(c, &c->G_L1pd, 8192 * 100));
@@ -205,6 +205,40 @@ int net_alloc(fg_ctx* c) {
       FG_TRY(dalloc(c, &t.D_Wf_lo[i], n));
       FG_TRY(dalloc(c, &t.D_Wd_hi[i], n));
       FG_TRY(dalloc(c, &t.D_Wd_lo[i], n));
+      FG_TRY(dalloc(c, &t.D_Wf_hh[i], n / 2));
+      FG_TRY(dalloc(c, &t.D_Wf_hl[i], n / 2));
+      FG_TRY(dalloc(c, &t.D_Wd_hh[i], n / 2));
+      FG_TRY(dalloc(c, &t.D_Wd_hl[i], n / 2));
+    }
+    // FP16 split twins (halves: half the floats)
+    FG_TRY(dalloc(c, &t.G_h0_hh, B * 4096));
+    FG_TRY(dalloc(c, &t.G_h0_hl, B * 4096));
+    FG_TRY(dalloc(c, &t.G_h1_hh, B * 32768));
+    FG_TRY(dalloc(c, &t.G_h1_hl, B * 32768));
+    FG_TRY(dalloc(c, &t.dy_hh, B * 65536));
+    FG_TRY(dalloc(c, &t.dy_hl, B * 65536));
+    for (int i = 0; i < 2; ++i) {
+      FG_TRY(dalloc(c, &t.G_Wf_hh[i], 18 * 256 * 128));
+      FG_TRY(dalloc(c, &t.G_Wf_hl[i], 18 * 256 * 128));
+      FG_TRY(dalloc(c, &t.G_Wd_hh[i], 18 * 256 * 128));
+      FG_TRY(dalloc(c, &t.G_Wd_hl[i], 18 * 256 * 128));
+    }
+    for (int i = 0; i < 3; ++i) {
+      const size_t n = B * (size_t)kDhw[i + 1] * kDhw[i + 1] * kDcout[i];
+      FG_TRY(dalloc(c, &t.D_p_hh[i], n / 2));
+      FG_TRY(dalloc(c, &t.D_p_hl[i], n / 2));
+    }
+    FG_TRY(dalloc(c, &t.G_x_hh, B * 64));
+    FG_TRY(dalloc(c, &t.G_x_hl, B * 64));
+    FG_TRY(dalloc(c, &t.G_L1w_hh, 8192 * 64));
+    FG_TRY(dalloc(c, &t.G_L1w_hl, 8192 * 64));
+    for (int i = 0; i < 2; ++i) {
+      FG_TRY(dalloc(c, &t.D_lin_hh[i], B * (i == 0 ? 1024 : 256)));
+      FG_TRY(dalloc(c, &t.D_lin_hl[i], B * (i == 0 ? 1024 : 256)));
+    }
+    for (int i = 0; i < 4; ++i) {
+      FG_TRY(dalloc(c, &t.D_Lw_hh[i], i < 2 ? 512 * 1024 : 512 * 256));
+      FG_TRY(dalloc(c, &t.D_Lw_hl[i], i < 2 ? 512 * 1024 : 512 * 256));
     }
   }
   FG_TRY(dalloc(c, &c->in_real, B * 1024 * C));
@@ -243,9 +277,15 @@ int net_pack_G(fg_ctx* c) {
     // G.L1 on the tensor cores: [8192'][100] -> [8192'][128] (pad columns stay zero), then the TF32 split
     FG_CUDA(cudaMemcpy2DAsync(t.G_L1pad, 128 * sizeof(float), c->G_L1p, 100 * sizeof(float), 100 * sizeof(float), 8192,
                               cudaMemcpyDeviceToDevice, c->stream));
-    FG_TRY(tc_split(c, t.G_L1pad, t.G_L1w_hi, t.G_L1w_lo, 8192 * 128));
-    FG_TRY(tc_pack_collapsed(c, c->PG + L.C1W, t.G_Wf_hi[0], t.G_Wf_lo[0], t.G_Wd_hi[0], t.G_Wd_lo[0], 256, 128));
-    FG_TRY(tc_pack_collapsed(c, c->PG + L.C2W, t.G_Wf_hi[1], t.G_Wf_lo[1], t.G_Wd_hi[1], t.G_Wd_lo[1], 128, 256));
+    if (c->mma_f16 && c->conv_impl == FG_CONV_TC_COLLAPSED) FG_TRY(tc_split_h(c, t.G_L1pad, t.G_L1w_hh, t.G_L1w_hl, 8192 * 128));
+    else FG_TRY(tc_split(c, t.G_L1pad, t.G_L1w_hi, t.G_L1w_lo, 8192 * 128));
+    if (c->mma_f16 && c->conv_impl == FG_CONV_TC_COLLAPSED) {  // forward and dgrad read the FP16 split; wgrad needs no weights
+      FG_TRY(tc_pack_collapsed_h(c, c->PG + L.C1W, t.G_Wf_hh[0], t.G_Wf_hl[0], t.G_Wd_hh[0], t.G_Wd_hl[0], 256, 128));
+      FG_TRY(tc_pack_collapsed_h(c, c->PG + L.C2W, t.G_Wf_hh[1], t.G_Wf_hl[1], t.G_Wd_hh[1], t.G_Wd_hl[1], 128, 256));
+    } else {
+      FG_TRY(tc_pack_collapsed(c, c->PG + L.C1W, t.G_Wf_hi[0], t.G_Wf_lo[0], t.G_Wd_hi[0], t.G_Wd_lo[0], 256, 128));
+      FG_TRY(tc_pack_collapsed(c, c->PG + L.C2W, t.G_Wf_hi[1], t.G_Wf_lo[1], t.G_Wd_hi[1], t.G_Wd_lo[1], 128, 256));
+    }
     if (c->conv_impl == FG_CONV_TC_DENSE) {
       FG_TRY(tc_pack_split(c, c->PG + L.C1W, t.G_Wx_hi[0], t.G_Wx_lo[0], nullptr, nullptr, 256, 128, 25));
       FG_TRY(tc_pack_split(c, c->PG + L.C2W, t.G_Wx_hi[1], t.G_Wx_lo[1], nullptr, nullptr, 128, 256, 25));
@@ -267,12 +307,23 @@ int net_pack_D(fg_ctx* c) {
   FG_TRY(k_pack_weights(c, c->PD + L.L2W, nullptr, c->D_L2pd, 512, 512, 1, 0, 0, 0, 0));
   if (c->conv_impl != FG_CONV_SIMT) {
     fg_ctx::TcBufs& t = c->tcb;
-    for (int i = 1; i < 4; ++i)
-      FG_TRY(tc_pack_split(c, c->PD + L.cW[i], t.D_Wf_hi[i], t.D_Wf_lo[i], t.D_Wd_hi[i], t.D_Wd_lo[i], kDcout[i], kDcin[i], 9));
-    FG_TRY(tc_split(c, c->D_L1p, t.D_Lw_hi[0], t.D_Lw_lo[0], 512 * 2048));
-    FG_TRY(tc_split(c, c->D_L1pd, t.D_Lw_hi[1], t.D_Lw_lo[1], 512 * 2048));
-    FG_TRY(tc_split(c, c->PD + L.L2W, t.D_Lw_hi[2], t.D_Lw_lo[2], 512 * 512));
-    FG_TRY(tc_split(c, c->D_L2pd, t.D_Lw_hi[3], t.D_Lw_lo[3], 512 * 512));
+    for (int i = 1; i < 4; ++i) {
+      if (c->mma_f16 && c->conv_impl == FG_CONV_TC_COLLAPSED)
+        FG_TRY(tc_pack_split_h(c, c->PD + L.cW[i], t.D_Wf_hh[i], t.D_Wf_hl[i], t.D_Wd_hh[i], t.D_Wd_hl[i], kDcout[i], kDcin[i], 9));
+      else
+        FG_TRY(tc_pack_split(c, c->PD + L.cW[i], t.D_Wf_hi[i], t.D_Wf_lo[i], t.D_Wd_hi[i], t.D_Wd_lo[i], kDcout[i], kDcin[i], 9));
+    }
+    if (c->mma_f16 && c->conv_impl == FG_CONV_TC_COLLAPSED) {
+      FG_TRY(tc_split_h(c, c->D_L1p, t.D_Lw_hh[0], t.D_Lw_hl[0], 512 * 2048));
+      FG_TRY(tc_split_h(c, c->D_L1pd, t.D_Lw_hh[1], t.D_Lw_hl[1], 512 * 2048));
+      FG_TRY(tc_split_h(c, c->PD + L.L2W, t.D_Lw_hh[2], t.D_Lw_hl[2], 512 * 512));
+      FG_TRY(tc_split_h(c, c->D_L2pd, t.D_Lw_hh[3], t.D_Lw_hl[3], 512 * 512));
+    } else {
+      FG_TRY(tc_split(c, c->D_L1p, t.D_Lw_hi[0], t.D_Lw_lo[0], 512 * 2048));
+      FG_TRY(tc_split(c, c->D_L1pd, t.D_Lw_hi[1], t.D_Lw_lo[1], 512 * 2048));
+      FG_TRY(tc_split(c, c->PD + L.L2W, t.D_Lw_hi[2], t.D_Lw_lo[2], 512 * 512));
+      FG_TRY(tc_split(c, c->D_L2pd, t.D_Lw_hi[3], t.D_Lw_lo[3], 512 * 512));
+    }
   }
   c->D_packed = true;
   return FG_OK;
@@ -304,12 +355,31 @@ static inline bool use_tc_wgrad(const fg_ctx* c, const ConvGeom& g) {
   return use_tc(c, g) && g.Cout % 128 == 0 && g.Cin % 64 == 0;
 }
 
+// ---- option "mma_f16": every tensor-core operand in the 3xFP16 split (k_conv_tc.cu), kind::f16 MMAs -------------------
+// Activations and gradients are scaled into fp16's range by a power of two found on the device (tc_amax): slot i of
+// c->amax_slot holds (max|x|, 1/scale) of one tensor; the consuming kernels multiply their result by the inverse scales.
+enum { kSlotDy = 0, kSlotH0 = 1, kSlotH1 = 2, kSlotDp = 3 /* +0..2 */, kSlotLin = 6 /* +0..1 */, kSlotX = 8 };
+static inline bool f16_on(const fg_ctx* c) { return c->mma_f16 && c->conv_impl == FG_CONV_TC_COLLAPSED; }
+static inline const float* inv_scale(const fg_ctx* c, int slot) { return c->amax_slot + 2 * slot + 1; }
+static int split_h_scaled(fg_ctx* c, const float* x, float* hh, float* hl, int64_t n, int slot) {
+  FG_TRY(tc_amax(c, x, n, c->amax_slot + 2 * slot));
+  return tc_split_h(c, x, hh, hl, n, c->amax_slot + 2 * slot);
+}
+
 // nn.Linear as a 1x1 convolution on a 1x1 image.  With only B rows the fp32 SIMT tiling leaves the GPU
 // idle (8 CTAs at B=256); the tcgen05 path splits the input on the fly and uses the pre-split weights.
+// f16 mode: `in16` is the fp32 input (always given), split into keep16_h/l (or the dY scratch) under amax slot `slot`
 static int lin_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp, int wi, const float* bias, float* out,
-                   ConvGeom g, float* keep_hi = nullptr, float* keep_lo = nullptr) {
+                   ConvGeom g, float* keep_hi = nullptr, float* keep_lo = nullptr, const float* in16 = nullptr,
+                   float* keep16_h = nullptr, float* keep16_l = nullptr, int slot = kSlotDy) {
   if (!use_tc(c, g)) return conv_fwd(c, tag, in, Wp, bias, out, g);
   fg_ctx::TcBufs& t = c->tcb;
+  if (f16_on(c) && in16) {
+    float *hh = keep16_h ? keep16_h : t.dy_hh, *hl = keep16_l ? keep16_l : t.dy_hl;
+    FG_TRY(split_h_scaled(c, in16, hh, hl, (int64_t)g.B * g.Cin, slot));
+    ScopedTimer tm(c, tag);
+    return tc_conv_fwd(c, hh, hl, t.D_Lw_hh[wi], t.D_Lw_hl[wi], bias, out, g, 0, nullptr, nullptr, 1, inv_scale(c, slot));
+  }
   float* hi = keep_hi ? keep_hi : t.dy_hi;  // forward keeps the split of its input for the tensor-core wgrad
   float* lo = keep_lo ? keep_lo : t.dy_lo;
   if (in) FG_TRY(tc_split(c, in, hi, lo, (int64_t)g.B * g.Cin));  // nullptr: the producer already wrote keep_hi / keep_lo
@@ -318,12 +388,16 @@ static int lin_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp,
 }
 // weight gradient of a Linear layer on the tensor cores: x split kept by the forward, dY split left in
 // tcb.dy_* by the dgrad call that must precede this one
+// f16 mode (xslot >= 0): x16_h/l = the FP16 split the forward kept (amax slot xslot), dY in t.dy_hh/hl (slot kSlotDy)
 static int lin_wgrad_tc(fg_ctx* c, const char* tag, const float* x_hi, const float* x_lo, ConvGeom g, float* dW, int cA,
-                        int cS) {
+                        int cS, const float* x16_h = nullptr, const float* x16_l = nullptr, int xslot = -1) {
   fg_ctx::TcBufs& t = c->tcb;
   {
     ScopedTimer tm(c, tag);
-    FG_TRY(tc_conv_wgrad(c, x_hi, x_lo, t.dy_hi, t.dy_lo, c->wgrad_ws, g));
+    if (f16_on(c) && xslot >= 0)
+      FG_TRY(tc_conv_wgrad(c, x16_h, x16_l, t.dy_hh, t.dy_hl, c->wgrad_ws, g, 1, inv_scale(c, kSlotDy), inv_scale(c, xslot)));
+    else
+      FG_TRY(tc_conv_wgrad(c, x_hi, x_lo, t.dy_hi, t.dy_lo, c->wgrad_ws, g));
   }
   return k_unpack_wgrad(c, c->wgrad_ws, dW, g.Cout, g.Cin, 1, 0, 0, cA, cS);
 }
@@ -337,9 +411,16 @@ static int g_ups_fwd(fg_ctx* c, int li, const char* tag, const float* h, float* 
   if (stat_parts) *stat_parts = 0;
   if (!use_tc(c, g)) return conv_fwd(c, tag, h, Wp, bias, z, g);
   fg_ctx::TcBufs& t = c->tcb;
+  float* st = want && c->bn_epilogue ? c->bn_parts : nullptr;
+  if (f16_on(c)) {  // 3xFP16 split of the fp32 activation (h0 / h1 always exist), kept for the weight gradient
+    float *hh = li == 0 ? t.G_h0_hh : t.G_h1_hh, *hl = li == 0 ? t.G_h0_hl : t.G_h1_hl;
+    const int slot = li == 0 ? kSlotH0 : kSlotH1;
+    FG_TRY(split_h_scaled(c, li == 0 ? c->G_h0 : c->G_h1, hh, hl, (int64_t)g.B * (g.H / 2) * (g.W / 2) * g.Cin, slot));
+    ScopedTimer tm(c, tag);
+    return tc_conv_fwd(c, hh, hl, t.G_Wf_hh[li], t.G_Wf_hl[li], bias, z, g, 2, st, st ? stat_parts : nullptr, 1, inv_scale(c, slot));
+  }
   if (h) FG_TRY(tc_split(c, h, h_hi, h_lo, (int64_t)g.B * (g.H / 2) * (g.W / 2) * g.Cin));  // nullptr: producer wrote hi/lo
   ScopedTimer tm(c, tag);
-  float* st = want && c->bn_epilogue ? c->bn_parts : nullptr;
   if (c->conv_impl == FG_CONV_TC_DENSE)
     return tc_conv_fwd(c, h_hi, h_lo, t.G_Wx_hi[li], t.G_Wx_lo[li], bias, z, g, 1, st, st ? stat_parts : nullptr);
   return tc_conv_fwd(c, h_hi, h_lo, t.G_Wf_hi[li], t.G_Wf_lo[li], bias, z, g, 2, st, st ? stat_parts : nullptr);
@@ -348,13 +429,26 @@ static int g_ups_fwd(fg_ctx* c, int li, const char* tag, const float* h, float* 
 // the LOW-RES input (tcgen05 path: the 2x2 sum of the upsample backward is folded into the dgrad GEMM) or the
 // full-resolution gradient that the consumer still has to sum 2x2 (SIMT path).
 static int g_ups_bwd(fg_ctx* c, int li, const char* wtag, const char* dtag, const float* h, const float* h_hi,
-                     const float* h_lo, const float* dz, const float* Wpd, ConvGeom g, float* dW, float* dh, bool* pooled) {
+                     const float* h_lo, const float* dz, const float* Wpd, ConvGeom g, float* dW, float* dh, bool* pooled,
+                     const float* dz_f32 = nullptr) {
   if (!use_tc_wgrad(c, g)) {
     FG_TRY(conv_wgrad(c, wtag, h, dz, g, dW, 0, 0, 0, 0));
     *pooled = false;
     return conv_fwd(c, dtag, dz, Wpd, nullptr, dh, ConvGeom{g.B, g.H, g.W, g.Cout, g.Cin, g.k, 1});
   }
   fg_ctx::TcBufs& t = c->tcb;
+  if (f16_on(c) && dz_f32) {  // weight and data gradient on the FP16 split of the (scaled) gradient
+    FG_TRY(split_h_scaled(c, dz_f32, t.dy_hh, t.dy_hl, (int64_t)g.B * g.H * g.W * g.Cout, kSlotDy));
+    {
+      ScopedTimer tm(c, wtag);
+      FG_TRY(tc_conv_wgrad(c, li == 0 ? t.G_h0_hh : t.G_h1_hh, li == 0 ? t.G_h0_hl : t.G_h1_hl, t.dy_hh, t.dy_hl, c->wgrad_ws, g, 1,
+                           inv_scale(c, kSlotDy), inv_scale(c, li == 0 ? kSlotH0 : kSlotH1)));
+    }
+    FG_TRY(tc_combine_collapsed_wgrad(c, c->wgrad_ws, dW, g.Cout, g.Cin));
+    *pooled = true;
+    ScopedTimer tm(c, dtag);
+    return tc_conv_dgrad_ups(c, t.dy_hh, t.dy_hl, t.G_Wd_hh[li], t.G_Wd_hl[li], dh, g, 1, inv_scale(c, kSlotDy));
+  }
   if (dz) FG_TRY(tc_split(c, dz, t.dy_hi, t.dy_lo, (int64_t)g.B * g.H * g.W * g.Cout));  // nullptr: producer wrote hi/lo
   {
     ScopedTimer tm(c, wtag);
@@ -383,9 +477,16 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
     fg_ctx::TcBufs& t = c->tcb;
     FG_CUDA(cudaMemcpy2DAsync(t.G_xpad, 128 * sizeof(float), c->G_noise, kNoiseDim * sizeof(float), kNoiseDim * sizeof(float), B,
                               cudaMemcpyDeviceToDevice, c->stream));
-    FG_TRY(tc_split(c, t.G_xpad, t.G_x_hi, t.G_x_lo, (int64_t)B * 128));  // kept for the weight gradient
-    ScopedTimer tm(c, "G.L1.fwd");
-    FG_TRY(tc_conv_fwd(c, t.G_x_hi, t.G_x_lo, t.G_L1w_hi, t.G_L1w_lo, c->G_L1p + 8192 * 100, c->G_z0, gL1, 0));
+    if (f16_on(c)) {
+      FG_TRY(split_h_scaled(c, t.G_xpad, t.G_x_hh, t.G_x_hl, (int64_t)B * 128, kSlotX));  // kept for the weight gradient
+      ScopedTimer tm(c, "G.L1.fwd");
+      FG_TRY(tc_conv_fwd(c, t.G_x_hh, t.G_x_hl, t.G_L1w_hh, t.G_L1w_hl, c->G_L1p + 8192 * 100, c->G_z0, gL1, 0, nullptr, nullptr, 1,
+                         inv_scale(c, kSlotX)));
+    } else {
+      FG_TRY(tc_split(c, t.G_xpad, t.G_x_hi, t.G_x_lo, (int64_t)B * 128));  // kept for the weight gradient
+      ScopedTimer tm(c, "G.L1.fwd");
+      FG_TRY(tc_conv_fwd(c, t.G_x_hi, t.G_x_lo, t.G_L1w_hi, t.G_L1w_lo, c->G_L1p + 8192 * 100, c->G_z0, gL1, 0));
+    }
   } else {
     FG_TRY(conv_fwd(c, "G.L1.fwd", c->G_noise, c->G_L1p, c->G_L1p + 8192 * 100, c->G_z0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}));
   }
@@ -406,7 +507,7 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
     FG_TRY(k_bn_eval_prep(c, c->bnG, c->bnG + 256, c->bn_mean1, c->bn_istd1, 256));
   }
   const ConvGeom gC2{B, 32, 32, 256, 128, 5, 2};
-  const bool h1_split = training && use_tc(c, gC2);  // tcgen05 path consumes h1 only as TF32 hi/lo
+  const bool h1_split = training && use_tc(c, gC2) && !f16_on(c);  // TF32 tcgen05 path consumes h1 only as TF32 hi/lo
   FG_TRY(k_bn_prelu_apply(c, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2,
                           c->G_h1, (int64_t)B * 256, 256, h1_split ? c->tcb.G_h1_hi : nullptr,
                           h1_split ? c->tcb.G_h1_lo : nullptr));
@@ -461,7 +562,7 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   FG_TRY(k_bn_bwd_finalize(c, c->bn_acc, c->bn_mg, G + L.g2, G + L.be2, (int64_t)B * 1024, 128));
   // in tcgen05 mode the BN-backward kernels also emit the TF32 hi/lo split of dz (no separate split pass)
   const ConvGeom gC2{B, 32, 32, 256, 128, 5, 2}, gC1{B, 16, 16, 128, 256, 5, 2};
-  const bool tc2 = use_tc_wgrad(c, gC2), tc1 = use_tc_wgrad(c, gC1);
+  const bool tc2 = use_tc_wgrad(c, gC2) && !f16_on(c), tc1 = use_tc_wgrad(c, gC1) && !f16_on(c);  // fused TF32 hi/lo of dz
   {
     ScopedTimer tm(c, "hbm.G.bn2.bwd_apply");
     FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_mg,
@@ -471,7 +572,7 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   // C2
   bool pooled = false;
   FG_TRY(g_ups_bwd(c, 1, "G.C2.wgrad", "G.C2.dgrad", c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, tc2 ? nullptr : c->G_dz2,
-                   c->G_C2pd, gC2, G + L.C2W, c->G_dfull, &pooled));
+                   c->G_C2pd, gC2, G + L.C2W, c->G_dfull, &pooled, c->G_dz2));
   // BN1 + PReLU (the 2x2 sum = backward of the nearest upsample is folded into the loads)
   FG_TRY(k_bn_prelu_bwd_reduce(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_acc,
                                G + L.a2, B, 16, 16, 256, pooled ? 0 : 1));
@@ -483,14 +584,18 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   // C1
   FG_TRY(g_ups_bwd(c, 0, "G.C1.wgrad", "G.C1.dgrad", c->G_h0, c->tcb.G_h0_hi, c->tcb.G_h0_lo, split1 ? nullptr : c->G_dz1,
                    c->G_C1pd,
-                   ConvGeom{B, 16, 16, 128, 256, 5, 2}, G + L.C1W, c->G_dfull, &pooled));
+                   ConvGeom{B, 16, 16, 128, 256, 5, 2}, G + L.C1W, c->G_dfull, &pooled, c->G_dz1));
   FG_TRY(k_prelu_bwd(c, c->G_dfull, c->G_z0, P + L.a1, c->G_dz0, G + L.a1, B, 8, 8, 128, pooled ? 0 : 1));
   // L1
   const ConvGeom gL1{B, 1, 1, 128, 8192, 1, 1};
   if (use_tc_wgrad(c, gL1)) {  // dW[8192'][128 (100 used)] = dz0^T x on the tensor cores (K = batch), pad columns dropped
     fg_ctx::TcBufs& t = c->tcb;
-    FG_TRY(tc_split(c, c->G_dz0, t.dy_hi, t.dy_lo, (int64_t)B * 8192));
-    {
+    if (f16_on(c)) {
+      FG_TRY(split_h_scaled(c, c->G_dz0, t.dy_hh, t.dy_hl, (int64_t)B * 8192, kSlotDy));
+      ScopedTimer tm(c, "G.L1.wgrad");
+      FG_TRY(tc_conv_wgrad(c, t.G_x_hh, t.G_x_hl, t.dy_hh, t.dy_hl, t.G_L1pad, gL1, 1, inv_scale(c, kSlotDy), inv_scale(c, kSlotX)));
+    } else {
+      FG_TRY(tc_split(c, c->G_dz0, t.dy_hi, t.dy_lo, (int64_t)B * 8192));
       ScopedTimer tm(c, "G.L1.wgrad");
       FG_TRY(tc_conv_wgrad(c, t.G_x_hi, t.G_x_lo, t.dy_hi, t.dy_lo, t.G_L1pad, gL1));
     }
@@ -529,9 +634,16 @@ int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hype
     const ConvGeom g{B, H, H, dcin(c, i), kDcout[i], 3, 1};
     fg_ctx::TcBufs& t = c->tcb;
     if (i > 0 && use_tc(c, g)) {
-      if (!have_split) FG_TRY(tc_split(c, cur, t.D_p_hi[i - 1], t.D_p_lo[i - 1], (int64_t)B * H * H * g.Cin));
-      ScopedTimer tm(c, tags[i]);
-      FG_TRY(tc_conv_fwd(c, t.D_p_hi[i - 1], t.D_p_lo[i - 1], t.D_Wf_hi[i], t.D_Wf_lo[i], P + L.cb[i], c->D_z[i], g, 0));
+      if (f16_on(c)) {  // FP16 split of the pooled activation, kept for the weight gradient
+        FG_TRY(split_h_scaled(c, cur, t.D_p_hh[i - 1], t.D_p_hl[i - 1], (int64_t)B * H * H * g.Cin, kSlotDp + i - 1));
+        ScopedTimer tm(c, tags[i]);
+        FG_TRY(tc_conv_fwd(c, t.D_p_hh[i - 1], t.D_p_hl[i - 1], t.D_Wf_hh[i], t.D_Wf_hl[i], P + L.cb[i], c->D_z[i], g, 0, nullptr,
+                           nullptr, 1, inv_scale(c, kSlotDp + i - 1)));
+      } else {
+        if (!have_split) FG_TRY(tc_split(c, cur, t.D_p_hi[i - 1], t.D_p_lo[i - 1], (int64_t)B * H * H * g.Cin));
+        ScopedTimer tm(c, tags[i]);
+        FG_TRY(tc_conv_fwd(c, t.D_p_hi[i - 1], t.D_p_lo[i - 1], t.D_Wf_hi[i], t.D_Wf_lo[i], P + L.cb[i], c->D_z[i], g, 0));
+      }
     } else {
       FG_TRY(conv_fwd(c, tags[i], cur, c->D_cp[i], P + L.cb[i], c->D_z[i], g));
     }
@@ -543,6 +655,7 @@ int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hype
     } else if (use_tc(c, gL1d)) {
       nhi = t.D_lin_hi[0]; nlo = t.D_lin_lo[0];
     }
+    if (f16_on(c)) nhi = nlo = nullptr;  // the FP16 split is made from the fp32 tensor (split_h_scaled)
     have_split = nhi != nullptr;
     FG_TRY(k_d_act_pool_fwd(c, c->D_z[i], P + L.ca[i], masks, kDmoff[i], 1.0f - h->p_spatial, c->D_p[i], B, H, H,
                             kDcout[i], nhi, nlo));
@@ -552,10 +665,10 @@ int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hype
   c->D_drop_scale = scale;
   c->D_spatial_eval = 1.0f - h->p_spatial;
   FG_TRY(lin_fwd(c, "D.L1.fwd", have_split ? nullptr : c->D_p[3], c->D_L1p, 0, P + L.L1b, c->D_zl1, gL1d,
-                 c->tcb.D_lin_hi[0], c->tcb.D_lin_lo[0]));
+                 c->tcb.D_lin_hi[0], c->tcb.D_lin_lo[0], c->D_p[3], c->tcb.D_lin_hh[0], c->tcb.D_lin_hl[0], kSlotLin));
   FG_TRY(k_lin_act_drop_fwd(c, c->D_zl1, P + L.a5, masks, 960, scale, c->D_hl1, B, 512));
   FG_TRY(lin_fwd(c, "D.L2.fwd", c->D_hl1, P + L.L2W, 2, P + L.L2b, c->D_zl2, ConvGeom{B, 1, 1, 512, 512, 1, 1},
-                 c->tcb.D_lin_hi[1], c->tcb.D_lin_lo[1]));
+                 c->tcb.D_lin_hi[1], c->tcb.D_lin_lo[1], c->D_hl1, c->tcb.D_lin_hh[1], c->tcb.D_lin_hl[1], kSlotLin + 1));
   FG_TRY(k_lin_act_drop_fwd(c, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_hl2, B, 512));
   {
     ScopedTimer tm(c, "D.L3.fwd");
@@ -593,8 +706,11 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
     if (!tcw2) FG_TRY(conv_wgrad(c, "D.L2.wgrad", c->D_hl1, c->D_dzl, gL2, G + L.L2W, 0, 0, 0, 0));
     FG_TRY(k_colsum_add(c, c->D_dzl, G + L.L2b, B, 512, 0, 0));
   }
-  FG_TRY(lin_fwd(c, "D.L2.dgrad", c->D_dzl, c->D_L2pd, 3, nullptr, c->D_dh, ConvGeom{B, 1, 1, 512, 512, 1, 1}));
-  if (tcw2) FG_TRY(lin_wgrad_tc(c, "D.L2.wgrad", c->tcb.D_lin_hi[1], c->tcb.D_lin_lo[1], gL2, G + L.L2W, 0, 0));
+  FG_TRY(lin_fwd(c, "D.L2.dgrad", c->D_dzl, c->D_L2pd, 3, nullptr, c->D_dh, ConvGeom{B, 1, 1, 512, 512, 1, 1}, nullptr, nullptr,
+                 c->D_dzl));
+  if (tcw2)
+    FG_TRY(lin_wgrad_tc(c, "D.L2.wgrad", c->tcb.D_lin_hi[1], c->tcb.D_lin_lo[1], gL2, G + L.L2W, 0, 0, c->tcb.D_lin_hh[1],
+                        c->tcb.D_lin_hl[1], kSlotLin + 1));
   FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl1, P + L.a5, masks, 960, scale, c->D_dzl, want_wgrad ? G + L.a5 : nullptr, B,
                             512));
   // L1
@@ -602,8 +718,11 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
     if (!tcw1) FG_TRY(conv_wgrad(c, "D.L1.wgrad", c->D_p[3], c->D_dzl, gL1, G + L.L1W, 0, 0, 512, 4));
     FG_TRY(k_colsum_add(c, c->D_dzl, G + L.L1b, B, 512, 0, 0));
   }
-  FG_TRY(lin_fwd(c, "D.L1.dgrad", c->D_dzl, c->D_L1pd, 1, nullptr, c->D_dp, ConvGeom{B, 1, 1, 512, 2048, 1, 1}));
-  if (tcw1) FG_TRY(lin_wgrad_tc(c, "D.L1.wgrad", c->tcb.D_lin_hi[0], c->tcb.D_lin_lo[0], gL1, G + L.L1W, 512, 4));
+  FG_TRY(lin_fwd(c, "D.L1.dgrad", c->D_dzl, c->D_L1pd, 1, nullptr, c->D_dp, ConvGeom{B, 1, 1, 512, 2048, 1, 1}, nullptr, nullptr,
+                 c->D_dzl));
+  if (tcw1)
+    FG_TRY(lin_wgrad_tc(c, "D.L1.wgrad", c->tcb.D_lin_hi[0], c->tcb.D_lin_lo[0], gL1, G + L.L1W, 512, 4, c->tcb.D_lin_hh[0],
+                        c->tcb.D_lin_hl[0], kSlotLin));
   static const char* wt[4] = {"D.C1.wgrad", "D.C2.wgrad", "D.C3.wgrad", "D.C4.wgrad"};
   static const char* dt[4] = {"D.C1.dgrad", "D.C2.dgrad", "D.C3.dgrad", "D.C4.dgrad"};
   for (int i = 3; i >= 0; --i) {
@@ -611,16 +730,22 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
     const float* in = i == 0 ? c->D_x : c->D_p[i - 1];
     const ConvGeom gf{B, H, H, cin, cout, 3, 1}, gd{B, H, H, cout, cin, 3, 1};
     const bool tc = i > 0 && use_tc(c, gf) && use_tc(c, gd);
+    const bool tc32 = tc && !f16_on(c);  // TF32 path: dz's hi/lo split comes out of the pooling-backward kernel
     fg_ctx::TcBufs& t = c->tcb;
     // dz and, for the tensor-core layers, its TF32 split in one pass
     FG_TRY(k_d_act_pool_bwd(c, c->D_dp, c->D_z[i], P + L.ca[i], masks, kDmoff[i], eval_scale, c->D_dz,
-                            want_wgrad ? G + L.ca[i] : nullptr, B, H, H, cout, tc ? t.dy_hi : nullptr, tc ? t.dy_lo : nullptr,
+                            want_wgrad ? G + L.ca[i] : nullptr, B, H, H, cout, tc32 ? t.dy_hi : nullptr, tc32 ? t.dy_lo : nullptr,
                             want_wgrad ? G + L.cb[i] : nullptr));  // + the conv bias gradient (column sums of dz)
+    if (tc && f16_on(c)) FG_TRY(split_h_scaled(c, c->D_dz, t.dy_hh, t.dy_hl, (int64_t)B * H * H * cout, kSlotDy));
     if (want_wgrad) {
       if (tc && use_tc_wgrad(c, gf)) {
         {
           ScopedTimer tm(c, wt[i]);
-          FG_TRY(tc_conv_wgrad(c, t.D_p_hi[i - 1], t.D_p_lo[i - 1], t.dy_hi, t.dy_lo, c->wgrad_ws, gf));
+          if (f16_on(c))
+            FG_TRY(tc_conv_wgrad(c, t.D_p_hh[i - 1], t.D_p_hl[i - 1], t.dy_hh, t.dy_hl, c->wgrad_ws, gf, 1, inv_scale(c, kSlotDy),
+                                 inv_scale(c, kSlotDp + i - 1)));
+          else
+            FG_TRY(tc_conv_wgrad(c, t.D_p_hi[i - 1], t.D_p_lo[i - 1], t.dy_hi, t.dy_lo, c->wgrad_ws, gf));
         }
         FG_TRY(k_unpack_wgrad(c, c->wgrad_ws, G + L.cW[i], cout, cin, 9, 0, 0, 0, 0));
       } else {
@@ -628,7 +753,11 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
       }
     }
     if (i > 0 || want_dx) {
-      if (tc) {
+      if (tc && f16_on(c)) {
+        ScopedTimer tm(c, dt[i]);
+        FG_TRY(tc_conv_fwd(c, t.dy_hh, t.dy_hl, t.D_Wd_hh[i], t.D_Wd_hl[i], nullptr, c->D_dp, gd, 0, nullptr, nullptr, 1,
+                           inv_scale(c, kSlotDy)));
+      } else if (tc) {
         ScopedTimer tm(c, dt[i]);
         FG_TRY(tc_conv_fwd(c, t.dy_hi, t.dy_lo, t.D_Wd_hi[i], t.D_Wd_lo[i], nullptr, c->D_dp, gd, 0));
       } else {
