@@ -57,7 +57,8 @@ int tc_conv_dgrad_ups(fg_ctx* c, const float* dy_hi, const float* dy_lo, const f
 // FP16 split of x (n % 4 == 0) into two __half arrays.  amax_slot (optional, device, 2 floats): x is first scaled by the
 // power of two that brings max|x| (slot[0], filled by tc_amax) into [2^14, 2^15); slot[1] receives the inverse scale.
 int tc_amax(fg_ctx* c, const float* x, int64_t n, float* amax_slot);
-int tc_split_h(fg_ctx* c, const float* x, float* hh, float* hl, int64_t n, float* amax_slot = nullptr);
+// inv_out (default amax_slot + 1) receives the inverse scale
+int tc_split_h(fg_ctx* c, const float* x, float* hh, float* hl, int64_t n, float* amax_slot = nullptr, float* inv_out = nullptr);
 int tc_pack_split_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK);
 int tc_pack_collapsed_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc);
 int tc_conv_wgrad(fg_ctx* c, const float* x_hi, const float* x_lo, const float* dy_hi, const float* dy_lo, float* out,

@@ -47,6 +47,25 @@ __device__ __forceinline__ double block_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// max|output| of an elementwise producer into a device word (option mma_f16: the power-of-two scale of the FP16 split
+// is derived from it, k_conv_tc.cu).  Non-negative floats order like their bit patterns, so atomicMax on the bits is exact
+// and order-independent (replicas stay identical).  Must be reached by all 32 lanes.
+__device__ __forceinline__ void amax_commit(unsigned* amax, float m) {
+  if (!amax) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+}
+__device__ __forceinline__ float amax4(float m, float a, float b, float c, float d) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(a), fabsf(b))), fmaxf(fabsf(c), fabsf(d)));
+}
+// host side: the producer launched next reports into c->amax_out (set by nets.cu) and marks the slot valid
+static inline unsigned* take_amax(fg_ctx* c) {
+  unsigned* p = c->amax_out;
+  if (p) c->amax_valid[c->amax_id] = true;
+  return p;
+}
+
 __global__ void fill_kernel(float* p, float v, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -165,15 +184,19 @@ int k_colsum_add(fg_ctx* c, const float* X, float* out, int64_t P, int N, int nA
 // nn.PReLU (one shared slope)
 // ------------------------------------------------------------------------------------------------
 __global__ void prelu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ slope, float* __restrict__ h,
-                                 int64_t n) {
+                                 int64_t n, unsigned* __restrict__ amax) {
   const float a = *slope;
+  float am = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = z[i];
-    h[i] = v > 0.f ? v : a * v;
+    const float o = v > 0.f ? v : a * v;
+    h[i] = o;
+    am = fmaxf(am, fabsf(o));
   }
+  amax_commit(amax, am);
 }
 int k_prelu_fwd(fg_ctx* c, const float* z, const float* slope, float* h, int64_t n) {
-  prelu_fwd_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(z, slope, h, n);
+  prelu_fwd_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(z, slope, h, n, take_amax(c));
   LAUNCH_CHECK(c);
   return FG_OK;
 }
@@ -190,10 +213,11 @@ __device__ __forceinline__ float load_dh(const float* __restrict__ dh, int b, in
 
 __global__ void prelu_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ z,
                                  const float* __restrict__ slope, float* __restrict__ dz, float* __restrict__ dslope, int B,
-                                 int H, int W, int C, int pool) {
+                                 int H, int W, int C, int pool, unsigned* __restrict__ amax) {
   const float a = *slope;
   const int64_t n = (int64_t)B * H * W * C;
   double s = 0;
+  float am = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i % C);
     int64_t r = i / C;
@@ -205,18 +229,21 @@ __global__ void prelu_bwd_kernel(const float* __restrict__ dh, const float* __re
     const float v = z[i];
     if (v > 0.f) {
       dz[i] = g;
+      am = fmaxf(am, fabsf(g));
     } else {
       dz[i] = a * g;
+      am = fmaxf(am, fabsf(a * g));
       s += (double)g * (double)v;
     }
   }
+  amax_commit(amax, am);
   s = block_sum(s);
   if (threadIdx.x == 0 && dslope) atomicAdd(dslope, (float)s);
 }
 int k_prelu_bwd(fg_ctx* c, const float* dh, const float* z, const float* slope, float* dz, float* dslope, int B, int H,
                 int W, int C, int pool) {
   const int64_t n = (int64_t)B * H * W * C;
-  prelu_bwd_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, c->stream>>>(dh, z, slope, dz, dslope, B, H, W, C, pool);
+  prelu_bwd_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, c->stream>>>(dh, z, slope, dz, dslope, B, H, W, C, pool, take_amax(c));
   LAUNCH_CHECK(c);
   return FG_OK;
 }
@@ -370,7 +397,8 @@ __global__ void bn_prelu_apply_kernel(const float* __restrict__ z, const float* 
                                       const float* __restrict__ istd, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, const float* __restrict__ slope,
                                       float* __restrict__ h, float* __restrict__ hi, float* __restrict__ lo, int64_t n4,
-                                      int C) {
+                                      int C, unsigned* __restrict__ amax) {
+  float am = 0.f;
   const bool act = slope != nullptr;
   const float a = act ? *slope : 1.f;
   const float4* z4 = reinterpret_cast<const float4*>(z);
@@ -397,6 +425,7 @@ __global__ void bn_prelu_apply_kernel(const float* __restrict__ z, const float* 
       o.w = o.w > 0.f ? o.w : a * o.w;
     }
     if (h) h4[i] = o;
+    am = amax4(am, o.x, o.y, o.z, o.w);
     if (hi) {  // TF32 hi/lo split for the tensor-core consumer, written here instead of by a separate pass
       float4 vh, vl;
       vh.x = __uint_as_float((__float_as_uint(o.x) + 0x1000u) & 0xFFFFE000u);
@@ -408,6 +437,7 @@ __global__ void bn_prelu_apply_kernel(const float* __restrict__ z, const float* 
       lo4[i] = vl;
     }
   }
+  amax_commit(amax, am);
 }
 __global__ void bn_prelu_apply_scalar_kernel(const float* __restrict__ z, const float* __restrict__ mean,
                                              const float* __restrict__ istd, const float* __restrict__ gamma,
@@ -426,7 +456,8 @@ int k_bn_prelu_apply(fg_ctx* c, const float* z, const float* mean, const float* 
                      const float* beta, const float* slope, float* h, int64_t P, int C, float* hi, float* lo) {
   const int64_t n = P * C;
   if (C % 4 == 0) {
-    bn_prelu_apply_kernel<<<grid_for(n / 4, 256), 256, 0, c->stream>>>(z, mean, istd, gamma, beta, slope, h, hi, lo, n / 4, C);
+    bn_prelu_apply_kernel<<<grid_for(n / 4, 256), 256, 0, c->stream>>>(z, mean, istd, gamma, beta, slope, h, hi, lo, n / 4, C,
+                                                                       take_amax(c));
   } else {
     if (hi || !h) {
       fg_set_error("bn_prelu_apply: hi/lo outputs need C %% 4 == 0");
@@ -558,7 +589,8 @@ __global__ void bn_prelu_bwd_apply4_kernel(const float* __restrict__ dh, const f
                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                            const float* __restrict__ slope, const float* __restrict__ mg,
                                            float* __restrict__ dz, float* __restrict__ hi, float* __restrict__ lo,
-                                           float* __restrict__ dbias, int64_t n4, int C) {
+                                           float* __restrict__ dbias, int64_t n4, int C, unsigned* __restrict__ amax) {
+  float am = 0.f;
   // dbias (optional): += column sums of dz = the gradient of the convolution bias in front of the BatchNorm.  The grid
   // stride is a multiple of C/4, so a thread always sees the same 4 channels: thread-local sums -> shared -> global
   __shared__ float bsum[1024];
@@ -590,6 +622,7 @@ __global__ void bn_prelu_bwd_apply4_kernel(const float* __restrict__ dh, const f
       o[j] = ga * is * (g - mg[ch + j] - xh * mg[C + ch + j]);
     }
     dz4[i] = make_float4(o[0], o[1], o[2], o[3]);
+    am = amax4(am, o[0], o[1], o[2], o[3]);
     bs[0] += o[0]; bs[1] += o[1]; bs[2] += o[2]; bs[3] += o[3];
     if (hi) {  // TF32 hi/lo split of dz for the tensor-core dgrad / wgrad, written by the producer
       float h[4];
@@ -599,6 +632,7 @@ __global__ void bn_prelu_bwd_apply4_kernel(const float* __restrict__ dh, const f
       lo4[i] = make_float4(o[0] - h[0], o[1] - h[1], o[2] - h[2], o[3] - h[3]);
     }
   }
+  amax_commit(amax, am);
   if (dbias) {
     __syncthreads();
     const int ch = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) % C4) * 4;
@@ -614,7 +648,7 @@ int k_bn_prelu_bwd_apply(fg_ctx* c, const float* dh, const float* z, const float
   const int64_t n = (int64_t)B * H * W * C;
   if (!pool && C % 4 == 0 && C <= 1024 && 256 % (C / 4) == 0) {
     bn_prelu_bwd_apply4_kernel<<<grid_for(n / 4, 256), 256, 0, c->stream>>>(dh, z, mean, istd, gamma, beta, slope, mg, dz,
-                                                                           hi, lo, dbias, n / 4, C);
+                                                                           hi, lo, dbias, n / 4, C, take_amax(c));
     LAUNCH_CHECK(c);
     return FG_OK;
   }
@@ -707,7 +741,9 @@ __device__ __forceinline__ void split4(const float4& o, float4* hi, float4* lo, 
 }
 __global__ void d_act_pool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ slope,
                                       const float* __restrict__ masks, int moff, float eval_scale, float* __restrict__ p,
-                                      float4* __restrict__ hi, float4* __restrict__ lo, int B, int H, int W, int C) {
+                                      float4* __restrict__ hi, float4* __restrict__ lo, int B, int H, int W, int C,
+                                      unsigned* __restrict__ amax) {
+  float am = 0.f;
   const float a = *slope;
   const uint32_t Ho = H / 2, Wo = W / 2, C4 = C / 4;
   const uint32_t n = (uint32_t)B * Ho * Wo * C4;
@@ -730,8 +766,10 @@ __global__ void d_act_pool_fwd_kernel(const float* __restrict__ z, const float* 
     o.z = (v0.z * m.z + v1.z * m.z + v2.z * m.z + v3.z * m.z) * 0.25f;
     o.w = (v0.w * m.w + v1.w * m.w + v2.w * m.w + v3.w * m.w) * 0.25f;
     p4[i] = o;
+    am = amax4(am, o.x, o.y, o.z, o.w);
     if (hi) split4(o, hi, lo, i);
   }
+  amax_commit(amax, am);
 }
 int k_d_act_pool_fwd(fg_ctx* c, const float* z, const float* slope, const float* masks, int moff, float eval_scale,
                      float* p, int B, int H, int W, int C, float* hi, float* lo) {
@@ -741,7 +779,7 @@ int k_d_act_pool_fwd(fg_ctx* c, const float* z, const float* slope, const float*
     return FG_ERR_UNSUPPORTED;
   }
   d_act_pool_fwd_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(z, slope, masks, moff, eval_scale, p, reinterpret_cast<float4*>(hi),
-                                                                 reinterpret_cast<float4*>(lo), B, H, W, C);
+                                                                 reinterpret_cast<float4*>(lo), B, H, W, C, take_amax(c));
   LAUNCH_CHECK(c);
   return FG_OK;
 }
@@ -749,7 +787,8 @@ __global__ void d_act_pool_bwd_kernel(const float* __restrict__ dp, const float*
                                       const float* __restrict__ slope, const float* __restrict__ masks, int moff,
                                       float eval_scale, float* __restrict__ dz, float* __restrict__ dslope,
                                       float4* __restrict__ hi, float4* __restrict__ lo, float* __restrict__ dbias, int B,
-                                      int H, int W, int C) {
+                                      int H, int W, int C, unsigned* __restrict__ amax) {
+  float am = 0.f;
   // one thread = one pooled pixel x 4 channels: reads dp once, handles its 2x2 window of z / dz.
   // dbias (optional): += column sums of dz (the conv bias gradient); a thread always sees the same 4 channels because the
   // grid stride is a multiple of C/4
@@ -791,11 +830,13 @@ __global__ void d_act_pool_bwd_kernel(const float* __restrict__ dp, const float*
       if (!(v.z > 0.f)) s = fmaf(g.z, v.z, s);
       if (!(v.w > 0.f)) s = fmaf(g.w, v.w, s);
       dz4[idx] = o;
+      am = amax4(am, o.x, o.y, o.z, o.w);
       bs[0] += o.x; bs[1] += o.y; bs[2] += o.z; bs[3] += o.w;
       if (hi) split4(o, hi, lo, idx);
     }
     sd += (double)s;
   }
+  amax_commit(amax, am);
   sd = block_sum(sd);
   if (threadIdx.x == 0 && dslope) atomicAdd(dslope, (float)sd);
   if (dbias) {
@@ -820,7 +861,7 @@ int k_d_act_pool_bwd(fg_ctx* c, const float* dp, const float* z, const float* sl
   const bool fuse = dbias && C <= 512 && 256 % (C / 4) == 0;
   d_act_pool_bwd_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, c->stream>>>(dp, z, slope, masks, moff, eval_scale, dz, dslope,
                                                                          reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo),
-                                                                         fuse ? dbias : nullptr, B, H, W, C);
+                                                                         fuse ? dbias : nullptr, B, H, W, C, take_amax(c));
   LAUNCH_CHECK(c);
   if (dbias && !fuse) return k_colsum_add(c, dz, dbias, (int64_t)B * H * W, C, 0, 0);
   return FG_OK;
@@ -828,7 +869,8 @@ int k_d_act_pool_bwd(fg_ctx* c, const float* dp, const float* z, const float* sl
 // D linear blocks: PReLU -> nn.Dropout(p) (v2: kept / (1-p) in training; identity in eval)
 __global__ void lin_act_drop_fwd_kernel(const float* __restrict__ z, const float* __restrict__ slope,
                                         const float* __restrict__ masks, int moff, float scale, float* __restrict__ h,
-                                        int B, int N) {
+                                        int B, int N, unsigned* __restrict__ amax) {
+  float am = 0.f;
   const float a = *slope;
   const int64_t n = (int64_t)B * N;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -836,18 +878,23 @@ __global__ void lin_act_drop_fwd_kernel(const float* __restrict__ z, const float
     const int b = (int)(i / N);
     const float v = z[i];
     const float act = v > 0.f ? v : a * v;
-    h[i] = masks ? act * masks[(int64_t)b * kMaskPerSample + moff + j] * scale : act;
+    const float o = masks ? act * masks[(int64_t)b * kMaskPerSample + moff + j] * scale : act;
+    h[i] = o;
+    am = fmaxf(am, fabsf(o));
   }
+  amax_commit(amax, am);
 }
 int k_lin_act_drop_fwd(fg_ctx* c, const float* z, const float* slope, const float* masks, int moff, float scale,
                        float* h, int B, int N) {
-  lin_act_drop_fwd_kernel<<<grid_for((int64_t)B * N, 256), 256, 0, c->stream>>>(z, slope, masks, moff, scale, h, B, N);
+  lin_act_drop_fwd_kernel<<<grid_for((int64_t)B * N, 256), 256, 0, c->stream>>>(z, slope, masks, moff, scale, h, B, N, take_amax(c));
   LAUNCH_CHECK(c);
   return FG_OK;
 }
 __global__ void lin_act_drop_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ z,
                                         const float* __restrict__ slope, const float* __restrict__ masks, int moff,
-                                        float scale, float* __restrict__ dz, float* __restrict__ dslope, int B, int N) {
+                                        float scale, float* __restrict__ dz, float* __restrict__ dslope, int B, int N,
+                                        unsigned* __restrict__ amax) {
+  float am = 0.f;
   const float a = *slope;
   const int64_t n = (int64_t)B * N;
   double s = 0;
@@ -858,18 +905,21 @@ __global__ void lin_act_drop_bwd_kernel(const float* __restrict__ dh, const floa
     const float v = z[i];
     if (v > 0.f) {
       dz[i] = g;
+      am = fmaxf(am, fabsf(g));
     } else {
       dz[i] = a * g;
+      am = fmaxf(am, fabsf(a * g));
       s += (double)g * (double)v;
     }
   }
+  amax_commit(amax, am);
   s = block_sum(s);
   if (threadIdx.x == 0 && dslope) atomicAdd(dslope, (float)s);
 }
 int k_lin_act_drop_bwd(fg_ctx* c, const float* dh, const float* z, const float* slope, const float* masks, int moff,
                        float scale, float* dz, float* dslope, int B, int N) {
   lin_act_drop_bwd_kernel<<<grid_for((int64_t)B * N, 256, 148), 256, 0, c->stream>>>(dh, z, slope, masks, moff, scale, dz,
-                                                                                   dslope, B, N);
+                                                                                   dslope, B, N, take_amax(c));
   LAUNCH_CHECK(c);
   return FG_OK;
 }

@@ -94,7 +94,7 @@ int net_alloc(fg_ctx* c) {
   FG_TRY(dalloc(c, &c->acc_hist, kAccHistMax));
   FG_CUDA(cudaMallocHost((void**)&c->hstats, sizeof(DeviceStats)));
   memset(c->hstats, 0, sizeof(DeviceStats));
-  FG_TRY(dalloc(c, &c->amax_slot, 32));
+  FG_TRY(dalloc(c, &c->amax_slot, 64));
   // packs
   FG_TRY(dalloc(c, &c->G_L1p, 8192 * 100 + 8192));  // + permuted bias behind the weights
   FG_TRY(dalloc(c, &c->G_L1pd, 8192 * 100));
@@ -358,12 +358,35 @@ static inline bool use_tc_wgrad(const fg_ctx* c, const ConvGeom& g) {
 // ---- option "mma_f16": every tensor-core operand in the 3xFP16 split (k_conv_tc.cu), kind::f16 MMAs -------------------
 // Activations and gradients are scaled into fp16's range by a power of two found on the device (tc_amax): slot i of
 // c->amax_slot holds (max|x|, 1/scale) of one tensor; the consuming kernels multiply their result by the inverse scales.
-enum { kSlotDy = 0, kSlotH0 = 1, kSlotH1 = 2, kSlotDp = 3 /* +0..2 */, kSlotLin = 6 /* +0..1 */, kSlotX = 8 };
+// One slot per tensor and pass, so that a producer can reduce max|output| while it writes the tensor (AmaxInto) instead of
+// a separate read pass; amax_reset() zeroes the max words (not the inverse scales, which the weight-gradient kernels of
+// a later pass still need) at the start of every forward / backward pass.
+enum { kSlotDy = 0, kSlotH0 = 1, kSlotH1 = 2, kSlotDp = 3 /* +0..2 */, kSlotLin = 6 /* +0..1 */, kSlotX = 8,
+       kSlotGdz = 9 /* +0..2: dz0, dz1, dz2 */, kSlotDdz = 12 /* +1..3 */, kSlotDzl = 16 /* +0..1 */, kNumSlots = 32 };
 static inline bool f16_on(const fg_ctx* c) { return c->mma_f16 && c->conv_impl == FG_CONV_TC_COLLAPSED; }
 static inline const float* inv_scale(const fg_ctx* c, int slot) { return c->amax_slot + 2 * slot + 1; }
-static int split_h_scaled(fg_ctx* c, const float* x, float* hh, float* hl, int64_t n, int slot) {
-  FG_TRY(tc_amax(c, x, n, c->amax_slot + 2 * slot));
-  return tc_split_h(c, x, hh, hl, n, c->amax_slot + 2 * slot);
+static int amax_reset(fg_ctx* c) {
+  if (!f16_on(c)) return FG_OK;
+  for (int i = 0; i < kNumSlots; ++i) c->amax_valid[i] = false;
+  FG_CUDA(cudaMemset2DAsync(c->amax_slot, 2 * sizeof(float), 0, sizeof(float), kNumSlots, c->stream));
+  return FG_OK;
+}
+struct AmaxInto {  // the ONE elementwise producer launched inside the scope reports max|output| into `slot`
+  fg_ctx* c;
+  AmaxInto(fg_ctx* c_, int slot) : c(c_) {
+    if (f16_on(c)) {
+      c->amax_out = reinterpret_cast<unsigned*>(c->amax_slot + 2 * slot);
+      c->amax_id = slot;
+    }
+  }
+  ~AmaxInto() { c->amax_out = nullptr; }
+};
+// slot: where the inverse scale goes (what the consumers read); amax_from: the slot a producer reduced max|x| into (-1: slot)
+static int split_h_scaled(fg_ctx* c, const float* x, float* hh, float* hl, int64_t n, int slot, int amax_from = -1) {
+  const int src = amax_from >= 0 && c->amax_valid[amax_from] ? amax_from : slot;
+  if (c->amax_valid[src]) c->amax_valid[src] = false;  // the producer already reduced max|x| into the slot
+  else FG_TRY(tc_amax(c, x, n, c->amax_slot + 2 * src));
+  return tc_split_h(c, x, hh, hl, n, c->amax_slot + 2 * src, c->amax_slot + 2 * slot + 1);
 }
 
 // nn.Linear as a 1x1 convolution on a 1x1 image.  With only B rows the fp32 SIMT tiling leaves the GPU
@@ -371,12 +394,12 @@ static int split_h_scaled(fg_ctx* c, const float* x, float* hh, float* hl, int64
 // f16 mode: `in16` is the fp32 input (always given), split into keep16_h/l (or the dY scratch) under amax slot `slot`
 static int lin_fwd(fg_ctx* c, const char* tag, const float* in, const float* Wp, int wi, const float* bias, float* out,
                    ConvGeom g, float* keep_hi = nullptr, float* keep_lo = nullptr, const float* in16 = nullptr,
-                   float* keep16_h = nullptr, float* keep16_l = nullptr, int slot = kSlotDy) {
+                   float* keep16_h = nullptr, float* keep16_l = nullptr, int slot = kSlotDy, int amax_from = -1) {
   if (!use_tc(c, g)) return conv_fwd(c, tag, in, Wp, bias, out, g);
   fg_ctx::TcBufs& t = c->tcb;
   if (f16_on(c) && in16) {
     float *hh = keep16_h ? keep16_h : t.dy_hh, *hl = keep16_l ? keep16_l : t.dy_hl;
-    FG_TRY(split_h_scaled(c, in16, hh, hl, (int64_t)g.B * g.Cin, slot));
+    FG_TRY(split_h_scaled(c, in16, hh, hl, (int64_t)g.B * g.Cin, slot, amax_from));
     ScopedTimer tm(c, tag);
     return tc_conv_fwd(c, hh, hl, t.D_Lw_hh[wi], t.D_Lw_hl[wi], bias, out, g, 0, nullptr, nullptr, 1, inv_scale(c, slot));
   }
@@ -430,7 +453,7 @@ static int g_ups_fwd(fg_ctx* c, int li, const char* tag, const float* h, float* 
 // full-resolution gradient that the consumer still has to sum 2x2 (SIMT path).
 static int g_ups_bwd(fg_ctx* c, int li, const char* wtag, const char* dtag, const float* h, const float* h_hi,
                      const float* h_lo, const float* dz, const float* Wpd, ConvGeom g, float* dW, float* dh, bool* pooled,
-                     const float* dz_f32 = nullptr) {
+                     const float* dz_f32 = nullptr, int dz_amax = -1) {
   if (!use_tc_wgrad(c, g)) {
     FG_TRY(conv_wgrad(c, wtag, h, dz, g, dW, 0, 0, 0, 0));
     *pooled = false;
@@ -438,7 +461,7 @@ static int g_ups_bwd(fg_ctx* c, int li, const char* wtag, const char* dtag, cons
   }
   fg_ctx::TcBufs& t = c->tcb;
   if (f16_on(c) && dz_f32) {  // weight and data gradient on the FP16 split of the (scaled) gradient
-    FG_TRY(split_h_scaled(c, dz_f32, t.dy_hh, t.dy_hl, (int64_t)g.B * g.H * g.W * g.Cout, kSlotDy));
+    FG_TRY(split_h_scaled(c, dz_f32, t.dy_hh, t.dy_hl, (int64_t)g.B * g.H * g.W * g.Cout, kSlotDy, dz_amax));
     {
       ScopedTimer tm(c, wtag);
       FG_TRY(tc_conv_wgrad(c, li == 0 ? t.G_h0_hh : t.G_h1_hh, li == 0 ? t.G_h0_hl : t.G_h1_hl, t.dy_hh, t.dy_hl, c->wgrad_ws, g, 1,
@@ -472,6 +495,7 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
     FG_CUDA(cudaMemcpyAsync(c->G_noise, noise, sizeof(float) * B * kNoiseDim, cudaMemcpyDeviceToDevice, c->stream));
   c->G_B = B;
   c->G_train = training;
+  FG_TRY(amax_reset(c));
   const ConvGeom gL1{B, 1, 1, 128, 8192, 1, 1};  // K padded 100 -> 128 for the tensor-core path
   if (use_tc(c, gL1)) {
     fg_ctx::TcBufs& t = c->tcb;
@@ -490,7 +514,10 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
   } else {
     FG_TRY(conv_fwd(c, "G.L1.fwd", c->G_noise, c->G_L1p, c->G_L1p + 8192 * 100, c->G_z0, ConvGeom{B, 1, 1, 100, 8192, 1, 1}));
   }
-  FG_TRY(k_prelu_fwd(c, c->G_z0, P + L.a1, c->G_h0, (int64_t)B * 8192));
+  {
+    AmaxInto am(c, kSlotH0);
+    FG_TRY(k_prelu_fwd(c, c->G_z0, P + L.a1, c->G_h0, (int64_t)B * 8192));
+  }
   // training: the BatchNorm statistics come out of the convolution's epilogue (per-tile partials) when it ran on
   // the tensor cores; otherwise a separate pass over z computes them
   int parts = training ? 1 : 0;
@@ -508,9 +535,12 @@ int net_G_forward(fg_ctx* c, const float* noise, int B, bool training) {
   }
   const ConvGeom gC2{B, 32, 32, 256, 128, 5, 2};
   const bool h1_split = training && use_tc(c, gC2) && !f16_on(c);  // TF32 tcgen05 path consumes h1 only as TF32 hi/lo
-  FG_TRY(k_bn_prelu_apply(c, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2,
-                          c->G_h1, (int64_t)B * 256, 256, h1_split ? c->tcb.G_h1_hi : nullptr,
-                          h1_split ? c->tcb.G_h1_lo : nullptr));
+  {
+    AmaxInto am(c, kSlotH1);
+    FG_TRY(k_bn_prelu_apply(c, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2,
+                            c->G_h1, (int64_t)B * 256, 256, h1_split ? c->tcb.G_h1_hi : nullptr,
+                            h1_split ? c->tcb.G_h1_lo : nullptr));
+  }
   parts = training ? 1 : 0;
   FG_TRY(g_ups_fwd(c, 1, "G.C2.fwd", h1_split ? nullptr : c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, c->G_C2p, P + L.C2b,
                    c->G_z2, gC2, &parts));
@@ -548,6 +578,7 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   const GLayout& L = c->gl;
   float *P = c->PG, *G = c->gG;
   const int B = c->G_B, C = c->C;
+  FG_TRY(amax_reset(c));
   FG_TRY(k_sigmoid_bwd(c, dy, c->G_y, c->G_dz3, (int64_t)B * 1024 * C));
   // C3
   FG_TRY(conv_wgrad(c, "G.C3.wgrad", c->G_h2, c->G_dz3, ConvGeom{B, 32, 32, 128, C, 3, 1}, G + L.C3W, 0, 0, 0, 0));
@@ -565,6 +596,7 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   const bool tc2 = use_tc_wgrad(c, gC2) && !f16_on(c), tc1 = use_tc_wgrad(c, gC1) && !f16_on(c);  // fused TF32 hi/lo of dz
   {
     ScopedTimer tm(c, "hbm.G.bn2.bwd_apply");
+    AmaxInto am(c, kSlotGdz + 2);
     FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z2, c->bn_mean2, c->bn_istd2, P + L.g2, P + L.be2, P + L.a3, c->bn_mg,
                                 c->G_dz2, B, 32, 32, 128, 0, tc2 ? c->tcb.dy_hi : nullptr, tc2 ? c->tcb.dy_lo : nullptr,
                                 G + L.C2b));  // + the bias gradient of C2 (column sums of dz2) in the same pass
@@ -572,26 +604,32 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
   // C2
   bool pooled = false;
   FG_TRY(g_ups_bwd(c, 1, "G.C2.wgrad", "G.C2.dgrad", c->G_h1, c->tcb.G_h1_hi, c->tcb.G_h1_lo, tc2 ? nullptr : c->G_dz2,
-                   c->G_C2pd, gC2, G + L.C2W, c->G_dfull, &pooled, c->G_dz2));
+                   c->G_C2pd, gC2, G + L.C2W, c->G_dfull, &pooled, c->G_dz2, kSlotGdz + 2));
   // BN1 + PReLU (the 2x2 sum = backward of the nearest upsample is folded into the loads)
   FG_TRY(k_bn_prelu_bwd_reduce(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_acc,
                                G + L.a2, B, 16, 16, 256, pooled ? 0 : 1));
   FG_TRY(k_bn_bwd_finalize(c, c->bn_acc, c->bn_mg, G + L.g1, G + L.be1, (int64_t)B * 256, 256));
   const bool split1 = tc1 && pooled;
-  FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_mg,
-                              c->G_dz1, B, 16, 16, 256, pooled ? 0 : 1, split1 ? c->tcb.dy_hi : nullptr,
-                              split1 ? c->tcb.dy_lo : nullptr, G + L.C1b));
+  {
+    AmaxInto am(c, kSlotGdz + 1);
+    FG_TRY(k_bn_prelu_bwd_apply(c, c->G_dfull, c->G_z1, c->bn_mean1, c->bn_istd1, P + L.g1, P + L.be1, P + L.a2, c->bn_mg,
+                                c->G_dz1, B, 16, 16, 256, pooled ? 0 : 1, split1 ? c->tcb.dy_hi : nullptr,
+                                split1 ? c->tcb.dy_lo : nullptr, G + L.C1b));
+  }
   // C1
   FG_TRY(g_ups_bwd(c, 0, "G.C1.wgrad", "G.C1.dgrad", c->G_h0, c->tcb.G_h0_hi, c->tcb.G_h0_lo, split1 ? nullptr : c->G_dz1,
                    c->G_C1pd,
-                   ConvGeom{B, 16, 16, 128, 256, 5, 2}, G + L.C1W, c->G_dfull, &pooled, c->G_dz1));
-  FG_TRY(k_prelu_bwd(c, c->G_dfull, c->G_z0, P + L.a1, c->G_dz0, G + L.a1, B, 8, 8, 128, pooled ? 0 : 1));
+                   ConvGeom{B, 16, 16, 128, 256, 5, 2}, G + L.C1W, c->G_dfull, &pooled, c->G_dz1, kSlotGdz + 1));
+  {
+    AmaxInto am(c, kSlotGdz);
+    FG_TRY(k_prelu_bwd(c, c->G_dfull, c->G_z0, P + L.a1, c->G_dz0, G + L.a1, B, 8, 8, 128, pooled ? 0 : 1));
+  }
   // L1
   const ConvGeom gL1{B, 1, 1, 128, 8192, 1, 1};
   if (use_tc_wgrad(c, gL1)) {  // dW[8192'][128 (100 used)] = dz0^T x on the tensor cores (K = batch), pad columns dropped
     fg_ctx::TcBufs& t = c->tcb;
     if (f16_on(c)) {
-      FG_TRY(split_h_scaled(c, c->G_dz0, t.dy_hh, t.dy_hl, (int64_t)B * 8192, kSlotDy));
+      FG_TRY(split_h_scaled(c, c->G_dz0, t.dy_hh, t.dy_hl, (int64_t)B * 8192, kSlotDy, kSlotGdz));
       ScopedTimer tm(c, "G.L1.wgrad");
       FG_TRY(tc_conv_wgrad(c, t.G_x_hh, t.G_x_hl, t.dy_hh, t.dy_hl, t.G_L1pad, gL1, 1, inv_scale(c, kSlotDy), inv_scale(c, kSlotX)));
     } else {
@@ -618,6 +656,7 @@ int net_G_backward(fg_ctx* c, const float* dy, float* dnoise) {
 int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hyper* h) {
   FG_REQUIRE(B >= 1 && B <= c->maxB, "D forward: batch %d out of range [1,%d]", B, c->maxB);
   FG_TRY(net_pack_D(c));
+  FG_TRY(amax_reset(c));
   const DLayout& L = c->dl;
   float* P = c->PD;
   if (x != c->D_x)
@@ -657,8 +696,11 @@ int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hype
     }
     if (f16_on(c)) nhi = nlo = nullptr;  // the FP16 split is made from the fp32 tensor (split_h_scaled)
     have_split = nhi != nullptr;
-    FG_TRY(k_d_act_pool_fwd(c, c->D_z[i], P + L.ca[i], masks, kDmoff[i], 1.0f - h->p_spatial, c->D_p[i], B, H, H,
-                            kDcout[i], nhi, nlo));
+    {
+      AmaxInto am(c, i < 3 ? kSlotDp + i : kSlotLin);  // p[0..2] feed c2..c4, p[3] the first Linear
+      FG_TRY(k_d_act_pool_fwd(c, c->D_z[i], P + L.ca[i], masks, kDmoff[i], 1.0f - h->p_spatial, c->D_p[i], B, H, H,
+                              kDcout[i], nhi, nlo));
+    }
     cur = c->D_p[i];
   }
   const float scale = 1.0f / (1.0f - h->p_drop);
@@ -666,7 +708,10 @@ int net_D_forward(fg_ctx* c, const float* x, int B, bool training, const fg_hype
   c->D_spatial_eval = 1.0f - h->p_spatial;
   FG_TRY(lin_fwd(c, "D.L1.fwd", have_split ? nullptr : c->D_p[3], c->D_L1p, 0, P + L.L1b, c->D_zl1, gL1d,
                  c->tcb.D_lin_hi[0], c->tcb.D_lin_lo[0], c->D_p[3], c->tcb.D_lin_hh[0], c->tcb.D_lin_hl[0], kSlotLin));
-  FG_TRY(k_lin_act_drop_fwd(c, c->D_zl1, P + L.a5, masks, 960, scale, c->D_hl1, B, 512));
+  {
+    AmaxInto am(c, kSlotLin + 1);
+    FG_TRY(k_lin_act_drop_fwd(c, c->D_zl1, P + L.a5, masks, 960, scale, c->D_hl1, B, 512));
+  }
   FG_TRY(lin_fwd(c, "D.L2.fwd", c->D_hl1, P + L.L2W, 2, P + L.L2b, c->D_zl2, ConvGeom{B, 1, 1, 512, 512, 1, 1},
                  c->tcb.D_lin_hi[1], c->tcb.D_lin_lo[1], c->D_hl1, c->tcb.D_lin_hh[1], c->tcb.D_lin_hl[1], kSlotLin + 1));
   FG_TRY(k_lin_act_drop_fwd(c, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_hl2, B, 512));
@@ -688,6 +733,7 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
   const int B = c->D_B;
   const float* masks = c->D_train ? c->D_masks : nullptr;
   const float scale = c->D_drop_scale, eval_scale = c->D_spatial_eval;
+  FG_TRY(amax_reset(c));
   // L3
   if (want_wgrad) {
     ScopedTimer tm(c, "D.L3.wgrad");
@@ -697,8 +743,11 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
     ScopedTimer tm(c, "D.L3.dgrad");
     FG_TRY(k_gemv_dgrad(c, dlogit, P + L.L3W, c->D_dh, B, 512));
   }
-  FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_dzl, want_wgrad ? G + L.a6 : nullptr, B,
-                            512));
+  {
+    AmaxInto am(c, kSlotDzl + 1);
+    FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl2, P + L.a6, masks, 1472, scale, c->D_dzl, want_wgrad ? G + L.a6 : nullptr, B,
+                              512));
+  }
   // L2
   const ConvGeom gL2{B, 1, 1, 512, 512, 1, 1}, gL1{B, 1, 1, 2048, 512, 1, 1};
   const bool tcw2 = want_wgrad && use_tc_wgrad(c, gL2), tcw1 = want_wgrad && use_tc_wgrad(c, gL1);
@@ -707,19 +756,22 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
     FG_TRY(k_colsum_add(c, c->D_dzl, G + L.L2b, B, 512, 0, 0));
   }
   FG_TRY(lin_fwd(c, "D.L2.dgrad", c->D_dzl, c->D_L2pd, 3, nullptr, c->D_dh, ConvGeom{B, 1, 1, 512, 512, 1, 1}, nullptr, nullptr,
-                 c->D_dzl));
+                 c->D_dzl, nullptr, nullptr, kSlotDy, kSlotDzl + 1));
   if (tcw2)
     FG_TRY(lin_wgrad_tc(c, "D.L2.wgrad", c->tcb.D_lin_hi[1], c->tcb.D_lin_lo[1], gL2, G + L.L2W, 0, 0, c->tcb.D_lin_hh[1],
                         c->tcb.D_lin_hl[1], kSlotLin + 1));
-  FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl1, P + L.a5, masks, 960, scale, c->D_dzl, want_wgrad ? G + L.a5 : nullptr, B,
-                            512));
+  {
+    AmaxInto am(c, kSlotDzl);
+    FG_TRY(k_lin_act_drop_bwd(c, c->D_dh, c->D_zl1, P + L.a5, masks, 960, scale, c->D_dzl, want_wgrad ? G + L.a5 : nullptr, B,
+                              512));
+  }
   // L1
   if (want_wgrad) {
     if (!tcw1) FG_TRY(conv_wgrad(c, "D.L1.wgrad", c->D_p[3], c->D_dzl, gL1, G + L.L1W, 0, 0, 512, 4));
     FG_TRY(k_colsum_add(c, c->D_dzl, G + L.L1b, B, 512, 0, 0));
   }
   FG_TRY(lin_fwd(c, "D.L1.dgrad", c->D_dzl, c->D_L1pd, 1, nullptr, c->D_dp, ConvGeom{B, 1, 1, 512, 2048, 1, 1}, nullptr, nullptr,
-                 c->D_dzl));
+                 c->D_dzl, nullptr, nullptr, kSlotDy, kSlotDzl));
   if (tcw1)
     FG_TRY(lin_wgrad_tc(c, "D.L1.wgrad", c->tcb.D_lin_hi[0], c->tcb.D_lin_lo[0], gL1, G + L.L1W, 512, 4, c->tcb.D_lin_hh[0],
                         c->tcb.D_lin_hl[0], kSlotLin));
@@ -733,10 +785,13 @@ int net_D_backward(fg_ctx* c, const float* dlogit, bool want_wgrad, bool want_dx
     const bool tc32 = tc && !f16_on(c);  // TF32 path: dz's hi/lo split comes out of the pooling-backward kernel
     fg_ctx::TcBufs& t = c->tcb;
     // dz and, for the tensor-core layers, its TF32 split in one pass
-    FG_TRY(k_d_act_pool_bwd(c, c->D_dp, c->D_z[i], P + L.ca[i], masks, kDmoff[i], eval_scale, c->D_dz,
-                            want_wgrad ? G + L.ca[i] : nullptr, B, H, H, cout, tc32 ? t.dy_hi : nullptr, tc32 ? t.dy_lo : nullptr,
-                            want_wgrad ? G + L.cb[i] : nullptr));  // + the conv bias gradient (column sums of dz)
-    if (tc && f16_on(c)) FG_TRY(split_h_scaled(c, c->D_dz, t.dy_hh, t.dy_hl, (int64_t)B * H * H * cout, kSlotDy));
+    {
+      AmaxInto am(c, kSlotDdz + i);
+      FG_TRY(k_d_act_pool_bwd(c, c->D_dp, c->D_z[i], P + L.ca[i], masks, kDmoff[i], eval_scale, c->D_dz,
+                              want_wgrad ? G + L.ca[i] : nullptr, B, H, H, cout, tc32 ? t.dy_hi : nullptr, tc32 ? t.dy_lo : nullptr,
+                              want_wgrad ? G + L.cb[i] : nullptr));  // + the conv bias gradient (column sums of dz)
+    }
+    if (tc && f16_on(c)) FG_TRY(split_h_scaled(c, c->D_dz, t.dy_hh, t.dy_hl, (int64_t)B * H * H * cout, kSlotDy, kSlotDdz + i));
     if (want_wgrad) {
       if (tc && use_tc_wgrad(c, gf)) {
         {
