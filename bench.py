@@ -94,7 +94,7 @@ def load_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
 
 
-def ncu_traffic(profile="r2_ncu_gc2fwd_v2.md"):
+def ncu_traffic(profile="r2_ncu_f16_tapconv.md"):
     """dram__bytes_read.sum + dram__bytes_write.sum of the G.C2 forward launch at batch 256 (the first kernel of the
     committed `ncu --set full` summary; a number taken under the profiler, quoted only as traffic, never as time)."""
     import re
@@ -110,7 +110,7 @@ def ncu_traffic(profile="r2_ncu_gc2fwd_v2.md"):
         return None, None
 
 
-def ncu_pipe_active(profile="r2_ncu_gc2fwd_v2.md"):
+def ncu_pipe_active(profile="r2_ncu_f16_tapconv.md"):
     """sm__pipe_tensor_cycles_active (% of peak) of the G.C2 forward launch in the committed `ncu --set full` summary"""
     import re
     try:
@@ -212,7 +212,7 @@ def secondary_configs(steps=5):
     try:
         import bench_configs as BC
         for job in (lambda: BC.train_small(16, 1, steps), lambda: BC.c2f(32, steps), lambda: BC.c2f(256, steps),
-                    lambda: BC.sample(16, steps), lambda: BC.sample(1024, steps)):
+                    lambda: BC.sample(16, steps), lambda: BC.sample(1024, steps), lambda: BC.train_s16(256, steps)):
             r = job()
             r.pop("layer_ms_per_step", None)
             res.append(r)
@@ -333,7 +333,8 @@ def main():
     hbm_bytes = {"hbm.G.bn2.stats": 1.5 * act,            # read z2
                  "hbm.G.bn2.apply": 1.5 * 2 * act,        # read z2, write h2
                  "hbm.G.bn2.bwd_reduce": 2 * act,         # read dh, z2
-                 "hbm.G.bn2.bwd_apply": 5 * act,          # read dh, z2; write dz2 + its TF32 hi/lo split
+                 # read dh, z2; write dz2 (+ its TF32 hi/lo split on the 3xTF32 path; the FP16 split is a separate pass)
+                 "hbm.G.bn2.bwd_apply": (3 if ctx.get_option("mma_f16") else 5) * act,
                  # the 3-channel-side 3x3 convolutions (k_conv_edge.cu): input + output of the images they process per step
                  "G.C3.fwd": 1.5 * B * 1024 * (128 + C) * 4,   # B/2 (D step) + B (G step) images
                  "G.C3.dgrad": B * 1024 * (C + 128) * 4,       # G step
@@ -347,11 +348,14 @@ def main():
         if n:
             hbm[name] = (nbytes, t / nprof)
     ctx.timing_enable(False)
-    tf32_peak = tf32_peak_n128 = None
+    tf32_peak = tf32_peak_n128 = f16_peak = None
     if rank == 0:
         try:
             tf32_peak = ctx.tf32_peak(20000)
-            os.environ["FG_TF32_PROBE_N"] = "128"  # the instruction shape the convolution kernels issue
+            os.environ["FG_TF32_PROBE_F16"] = "1"  # the same loop with kind::f16 instructions (128x256x16)
+            f16_peak = ctx.tf32_peak(20000)
+            os.environ.pop("FG_TF32_PROBE_F16")
+            os.environ["FG_TF32_PROBE_N"] = "128"  # the N=128 instruction shape
             tf32_peak_n128 = ctx.tf32_peak(40000)
             os.environ.pop("FG_TF32_PROBE_N")
         except Exception as e:  # the probe must never cost the headline
@@ -366,9 +370,12 @@ def main():
     tf_fwd = 1.5 * B * F_GC2 / t_fwd / 1e12 if t_fwd > 0 else 0.0
     t_c2 = (fam["G.C2.fwd"][0] + fam["G.C2.dgrad"][0] + fam["G.C2.wgrad"][0]) / 1e3
     tf_c2 = 3.5 * B * F_GC2 / t_c2 / 1e12 if t_c2 > 0 else 0.0
-    peak = peaks["bf16_sus"] / 2.0
+    f16 = bool(ctx.get_option("mma_f16")) and ctx.get_option("conv_impl") == 2
+    # kind::f16 MMAs run at the bf16 dense rate, kind::tf32 at half of it
+    peak = peaks["bf16_sus"] if f16 else peaks["bf16_sus"] / 2.0
+    mma_peak = f16_peak if f16 else tf32_peak
     traffic, traffic_src = ncu_traffic()
-    # executed tensor-core work of that launch: 3 MMAs per logical MMA (3xTF32), 9/25 of the taps (phase collapse)
+    # executed tensor-core work of that launch: 3 MMAs per logical MMA (3-term split), 9/25 of the taps (phase collapse)
     collapsed = ctx.get_option("conv_impl") == 2
     exec_ratio = 3.0 * (9.0 / 25.0 if collapsed else 1.0)
     pipe_pct, pipe_src = ncu_pipe_active()
@@ -377,7 +384,8 @@ def main():
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": workload_config(world, B),
-        "config_detail": {"conv_impl": ctx.get_option("conv_impl")},
+        "config_detail": {"conv_impl": ctx.get_option("conv_impl"), "mma_f16": int(f16),
+                          "operand_split": "3xFP16 (kind::f16, fp32 accumulate)" if f16 else "3xTF32 (kind::tf32)"},
         "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(real.nbytes + nD.nbytes + nG.nbytes), "d2h_bytes_per_step": 40},
         "gpu_launches": int(launches),
@@ -386,18 +394,21 @@ def main():
                      "bound": "tensor", "achieved": tf_fwd, "peak": peak, "unit": "TFLOP/s",
                      "frac": tf_fwd / peak, "traffic": traffic,
                      "traffic_note": "DRAM bytes of the batch-%d launch (%s); algorithmic bytes of that launch: "
-                                     "input hi+lo 2x67.1 MB + output 134.2 MB + weights 9.4 MB" % (256, traffic_src),
-                     "peak_source": "%s bf16 sustained %.1f TF / 2 (kind::tf32 is half rate); algorithmic fp32 FLOPs" % (
+                                     "input hi+lo %s MB + output 134.2 MB + weights %s MB" % (
+                                         256, traffic_src, "2x33.6" if f16 else "2x67.1", "4.7" if f16 else "9.4"),
+                     "peak_source": ("%s bf16 sustained %.1f TF (kind::f16 runs at the bf16 rate); algorithmic fp32 FLOPs" if f16 else
+                                     "%s bf16 sustained %.1f TF / 2 (kind::tf32 is half rate); algorithmic fp32 FLOPs") % (
                          peaks["src"], peaks["bf16_sus"]),
                      "executed_mma_tflops": tf_fwd * exec_ratio,
-                     "executed_note": "kind::tf32 MMAs actually issued: 3 per logical MMA (hi*hi + hi*lo + lo*hi)%s" % (
-                         " x 9/25 taps (upsample folded into four 3x3 phase convolutions)" if collapsed else ""),
+                     "executed_note": "kind::%s MMAs actually issued: 3 per logical MMA (hi*hi + hi*lo + lo*hi)%s" % (
+                         "f16" if f16 else "tf32", " x 9/25 taps (upsample folded into four 3x3 phase convolutions)" if collapsed else ""),
+                     "measured_f16_peak": f16_peak,
                      "measured_tf32_peak": tf32_peak,
                      "measured_tf32_peak_n128": tf32_peak_n128,
                      "measured_tf32_peak_note": "fg_bench_tf32_peak: back-to-back tcgen05.mma.kind::tf32 128x256x8, cta_group::1, "
                                                 "smem-resident operands, all SMs, run at bench clocks right after the timed region",
-                     "frac_executed_vs_measured_tf32": (tf_fwd * exec_ratio / tf32_peak) if tf32_peak else None,
-                     "frac_algorithmic_vs_measured_tf32": (tf_fwd / tf32_peak) if tf32_peak else None,
+                     "frac_executed_vs_measured_mma_peak": (tf_fwd * exec_ratio / mma_peak) if mma_peak else None,
+                     "frac_algorithmic_vs_measured_mma_peak": (tf_fwd / mma_peak) if mma_peak else None,
                      "pipe_active_pct": pipe_pct, "pipe_active_src": pipe_src,
                      "family_fwd_dgrad_wgrad_tflops": tf_c2,
                      "step_algorithmic_tflops": F_ITER_PER_IMG * B * K / (ms / 1e3) / 1e12},

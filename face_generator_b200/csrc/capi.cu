@@ -114,6 +114,12 @@ int fg_destroy(fg_ctx* c) {
   if (!c) return FG_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->comm_stream) {
+    cudaStreamSynchronize(c->comm_stream);
+    cudaStreamDestroy(c->comm_stream);
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_join);
+  }
   tc_destroy(c);
   net_free(c);
   for (auto& kv : c->timers)
@@ -169,6 +175,10 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
     c->G_packed = c->D_packed = false;
     return FG_OK;
   }
+  if (!strcmp(key, "dp_overlap")) {  // 1 (default): D's all-reduce + optimizer overlap the G step's G forward (data parallel only)
+    c->dp_overlap = v != 0;
+    return FG_OK;
+  }
   if (!strcmp(key, "debug_keep")) {  // keep the D step's pre-activations of fg_train_step ("Dstep.*" debug tensors)
     c->debug_keep = v != 0;
     return FG_OK;
@@ -200,6 +210,7 @@ int64_t fg_get_option(fg_ctx* c, const char* key) {
   if (!strcmp(key, "bn_epilogue")) return c->bn_epilogue;
   if (!strcmp(key, "edge_impl")) return c->edge_impl;
   if (!strcmp(key, "mma_f16")) return c->mma_f16;
+  if (!strcmp(key, "dp_overlap")) return c->dp_overlap;
   if (!strcmp(key, "optimizer_D")) return c->opt_D;
   if (!strcmp(key, "optimizer_G")) return c->opt_G;
   return -1;

@@ -145,6 +145,11 @@ struct fg_ctx {
   // data parallel
   void* nccl_comm = nullptr;
   int world = 1, rank = 0;
+  // option "dp_overlap" (default 1): D's all-reduce + accuracy gate + optimizer run on comm_stream while the compute
+  // stream already runs the G step's G forward (which only needs G's parameters); joined before D is used again
+  int dp_overlap = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // debug (tests): "debug_keep" = 1 keeps a copy of the D step's pre-activations of fg_train_step, which the G
   // step's D forward overwrites (the strict gradient-parity tests read PReLU branch decisions from them)
   bool debug_keep = false;

@@ -900,12 +900,35 @@ int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const
     c->keep_B = B;
   }
   FG_TRY(net_D_backward(c, c->D_dlogit, true, false));
-  if (c->world > 1) FG_TRY(net_allreduce_grads(c, FG_NET_D));
-  FG_TRY(k_gate_and_prep(c, FG_NET_D, h, c->tailD, B, world));
-  FG_TRY(net_optim(c, FG_NET_D, h, 1.0f / world, true));
+  const bool overlap = c->world > 1 && c->dp_overlap && !c->timing;
+  if (overlap) {
+    // D's gradient all-reduce, gate and optimizer on the communication stream; the G step's G forward (it depends on G's
+    // parameters only) proceeds on the compute stream and D is joined before its next forward.  The replicas stay
+    // bit-identical: the same reductions in the same order, only on another stream.
+    if (!c->comm_stream) {
+      FG_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+      FG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      FG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    FG_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    FG_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
+    cudaStream_t compute = c->stream;
+    c->stream = c->comm_stream;
+    int r = net_allreduce_grads(c, FG_NET_D);
+    if (r == FG_OK) r = k_gate_and_prep(c, FG_NET_D, h, c->tailD, B, world);
+    if (r == FG_OK) r = net_optim(c, FG_NET_D, h, 1.0f / world, true);
+    if (r == FG_OK && cudaEventRecord(c->ev_join, c->comm_stream) != cudaSuccess) r = FG_ERR_CUDA;
+    c->stream = compute;
+    FG_TRY(r);
+  } else {
+    if (c->world > 1) FG_TRY(net_allreduce_grads(c, FG_NET_D));
+    FG_TRY(k_gate_and_prep(c, FG_NET_D, h, c->tailD, B, world));
+    FG_TRY(net_optim(c, FG_NET_D, h, 1.0f / world, true));
+  }
   // ---- G step (adversarial.lua:275-288) ----
   FG_TRY(net_zero_grads(c, FG_NET_G));
   FG_TRY(net_G_forward(c, noiseG, B, true));
+  if (overlap) FG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   if (masksG)
     FG_CUDA(cudaMemcpyAsync(c->D_masks, masksG, sizeof(float) * (size_t)B * kMaskPerSample, cudaMemcpyDeviceToDevice,
                             c->stream));

@@ -143,13 +143,52 @@ def train_small(B, C, steps):
     return out
 
 
+def train_s16(B, steps):
+    """train.lua --scale 16 (G16 / D16_d, models.lua:27-51, :279-316): one adversarial.lua iteration on 16x16 images"""
+    C = 3
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    ctx = fg.Context(0, max_batch=B, channels=C)
+    net = fg.S16(ctx)
+    rng = np.random.default_rng(4)
+    nG, nD = net.count(NET_G), net.count(NET_D)
+    # fan-in scaled synthetic weights, PReLU slopes 0.25 (single floats are the only size-1 tensors besides the last bias)
+    net.set_params(NET_G, (rng.standard_normal(nG) * 0.02).astype(np.float32))
+    net.set_params(NET_D, (rng.standard_normal(nD) * 0.02).astype(np.float32))
+    real = rng.random((B // 2, C, 16, 16)).astype(np.float32)
+    zD = rng.uniform(-1, 1, (B // 2, 100)).astype(np.float32)
+    zG = rng.uniform(-1, 1, (B, 100)).astype(np.float32)
+    dev = [ctx.dev_array(a) for a in (real, zD, zG)]
+    hyper = fg.hyper_default()
+    seed = [0]
+
+    def step():
+        seed[0] += 1
+        net.train_step(hyper, B, dev[0], dev[1], dev[2], None, None, seed[0], want_stats=False)
+
+    def step_e2e():
+        seed[0] += 1
+        return net.train_step(hyper, B, real, zD, zG, None, None, seed[0], want_stats=True)
+
+    for _ in range(3):
+        step()
+    ms = timed(ctx, step, steps)
+    ms_e2e = timed(ctx, step_e2e, max(3, steps // 2))
+    out = {"config": "train.lua --scale 16: colour 3x16x16, batch %d, G16 / D16_d, 1 D-iter + 1 G-iter, Adam" % B,
+           "metric": "train images/sec", "value": B / (ms / 1e3), "unit": "images/s", "ms_per_step": ms,
+           "e2e": {"value": B / (ms_e2e / 1e3), "unit": "images/s", "ms_per_step": ms_e2e}, "dtype": "f32"}
+    net.close()
+    ctx.close()
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--only", default="", help="c2f | sample | small")
+    ap.add_argument("--only", default="", help="c2f | sample | small | s16")
     a = ap.parse_args()
     jobs = [("c2f", lambda: c2f(32, a.steps)), ("c2f", lambda: c2f(256, a.steps)), ("sample", lambda: sample(16, a.steps)),
-            ("sample", lambda: sample(1024, a.steps)), ("small", lambda: train_small(16, 1, a.steps))]
+            ("sample", lambda: sample(1024, a.steps)), ("small", lambda: train_small(16, 1, a.steps)),
+            ("s16", lambda: train_s16(256, a.steps))]
     for kind, job in jobs:
         if not a.only or a.only == kind:
             print(json.dumps(job()), flush=True)

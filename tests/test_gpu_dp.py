@@ -221,3 +221,62 @@ def test_dp_resume_broadcasts_step_counters():
     assert got[0][2] == got[1][2] == (10, 8)
     for k in (3, 4, 5):
         np.testing.assert_array_equal(got[0][k], got[1][k])
+
+
+def _worker_overlap(rank, world, port, q):
+    import torch.distributed as dist
+    import parity_utils as PU
+    import face_generator_b200 as fg
+    from face_generator_b200.lib import NET_D, NET_G
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, C = 16, 3
+    base = PU.make_case(B, C, seed=800)
+    cases = [PU.make_case(B, C, seed=801 + rank + 10 * s) for s in range(3)]
+    res = []
+    for overlap in (1, 0):
+        ctx = fg.Context(rank, max_batch=B, channels=C)
+        ctx.set_option("dp_overlap", overlap)
+        ctx.set_params(NET_G, base["PG"])
+        ctx.set_params(NET_D, base["PD"])
+        ids = [ctx.dp_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.dp_init(ids[0], world, rank)
+        ctx.dp_broadcast_params()
+        sts = [ctx.train_step(fg.hyper_default(), B, cs["real"], cs["noise_D"], cs["noise_G"], cs["masks_D"], cs["masks_G"])
+               for cs in cases]
+        res.append((ctx.get_params(NET_D), ctx.get_params(NET_G), [s["loss_D"] for s in sts], [s["loss_G"] for s in sts],
+                    [list(s["conf"]) for s in sts]))
+        dist.barrier()
+        ctx.close()
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_overlap_is_bit_identical_to_serial():
+    """option dp_overlap: D's all-reduce + gate + optimizer on the communication stream while the G step's G forward
+    runs -- three steps give exactly the parameters, losses and confusion counts of the serial schedule, on both ranks."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, port = 2, 29761
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_worker_overlap, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r = q.get(timeout=600)
+        got[r[0]] = r[1]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for r in range(world):
+        ov, ser = got[r]
+        np.testing.assert_array_equal(ov[0], ser[0])
+        np.testing.assert_array_equal(ov[1], ser[1])
+        assert ov[2] == ser[2] and ov[3] == ser[3] and ov[4] == ser[4]
+    np.testing.assert_array_equal(got[0][0][0], got[1][0][0])  # replicas identical
+    np.testing.assert_array_equal(got[0][0][1], got[1][0][1])
