@@ -247,7 +247,13 @@ def main():
     # asked for; INIT lines carry "nranks N" by default) goes to stderr instead of being switched off
     os.environ.setdefault("NCCL_DEBUG", "INFO")
     os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # (NCCL_DEBUG_FILE=/dev/stderr produced nothing under torchrun on the GPU boxes: log to a per-process file and relay
+    # it to stderr at the end of the run)
+    nccl_log = None
+    if world > 1 and "NCCL_DEBUG_FILE" not in os.environ:
+        import tempfile
+        nccl_log = os.path.join(tempfile.gettempdir(), "fg_b200_nccl_%d.log" % os.getpid())
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
     if world > 1:
         import torch.distributed as dist  # plumbing only: rendezvous, barrier, max-over-ranks
         dist.init_process_group("gloo")
@@ -360,6 +366,10 @@ def main():
             os.environ.pop("FG_TF32_PROBE_N")
         except Exception as e:  # the probe must never cost the headline
             sys.stderr.write("tf32 peak probe failed: %s\n" % e)
+    if nccl_log and os.path.exists(nccl_log):  # NCCL's own INIT lines ("... rank r nranks N ...") -> stderr
+        sys.stderr.write(open(nccl_log).read())
+        sys.stderr.flush()
+        os.remove(nccl_log)
     if rank != 0:
         return
     peaks = load_peaks()

@@ -93,6 +93,7 @@ int fg_create(fg_ctx** out, int device, int max_batch, int channels) {
   c->C = channels;
   c->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("FG_MMA_F16")) c->mma_f16 = atoi(e) != 0;  // experiment switch for option "mma_f16"
+  if (const char* e = getenv("FG_DP_OVERLAP")) c->dp_overlap = atoi(e) != 0;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     fg_set_error("fg_create: cudaStreamCreate failed");
     delete c;

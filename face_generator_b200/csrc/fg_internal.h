@@ -148,6 +148,7 @@ struct fg_ctx {
   // option "dp_overlap" (default 1): D's all-reduce + accuracy gate + optimizer run on comm_stream while the compute
   // stream already runs the G step's G forward (which only needs G's parameters); joined before D is used again
   int dp_overlap = 1;
+  int reserve_sms = 0;  // SMs the persistent convolution kernels leave free while a collective runs next to them
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // debug (tests): "debug_keep" = 1 keeps a copy of the D step's pre-activations of fg_train_step, which the G

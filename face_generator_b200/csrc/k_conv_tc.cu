@@ -736,7 +736,7 @@ static int tc_chunk(bool forward_type = false) {
 }
 
 static int launch_tapconv(fg_ctx* c, const TcFwdParams& p, int BN, int f16 = 0) {
-  dim3 grid(std::min(p.ntiles, c->sm_count));
+  dim3 grid(std::min(p.ntiles, std::max(1, c->sm_count - c->reserve_sms)));
   if (f16) {
     if (BN == 128) tapconv_tc_kernel<128, true><<<grid, 192, fwd_smem<128>(), c->stream>>>(p);
     else tapconv_tc_kernel<64, true><<<grid, 192, fwd_smem<64>(), c->stream>>>(p);

@@ -927,7 +927,14 @@ int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const
   }
   // ---- G step (adversarial.lua:275-288) ----
   FG_TRY(net_zero_grads(c, FG_NET_G));
-  FG_TRY(net_G_forward(c, noiseG, B, true));
+  {
+    // while the collective is in flight the persistent convolution kernels leave a few SMs to it (FG_DP_RESERVE_SMS)
+    static const int reserve = getenv("FG_DP_RESERVE_SMS") ? atoi(getenv("FG_DP_RESERVE_SMS")) : 0;
+    c->reserve_sms = overlap ? reserve : 0;
+    const int r = net_G_forward(c, noiseG, B, true);
+    c->reserve_sms = 0;
+    FG_TRY(r);
+  }
   if (overlap) FG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   if (masksG)
     FG_CUDA(cudaMemcpyAsync(c->D_masks, masksG, sizeof(float) * (size_t)B * kMaskPerSample, cudaMemcpyDeviceToDevice,
