@@ -14,6 +14,8 @@ struct ConvL {  // NHWC, stride 1, "same" padding (a strided layer runs at strid
   float* bp = nullptr;                                                            // bias in our row order (nA != 0)
   float *Wf_hi = nullptr, *Wf_lo = nullptr, *Wd_hi = nullptr, *Wd_lo = nullptr;   // TF32 splits of the packs
   float *x_hi = nullptr, *x_lo = nullptr;                                         // split of the input (fwd -> wgrad)
+  float* sx = nullptr;       // device (max|x|, 1/scale) of the input's FP16 split (option mma_f16)
+  bool packed_f16 = false;   // the hi/lo buffers currently hold the FP16 split (set by convl_pack)
   // Layers whose output side is too narrow for a tensor-core tile still run there with zero-padded channels:
   //   pad_out (Cout <= 4, e.g. the 256->C 7x7 output layer): forward with the weights padded to pad_out rows;
   //           wgrad with the roles swapped (big channel count on the 128-row M side, padded dY on the N side)
@@ -35,8 +37,11 @@ struct ConvLEnv {
   float *dy_hi = nullptr, *dy_lo = nullptr;     // TF32 split of the current dY (largest layer output)
   float *pad_hi = nullptr, *pad_lo = nullptr;   // channel-padded TF32 split of dY (pad_out / pad_dy layers)
   float* ws = nullptr;                          // packed weight-gradient workspace (largest layer)
+  float* sdy = nullptr;                         // device (max|dY|, 1/scale) of the current dY's FP16 split
 };
 
+// what the weight packs depend on besides the parameters: re-pack when it changes
+inline int pack_key(const fg_ctx* c) { return c->conv_impl | (c->mma_f16 << 4); }
 int convl_dalloc(ConvLEnv& e, float** p, size_t elems);  // zero-filled device buffer, owned by *e.allocs
 int convl_alloc(ConvLEnv& e, ConvL& L);
 int convl_pack(fg_ctx* c, ConvL& L, const float* P);

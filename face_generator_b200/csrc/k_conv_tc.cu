@@ -27,6 +27,7 @@
 
 #include "fg_internal.h"
 #include "k_conv_tc.h"
+#include "k_f16split.cuh"
 
 namespace {
 
@@ -220,15 +221,6 @@ __global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi
   }
 }
 
-// 3xFP16 split: x ~= hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 significant bits like the TF32
-// split, operands of kind::f16 MMAs (2x the TF32 rate, 4 bytes per element for hi+lo instead of 8).  fp16 subnormals
-// keep the ABSOLUTE error at 2^-36, so a tensor whose max is in [2^-13, 65504] is represented to 2^-23 of that max;
-// activations and weights are used as they are, gradients are first scaled by a power of two (tc_amax).
-__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
-  const float xc = fminf(fmaxf(x, -65504.f), 65504.f);
-  hi = __float2half_rn(xc);
-  lo = __float2half_rn(fminf(fmaxf((x - __half2float(hi)) * 2048.f, -65504.f), 65504.f));
-}
 __global__ void amax_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__ slot) {
   const float4* x4 = reinterpret_cast<const float4*>(x);
   float m = 0.f;
@@ -239,14 +231,6 @@ __global__ void amax_kernel(const float* __restrict__ x, int64_t n4, unsigned* _
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));  // non-negative floats order like their bits
-}
-// power of two that brings amax into [2^14, 2^15) (1 for an all-zero tensor); exponent clamped so that s and 1/s are normal
-__device__ __forceinline__ float scale_for_amax(float amax) {
-  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
-  int ex;
-  frexpf(amax, &ex);  // amax = m * 2^ex, m in [0.5, 1)
-  const int e = max(-100, min(100, 15 - ex));
-  return ldexpf(1.f, e);
 }
 template <bool ALIGNED>
 __global__ void split_h_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4,

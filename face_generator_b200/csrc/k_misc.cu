@@ -6,6 +6,7 @@
 #include <cmath>
 
 #include "fg_internal.h"
+#include "k_f16split.cuh"
 #include "k_misc.h"
 
 #define LAUNCH_CHECK(c)                 \
@@ -224,6 +225,34 @@ __global__ void pad_split_kernel(const float* __restrict__ src, float* __restric
     lo[i] = l;
   }
 }
+// the same into the 3xFP16 split (halves), values scaled by the power of two derived from amax_slot[0] (tc_amax)
+__global__ void pad_split_h_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, int64_t P,
+                                   int Cs, int Cp, float* __restrict__ amax_slot) {
+  const float s = amax_slot ? scale_for_amax(amax_slot[0]) : 1.f;
+  if (amax_slot && blockIdx.x == 0 && threadIdx.x == 0) amax_slot[1] = 1.f / s;
+  const int64_t n = P * Cp;
+  GRID_STRIDE(i, n) {
+    const int ch = (int)(i % Cp);
+    __half h = __float2half_rn(0.f), l = h;
+    if (ch < Cs) split_f16(src[(i / Cp) * Cs + ch] * s, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+__global__ void pack_pad_split_h_kernel(const float* __restrict__ W, __half* __restrict__ hi, __half* __restrict__ lo, int N,
+                                        int Np, int Cc, int KK) {
+  const int64_t n = (int64_t)N * Cc * KK;
+  GRID_STRIDE(i, n) {
+    const int t = (int)(i % KK);
+    const int64_t r = i / KK;
+    const int ch = (int)(r % Cc), row = (int)(r / Cc);
+    __half h, l;
+    split_f16(W[i], h, l);
+    const int64_t j = ((int64_t)t * Np + row) * Cc + ch;
+    hi[j] = h;
+    lo[j] = l;
+  }
+}
 // dst[p][n] = src[p][n] + bias[n] for n < Cs  (src rows are Cp wide)
 __global__ void compact_bias_kernel(const float* __restrict__ src, const float* __restrict__ bias, float* __restrict__ dst,
                                     int64_t P, int Cs, int Cp) {
@@ -273,6 +302,18 @@ __global__ void unpack_wgrad_swapped_kernel(const float* __restrict__ Gt, float*
 
 int k_pad_split(fg_ctx* c, const float* src, float* hi, float* lo, int64_t P, int Cs, int Cp) {
   pad_split_kernel<<<grid_for(P * Cp, 256), 256, 0, c->stream>>>(src, hi, lo, P, Cs, Cp);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int k_pad_split_h(fg_ctx* c, const float* src, float* hi, float* lo, int64_t P, int Cs, int Cp, float* amax_slot) {
+  pad_split_h_kernel<<<grid_for(P * Cp, 256), 256, 0, c->stream>>>(src, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), P,
+                                                                   Cs, Cp, amax_slot);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int k_pack_pad_split_h(fg_ctx* c, const float* W, float* hi, float* lo, int N, int Np, int Cc, int KK) {
+  pack_pad_split_h_kernel<<<grid_for((int64_t)N * Cc * KK, 256), 256, 0, c->stream>>>(W, reinterpret_cast<__half*>(hi),
+                                                                                      reinterpret_cast<__half*>(lo), N, Np, Cc, KK);
   LAUNCH_CHECK(c);
   return FG_OK;
 }

@@ -14,6 +14,9 @@ int k_bernoulli_keep(fg_ctx* c, float* out, int64_t n, uint64_t seed, float p_dr
 // channel padding around the tensor-core kernels (layers with a narrow output side)
 int k_pad_split(fg_ctx* c, const float* src, float* hi, float* lo, int64_t P, int Cs, int Cp);       // [P][Cs] -> TF32 hi/lo [P][Cp]
 int k_compact_bias(fg_ctx* c, const float* src, const float* bias, float* dst, int64_t P, int Cs, int Cp);
+// 3xFP16-split variants (halves in the same buffers; amax_slot: (max|src|, 1/scale) pair filled by tc_amax / written here)
+int k_pad_split_h(fg_ctx* c, const float* src, float* hi, float* lo, int64_t P, int Cs, int Cp, float* amax_slot);
+int k_pack_pad_split_h(fg_ctx* c, const float* W, float* hi, float* lo, int N, int Np, int Cc, int KK);
 int k_pack_pad_split(fg_ctx* c, const float* W, float* hi, float* lo, int N, int Np, int Cc, int KK);  // W[N][Cc][KK] -> [t][Np][Cc]
 int k_unpack_wgrad_pad(fg_ctx* c, const float* G, float* dW, int N, int Np, int Cc, int KK);          // dW += G[t][n<N][c]
 int k_unpack_wgrad_swapped(fg_ctx* c, const float* Gt, float* dW, int N, int Np, int Cc, int KK);     // dW += Gt[KK-1-t][c][n<N]

@@ -179,18 +179,18 @@ int c2f_alloc(fg_c2f* n) {
 // packs are rebuilt after every optimizer step / set_params, and when the ctx's "conv_impl" changed since the last
 // pack (the TF32 splits are only produced for the tensor-core implementations)
 int pack_G(fg_c2f* n) {
-  if (n->G_packed && n->G_pack_impl == n->c->conv_impl) return FG_OK;
+  if (n->G_packed && n->G_pack_impl == pack_key(n->c)) return FG_OK;
   for (int i = 0; i < 5; ++i) FG_TRY(convl_pack(n->c, n->Gc[i], n->PG));
   n->G_packed = true;
-  n->G_pack_impl = n->c->conv_impl;
+  n->G_pack_impl = pack_key(n->c);
   return FG_OK;
 }
 int pack_D(fg_c2f* n) {
-  if (n->D_packed && n->D_pack_impl == n->c->conv_impl) return FG_OK;
+  if (n->D_packed && n->D_pack_impl == pack_key(n->c)) return FG_OK;
   for (int i = 0; i < 4; ++i) FG_TRY(convl_pack(n->c, n->Dc[i], n->PD));
   FG_TRY(convl_pack(n->c, n->DL1, n->PD));
   n->D_packed = true;
-  n->D_pack_impl = n->c->conv_impl;
+  n->D_pack_impl = pack_key(n->c);
   return FG_OK;
 }
 

@@ -128,6 +128,7 @@ struct UpsL {  // nn.SpatialUpSamplingNearest(2) -> 5x5 "same" convolution; H = 
   float *Wp = nullptr, *Wpd = nullptr;                                            // fp32 tap-major packs (FFMA path)
   float *Wf_hi = nullptr, *Wf_lo = nullptr, *Wd_hi = nullptr, *Wd_lo = nullptr;   // phase-collapsed TF32 packs [36][..][..]
   float *h_hi = nullptr, *h_lo = nullptr;                                         // split of the low-res input (fwd -> wgrad)
+  float* sx = nullptr;                                                            // (max|h|, 1/scale) of its FP16 split
   const char *tf = "", *td = "", *tw = "";
   ConvGeom geom(int B) const { return ConvGeom{B, H, H, Cin, Cout, 5, 2}; }
 };
@@ -172,6 +173,8 @@ namespace {
 int dalloc(fg_s16* n, float** p, size_t elems) { return convl_dalloc(n->env, p, elems); }
 inline bool use_tc(const fg_ctx* c, const ConvGeom& g) { return c->conv_impl != FG_CONV_SIMT && tc_conv_eligible(g); }
 inline bool use_tc_wgrad(const fg_ctx* c, const ConvGeom& g) { return use_tc(c, g) && g.Cout % 128 == 0 && g.Cin % 64 == 0; }
+// option "mma_f16": the upsampled layers' hi/lo buffers hold the 3xFP16 split (see convl.cu)
+inline bool f16_on(const fg_ctx* c) { return c->mma_f16 && c->conv_impl == FG_CONV_TC_COLLAPSED; }
 
 void make_layouts(fg_s16* n) {
   const int C = n->C;
@@ -287,6 +290,7 @@ int s16_alloc(fg_s16* n) {
     const size_t nx = B * (U.H / 2) * (U.H / 2) * U.Cin;
     FG_TRY(dalloc(n, &U.h_hi, nx));
     FG_TRY(dalloc(n, &U.h_lo, nx));
+    FG_TRY(dalloc(n, &U.sx, 2));
   }
   FG_TRY(dalloc(n, &n->G_x, B * 100));
   FG_TRY(dalloc(n, &n->G_z0, B * 2048));
@@ -357,29 +361,31 @@ int s16_alloc(fg_s16* n) {
 
 int pack_G(fg_s16* n) {
   fg_ctx* c = n->c;
-  if (n->G_packed && n->G_pack_impl == c->conv_impl) return FG_OK;
+  if (n->G_packed && n->G_pack_impl == pack_key(c)) return FG_OK;
   FG_TRY(convl_pack(c, n->GL1, n->PG));
   FG_TRY(convl_pack(c, n->GC3, n->PG));
   for (int i = 0; i < 2; ++i) {
     UpsL& U = n->GU[i];
-    if (use_tc_wgrad(c, U.geom(n->maxB)))
+    if (use_tc_wgrad(c, U.geom(n->maxB)) && f16_on(c))
+      FG_TRY(tc_pack_collapsed_h(c, n->PG + U.w_off, U.Wf_hi, U.Wf_lo, U.Wd_hi, U.Wd_lo, U.Cout, U.Cin));
+    else if (use_tc_wgrad(c, U.geom(n->maxB)))
       FG_TRY(tc_pack_collapsed(c, n->PG + U.w_off, U.Wf_hi, U.Wf_lo, U.Wd_hi, U.Wd_lo, U.Cout, U.Cin));
     else
       FG_TRY(k_pack_weights(c, n->PG + U.w_off, U.Wp, U.Wpd, U.Cout, U.Cin, 25, 0, 0, 0, 0));
   }
   n->G_packed = true;
-  n->G_pack_impl = c->conv_impl;
+  n->G_pack_impl = pack_key(c);
   return FG_OK;
 }
 int pack_D(fg_s16* n) {
   fg_ctx* c = n->c;
-  if (n->D_packed && n->D_pack_impl == c->conv_impl) return FG_OK;
+  if (n->D_packed && n->D_pack_impl == pack_key(c)) return FG_OK;
   for (int i = 0; i < 4; ++i) FG_TRY(convl_pack(c, n->Dc[i], n->PD));
   FG_TRY(convl_pack(c, n->DF1, n->PD));
   FG_TRY(convl_pack(c, n->DE1, n->PD));
   FG_TRY(convl_pack(c, n->DE2, n->PD));
   n->D_packed = true;
-  n->D_pack_impl = c->conv_impl;
+  n->D_pack_impl = pack_key(c);
   return FG_OK;
 }
 
@@ -396,10 +402,18 @@ int ups_fwd(fg_s16* n, UpsL& U, const float* h, float* z, int B, int* parts) {
     ScopedTimer tm(c, U.tf);
     return k_conv_simt(c, h, U.Wp, n->PG + U.b_off, z, g);
   }
-  FG_TRY(tc_split(c, h, U.h_hi, U.h_lo, (int64_t)B * (U.H / 2) * (U.H / 2) * U.Cin));  // kept for the weight gradient
+  const int64_t nh = (int64_t)B * (U.H / 2) * (U.H / 2) * U.Cin;
+  const bool h16 = f16_on(c);
+  if (h16) {
+    FG_TRY(tc_amax(c, h, nh, U.sx));
+    FG_TRY(tc_split_h(c, h, U.h_hi, U.h_lo, nh, U.sx));
+  } else {
+    FG_TRY(tc_split(c, h, U.h_hi, U.h_lo, nh));  // kept for the weight gradient
+  }
   ScopedTimer tm(c, U.tf);
   float* st = want && c->bn_epilogue ? c->bn_parts : nullptr;
-  return tc_conv_fwd(c, U.h_hi, U.h_lo, U.Wf_hi, U.Wf_lo, n->PG + U.b_off, z, g, 2, st, st ? parts : nullptr);
+  return tc_conv_fwd(c, U.h_hi, U.h_lo, U.Wf_hi, U.Wf_lo, n->PG + U.b_off, z, g, 2, st, st ? parts : nullptr, h16,
+                     h16 ? U.sx + 1 : nullptr);
 }
 // dW += wgrad; dh = dgrad.  *pooled: dh already is the gradient of the LOW-RES input (tcgen05 path folds the 2x2 sum of
 // the upsample backward into the dgrad GEMM); otherwise dh is the full-resolution gradient the consumer sums 2x2.
@@ -416,15 +430,23 @@ int ups_bwd(fg_s16* n, UpsL& U, const float* h, const float* dz, float* dh, int 
     ScopedTimer tm(c, U.td);
     return k_conv_simt(c, dz, U.Wpd, nullptr, dh, ConvGeom{B, U.H, U.H, U.Cout, U.Cin, 5, 1});
   }
-  FG_TRY(tc_split(c, dz, n->dy_hi, n->dy_lo, (int64_t)B * U.H * U.H * U.Cout));
+  const int64_t ndz = (int64_t)B * U.H * U.H * U.Cout;
+  const bool h16 = f16_on(c);
+  float* sdy = n->env.sdy;
+  if (h16) {
+    FG_TRY(tc_amax(c, dz, ndz, sdy));
+    FG_TRY(tc_split_h(c, dz, n->dy_hi, n->dy_lo, ndz, sdy));
+  } else {
+    FG_TRY(tc_split(c, dz, n->dy_hi, n->dy_lo, ndz));
+  }
   {
     ScopedTimer tm(c, U.tw);
-    FG_TRY(tc_conv_wgrad(c, U.h_hi, U.h_lo, n->dy_hi, n->dy_lo, n->ws, g));
+    FG_TRY(tc_conv_wgrad(c, U.h_hi, U.h_lo, n->dy_hi, n->dy_lo, n->ws, g, h16, h16 ? sdy + 1 : nullptr, h16 ? U.sx + 1 : nullptr));
   }
   FG_TRY(tc_combine_collapsed_wgrad(c, n->ws, n->gG + U.w_off, U.Cout, U.Cin));
   *pooled = true;
   ScopedTimer tm(c, U.td);
-  return tc_conv_dgrad_ups(c, n->dy_hi, n->dy_lo, U.Wd_hi, U.Wd_lo, dh, g);
+  return tc_conv_dgrad_ups(c, n->dy_hi, n->dy_lo, U.Wd_hi, U.Wd_lo, dh, g, h16, h16 ? sdy + 1 : nullptr);
 }
 
 // BatchNorm statistics of layer i (0: 256 channels at 8x8, 1: 128 channels at 16x16) -> bn_mean / bn_istd
