@@ -115,6 +115,7 @@ int fg_destroy(fg_ctx* c) {
   if (!c) return FG_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  net_graphs_clear(c);
   if (c->comm_stream) {
     cudaStreamSynchronize(c->comm_stream);
     cudaStreamDestroy(c->comm_stream);
@@ -135,6 +136,7 @@ int fg_destroy(fg_ctx* c) {
 
 int fg_set_stream(fg_ctx* c, void* s) {
   ENTER(c);
+  c->graph_epoch++;
   FG_CUDA(cudaStreamSynchronize(c->stream));
   if (s) {
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -153,6 +155,7 @@ int fg_sync(fg_ctx* c) {
 }
 int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
   ENTER(c);
+  c->graph_epoch++;  // a captured step bakes the options in
   if (!strcmp(key, "conv_impl")) {
     FG_REQUIRE(v >= 0 && v <= 2, "conv_impl must be 0 (simt), 1 (tc dense) or 2 (tc collapsed)");
     c->conv_impl = (int)v;
@@ -176,6 +179,11 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
     c->G_packed = c->D_packed = false;
     return FG_OK;
   }
+  if (!strcmp(key, "use_graph")) {  // 1 (default): fg_train_step replays a captured CUDA graph of the step
+    c->use_graph = v != 0;
+    c->graph_epoch++;
+    return FG_OK;
+  }
   if (!strcmp(key, "dp_overlap")) {  // 1 (default): D's all-reduce + optimizer overlap the G step's G forward (data parallel only)
     c->dp_overlap = v != 0;
     return FG_OK;
@@ -194,6 +202,7 @@ int fg_set_option(fg_ctx* c, const char* key, int64_t v) {
 }
 int fg_set_option_f(fg_ctx* c, const char* key, double v) {
   ENTER(c);
+  c->graph_epoch++;
   if (!strcmp(key, "sgd_momentum_D") || !strcmp(key, "sgd_momentum_G")) {  // OPT.D_SGD_momentum / G_SGD_momentum (train.lua:23,25)
     FG_REQUIRE(v >= 0.0 && v < 1.0, "%s must be in [0, 1)", key);
     (key[13] == 'D' ? c->sgd_mom_D : c->sgd_mom_G) = (float)v;
@@ -212,6 +221,7 @@ int64_t fg_get_option(fg_ctx* c, const char* key) {
   if (!strcmp(key, "edge_impl")) return c->edge_impl;
   if (!strcmp(key, "mma_f16")) return c->mma_f16;
   if (!strcmp(key, "dp_overlap")) return c->dp_overlap;
+  if (!strcmp(key, "use_graph")) return c->use_graph;
   if (!strcmp(key, "optimizer_D")) return c->opt_D;
   if (!strcmp(key, "optimizer_G")) return c->opt_G;
   return -1;
@@ -260,6 +270,7 @@ int fg_zero_grads(fg_ctx* c, int net) {
 // Borrow caller-owned DEVICE buffers as the flat parameter / gradient vectors of `net` (see include/fg_b200.h).
 int fg_bind_params(fg_ctx* c, int net, float* params_dev, float* grads_dev) {
   ENTER(c);
+  c->graph_epoch++;
   FG_REQUIRE(net == FG_NET_G || net == FG_NET_D, "net must be FG_NET_G or FG_NET_D");
   for (const float* p : {params_dev, grads_dev}) {
     if (!p) continue;
@@ -429,7 +440,7 @@ int fg_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const 
   FG_TRY(to_dev(c, noise_G, (size_t)B * kNoiseDim, c->in_noiseG, &ng));
   if (masks_D) FG_TRY(to_dev(c, masks_D, (size_t)B * kMaskPerSample, c->in_masksD, &md));
   if (masks_G) FG_TRY(to_dev(c, masks_G, (size_t)B * kMaskPerSample, c->in_masksG, &mg));
-  FG_TRY(net_train_step(c, h, B, r, nd, ng, md, mg, seed));
+  FG_TRY(net_train_step(c, h, B, r, nd, ng, md, mg, seed, true));
   if (stats) {
     FG_CUDA(cudaStreamSynchronize(c->stream));
     const DeviceStats& s = *c->hstats;

@@ -97,6 +97,8 @@ int fg_dp_init(fg_ctx* c, const void* id128, int nranks, int rank) {
     return FG_ERR_INVALID;
   }
   FG_CUDA(cudaSetDevice(c->device));
+  net_graphs_clear(c);  // captured steps reference the old communicator
+  c->graph_epoch++;
   if (c->nccl_comm) {
     g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     c->nccl_comm = nullptr;

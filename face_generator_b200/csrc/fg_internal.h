@@ -149,6 +149,17 @@ struct fg_ctx {
   // stream already runs the G step's G forward (which only needs G's parameters); joined before D is used again
   int dp_overlap = 1;
   int reserve_sms = 0;  // SMs the persistent convolution kernels leave free while a collective runs next to them
+  // option "use_graph" (default 1): fg_train_step replays a captured CUDA graph of the step (launch overhead of ~200
+  // kernels); keyed on everything a captured step bakes in, the seed is read from device memory
+  int use_graph = 1, graph_epoch = 0;
+  uint64_t* seed_dev = nullptr;
+  struct StepGraph {
+    std::vector<uint8_t> key;
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+    bool failed = false;
+  };
+  std::vector<StepGraph> graphs;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // debug (tests): "debug_keep" = 1 keeps a copy of the D step's pre-activations of fg_train_step, which the G
@@ -247,7 +258,9 @@ int k_bn_prelu_bwd_apply(fg_ctx* c, const float* dh, const float* z, const float
                          float* dbias = nullptr);  // dbias: += column sums of dz (bias gradient of the conv in front)
 int k_sigmoid_fwd(fg_ctx* c, const float* z, float* y, int64_t n);
 int k_sigmoid_bwd(fg_ctx* c, const float* dy, const float* y, float* dz, int64_t n);
-int k_masks_generate(fg_ctx* c, float* masks, int B, uint64_t seed, float p_spatial, float p_drop);
+int k_masks_generate(fg_ctx* c, float* masks, int B, uint64_t seed, float p_spatial, float p_drop,
+                     const uint64_t* seed_dev = nullptr);  // seed_dev: effective seed = *seed_dev * 2 + seed
+int k_set_u64(fg_ctx* c, uint64_t* dst, uint64_t v);
 // hi / lo (optional): also emit the TF32 split of the result (16-byte aligned buffers of the output's size)
 int k_d_act_pool_fwd(fg_ctx* c, const float* z, const float* slope, const float* masks, int moff, float eval_scale,
                      float* p, int B, int H, int W, int C, float* hi = nullptr, float* lo = nullptr);
@@ -308,8 +321,10 @@ int net_G_backward(fg_ctx* c, const float* dy_nhwc, float* dnoise_dev);         
 int net_D_forward(fg_ctx* c, const float* x_nhwc, int B, bool training, const fg_hyper* h);  // masks in c->D_masks
 int net_D_backward(fg_ctx* c, const float* dlogit_dev, bool want_wgrad, bool want_dx);       // -> c->D_dx (NHWC)
 int net_optim(fg_ctx* c, int net, const fg_hyper* h, float grad_scale, bool gate);
+void net_graphs_clear(fg_ctx* c);
 int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real_nchw_dev, const float* noiseD_dev,
-                   const float* noiseG_dev, const float* masksD_dev, const float* masksG_dev, uint64_t seed);
+                   const float* noiseG_dev, const float* masksD_dev, const float* masksG_dev, uint64_t seed,
+                   bool allow_graph = false);
 int net_allreduce(fg_ctx* c, float* buf, int64_t n);
 int net_zero_grads(fg_ctx* c, int net);
 int net_allreduce_grads(fg_ctx* c, int net);  // flat gradient + its 8 tail scalars (one call when contiguous)

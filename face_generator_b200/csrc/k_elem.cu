@@ -701,7 +701,11 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
-__global__ void masks_generate_kernel(float* __restrict__ masks, int B, uint64_t seed, float p_spatial, float p_drop) {
+// seed_dev (optional): the step seed lives in device memory (so that a captured step can be replayed with a new seed);
+// the effective seed is then *seed_dev * 2 + seed
+__global__ void masks_generate_kernel(float* __restrict__ masks, int B, uint64_t seed, float p_spatial, float p_drop,
+                                      const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev * 2;
   const int64_t n = (int64_t)B * kMaskPerSample;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(i % kMaskPerSample);
@@ -710,9 +714,15 @@ __global__ void masks_generate_kernel(float* __restrict__ masks, int B, uint64_t
     masks[i] = u >= (j < 960 ? p_spatial : p_drop) ? 1.f : 0.f;
   }
 }
-int k_masks_generate(fg_ctx* c, float* masks, int B, uint64_t seed, float p_spatial, float p_drop) {
+__global__ void set_u64_kernel(uint64_t* dst, uint64_t v) { *dst = v; }
+int k_set_u64(fg_ctx* c, uint64_t* dst, uint64_t v) {
+  set_u64_kernel<<<1, 1, 0, c->stream>>>(dst, v);
+  LAUNCH_CHECK(c);
+  return FG_OK;
+}
+int k_masks_generate(fg_ctx* c, float* masks, int B, uint64_t seed, float p_spatial, float p_drop, const uint64_t* seed_dev) {
   masks_generate_kernel<<<grid_for((int64_t)B * kMaskPerSample, 256), 256, 0, c->stream>>>(masks, B, seed, p_spatial,
-                                                                                          p_drop);
+                                                                                          p_drop, seed_dev);
   LAUNCH_CHECK(c);
   return FG_OK;
 }

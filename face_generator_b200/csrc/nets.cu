@@ -95,6 +95,11 @@ int net_alloc(fg_ctx* c) {
   FG_CUDA(cudaMallocHost((void**)&c->hstats, sizeof(DeviceStats)));
   memset(c->hstats, 0, sizeof(DeviceStats));
   FG_TRY(dalloc(c, &c->amax_slot, 64));
+  {
+    float* sd = nullptr;
+    FG_TRY(dalloc(c, &sd, 2));
+    c->seed_dev = reinterpret_cast<uint64_t*>(sd);
+  }
   // packs
   FG_TRY(dalloc(c, &c->G_L1p, 8192 * 100 + 8192));  // + permuted bias behind the weights
   FG_TRY(dalloc(c, &c->G_L1pd, 8192 * 100));
@@ -872,9 +877,11 @@ int net_allreduce_grads(fg_ctx* c, int net) {
 // ---------------------------------------------------------------------------------------------------
 // one iteration of the adversarial.lua loop body (D_iterations = G_iterations = 1)
 // ---------------------------------------------------------------------------------------------------
-int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const float* noiseD, const float* noiseG,
-                   const float* masksD, const float* masksG, uint64_t seed) {
-  FG_REQUIRE(B >= 4 && B % 2 == 0 && B <= c->maxB, "train step: batch %d must be even, >=4 and <= %d", B, c->maxB);
+// the step proper; the seed of the device-drawn dropout masks is read from c->seed_dev
+static int train_step_body(fg_ctx* c, const fg_hyper* h, int B, const float* real, const float* noiseD, const float* noiseG,
+                           const float* masksD, const float* masksG) {
+  const uint64_t seed = 0;
+  const uint64_t* seed_dev = c->seed_dev;
   const int Bh = B / 2, C = c->C;
   const size_t img = (size_t)C * 1024;
   const float world = (float)c->world;
@@ -886,7 +893,7 @@ int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const
     FG_CUDA(cudaMemcpyAsync(c->D_masks, masksD, sizeof(float) * (size_t)B * kMaskPerSample, cudaMemcpyDeviceToDevice,
                             c->stream));
   else
-    FG_TRY(k_masks_generate(c, c->D_masks, B, seed * 2 + 1, h->p_spatial, h->p_drop));
+    FG_TRY(k_masks_generate(c, c->D_masks, B, seed * 2 + 1, h->p_spatial, h->p_drop, seed_dev));
   FG_TRY(net_zero_grads(c, FG_NET_D));
   FG_TRY(net_D_forward(c, c->D_x, B, true, h));
   FG_TRY(k_sigmoid_bce(c, c->D_logit, c->D_out, c->D_dlogit, &c->dstats->loss_D, c->tailD, B, Bh));
@@ -940,7 +947,7 @@ int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const
     FG_CUDA(cudaMemcpyAsync(c->D_masks, masksG, sizeof(float) * (size_t)B * kMaskPerSample, cudaMemcpyDeviceToDevice,
                             c->stream));
   else
-    FG_TRY(k_masks_generate(c, c->D_masks, B, seed * 2 + 2, h->p_spatial, h->p_drop));
+    FG_TRY(k_masks_generate(c, c->D_masks, B, seed * 2 + 2, h->p_spatial, h->p_drop, seed_dev));
   FG_TRY(net_D_forward(c, c->G_y, B, true, h));
   FG_TRY(k_sigmoid_bce(c, c->D_logit, c->D_out, c->D_dlogit, &c->dstats->loss_G, c->tailG, B, B));
   FG_TRY(net_D_backward(c, c->D_dlogit, false, true));  // D's weight grads are discarded by the reference (:209 vs :92)
@@ -949,5 +956,80 @@ int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const
   FG_TRY(k_gate_and_prep(c, FG_NET_G, h, c->tailG, B, world));
   FG_TRY(net_optim(c, FG_NET_G, h, 1.0f / world, false));
   FG_CUDA(cudaMemcpyAsync(c->hstats, c->dstats, sizeof(DeviceStats), cudaMemcpyDeviceToHost, c->stream));
+  return FG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CUDA-graph replay of the step.  A step is ~200 launches of mostly short kernels; replaying a captured graph removes
+// the launch gaps (measured 4.19 -> 3.87 ms at batch 256).  A graph bakes in every kernel argument, so it is keyed on all
+// of them: batch, hyper-parameters, input / parameter pointers, option epoch.  The first step with a new key runs
+// eagerly (it also performs the lazy allocations), the second is captured, later ones are replayed.
+// ---------------------------------------------------------------------------------------------------
+void net_graphs_clear(fg_ctx* c) {
+  for (auto& g : c->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  c->graphs.clear();
+}
+namespace {
+template <class T>
+void key_add(std::vector<uint8_t>& k, const T& v) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(&v);
+  k.insert(k.end(), p, p + sizeof(T));
+}
+}  // namespace
+
+int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const float* noiseD, const float* noiseG,
+                   const float* masksD, const float* masksG, uint64_t seed, bool allow_graph) {
+  FG_REQUIRE(B >= 4 && B % 2 == 0 && B <= c->maxB, "train step: batch %d must be even, >=4 and <= %d", B, c->maxB);
+  FG_TRY(k_set_u64(c, c->seed_dev, seed));
+  static const bool env_off = getenv("FG_GRAPH") && atoi(getenv("FG_GRAPH")) == 0;
+  if (!allow_graph || !c->use_graph || env_off || c->timing || c->debug_keep)
+    return train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG);
+  std::vector<uint8_t> key;
+  key_add(key, c->graph_epoch);
+  key_add(key, B);
+  key_add(key, *h);
+  const void* ptrs[] = {real, noiseD, noiseG, masksD, masksG, c->PG, c->PD, c->gG, c->gD, (const void*)c->stream, c->nccl_comm};
+  key_add(key, ptrs);
+  fg_ctx::StepGraph* e = nullptr;
+  for (auto& g : c->graphs)
+    if (g.key == key) e = &g;
+  if (!e) {
+    if (c->graphs.size() >= 8) {  // oldest out
+      if (c->graphs.front().exec) cudaGraphExecDestroy(c->graphs.front().exec);
+      c->graphs.erase(c->graphs.begin());
+    }
+    c->graphs.emplace_back();
+    c->graphs.back().key = key;
+    return train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG);  // eager: warms every lazy allocation
+  }
+  if (e->failed) return train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG);
+  if (!e->exec) {
+    // the captured step must contain both weight-pack sequences whatever the flags say right now
+    c->G_packed = c->D_packed = false;
+    const int64_t l0 = c->launches;
+    FG_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    const int r = train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+    cudaGraphExec_t ex = nullptr;
+    if (r == FG_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) {
+      e->exec = ex;
+      e->launches = c->launches - l0;
+      c->launches = l0;
+    } else {
+      cudaGetLastError();
+      e->failed = true;
+    }
+    if (g) cudaGraphDestroy(g);
+    FG_TRY(r);
+    if (e->failed) {  // nothing ran during the failed capture
+      FG_TRY(k_set_u64(c, c->seed_dev, seed));
+      return train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG);
+    }
+  }
+  FG_CUDA(cudaGraphLaunch(e->exec, c->stream));
+  c->launches += e->launches;
+  c->G_packed = c->D_packed = false;  // as after any step: the optimizers moved the parameters
   return FG_OK;
 }
