@@ -366,10 +366,16 @@ def main():
             os.environ.pop("FG_TF32_PROBE_N")
         except Exception as e:  # the probe must never cost the headline
             sys.stderr.write("tf32 peak probe failed: %s\n" % e)
-    if nccl_log and os.path.exists(nccl_log):  # NCCL's own INIT lines ("... rank r nranks N ...") -> stderr
-        sys.stderr.write(open(nccl_log).read())
-        sys.stderr.flush()
-        os.remove(nccl_log)
+    if nccl_log:  # NCCL's own INIT lines ("... rank r nranks N ...") -> stderr
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)  # NCCL keeps its debug FILE* fully buffered: flush every C stream first
+            if os.path.exists(nccl_log):
+                sys.stderr.write(open(nccl_log).read())
+                sys.stderr.flush()
+                os.remove(nccl_log)
+        except Exception as e:
+            sys.stderr.write("could not relay the NCCL log: %s\n" % e)
     if rank != 0:
         return
     peaks = load_peaks()

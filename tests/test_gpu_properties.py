@@ -84,3 +84,33 @@ def test_in_kernel_dropout_rates(big):
     m = ctx.debug_tensor("D.masks").reshape(B, -1)
     assert abs(m[:, :960].mean() - 0.8) < 0.01 and abs(m[:, 960:].mean() - 0.5) < 0.01
     assert set(np.unique(m)) <= {0.0, 1.0}
+
+
+@pytest.mark.parametrize("opt,val", [("mma_f16", 0), ("use_graph", 0), ("bn_epilogue", 0), ("edge_impl", 0)])
+def test_alternative_code_paths_agree_with_the_default(opt, val):
+    """Every option selects another implementation of the same arithmetic: three steps at batch 64 with device-drawn
+    dropout masks (the same seeds) give the default path's losses and confusion counts.  mma_f16 = 0 is the 3xTF32
+    operand split instead of 3xFP16, use_graph = 0 eager launches instead of the captured step, bn_epilogue = 0 the
+    separate BatchNorm statistics pass, edge_impl = 0 the round-1 kernels of the 3-channel-side convolutions."""
+    import face_generator_b200 as fg
+    from face_generator_b200.lib import NET_D, NET_G
+    B, C = 64, 3
+    case = PU.make_case(B, C, seed=2024)
+    res = []
+    for setting in (None, (opt, val)):
+        ctx = fg.Context(0, max_batch=B, channels=C)
+        if setting:
+            ctx.set_option(*setting)
+            assert ctx.get_option(opt) == val
+        ctx.set_params(NET_G, case["PG"])
+        ctx.set_params(NET_D, case["PD"])
+        h = fg.hyper_default()
+        sts = [ctx.train_step(h, B, case["real"], case["noise_D"], case["noise_G"], None, None, 100 + i) for i in range(3)]
+        res.append((sts, ctx.get_params(NET_G)))
+        ctx.close()
+    for a, b in zip(res[0][0], res[1][0]):
+        assert list(a["conf"]) == list(b["conf"]) and a["t_D"] == b["t_D"] and a["t_G"] == b["t_G"]
+        assert abs(a["loss_D"] - b["loss_D"]) < 2e-4 * max(1.0, abs(a["loss_D"]))
+        assert abs(a["loss_G"] - b["loss_G"]) < 2e-3 * max(1.0, abs(a["loss_G"]))  # behind Adam's +-lr amplification
+    d = np.abs(res[0][1].astype(np.float64) - res[1][1])
+    assert d.max() <= 3 * 2e-3 + 1e-6 and np.mean(d > 1e-5) < 0.05  # parameters: equal up to +-lr flips on noise-level gradients
