@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -322,6 +323,8 @@ int net_D_forward(fg_ctx* c, const float* x_nhwc, int B, bool training, const fg
 int net_D_backward(fg_ctx* c, const float* dlogit_dev, bool want_wgrad, bool want_dx);       // -> c->D_dx (NHWC)
 int net_optim(fg_ctx* c, int net, const fg_hyper* h, float grad_scale, bool gate);
 void net_graphs_clear(fg_ctx* c);
+int net_graph_run(fg_ctx* c, std::vector<fg_ctx::StepGraph>& cache, const std::vector<uint8_t>& key, uint64_t seed,
+                  const std::function<int()>& body, const std::function<void()>& repack, bool allow_graph);
 int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real_nchw_dev, const float* noiseD_dev,
                    const float* noiseG_dev, const float* masksD_dev, const float* masksG_dev, uint64_t seed,
                    bool allow_graph = false);

@@ -321,6 +321,79 @@ __global__ void pack_split_kernel(const float* __restrict__ W, T* __restrict__ f
     }
   }
 }
+// The two packs want opposite thread orders (forward: channel fastest, dgrad: output row fastest); written from one
+// thread order, one of them degenerates into 2-byte scattered stores (31 us per 5x5 layer).  These variants stage a
+// 16 x 16 (n, c) tile of the weights in shared memory (coalesced 1.6 KB rows) and write each pack from its own order:
+// every global access is a full 32-byte sector.  Same sums in the same order as the element-wise kernels above.
+template <class T>
+__global__ void __launch_bounds__(256) pack_collapsed_tile_kernel(const float* __restrict__ W, T* __restrict__ f_hi,
+                                                                  T* __restrict__ f_lo, T* __restrict__ d_hi,
+                                                                  T* __restrict__ d_lo, int N, int Cc) {
+  __shared__ float w[16][16 * 25 + 1];
+  const int n0 = blockIdx.y * 16, c0 = blockIdx.x * 16;
+  for (int i = threadIdx.x; i < 16 * 400; i += 256) {
+    const int nl = i / 400, r = i - nl * 400;
+    w[nl][r] = W[((int64_t)(n0 + nl) * Cc + c0) * 25 + r];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    // pass 0: forward pack, channel fastest; pass 1: dgrad pack, output row fastest
+    const int nl = pass == 0 ? (threadIdx.x >> 4) : (threadIdx.x & 15);
+    const int cl = pass == 0 ? (threadIdx.x & 15) : (threadIdx.x >> 4);
+    const float* p = &w[nl][cl * 25];
+    for (int tp = 0; tp < 36; ++tp) {
+      const int ph = tp / 9, ty = (tp % 9) / 3, tx = tp % 3;
+      int h0, h1, w0, w1;
+      group_range(ph >> 1, ty, h0, h1);
+      group_range(ph & 1, tx, w0, w1);
+      float s = 0.f;
+      for (int kh = h0; kh <= h1; ++kh)
+        for (int kw = w0; kw <= w1; ++kw) s += p[kh * 5 + kw];
+      T hi, lo;
+      SplitTo<T>::run(s, hi, lo);
+      if (pass == 0) {
+        const int64_t i = ((int64_t)tp * N + n0 + nl) * Cc + c0 + cl;
+        f_hi[i] = hi;
+        f_lo[i] = lo;
+      } else {
+        const int64_t j = ((int64_t)tp * Cc + c0 + cl) * N + n0 + nl;
+        d_hi[j] = hi;
+        d_lo[j] = lo;
+      }
+    }
+  }
+}
+template <class T, int KK>
+__global__ void __launch_bounds__(256) pack_split_tile_kernel(const float* __restrict__ W, T* __restrict__ f_hi,
+                                                              T* __restrict__ f_lo, T* __restrict__ d_hi,
+                                                              T* __restrict__ d_lo, int N, int Cc) {
+  __shared__ float w[16][16 * KK + 1];
+  const int n0 = blockIdx.y * 16, c0 = blockIdx.x * 16;
+  for (int i = threadIdx.x; i < 16 * 16 * KK; i += 256) {
+    const int nl = i / (16 * KK), r = i - nl * 16 * KK;
+    w[nl][r] = W[((int64_t)(n0 + nl) * Cc + c0) * KK + r];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int pass = 0; pass < (d_hi ? 2 : 1); ++pass) {
+    const int nl = pass == 0 ? (threadIdx.x >> 4) : (threadIdx.x & 15);
+    const int cl = pass == 0 ? (threadIdx.x & 15) : (threadIdx.x >> 4);
+    for (int t = 0; t < KK; ++t) {
+      T hi, lo;
+      SplitTo<T>::run(w[nl][cl * KK + t], hi, lo);
+      if (pass == 0) {
+        const int64_t jf = ((int64_t)t * N + n0 + nl) * Cc + c0 + cl;
+        f_hi[jf] = hi;
+        f_lo[jf] = lo;
+      } else {
+        const int64_t jd = ((int64_t)(KK - 1 - t) * Cc + c0 + cl) * N + n0 + nl;
+        d_hi[jd] = hi;
+        d_lo[jd] = lo;
+      }
+    }
+  }
+}
 // collapsed wgrad G[ph][ty][tx][n][c] -> dW[n][c][5][5] += sum over the 4 phases
 __global__ void combine_collapsed_wgrad_kernel(const float* __restrict__ G, float* __restrict__ dW, int N, int Cc) {
   const int64_t total = (int64_t)N * Cc * 25;
@@ -665,6 +738,12 @@ int tc_split_h(fg_ctx* c, const float* x, float* hh, float* hl, int64_t n, float
   return FG_OK;
 }
 int tc_pack_split_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK) {
+  if (KK == 9 && N % 16 == 0 && Cc % 16 == 0) {
+    pack_split_tile_kernel<__half, 9><<<dim3(Cc / 16, N / 16), 256, 0, c->stream>>>(W, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi,
+                                                                                    (__half*)d_lo, N, Cc);
+    LAUNCH_CHECK(c);
+    return FG_OK;
+  }
   int64_t g = ((int64_t)N * Cc * KK + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   pack_split_kernel<__half><<<(int)g, 256, 0, c->stream>>>(W, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi, (__half*)d_lo, N, Cc, KK);
@@ -672,6 +751,12 @@ int tc_pack_split_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* 
   return FG_OK;
 }
 int tc_pack_collapsed_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc) {
+  if (N % 16 == 0 && Cc % 16 == 0) {
+    pack_collapsed_tile_kernel<__half><<<dim3(Cc / 16, N / 16), 256, 0, c->stream>>>(W, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi,
+                                                                                     (__half*)d_lo, N, Cc);
+    LAUNCH_CHECK(c);
+    return FG_OK;
+  }
   int64_t g = ((int64_t)36 * N * Cc + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   pack_collapsed_kernel<__half><<<(int)g, 256, 0, c->stream>>>(W, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi, (__half*)d_lo, N, Cc);
@@ -679,6 +764,11 @@ int tc_pack_collapsed_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, flo
   return FG_OK;
 }
 int tc_pack_split(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK) {
+  if (KK == 9 && N % 16 == 0 && Cc % 16 == 0) {
+    pack_split_tile_kernel<float, 9><<<dim3(Cc / 16, N / 16), 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc);
+    LAUNCH_CHECK(c);
+    return FG_OK;
+  }
   int64_t g = ((int64_t)N * Cc * KK + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   pack_split_kernel<float><<<(int)g, 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc, KK);
@@ -686,6 +776,11 @@ int tc_pack_split(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_
   return FG_OK;
 }
 int tc_pack_collapsed(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc) {
+  if (N % 16 == 0 && Cc % 16 == 0) {
+    pack_collapsed_tile_kernel<float><<<dim3(Cc / 16, N / 16), 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc);
+    LAUNCH_CHECK(c);
+    return FG_OK;
+  }
   int64_t g = ((int64_t)36 * N * Cc + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   pack_collapsed_kernel<float><<<(int)g, 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc);

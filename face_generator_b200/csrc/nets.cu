@@ -978,38 +978,33 @@ void key_add(std::vector<uint8_t>& k, const T& v) {
 }
 }  // namespace
 
-int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const float* noiseD, const float* noiseG,
-                   const float* masksD, const float* masksG, uint64_t seed, bool allow_graph) {
-  FG_REQUIRE(B >= 4 && B % 2 == 0 && B <= c->maxB, "train step: batch %d must be even, >=4 and <= %d", B, c->maxB);
+// Runs `body` (a sequence of launches on c->stream that reads its seed from c->seed_dev) eagerly the first time a key
+// is seen, captures it the second time and replays the captured graph afterwards.  `repack` is called before the
+// capture and after every replay: it must mark the weight packs stale (the captured sequence has to contain the pack
+// kernels whatever the flags said at capture time, and a replayed optimizer step invalidates them again).
+int net_graph_run(fg_ctx* c, std::vector<fg_ctx::StepGraph>& cache, const std::vector<uint8_t>& key, uint64_t seed,
+                  const std::function<int()>& body, const std::function<void()>& repack, bool allow_graph) {
   FG_TRY(k_set_u64(c, c->seed_dev, seed));
   static const bool env_off = getenv("FG_GRAPH") && atoi(getenv("FG_GRAPH")) == 0;
-  if (!allow_graph || !c->use_graph || env_off || c->timing || c->debug_keep)
-    return train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG);
-  std::vector<uint8_t> key;
-  key_add(key, c->graph_epoch);
-  key_add(key, B);
-  key_add(key, *h);
-  const void* ptrs[] = {real, noiseD, noiseG, masksD, masksG, c->PG, c->PD, c->gG, c->gD, (const void*)c->stream, c->nccl_comm};
-  key_add(key, ptrs);
+  if (!allow_graph || !c->use_graph || env_off || c->timing || c->debug_keep) return body();
   fg_ctx::StepGraph* e = nullptr;
-  for (auto& g : c->graphs)
+  for (auto& g : cache)
     if (g.key == key) e = &g;
   if (!e) {
-    if (c->graphs.size() >= 8) {  // oldest out
-      if (c->graphs.front().exec) cudaGraphExecDestroy(c->graphs.front().exec);
-      c->graphs.erase(c->graphs.begin());
+    if (cache.size() >= 8) {  // oldest out
+      if (cache.front().exec) cudaGraphExecDestroy(cache.front().exec);
+      cache.erase(cache.begin());
     }
-    c->graphs.emplace_back();
-    c->graphs.back().key = key;
-    return train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG);  // eager: warms every lazy allocation
+    cache.emplace_back();
+    cache.back().key = key;
+    return body();  // eager: warms every lazy allocation
   }
-  if (e->failed) return train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG);
+  if (e->failed) return body();
   if (!e->exec) {
-    // the captured step must contain both weight-pack sequences whatever the flags say right now
-    c->G_packed = c->D_packed = false;
+    repack();
     const int64_t l0 = c->launches;
     FG_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
-    const int r = train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG);
+    const int r = body();
     cudaGraph_t g = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
     cudaGraphExec_t ex = nullptr;
@@ -1025,11 +1020,25 @@ int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const
     FG_TRY(r);
     if (e->failed) {  // nothing ran during the failed capture
       FG_TRY(k_set_u64(c, c->seed_dev, seed));
-      return train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG);
+      return body();
     }
   }
   FG_CUDA(cudaGraphLaunch(e->exec, c->stream));
   c->launches += e->launches;
-  c->G_packed = c->D_packed = false;  // as after any step: the optimizers moved the parameters
+  repack();
   return FG_OK;
+}
+
+int net_train_step(fg_ctx* c, const fg_hyper* h, int B, const float* real, const float* noiseD, const float* noiseG,
+                   const float* masksD, const float* masksG, uint64_t seed, bool allow_graph) {
+  FG_REQUIRE(B >= 4 && B % 2 == 0 && B <= c->maxB, "train step: batch %d must be even, >=4 and <= %d", B, c->maxB);
+  std::vector<uint8_t> key;
+  key_add(key, c->graph_epoch);
+  key_add(key, B);
+  key_add(key, *h);
+  const void* ptrs[] = {real, noiseD, noiseG, masksD, masksG, c->PG, c->PD, c->gG, c->gD, (const void*)c->stream, c->nccl_comm};
+  key_add(key, ptrs);
+  return net_graph_run(
+      c, c->graphs, key, seed, [&]() { return train_step_body(c, h, B, real, noiseD, noiseG, masksD, masksG); },
+      [c]() { c->G_packed = c->D_packed = false; }, allow_graph);
 }

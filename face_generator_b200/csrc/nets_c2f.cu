@@ -47,6 +47,7 @@ struct fg_c2f {
   float D_scale = 2.f;
   std::vector<void*> allocs;
   ConvLEnv env;  // shared scratch of the ConvL layers (filled by c2f_alloc)
+  std::vector<fg_ctx::StepGraph> graphs;  // captured train steps
 };
 
 namespace {
@@ -365,7 +366,7 @@ int train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_diff, cons
   if (masksD)
     FG_CUDA(cudaMemcpyAsync(n->D_masks, masksD, sizeof(float) * (size_t)B * kC2fMask, cudaMemcpyDeviceToDevice, c->stream));
   else
-    FG_TRY(k_bernoulli_keep(c, n->D_masks, (int64_t)B * kC2fMask, seed * 2 + 1, h->p_drop));
+    FG_TRY(k_bernoulli_keep(c, n->D_masks, (int64_t)B * kC2fMask, 1, h->p_drop, c->seed_dev));
   FG_CUDA(cudaMemsetAsync(n->gD, 0, sizeof(float) * (n->nD + kGradTail), c->stream));
   FG_TRY(D_forward(n, n->io, n->D_cond, B, true, h->p_drop));
   FG_TRY(k_sigmoid_bce(c, n->D_logit, n->D_out, n->D_dlogit, &n->dstats->loss_D, n->gD + n->nD, B, Bh));
@@ -380,7 +381,7 @@ int train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_diff, cons
   if (masksG)
     FG_CUDA(cudaMemcpyAsync(n->D_masks, masksG, sizeof(float) * (size_t)B * kC2fMask, cudaMemcpyDeviceToDevice, c->stream));
   else
-    FG_TRY(k_bernoulli_keep(c, n->D_masks, (int64_t)B * kC2fMask, seed * 2 + 2, h->p_drop));
+    FG_TRY(k_bernoulli_keep(c, n->D_masks, (int64_t)B * kC2fMask, 2, h->p_drop, c->seed_dev));
   FG_TRY(D_forward(n, n->G_z[4], n->D_cond, B, true, h->p_drop));
   FG_TRY(k_sigmoid_bce(c, n->D_logit, n->D_out, n->D_dlogit, &n->dstats->loss_G, n->gG + n->nG, B, B));
   FG_TRY(D_backward(n, n->D_dlogit, false, true));  // D's weight grads are zeroed before use (:45) -> skipped
@@ -429,6 +430,8 @@ int fg_c2f_destroy(fg_c2f* n) {
     cudaSetDevice(n->c->device);
     cudaStreamSynchronize(n->c->stream);
   }
+  for (auto& g : n->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (void* p : n->allocs) cudaFree(p);
   if (n->hstats) cudaFreeHost(n->hstats);
   delete n;
@@ -612,7 +615,18 @@ int fg_c2f_train_step(fg_c2f* n, const fg_hyper* h, int B, const float* real_dif
   FG_TRY(to_dev(c, noise_G, (size_t)B * 1024, n->in_e, &ng));
   if (masks_D) FG_TRY(to_dev(c, masks_D, (size_t)B * kC2fMask, n->in_m1, &md));
   if (masks_G) FG_TRY(to_dev(c, masks_G, (size_t)B * kC2fMask, n->in_m2, &mg));
-  FG_TRY(train_step(n, h, B, rd, cd, nd, cg, ng, md, mg, seed));
+  {  // eager the first time, then a captured CUDA graph of the step (nets.cu net_graph_run); the seed is read on the device
+    std::vector<uint8_t> key;
+    auto add = [&key](const void* p, size_t nb) { key.insert(key.end(), (const uint8_t*)p, (const uint8_t*)p + nb); };
+    const void* ptrs[] = {rd, cd, nd, cg, ng, md, mg, (const void*)c->stream, c->nccl_comm};
+    const int meta[3] = {c->graph_epoch, B, pack_key(c)};
+    add(meta, sizeof(meta));
+    add(h, sizeof(*h));
+    add(ptrs, sizeof(ptrs));
+    FG_TRY(net_graph_run(
+        c, n->graphs, key, seed, [&]() { return train_step(n, h, B, rd, cd, nd, cg, ng, md, mg, 0); },
+        [n]() { n->G_packed = n->D_packed = false; }, true));
+  }
   if (stats) {
     FG_CUDA(cudaStreamSynchronize(c->stream));
     const DeviceStats& s = *n->hstats;

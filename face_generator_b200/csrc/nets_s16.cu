@@ -167,6 +167,7 @@ struct fg_s16 {
   bool G_valid = false, G_train = true, D_valid = false, D_train = true;
   std::vector<void*> allocs;
   ConvLEnv env;
+  std::vector<fg_ctx::StepGraph> graphs;  // captured train steps
 };
 
 namespace {
@@ -677,7 +678,7 @@ int train_step(fg_s16* n, const fg_hyper* h, int B, const float* real, const flo
   if (masksD)
     FG_CUDA(cudaMemcpyAsync(n->D_masks, masksD, sizeof(float) * (size_t)B * kS16Mask, cudaMemcpyDeviceToDevice, c->stream));
   else
-    FG_TRY(k_bernoulli_keep(c, n->D_masks, (int64_t)B * kS16Mask, seed * 2 + 1, 0.5f));
+    FG_TRY(k_bernoulli_keep(c, n->D_masks, (int64_t)B * kS16Mask, 1, 0.5f, c->seed_dev));
   FG_CUDA(cudaMemsetAsync(n->gD, 0, sizeof(float) * (n->nD + kGradTail), c->stream));
   FG_TRY(D_forward(n, n->D_x, B, true));
   FG_TRY(k_sigmoid_bce(c, n->D_logit, n->D_out, n->D_dlogit, &n->dstats->loss_D, n->gD + n->nD, B, Bh));
@@ -691,7 +692,7 @@ int train_step(fg_s16* n, const fg_hyper* h, int B, const float* real, const flo
   if (masksG)
     FG_CUDA(cudaMemcpyAsync(n->D_masks, masksG, sizeof(float) * (size_t)B * kS16Mask, cudaMemcpyDeviceToDevice, c->stream));
   else
-    FG_TRY(k_bernoulli_keep(c, n->D_masks, (int64_t)B * kS16Mask, seed * 2 + 2, 0.5f));
+    FG_TRY(k_bernoulli_keep(c, n->D_masks, (int64_t)B * kS16Mask, 2, 0.5f, c->seed_dev));
   FG_TRY(D_forward(n, n->G_y, B, true));
   FG_TRY(k_sigmoid_bce(c, n->D_logit, n->D_out, n->D_dlogit, &n->dstats->loss_G, n->gG + n->nG, B, B));
   FG_TRY(D_backward(n, n->D_dlogit, false, true));  // D's weight grads are discarded by the reference (:209 vs :92)
@@ -740,6 +741,8 @@ int fg_s16_destroy(fg_s16* n) {
     cudaSetDevice(n->c->device);
     cudaStreamSynchronize(n->c->stream);
   }
+  for (auto& g : n->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (void* p : n->allocs) cudaFree(p);
   if (n->hstats) cudaFreeHost(n->hstats);
   delete n;
@@ -911,7 +914,18 @@ int fg_s16_train_step(fg_s16* n, const fg_hyper* h, int B, const float* real, co
   FG_TRY(fg_to_dev(c, noise_G, (size_t)B * 100, n->in_c, &ng));
   if (masks_D) FG_TRY(fg_to_dev(c, masks_D, (size_t)B * kS16Mask, n->in_m1, &md));
   if (masks_G) FG_TRY(fg_to_dev(c, masks_G, (size_t)B * kS16Mask, n->in_m2, &mg));
-  FG_TRY(train_step(n, h, B, rd, nd, ng, md, mg, seed));
+  {  // eager the first time, then a captured CUDA graph of the step (nets.cu net_graph_run); the seed is read on the device
+    std::vector<uint8_t> key;
+    auto add = [&key](const void* p, size_t nb) { key.insert(key.end(), (const uint8_t*)p, (const uint8_t*)p + nb); };
+    const void* ptrs[] = {rd, nd, ng, md, mg, (const void*)c->stream, c->nccl_comm};
+    const int meta[3] = {c->graph_epoch, B, pack_key(c)};
+    add(meta, sizeof(meta));
+    add(h, sizeof(*h));
+    add(ptrs, sizeof(ptrs));
+    FG_TRY(net_graph_run(
+        c, n->graphs, key, seed, [&]() { return train_step(n, h, B, rd, nd, ng, md, mg, 0); },
+        [n]() { n->G_packed = n->D_packed = false; }, true));
+  }
   if (stats) {
     FG_CUDA(cudaStreamSynchronize(c->stream));
     const DeviceStats& s = *n->hstats;

@@ -112,5 +112,8 @@ def test_alternative_code_paths_agree_with_the_default(opt, val):
         assert list(a["conf"]) == list(b["conf"]) and a["t_D"] == b["t_D"] and a["t_G"] == b["t_G"]
         assert abs(a["loss_D"] - b["loss_D"]) < 2e-4 * max(1.0, abs(a["loss_D"]))
         assert abs(a["loss_G"] - b["loss_G"]) < 2e-3 * max(1.0, abs(a["loss_G"]))  # behind Adam's +-lr amplification
+    # parameters after three Adam steps: a PReLU pre-activation within rounding noise of 0 may take the other branch under
+    # another operand rounding (section 5 of DESIGN.md), which moves G's gradient by ~1e-2 relative and an Adam update
+    # by ~1e-5; noise-level gradients flip whole +-lr steps.  Bound: a few lr at most, and almost everything within 1e-4.
     d = np.abs(res[0][1].astype(np.float64) - res[1][1])
-    assert d.max() <= 3 * 2e-3 + 1e-6 and np.mean(d > 1e-5) < 0.05  # parameters: equal up to +-lr flips on noise-level gradients
+    assert d.max() <= 3 * 2e-3 + 1e-6 and np.mean(d > 1e-4) < 0.02, (d.max(), np.mean(d > 1e-4))
