@@ -7,15 +7,35 @@ both Adam updates) on synthetic 3x32x32 batches, batch 256 per GPU (BASELINE.jso
                                                              itself cannot run in this image)
 Prints ONE JSON line on rank 0.
 """
-import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+# stdout carries exactly ONE line (the JSON result of rank 0).  NCCL logs to the process's stdout (fd 1) -- the box
+# environment presets NCCL_DEBUG=VERSION, and settings made later in the process (NCCL_DEBUG_FILE, tried in round 2)
+# were not picked up -- so: keep a private handle on the real stdout for the result line, point fd 1 at stderr for
+# everything any native library prints, and raise NCCL's level to INFO (INIT lines: "... rank r nranks N ...") before
+# anything else is imported, unless the caller already asked for INFO / TRACE.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+
+def emit(obj):
+    """the one result line, on the real stdout"""
+    _RESULT_OUT.write(json.dumps(obj) + "\n")
+    _RESULT_OUT.flush()
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -194,14 +214,14 @@ def run_reference(args, rank, world):
     whole = "the whole 256-image batch" if b == 256 else "a %d-image sample of the 256-image batch" % b
     sample = "%s per step, %d steps, fp32 oracle port (THNN algorithm, %s), %d threads" % (whole, args.steps, port.gemm,
                                                                                          port.O.num_threads())
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
         "reference_detail": {"device": "cpu", "images_per_step": b, "gemm": port.gemm},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": port.O.num_threads(), "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def secondary_configs(steps=5):
@@ -243,17 +263,7 @@ def main():
     from face_generator_b200.lib import NET_D, NET_G, PinnedArray
     B, C, K, W = args.batch, 3, args.steps, max(args.warmup, 3)
     dist = None
-    # rank 0 must print ONE line on stdout; NCCL logs to stdout by default, so its log (whatever level the caller
-    # asked for; INIT lines carry "nranks N" by default) goes to stderr instead of being switched off
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-    # (NCCL_DEBUG_FILE=/dev/stderr produced nothing under torchrun on the GPU boxes: log to a per-process file and relay
-    # it to stderr at the end of the run)
-    nccl_log = None
-    if world > 1 and "NCCL_DEBUG_FILE" not in os.environ:
-        import tempfile
-        nccl_log = os.path.join(tempfile.gettempdir(), "fg_b200_nccl_%d.log" % os.getpid())
-        os.environ["NCCL_DEBUG_FILE"] = nccl_log
+    # (NCCL's log -- INIT lines carry "nranks N" -- goes to stderr: see the top of this file)
     if world > 1:
         import torch.distributed as dist  # plumbing only: rendezvous, barrier, max-over-ranks
         dist.init_process_group("gloo")
@@ -366,16 +376,6 @@ def main():
             os.environ.pop("FG_TF32_PROBE_N")
         except Exception as e:  # the probe must never cost the headline
             sys.stderr.write("tf32 peak probe failed: %s\n" % e)
-    if nccl_log:  # NCCL's own INIT lines ("... rank r nranks N ...") -> stderr
-        try:
-            import ctypes
-            ctypes.CDLL(None).fflush(None)  # NCCL keeps its debug FILE* fully buffered: flush every C stream first
-            if os.path.exists(nccl_log):
-                sys.stderr.write(open(nccl_log).read())
-                sys.stderr.flush()
-                os.remove(nccl_log)
-        except Exception as e:
-            sys.stderr.write("could not relay the NCCL log: %s\n" % e)
     if rank != 0:
         return
     peaks = load_peaks()
@@ -448,7 +448,7 @@ def main():
         out["cpu_baseline"] = {"value": b * it / t, "unit": "images/s", "cores": port.O.num_threads(), "kind": "port",
                                "sample": "%d iteration(s) at batch %d of %d (colour) of the fp32 oracle port (%s), %.1f s" % (
                                    it, b, B, port.gemm, t)}
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":
