@@ -51,6 +51,31 @@ for C, B, impl in ((3, 12, 2), (1, 6, 0)):  # ragged batches on purpose (not mul
     assert np.isfinite(st["loss_D"]) and np.isfinite(st["loss_G"])
     S.approx_parzen(net, diff[:2] + cr[:2], cr[:2], 5, rng)
     net.close()
+    # the --scale 16 nets, three identical calls: eager, captured, replayed
+    s16 = fg.S16(ctx)
+    s16.set_params(NET_G, (rng.standard_normal(s16.count(NET_G)) * 0.02).astype(np.float32))
+    s16.set_params(NET_D, (rng.standard_normal(s16.count(NET_D)) * 0.02).astype(np.float32))
+    r16 = rng.random((B // 2, C, 16, 16)).astype(np.float32)
+    zD, zG = rng.uniform(-1, 1, (B // 2, 100)).astype(np.float32), rng.uniform(-1, 1, (B, 100)).astype(np.float32)
+    for i in range(3):
+        st = s16.train_step(fg.hyper_default(), B, r16, zD, zG, None, None, 20 + i)
+        assert np.isfinite(st["loss_D"]) and np.isfinite(st["loss_G"])
+    s16.close()
+    # the 32x32 step through eager / capture / replay, on both operand splits
+    for f16 in (1, 0):
+        ctx.set_option("mma_f16", f16)
+        for i in range(3):
+            st = ctx.train_step(hyper, B, real, nD, nG, None, None, 30 + i)
+            assert np.isfinite(st["loss_D"]) and np.isfinite(st["loss_G"])
+    # SpatialConvolutionUpsample with factor 2 (L-op), both directions
+    from face_generator_b200.lib import _ptr
+    xs = rng.standard_normal((2, 64, 8, 8)).astype(np.float32)
+    ws = (rng.standard_normal((64, 64, 3, 3)) * 0.05).astype(np.float32)
+    bs, ys = np.zeros(64, np.float32), np.empty((2, 16, 16, 16), np.float32)
+    assert ctx.lib.fg_scu_forward(ctx.h, _ptr(xs), _ptr(ws), _ptr(bs), _ptr(ys), 2, 64, 8, 8, 16, 3, 2) == 0
+    dxs, dws = np.empty_like(xs), np.zeros_like(ws)
+    assert ctx.lib.fg_scu_backward_data(ctx.h, _ptr(ys), _ptr(ws), _ptr(dxs), 2, 64, 8, 8, 16, 3, 2) == 0
+    assert ctx.lib.fg_scu_backward_filter(ctx.h, _ptr(xs), _ptr(ys), _ptr(dws), None, 2, 64, 8, 8, 16, 3, 2) == 0
     ds.close()
     ctx.close()
     print("ok", C, B, impl, flush=True)
