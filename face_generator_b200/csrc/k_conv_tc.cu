@@ -230,7 +230,9 @@ __global__ void amax_kernel(const float* __restrict__ x, int64_t n4, unsigned* _
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));  // non-negative floats order like their bits
+  // non-negative floats order like their bits; a plain load first so that only warps raising the maximum issue the atomic
+  if ((threadIdx.x & 31) == 0 && m > 0.f && __float_as_uint(m) > *reinterpret_cast<volatile unsigned*>(slot))
+    atomicMax(slot, __float_as_uint(m));
 }
 template <bool ALIGNED>
 __global__ void split_h_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4,
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(256) pack_collapsed_tile_kernel(const float* _
     const int nl = pass == 0 ? (threadIdx.x >> 4) : (threadIdx.x & 15);
     const int cl = pass == 0 ? (threadIdx.x & 15) : (threadIdx.x >> 4);
     const float* p = &w[nl][cl * 25];
-    for (int tp = 0; tp < 36; ++tp) {
+    for (int tp = blockIdx.z * 9; tp < blockIdx.z * 9 + 9; ++tp) {  // grid.z = the 4 output phases
       const int ph = tp / 9, ty = (tp % 9) / 3, tx = tp % 3;
       int h0, h1, w0, w1;
       group_range(ph >> 1, ty, h0, h1);
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(256) pack_split_tile_kernel(const float* __res
   for (int pass = 0; pass < (d_hi ? 2 : 1); ++pass) {
     const int nl = pass == 0 ? (threadIdx.x >> 4) : (threadIdx.x & 15);
     const int cl = pass == 0 ? (threadIdx.x & 15) : (threadIdx.x >> 4);
-    for (int t = 0; t < KK; ++t) {
+    for (int t = blockIdx.z; t < KK; t += gridDim.z) {  // grid.z splits the taps
       T hi, lo;
       SplitTo<T>::run(w[nl][cl * KK + t], hi, lo);
       if (pass == 0) {
@@ -739,7 +741,7 @@ int tc_split_h(fg_ctx* c, const float* x, float* hh, float* hl, int64_t n, float
 }
 int tc_pack_split_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK) {
   if (KK == 9 && N % 16 == 0 && Cc % 16 == 0) {
-    pack_split_tile_kernel<__half, 9><<<dim3(Cc / 16, N / 16), 256, 0, c->stream>>>(W, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi,
+    pack_split_tile_kernel<__half, 9><<<dim3(Cc / 16, N / 16, 3), 256, 0, c->stream>>>(W, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi,
                                                                                     (__half*)d_lo, N, Cc);
     LAUNCH_CHECK(c);
     return FG_OK;
@@ -752,7 +754,7 @@ int tc_pack_split_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* 
 }
 int tc_pack_collapsed_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc) {
   if (N % 16 == 0 && Cc % 16 == 0) {
-    pack_collapsed_tile_kernel<__half><<<dim3(Cc / 16, N / 16), 256, 0, c->stream>>>(W, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi,
+    pack_collapsed_tile_kernel<__half><<<dim3(Cc / 16, N / 16, 4), 256, 0, c->stream>>>(W, (__half*)f_hi, (__half*)f_lo, (__half*)d_hi,
                                                                                      (__half*)d_lo, N, Cc);
     LAUNCH_CHECK(c);
     return FG_OK;
@@ -765,7 +767,7 @@ int tc_pack_collapsed_h(fg_ctx* c, const float* W, float* f_hi, float* f_lo, flo
 }
 int tc_pack_split(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc, int KK) {
   if (KK == 9 && N % 16 == 0 && Cc % 16 == 0) {
-    pack_split_tile_kernel<float, 9><<<dim3(Cc / 16, N / 16), 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc);
+    pack_split_tile_kernel<float, 9><<<dim3(Cc / 16, N / 16, 3), 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc);
     LAUNCH_CHECK(c);
     return FG_OK;
   }
@@ -777,7 +779,7 @@ int tc_pack_split(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_
 }
 int tc_pack_collapsed(fg_ctx* c, const float* W, float* f_hi, float* f_lo, float* d_hi, float* d_lo, int N, int Cc) {
   if (N % 16 == 0 && Cc % 16 == 0) {
-    pack_collapsed_tile_kernel<float><<<dim3(Cc / 16, N / 16), 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc);
+    pack_collapsed_tile_kernel<float><<<dim3(Cc / 16, N / 16, 4), 256, 0, c->stream>>>(W, f_hi, f_lo, d_hi, d_lo, N, Cc);
     LAUNCH_CHECK(c);
     return FG_OK;
   }

@@ -54,7 +54,12 @@ __device__ __forceinline__ void amax_commit(unsigned* amax, float m) {
   if (!amax) return;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+  // thousands of warps hit ONE word: an atomic per warp serialises at the L2 (measured 100+ us on the pooling kernels).
+  // A plain load first: only a warp that would actually raise the maximum issues the atomic (a handful per launch).
+  if ((threadIdx.x & 31) == 0 && m > 0.f) {
+    const unsigned bits = __float_as_uint(m);
+    if (bits > *reinterpret_cast<volatile unsigned*>(amax)) atomicMax(amax, bits);
+  }
 }
 __device__ __forceinline__ float amax4(float m, float a, float b, float c, float d) {
   return fmaxf(fmaxf(m, fmaxf(fabsf(a), fabsf(b))), fmaxf(fabsf(c), fabsf(d)));
