@@ -42,6 +42,20 @@ def test_s16_param_counts_match_oracle():
     assert lib.fg_s16_mask_per_sample() == OS.MASK_PER_SAMPLE == S16_MASK_PER_SAMPLE
 
 
+def test_oracle_reproduces_s16_golden():
+    """the committed vectors (tests/golden/make_golden_s16.py) pin the oracle's --scale 16 iteration"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "s16_train_color_b8.npz"), allow_pickle=False)
+    B, C = int(g["B"]), int(g["C"])
+    case = SU.make_case(B, C, seed=int(g["seed"]), init=str(g["init"]))
+    assert abs(sum(np.abs(case[k]).sum() for k in sorted(case)) - float(g["input_checksum"])) < 1e-5
+    res = SU.oracle_iteration(case, B, C)
+    assert abs(res["lossD"] - float(g["lossD"])) < 1e-10 and abs(res["lossG"] - float(g["lossG"])) < 1e-10
+    np.testing.assert_array_equal(res["conf"], g["conf"])
+    assert PU.relerr(res["gradD"][::1009], g["gradD"]) < 1e-9 and PU.relerr(res["gradG"][::1009], g["gradG"]) < 1e-9
+    assert PU.relerr(res["PD"][::1009], g["PD"]) < 1e-12 and PU.relerr(res["bn"], g["bn"]) < 1e-12
+
+
 # ------------------------------------------------------------------------------------------ GPU
 def _ctx(B, C, impl):
     import face_generator_b200 as fg
@@ -165,6 +179,30 @@ def test_gpu_s16_train_step_matches_oracle(C, B, impl):
         big = np.abs(g) > 1e-3 * np.abs(g).max()
         assert np.abs((P1 - P0)[big] - (R1 - P0)[big]).max() < 2e-5, key  # lr = 1e-3
     assert PU.relerr(net.get_bn_state(), ref["bn"]) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl", [0, 2])
+def test_gpu_s16_train_step_matches_golden(impl):
+    """the same step against the committed golden vectors (no oracle run on the GPU box)"""
+    import os
+    from face_generator_b200.lib import NET_D, NET_G, hyper_default
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "s16_train_color_b8.npz"), allow_pickle=False)
+    B, C = int(g["B"]), int(g["C"])
+    case = SU.make_case(B, C, seed=int(g["seed"]), init=str(g["init"]))
+    ctx, net = _ctx(B, C, impl)
+    net.set_params(NET_G, case["PG"])
+    net.set_params(NET_D, case["PD"])
+    h = hyper_default()
+    st = net.train_step(h, B, case["real"], case["noise_D"], case["noise_G"], case["masks_D"], case["masks_G"])
+    assert abs(st["loss_D"] - float(g["lossD"])) < TOL * max(1.0, abs(float(g["lossD"])))
+    assert abs(st["loss_G"] - float(g["lossG"])) < 2e-3 * max(1.0, abs(float(g["lossG"])))
+    assert list(st["conf"]) == [int(v) for v in g["conf"]]
+    mD, _, _ = net.get_adam_state(NET_D)
+    assert np.abs(mD[::1009] / (1.0 - h.beta1) - g["gradD"]).max() < TOL * float(g["gradD_absmax"])
+    mG, _, _ = net.get_adam_state(NET_G)
+    assert np.abs(mG[::1009] / (1.0 - h.beta1) - g["gradG"]).max() < 5e-3 * float(g["gradG_absmax"])
+    assert PU.relerr(net.get_bn_state(), g["bn"]) < 1e-3
 
 
 @pytest.mark.gpu
