@@ -113,3 +113,58 @@ def test_D16_fwd_bwd_matches_torch(C):
         n = int(np.prod(s))
         assert rel(dP[o:o + n], gt[o:o + n]) < 1e-9, k
     assert rel(dimg, it.grad.numpy()) < 1e-9  # ConcatTable: both branches contribute to the input gradient
+
+
+def test_s16_iteration_composition_matches_torch():
+    """tests/s16_utils.oracle_iteration (the checker of fg_s16_train_step) against the same adversarial.lua:240-288
+    iteration written with PyTorch autograd in fp64: BCE (2015 Lua eps form), L2 penalty -> clamp, the D step's Adam
+    update feeding the G step, D's weight gradients discarded in the G step."""
+    import s16_utils as SU
+    B, C = 8, 3
+    case = SU.make_case(B, C, seed=77, init="near")
+    hp = SU.HYPER
+    ref = SU.oracle_iteration(case, B, C)
+    t64 = lambda a: torch.tensor(np.asarray(a, np.float64))
+
+    def bce(out, target):  # nn.BCECriterion of the 2015 Torch: -(t log(x+eps) + (1-t) log(1-x+eps)), eps = 1e-12, mean
+        eps = 1e-12
+        return -(target * torch.log(out + eps) + (1 - target) * torch.log(1 - out + eps)).mean()
+
+    def clamp_pen(P, g, l1_loss, l1_grad, l2, c):
+        g = g + l1_grad * torch.sign(P) + l2 * P
+        return g.clamp(-c, c), l1_loss * P.abs().sum() + 0.5 * l2 * (P * P).sum()
+
+    PG, PD = t64(case["PG"]).requires_grad_(True), t64(case["PD"]).requires_grad_(True)
+    # ---- D step ----
+    with torch.no_grad():
+        fake = torch_G16(PG, t64(case["noise_D"]), C)
+    assert rel(ref["fake"], fake.numpy()) < 1e-10
+    x = torch.cat([t64(case["real"]), fake])
+    tg = torch.cat([torch.ones(B // 2, dtype=torch.float64), torch.zeros(B // 2, dtype=torch.float64)])
+    out = torch_D16(PD, x, t64(case["masks_D"]), C)
+    lossD = bce(out, tg)
+    gD, = torch.autograd.grad(lossD, PD)
+    gD, pen = clamp_pen(PD.detach(), gD, hp["D_L1"], hp["D_L1"], hp["D_L2"], hp["D_clamp"])
+    assert abs(float((lossD + pen).detach()) - ref["lossD"]) < 1e-9 * max(1.0, abs(ref["lossD"]))
+    assert rel(ref["gradD"], gD.numpy()) < 1e-8
+    # interruptableAdam at t = 1 (interruptable_optimizers.lua:49-94): m = (1-b1) g, v = (1-b2) g^2
+    b1, b2, eps, lr = hp["beta1"], hp["beta2"], hp["eps"], hp["lr_D"]
+    m, v = (1 - b1) * gD, (1 - b2) * gD * gD
+    step = lr * np.sqrt(1 - b2) / (1 - b1)
+    PD1 = (PD.detach() - step * m / (v.sqrt() + eps)).requires_grad_(True)
+    assert rel(ref["PD"], PD1.detach().numpy()) < 1e-10
+    # ---- G step ----
+    img = torch_G16(PG, t64(case["noise_G"]), C)
+    outG = torch_D16(PD1, img, t64(case["masks_G"]), C)
+    lossG = bce(outG, torch.ones(B, dtype=torch.float64))
+    gG, = torch.autograd.grad(lossG, PG)
+    gG, penG = clamp_pen(PG.detach(), gG, hp["G_L1"], hp["G_L2"], hp["G_L2"], hp["G_clamp"])  # the :223 quirk
+    assert abs(float((lossG + penG).detach()) - ref["lossG"]) < 1e-9 * max(1.0, abs(ref["lossG"]))
+    LG = OS.G_layout(C)
+    scale = np.abs(ref["gradG"]).max()
+    for k, (o, s) in LG.items():
+        n = int(np.prod(s))
+        if k in ("C1b", "C2b"):
+            assert np.abs(ref["gradG"][o:o + n]).max() < 1e-9 * scale
+            continue
+        assert rel(ref["gradG"][o:o + n], gG.numpy()[o:o + n]) < 1e-7, k
