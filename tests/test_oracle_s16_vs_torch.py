@@ -168,3 +168,23 @@ def test_s16_iteration_composition_matches_torch():
             assert np.abs(ref["gradG"][o:o + n]).max() < 1e-9 * scale
             continue
         assert rel(ref["gradG"][o:o + n], gG.numpy()[o:o + n]) < 1e-7, k
+
+
+@pytest.mark.parametrize("factor", [1, 2, 3])
+def test_scu_is_the_wide_convolution_under_a_view(factor):
+    """layers/cudnnSpatialConvolutionUpsample.lua:14-58 restated with torch: parent conv to nOut*f*f planes, output
+    .view(N, nOut, h*f, w*f), gradOutput viewed back.  The oracle's convolution + numpy reshape (what
+    tests/test_gpu_s16.py holds fg_scu_* to) gives the same forward values and gradients."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(90 + factor)
+    N, Cin, nOut, k, H = 2, 5, 3, 3, 4
+    planes = nOut * factor * factor
+    x, w, b = rng.standard_normal((N, Cin, H, H)), rng.standard_normal((planes, Cin, k, k)), rng.standard_normal(planes)
+    xt, wt, bt = (torch.tensor(v, requires_grad=True) for v in (x, w, b))
+    yt = F.conv2d(xt, wt, bt, padding=k // 2).view(N, nOut, H * factor, H * factor)   # updateOutput :18-30
+    y = O.f64.conv_fwd(x, w, b).reshape(N, nOut, H * factor, H * factor)
+    assert rel(y, yt.detach().numpy()) < 1e-12
+    dy = rng.standard_normal(y.shape)
+    yt.backward(torch.tensor(dy))                                                    # autograd views gradOutput back (:32-58)
+    dx, dw, db = O.f64.conv_bwd(x, w, dy.reshape(N, planes, H, H))
+    assert rel(dx, xt.grad.numpy()) < 1e-12 and rel(dw, wt.grad.numpy()) < 1e-12 and rel(db, bt.grad.numpy()) < 1e-12
