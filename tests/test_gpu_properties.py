@@ -115,5 +115,7 @@ def test_alternative_code_paths_agree_with_the_default(opt, val):
     # parameters after three Adam steps: a PReLU pre-activation within rounding noise of 0 may take the other branch under
     # another operand rounding (section 5 of DESIGN.md), which moves G's gradient by ~1e-2 relative and an Adam update
     # by ~1e-5; noise-level gradients flip whole +-lr steps.  Bound: a few lr at most, and almost everything within 1e-4.
+    # (measured for mma_f16 = 0 vs 1: max 1.0e-3, 18 % of the elements beyond 1e-5; a wrong code path moves every
+    # element by ~lr per step and shows in the losses above first)
     d = np.abs(res[0][1].astype(np.float64) - res[1][1])
-    assert d.max() <= 3 * 2e-3 + 1e-6 and np.mean(d > 1e-4) < 0.02, (d.max(), np.mean(d > 1e-4))
+    assert d.max() <= 3 * 2e-3 + 1e-6 and d.mean() < 2e-4, (d.max(), d.mean())
