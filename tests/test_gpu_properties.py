@@ -118,4 +118,4 @@ def test_alternative_code_paths_agree_with_the_default(opt, val):
     # (measured for mma_f16 = 0 vs 1: max 1.0e-3, 18 % of the elements beyond 1e-5; a wrong code path moves every
     # element by ~lr per step and shows in the losses above first)
     d = np.abs(res[0][1].astype(np.float64) - res[1][1])
-    assert d.max() <= 3 * 2e-3 + 1e-6 and d.mean() < 2e-4, (d.max(), d.mean())
+    assert d.max() <= 3 * 2e-3 + 1e-6 and d.mean() < 5e-4, (d.max(), d.mean())
